@@ -1,0 +1,192 @@
+"""Host-side mirror of the reference's resampler interface over the C ABI.
+
+``RateConverter`` is the reference's ``resampler_link`` (chain.h:22-43): open / push / pull / drain / close
+on interleaved float32 HOST buffers. ``BatchConverter`` is the device-resident extension (RRX_batch_*).
+Both take the C library as a parameter so the test suite can run the identical Python code over the host
+emulation build; the package-level constructors always use the CUDA library."""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import RR_OK, Plan, RateError
+
+
+class RateConverter:
+    """engine: 'auto' = RR_open (Best -> fp64 engine, Normal -> fp32 engine, rate/rate_uni.c:38-51);
+    'float' / 'double' = RR_ctor_float / RR_ctor_double with the config's quality (rate/rate_i.h:39-43)."""
+
+    def __init__(self, cfg, nchannels, engine="auto", lib=None):
+        self.lib = lib or _capi.product()
+        self.nch = int(nchannels)
+        self.h = C.c_void_p()
+        if engine == "auto":
+            rc = self.lib.RR_open(C.byref(cfg), self.nch, C.byref(self.h))
+            if rc != RR_OK:
+                raise RateError(self.lib, rc, "RR_open")
+        else:
+            ctor = {"float": self.lib.RR_ctor_float, "double": self.lib.RR_ctor_double,
+                    "SSE": self.lib.RR_ctor_SSE, "SSE3": self.lib.RR_ctor_SSE3}[engine]
+            self.h = C.c_void_p(ctor(C.byref(cfg), self.nch))
+            if not self.h.value:
+                raise RateError(self.lib, _capi.RR_INTERNAL, "RR_ctor_" + engine)
+        self.sample_bytes = self.plan()["sample_bytes"]
+        self.dtype = np.float32 if self.sample_bytes == 4 else np.float64
+
+    def plan(self):
+        p = Plan()
+        rc = self.lib.RRX_plan_dump(self.h, C.byref(p))
+        if rc != RR_OK:
+            raise RateError(self.lib, rc, "RRX_plan_dump")
+        return p.as_dict()
+
+    def push(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        assert x.ndim == 2 and x.shape[1] == self.nch
+        rc = self.lib.RR_push(self.h, x.ctypes.data, x.shape[0])
+        if rc != RR_OK:
+            raise RateError(self.lib, rc, "RR_push")
+
+    def pull(self, osamp):
+        out = np.empty((osamp, self.nch), dtype=np.float32)
+        ogen = C.c_size_t(0)
+        rc = self.lib.RR_pull(self.h, out.ctypes.data, osamp, C.byref(ogen))
+        if rc != RR_OK:
+            raise RateError(self.lib, rc, "RR_pull")
+        return out[:ogen.value]
+
+    def pull_native(self, osamp):
+        out = np.empty((self.nch, osamp), dtype=self.dtype)
+        ogen = C.c_size_t(0)
+        rc = self.lib.RRX_pull_native(self.h, out.ctypes.data, osamp, C.byref(ogen))
+        if rc != RR_OK:
+            raise RateError(self.lib, rc, "RRX_pull_native")
+        return out[:, :ogen.value]
+
+    def flow(self, x, osamp):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        out = np.empty((osamp, self.nch), dtype=np.float32)
+        iused, ogen = C.c_size_t(0), C.c_size_t(0)
+        rc = self.lib.RR_flow(self.h, x.ctypes.data if x.shape[0] else None, out.ctypes.data, x.shape[0], osamp,
+                              C.byref(iused), C.byref(ogen))
+        if rc != RR_OK:
+            raise RateError(self.lib, rc, "RR_flow")
+        return out[:ogen.value], iused.value
+
+    def drain(self):
+        rc = self.lib.RR_drain(self.h)
+        if rc != RR_OK:
+            raise RateError(self.lib, rc, "RR_drain")
+
+    def dft_spectrum(self, instance):
+        n = self.lib.RRX_dft_spectrum(self.h, instance, None, 0)
+        out = np.empty(max(n, 0), dtype=self.dtype)
+        if n > 0:
+            self.lib.RRX_dft_spectrum(self.h, instance, out.ctypes.data, n)
+        return out
+
+    def close(self):
+        if self.h is not None and self.h.value:
+            self.lib.RR_close(C.byref(self.h))
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def resample(cfg, x, engine="float", chunk=65536, native=False, pull_chunk=None, lib=None):
+    """Push ``x`` ([frames, nch] float32) in ``chunk``-frame pieces, pulling everything after each push,
+    then drain: the driving pattern of foo_dsp_rate.cpp:165-187,218-313. Returns (y, counts)."""
+    nch = x.shape[1]
+    r = RateConverter(cfg, nch, engine, lib=lib)
+    pull_chunk = pull_chunk or max(chunk * 4, 1 << 16)
+    outs, counts = [], []
+
+    def pull_all():
+        tot = 0
+        while True:
+            y = (r.pull_native(pull_chunk).T.copy() if native else r.pull(pull_chunk).copy())
+            if y.shape[0] == 0:
+                break
+            outs.append(y)
+            tot += y.shape[0]
+        counts.append(tot)
+
+    step = min(chunk, r.plan()["isamp_max"])
+    for s in range(0, x.shape[0], step):
+        r.push(x[s:s + step])
+        pull_all()
+    r.drain()
+    pull_all()
+    dt = r.dtype if native else np.float32
+    r.close()
+    y = np.concatenate(outs, axis=0) if outs else np.zeros((0, nch), dtype=dt)
+    return y, counts
+
+
+class BatchConverter:
+    """Device-resident batch: nstreams x nchannels lanes of equal length, one shot. Pointers are raw device
+    addresses (ints): pass ``tensor.data_ptr()`` of CUDA tensors, or numpy ``ctypes.data`` under emulation."""
+
+    def __init__(self, cfg, nchannels, nstreams, frames_in_max, engine="float", device=-1, lib=None):
+        self.lib = lib or _capi.product()
+        self.nch, self.nstreams = int(nchannels), int(nstreams)
+        self.sample_bytes = 4 if engine == "float" else 8
+        self.b = C.c_void_p()
+        rc = self.lib.RRX_batch_open(C.byref(cfg), self.sample_bytes, self.nch, self.nstreams, int(frames_in_max),
+                                     int(device), C.byref(self.b))
+        if rc != RR_OK:
+            raise RateError(self.lib, rc, "RRX_batch_open")
+
+    def plan(self):
+        p = Plan()
+        self.lib.RRX_batch_plan(self.b, C.byref(p))
+        return p.as_dict()
+
+    def frames_out(self, frames_in):
+        return int(self.lib.RRX_batch_frames_out(self.b, int(frames_in)))
+
+    def process(self, d_in, frames_in, d_out, stream=0):
+        rc = self.lib.RRX_batch_process(self.b, d_in, int(frames_in), d_out, stream)
+        if rc != RR_OK:
+            raise RateError(self.lib, rc, "RRX_batch_process")
+
+    def process_native(self, d_in, frames_in, d_out, stream=0):
+        rc = self.lib.RRX_batch_process_native(self.b, d_in, int(frames_in), d_out, stream)
+        if rc != RR_OK:
+            raise RateError(self.lib, rc, "RRX_batch_process_native")
+
+    def input_window(self, frames_in_total, out_begin, out_count):
+        f, c = C.c_uint64(0), C.c_uint64(0)
+        rc = self.lib.RRX_batch_input_window(self.b, int(frames_in_total), int(out_begin), int(out_count),
+                                             C.byref(f), C.byref(c))
+        if rc != RR_OK:
+            raise RateError(self.lib, rc, "RRX_batch_input_window")
+        return f.value, c.value
+
+    def process_range(self, d_in_window, window_first, window_frames, frames_in_total, out_begin, out_count,
+                      d_out, stream=0):
+        rc = self.lib.RRX_batch_process_range(self.b, d_in_window, int(window_first), int(window_frames),
+                                              int(frames_in_total), int(out_begin), int(out_count), d_out, stream)
+        if rc != RR_OK:
+            raise RateError(self.lib, rc, "RRX_batch_process_range")
+
+    def last_launches(self):
+        return int(self.lib.RRX_batch_last_launches(self.b))
+
+    def flops(self, frames_in):
+        return float(self.lib.RRX_batch_flops(self.b, int(frames_in)))
+
+    def close(self):
+        if self.b is not None and self.b.value:
+            self.lib.RRX_batch_close(C.byref(self.b))
+        self.b = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

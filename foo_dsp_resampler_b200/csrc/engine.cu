@@ -1,0 +1,1092 @@
+// engine.cu -- device engine: table upload, stage launches, and the two front-ends (batch / streaming).
+//
+// Built by nvcc for sm_100a this is the product. With -DB200RATE_EMU (tests/emu only) the "device" is
+// host memory and a launch is a serial loop over the same CTA programs, which lets the host-side
+// orchestration and all index arithmetic be checked against the oracle where no GPU exists. The EMU
+// build is test infrastructure and is never part of libb200rate.so.
+//
+// Coordinates: FIFO i feeds stage i and starts with `preload` zeros (rate/rate_base.h:417-421); stage i
+// output k lands at coordinate preload[i+1] + k of FIFO i+1. All block / phase positions are closed-form
+// functions of absolute indices, so any range of any stage can be (re)computed independently -- the
+// property the reference only has implicitly through its FIFO state (rate/rate_base.h:96-128).
+#include "engine.hpp"
+
+#include <algorithm>
+#include <cassert>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <type_traits>
+#include <vector>
+
+#include "fft_tables.hpp"
+#include "rate_kernels.cuh"
+
+#ifndef B200RATE_EMU
+#include <cuda_runtime.h>
+#endif
+
+namespace b200rate {
+
+// ===================================================================================================
+// error plumbing
+// ===================================================================================================
+static thread_local std::string g_last_error;
+void set_last_error(const std::string &msg) { g_last_error = msg; }
+const char *last_error() { return g_last_error.c_str(); }
+
+// ===================================================================================================
+// backend: CUDA, or host emulation for tests
+// ===================================================================================================
+#ifdef B200RATE_EMU
+typedef void *stream_t;
+static int be_set_device(int) { return RR_OK; }
+static int be_malloc(void **p, size_t n) { *p = calloc(1, n ? n : 1); return *p ? RR_OK : RR_ENOMEM; }
+static void be_free(void *p) { free(p); }
+static int be_h2d(void *d, const void *h, size_t n, stream_t) { memcpy(d, h, n); return RR_OK; }
+static int be_d2h(void *h, const void *d, size_t n, stream_t) { memcpy(h, d, n); return RR_OK; }
+static int be_sync(stream_t) { return RR_OK; }
+static int be_num_sms() { return 1; }
+static size_t be_max_smem() { return 227 * 1024; }
+#else
+typedef cudaStream_t stream_t;
+static int cuda_fail(cudaError_t e, const char *what)
+{
+  set_last_error(std::string(what) + ": " + cudaGetErrorString(e));
+  return e == cudaErrorMemoryAllocation ? RR_ENOMEM : RR_INTERNAL;
+}
+#define CUDA_TRY(expr)                                           \
+  do {                                                           \
+    cudaError_t e_ = (expr);                                     \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #expr);          \
+  } while (0)
+static int be_set_device(int dev)
+{
+  if (dev >= 0) CUDA_TRY(cudaSetDevice(dev));
+  int cur = -1;
+  CUDA_TRY(cudaGetDevice(&cur));
+  CUDA_TRY(cudaFree(0));
+  return RR_OK;
+}
+static int be_malloc(void **p, size_t n) { CUDA_TRY(cudaMalloc(p, n ? n : 1)); return RR_OK; }
+static void be_free(void *p) { if (p) cudaFree(p); }
+static int be_h2d(void *d, const void *h, size_t n, stream_t s)
+{
+  CUDA_TRY(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s));
+  return RR_OK;
+}
+static int be_d2h(void *h, const void *d, size_t n, stream_t s)
+{
+  CUDA_TRY(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s));
+  return RR_OK;
+}
+static int be_sync(stream_t s) { CUDA_TRY(cudaStreamSynchronize(s)); return RR_OK; }
+static int be_num_sms()
+{
+  int dev = 0, n = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  return n;
+}
+static size_t be_max_smem()
+{
+  int dev = 0, n = 48 * 1024;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  return static_cast<size_t>(n);
+}
+#endif
+
+// ===================================================================================================
+// kernels
+// ===================================================================================================
+constexpr int kDftThreads = 256;
+constexpr int kTileThreads = 256;
+constexpr int kPolyTile = 2048;      // outputs per CTA tile
+constexpr int kHalfTile = 2048;
+constexpr int kCopyTile = 4096;      // elements per CTA tile (lane-fastest)
+
+struct CopyParams {                  // out[coord c0 + j] = in[coord c0 + j + in_shift]
+  LaneView in, out;
+  long long c0, n, in_shift;
+  int nlanes;
+};
+
+template <class InT, class OutT>
+RR_PROG void copy_program(const CopyParams &p, long long work)
+{
+  const long long total = p.n * p.nlanes;
+  const long long e0 = work * kCopyTile;
+  const int cnt = (total - e0) < kCopyTile ? (int)(total - e0) : kCopyTile;
+  const long long j0 = e0 / p.nlanes;
+  const unsigned l0 = (unsigned)(e0 - j0 * p.nlanes);
+  cta_for(cnt, [&](int t) {
+    const unsigned u = l0 + (unsigned)t, dj = u / (unsigned)p.nlanes;
+    const int l = (int)(u - dj * (unsigned)p.nlanes);
+    const long long j = j0 + dj;
+    const OutT v = (OutT)view_read<InT, InT>(p.in, lane_offset(p.in, l), p.c0 + j + p.in_shift);
+    view_write<OutT, OutT>(p.out, lane_offset(p.out, l), p.c0 + j, v);
+  });
+}
+
+#ifndef B200RATE_EMU
+extern __shared__ __align__(16) unsigned char rr_smem_raw[];
+
+template <class T, class InT, class OutT>
+__global__ void __launch_bounds__(kDftThreads) dft_kernel(const __grid_constant__ DftParams<T> p, long long nwork)
+{
+  T *smem = reinterpret_cast<T *>(rr_smem_raw);
+  for (long long w = blockIdx.x; w < nwork; w += gridDim.x) dft_stage_program<T, InT, OutT>(p, w, smem);
+}
+template <class T, class InT, class OutT>
+__global__ void __launch_bounds__(kTileThreads) poly0_kernel(const __grid_constant__ PolyParams<T> p, long long nwork)
+{
+  T *smem = reinterpret_cast<T *>(rr_smem_raw);
+  for (long long w = blockIdx.x; w < nwork; w += gridDim.x) poly0_program<T, InT, OutT>(p, w, smem);
+}
+template <class T, class InT, class OutT>
+__global__ void __launch_bounds__(kTileThreads) polyN_kernel(const __grid_constant__ PolyParams<T> p, long long nwork)
+{
+  T *smem = reinterpret_cast<T *>(rr_smem_raw);
+  for (long long w = blockIdx.x; w < nwork; w += gridDim.x) polyN_program<T, InT, OutT>(p, w, smem);
+}
+template <class T, class InT, class OutT>
+__global__ void __launch_bounds__(kTileThreads) halfband_kernel(const __grid_constant__ HalfbandParams<T> p, long long nwork)
+{
+  T *smem = reinterpret_cast<T *>(rr_smem_raw);
+  for (long long w = blockIdx.x; w < nwork; w += gridDim.x) halfband_program<T, InT, OutT>(p, w, smem);
+}
+template <class InT, class OutT>
+__global__ void __launch_bounds__(kTileThreads) copy_kernel(const __grid_constant__ CopyParams p, long long nwork)
+{
+  for (long long w = blockIdx.x; w < nwork; w += gridDim.x) copy_program<InT, OutT>(p, w);
+}
+
+struct LaunchInfo { int blocks_per_sm; size_t smem_set; };
+static std::map<std::pair<const void *, size_t>, LaunchInfo> &launch_cache()
+{
+  static std::map<std::pair<const void *, size_t>, LaunchInfo> c;
+  return c;
+}
+
+template <class Kernel, class Params>
+static int launch_persistent(Kernel kernel, const Params &p, long long nwork, int threads, size_t smem, stream_t s)
+{
+  if (nwork <= 0) return RR_OK;
+  const void *key = reinterpret_cast<const void *>(kernel);
+  auto &cache = launch_cache();
+  auto it = cache.find(std::make_pair(key, smem));
+  if (it == cache.end()) {
+    if (smem > 48 * 1024)
+      CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    int occ = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
+    if (occ < 1) { set_last_error("kernel does not fit on an SM"); return RR_INTERNAL; }
+    it = cache.emplace(std::make_pair(key, smem), LaunchInfo{occ, smem}).first;
+  } else if (smem > 48 * 1024) {
+    // the attribute is per function, the largest request so far wins; re-arm when this one is larger
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  }
+  const long long resident = static_cast<long long>(it->second.blocks_per_sm) * be_num_sms();
+  const unsigned grid = static_cast<unsigned>(std::min<long long>(nwork, resident));
+  kernel<<<grid, threads, smem, s>>>(p, nwork);
+  CUDA_TRY(cudaGetLastError());
+  return RR_OK;
+}
+#endif  // !B200RATE_EMU
+
+// Typed dispatch. For the fp32 engine every buffer is float; the fp64 engine reads float at the caller
+// boundary and double in between.
+template <class T> struct Launch {
+  static constexpr bool kIsF32 = std::is_same<T, float>::value;
+
+#ifdef B200RATE_EMU
+  template <class F> static int serial(long long nwork, size_t smem_bytes, F body)
+  {
+    std::vector<unsigned char> smem(smem_bytes + 64);
+    for (long long w = 0; w < nwork; ++w) body(w, reinterpret_cast<T *>(smem.data()));
+    return RR_OK;
+  }
+#endif
+
+#define RR_DISPATCH_IO(CALL)                                                       \
+  do {                                                                             \
+    if (kIsF32 || (!in_f32 && !out_f32)) return CALL(T, T);                        \
+    if (in_f32 && out_f32) return CALL(float, float);                              \
+    if (in_f32) return CALL(float, T);                                             \
+    return CALL(T, float);                                                         \
+  } while (0)
+
+  static int dft(const DftParams<T> &p, bool in_f32, bool out_f32, long long nwork, size_t smem, stream_t s)
+  {
+#ifdef B200RATE_EMU
+#define RR_CALL(I, O) serial(nwork, smem, [&](long long w, T *sm) { dft_stage_program<T, I, O>(p, w, sm); })
+#else
+#define RR_CALL(I, O) launch_persistent(dft_kernel<T, I, O>, p, nwork, kDftThreads, smem, s)
+#endif
+    (void)s;
+    RR_DISPATCH_IO(RR_CALL);
+#undef RR_CALL
+  }
+  static int poly0(const PolyParams<T> &p, bool in_f32, bool out_f32, long long nwork, size_t smem, stream_t s)
+  {
+#ifdef B200RATE_EMU
+#define RR_CALL(I, O) serial(nwork, smem, [&](long long w, T *sm) { poly0_program<T, I, O>(p, w, sm); })
+#else
+#define RR_CALL(I, O) launch_persistent(poly0_kernel<T, I, O>, p, nwork, kTileThreads, smem, s)
+#endif
+    (void)s;
+    RR_DISPATCH_IO(RR_CALL);
+#undef RR_CALL
+  }
+  static int polyN(const PolyParams<T> &p, bool in_f32, bool out_f32, long long nwork, size_t smem, stream_t s)
+  {
+#ifdef B200RATE_EMU
+#define RR_CALL(I, O) serial(nwork, smem, [&](long long w, T *sm) { polyN_program<T, I, O>(p, w, sm); })
+#else
+#define RR_CALL(I, O) launch_persistent(polyN_kernel<T, I, O>, p, nwork, kTileThreads, smem, s)
+#endif
+    (void)s;
+    RR_DISPATCH_IO(RR_CALL);
+#undef RR_CALL
+  }
+  static int halfband(const HalfbandParams<T> &p, bool in_f32, bool out_f32, long long nwork, size_t smem, stream_t s)
+  {
+#ifdef B200RATE_EMU
+#define RR_CALL(I, O) serial(nwork, smem, [&](long long w, T *sm) { halfband_program<T, I, O>(p, w, sm); })
+#else
+#define RR_CALL(I, O) launch_persistent(halfband_kernel<T, I, O>, p, nwork, kTileThreads, smem, s)
+#endif
+    (void)s;
+    RR_DISPATCH_IO(RR_CALL);
+#undef RR_CALL
+  }
+  static int copy(const CopyParams &p, bool in_f32, bool out_f32, stream_t s)
+  {
+    const long long nwork = (p.n * p.nlanes + kCopyTile - 1) / kCopyTile;
+#ifdef B200RATE_EMU
+#define RR_CALL(I, O) serial(nwork, 0, [&](long long w, T *) { copy_program<I, O>(p, w); })
+#else
+#define RR_CALL(I, O) launch_persistent(copy_kernel<I, O>, p, nwork, kTileThreads, 0, s)
+#endif
+    (void)s;
+    RR_DISPATCH_IO(RR_CALL);
+#undef RR_CALL
+  }
+#undef RR_DISPATCH_IO
+};
+
+// ===================================================================================================
+// stage geometry (host) -- closed forms of the reference's per-call bookkeeping
+// ===================================================================================================
+struct StageGeom {
+  int kind = 0, preload = 0;
+  // half-band
+  int hb_c = 0;
+  // dft
+  int N = 0, ov = 0, V = 0, L = 1, step = 1, in_mode = 0, Pf = 0, Ni = 0, remL0 = 0, q = 0, kept = 0, filter = 0;
+  // poly
+  int n = 0, Lp = 1, order = 0, phase_bits = 0, pre_post = 0;
+  long long at0 = 0, pstep = 1;    // vpoly0: units of 1/L input samples; vpoly1..3: 32.32 fixed point
+};
+
+typedef __int128 i128;
+
+static inline long long ceil_div(long long a, long long b) { return a <= 0 ? 0 : (a + b - 1) / b; }
+
+// ---- DFT block geometry ----
+static long long dft_Rb(const StageGeom &g, long long b)
+{
+  if (g.in_mode != DFT_IN_ZERO_STUFF) return b * static_cast<long long>(g.q);
+  const long long Pb = b * static_cast<long long>(g.V);
+  return Pb <= g.remL0 ? 0 : (Pb - g.remL0 + g.L - 1) / g.L;
+}
+static int dft_remLb(const StageGeom &g, long long b)
+{
+  if (g.in_mode != DFT_IN_ZERO_STUFF) return g.remL0;
+  return static_cast<int>(g.remL0 + static_cast<long long>(g.L) * dft_Rb(g, b) - b * static_cast<long long>(g.V));
+}
+static long long dft_span(const StageGeom &g, long long b)   // inputs a block touches
+{
+  if (g.in_mode == DFT_IN_FREQ_UP) return g.Pf;
+  if (g.in_mode == DFT_IN_COPY) return g.N;
+  return (g.N - dft_remLb(g, b) + g.L - 1) / g.L;
+}
+static long long dft_kfirst(const StageGeom &g, long long b)  // first output index of block b
+{
+  if (g.step == 1) return b * static_cast<long long>(g.V);
+  if (g.step > 1) return (b * static_cast<long long>(g.V) + g.step - 1) / g.step;
+  return b * static_cast<long long>(g.kept);
+}
+static long long dft_block_of(const StageGeom &g, long long k)
+{
+  if (g.step == 1) return k / g.V;
+  if (g.step > 1) return (k * g.step) / g.V;
+  return k / g.kept;
+}
+// blocks runnable once `W` samples are in the input FIFO (dft_filter.h:78), starting the search at `from`
+static long long dft_blocks_ready(const StageGeom &g, long long W, long long from)
+{
+  long long b = from;
+  while (dft_remLb(g, b) + static_cast<long long>(g.L) * (W - dft_Rb(g, b)) >= g.N) ++b;
+  return b;
+}
+
+// ---- polyphase geometry ----
+static long long poly_q(const StageGeom &g, long long i)      // first input coordinate (minus pre) of output i
+{
+  if (g.order == 0) return (g.at0 + i * g.pstep) / g.Lp;
+  return static_cast<long long>((static_cast<i128>(g.at0) + static_cast<i128>(i) * g.pstep) >> 32);
+}
+static long long poly_ready(const StageGeom &g, long long W)  // outputs available once W samples are in
+{
+  const long long avail = W - g.pre_post;
+  if (avail <= 0) return 0;
+  if (g.order == 0) return ceil_div(avail * g.Lp - g.at0, g.pstep);
+  const i128 lim = (static_cast<i128>(avail) << 32) - g.at0;
+  return lim <= 0 ? 0 : static_cast<long long>((lim + g.pstep - 1) / g.pstep);
+}
+static long long half_ready(const StageGeom &g, long long W)  // rate_filters_generic.h:83 in closed form
+{
+  const long long x = W - 4 * g.hb_c + 1;
+  return x <= 0 ? 0 : x / 2;
+}
+
+struct StageRange {
+  long long w0 = 0, wn = 0;             // dft: first block / blocks; others: first output / outputs
+  long long prod_lo = 0, prod_hi = 0;   // output indices produced
+  long long need_lo = 0, need_hi = 0;   // input FIFO coordinates read
+};
+
+// Work a stage must do so that outputs [klo, khi) exist, and the input coordinates that work reads.
+static StageRange stage_range_for_outputs(const StageGeom &g, long long klo, long long khi)
+{
+  StageRange r;
+  if (khi <= klo) return r;
+  if (g.kind == RR_STAGE_HALFBAND) {
+    r.w0 = klo; r.wn = khi - klo; r.prod_lo = klo; r.prod_hi = khi;
+    r.need_lo = 2 * klo + 1; r.need_hi = 2 * khi + 4 * g.hb_c - 2;
+  } else if (g.kind == RR_STAGE_DFT) {
+    const long long b0 = dft_block_of(g, klo), b1 = dft_block_of(g, khi - 1) + 1;
+    r.w0 = b0; r.wn = b1 - b0;
+    r.prod_lo = dft_kfirst(g, b0); r.prod_hi = dft_kfirst(g, b1);
+    r.need_lo = dft_Rb(g, b0); r.need_hi = dft_Rb(g, b1 - 1) + dft_span(g, b1 - 1);
+  } else {
+    r.w0 = klo; r.wn = khi - klo; r.prod_lo = klo; r.prod_hi = khi;
+    r.need_lo = poly_q(g, klo); r.need_hi = poly_q(g, khi - 1) + g.n;
+  }
+  return r;
+}
+
+// ===================================================================================================
+// Engine<T>: plan + device tables + stage launch
+// ===================================================================================================
+template <class T> class Engine {
+ public:
+  Design design;
+  int ns = 0;
+  StageGeom geom[RR_MAX_STAGES];
+  int launches = 0;
+
+  ~Engine() { for (void *p : allocs_) be_free(p); }
+
+  int init(const RR_config &cfg, int device)
+  {
+    int rc = build_design(cfg, static_cast<int>(sizeof(T)), design);
+    if (rc != RR_OK) { set_last_error("invalid resampler configuration"); return rc; }
+    if ((rc = be_set_device(device)) != RR_OK) return rc;
+    ns = design.plan.num_stages;
+    num_sms_ = be_num_sms();
+    max_smem_ = be_max_smem();
+    leaf_constants<T>(sqrthalf_, c16_1_, c16_3_);
+    for (int i = 0; i < ns; ++i) {
+      const rr_stage_plan &sp = design.plan.st[i];
+      StageGeom &g = geom[i];
+      g.kind = sp.kind; g.preload = sp.preload;
+      if (sp.kind == RR_STAGE_HALFBAND) g.hb_c = sp.hb_coefs;
+      else if (sp.kind == RR_STAGE_DFT) {
+        g.N = sp.dft_length; g.ov = sp.num_taps - 1; g.V = g.N - g.ov; g.L = sp.L; g.step = sp.step_int;
+        g.filter = sp.dft_filter_num;
+        const bool pow2 = sp.L >= 2 && (sp.L & (sp.L - 1)) == 0;
+        g.in_mode = pow2 ? DFT_IN_FREQ_UP : sp.L == 1 ? DFT_IN_COPY : DFT_IN_ZERO_STUFF;
+        g.Pf = pow2 ? g.N / g.L : g.N;
+        g.Ni = g.step < 0 ? g.N >> (-g.step) : g.N;
+        g.remL0 = sp.remL;
+        g.q = (g.N - g.ov - g.remL0 + g.L - 1) / g.L;
+        g.kept = g.step < 0 ? g.N - ((((1 << (-g.step)) - 1) * g.N + g.ov) >> (-g.step)) : g.V;
+        if (g.Pf < 64 || g.Ni < 64) { set_last_error("DFT stage too short"); return RR_INTERNAL; }
+      } else {
+        g.n = sp.n; g.Lp = sp.L; g.order = sp.interp_order; g.phase_bits = sp.phase_bits; g.pre_post = sp.pre_post;
+        if (g.order == 0) { g.at0 = sp.at >> 32; g.pstep = sp.step >> 32; }
+        else { g.at0 = sp.at; g.pstep = sp.step; }
+      }
+    }
+    return upload_tables();
+  }
+
+  // Launch stage i: dft -> blocks [w0, w0+wn); others -> outputs [w0, w0+wn), for every lane of the views.
+  int run_stage(int i, const LaneView &in, bool in_f32, const LaneView &out, bool out_f32, long long out_preload,
+                long long w0, long long wn, int nlanes, stream_t s)
+  {
+    if (wn <= 0 || nlanes <= 0) return RR_OK;
+    const StageGeom &g = geom[i];
+    ++launches;
+    if (g.kind == RR_STAGE_DFT) {
+      DftParams<T> p = dft_params_[i];
+      p.in = in; p.out = out; p.out_preload = out_preload;
+      p.block0 = w0; p.nblocks = static_cast<int>(wn); p.nlanes = nlanes;
+      p.lanes_per_cta = dft_lanes_per_cta(g, nlanes);
+      const size_t smem = sizeof(T) * dft_smem_elems<T>(g.N, p.lanes_per_cta, &p.xstride, &p.ystride);
+      const long long groups = (nlanes + p.lanes_per_cta - 1) / p.lanes_per_cta;
+      return Launch<T>::dft(p, in_f32, out_f32, wn * groups, smem, s);
+    }
+    if (g.kind == RR_STAGE_HALFBAND) {
+      HalfbandParams<T> p = half_params_[i];
+      p.in = in; p.out = out; p.out_preload = out_preload; p.out0 = w0; p.nout = wn; p.nlanes = nlanes;
+      p.tile = kHalfTile;
+      const long long tiles = (wn + p.tile - 1) / p.tile;
+      const size_t smem = sizeof(T) * static_cast<size_t>(2 * p.tile + 4 * p.ncoef);
+      return Launch<T>::halfband(p, in_f32, out_f32, tiles * nlanes, smem, s);
+    }
+    PolyParams<T> p = poly_params_[i];
+    p.in = in; p.out = out; p.out_preload = out_preload; p.out0 = w0; p.nout = wn; p.nlanes = nlanes;
+    p.tile = kPolyTile;
+    // window of one tile: worst-case start phase (L-1) plus (tile-1) steps, plus the taps
+    long long win;
+    if (g.order == 0) win = ((g.Lp - 1) + static_cast<long long>(p.tile - 1) * g.pstep) / g.Lp + g.n + 1;
+    else win = static_cast<long long>(((static_cast<i128>(0xffffffffll) + static_cast<i128>(p.tile - 1) * g.pstep) >> 32)) + g.n + 1;
+    while (win * sizeof(T) > max_smem_ / 2 && p.tile > 64) {   // very steep decimation: shrink the tile
+      p.tile >>= 1;
+      if (g.order == 0) win = ((g.Lp - 1) + static_cast<long long>(p.tile - 1) * g.pstep) / g.Lp + g.n + 1;
+      else win = static_cast<long long>(((static_cast<i128>(0xffffffffll) + static_cast<i128>(p.tile - 1) * g.pstep) >> 32)) + g.n + 1;
+    }
+    p.win_cap = static_cast<int>(win);
+    const long long tiles = (wn + p.tile - 1) / p.tile;
+    const size_t smem = sizeof(T) * static_cast<size_t>(win);
+    if (g.order == 0) return Launch<T>::poly0(p, in_f32, out_f32, tiles * nlanes, smem, s);
+    return Launch<T>::polyN(p, in_f32, out_f32, tiles * nlanes, smem, s);
+  }
+
+  int copy(const LaneView &in, bool in_f32, const LaneView &out, bool out_f32, long long c0, long long n,
+           long long in_shift, int nlanes, stream_t s)
+  {
+    if (n <= 0) return RR_OK;
+    ++launches;
+    CopyParams p{in, out, c0, n, in_shift, nlanes};
+    return Launch<T>::copy(p, in_f32, out_f32, s);
+  }
+
+  int dft_spectrum_host(int instance, void *out, int max_n) const
+  {
+    if (!dft_coef_dev_[instance]) return 0;
+    const int N = design.dft[instance].dft_length;
+    const int n = std::min(N, max_n);
+    if (n > 0) {
+      if (be_d2h(out, dft_coef_dev_[instance], sizeof(T) * static_cast<size_t>(n), 0) != RR_OK) return -1;
+      if (be_sync(0) != RR_OK) return -1;
+    }
+    return N;
+  }
+
+  // Algorithmic flop count of the work described by per-stage ranges (SURVEY.md 8d accounting).
+  double flops_of(const StageRange *r) const
+  {
+    auto sr = [](double M) { return 4 * M * std::log2(M) - 6 * M + 8; };
+    double total = 0;
+    for (int i = 0; i < ns; ++i) {
+      const StageGeom &g = geom[i];
+      if (g.kind == RR_STAGE_DFT)
+        total += static_cast<double>(r[i].wn) *
+                 (sr(g.Pf / 2.) + 18. * g.Pf / 4 + 6. * g.Ni / 2 + 18. * g.Ni / 4 + sr(g.Ni / 2.));
+      else if (g.kind == RR_STAGE_HALFBAND) total += static_cast<double>(r[i].wn) * (1 + 3. * g.hb_c);
+      else total += static_cast<double>(r[i].wn) * g.n * (2. + 2. * g.order);
+    }
+    return total;
+  }
+
+ private:
+  std::vector<void *> allocs_;
+  int num_sms_ = 148;
+  size_t max_smem_ = 48 * 1024;
+  T sqrthalf_, c16_1_, c16_3_;
+  DftParams<T> dft_params_[RR_MAX_STAGES];
+  PolyParams<T> poly_params_[RR_MAX_STAGES];
+  HalfbandParams<T> half_params_[RR_MAX_STAGES];
+  T *dft_coef_dev_[2] = {nullptr, nullptr};
+
+  struct DevSched { CfftSched fwd, inv; const T *pyramid; };
+  std::map<int, DevSched> sched_;          // by complex bits
+  std::map<int, const T *> tcos_;          // by real bits
+
+  int dft_lanes_per_cta(const StageGeom &g, int nlanes) const
+  {
+    if (nlanes < 2) return 1;
+    int x = 0, y = 0;
+    const size_t two = sizeof(T) * dft_smem_elems<T>(g.N, 2, &x, &y);
+    return two <= 72 * 1024 ? 2 : 1;       // keep >= 3 CTAs per SM resident
+  }
+
+  template <class E> int upload(const std::vector<E> &v, const E **dev)
+  {
+    void *p = nullptr;
+    int rc = be_malloc(&p, v.size() * sizeof(E) + 16);
+    if (rc != RR_OK) return rc;
+    allocs_.push_back(p);
+    if (!v.empty() && (rc = be_h2d(p, v.data(), v.size() * sizeof(E), 0)) != RR_OK) return rc;
+    *dev = static_cast<const E *>(p);
+    return RR_OK;
+  }
+
+  int get_sched(int bits, const DevSched **out)
+  {
+    auto it = sched_.find(bits);
+    if (it == sched_.end()) {
+      const CfftHostSched h = build_cfft_sched(bits);
+      DevSched d{};
+      int rc;
+      const uint16_t *leaf16 = nullptr, *leaf8 = nullptr, *g16[2] = {nullptr, nullptr}, *g8[2] = {nullptr, nullptr}, *nodes = nullptr;
+      if ((rc = upload(h.leaf16_off, &leaf16)) || (rc = upload(h.leaf8_off, &leaf8)) ||
+          (rc = upload(h.gather16[0], &g16[0])) || (rc = upload(h.gather16[1], &g16[1])) ||
+          (rc = upload(h.gather8[0], &g8[0])) || (rc = upload(h.gather8[1], &g8[1])) ||
+          (rc = upload(h.node_off, &nodes)) || (rc = upload(twiddle_pyramid<T>(h), &d.pyramid)))
+        return rc;
+      for (int inv = 0; inv < 2; ++inv) {
+        CfftSched &c = inv ? d.inv : d.fwd;
+        c.bits = bits;
+        c.n16 = static_cast<int>(h.leaf16_off.size()); c.n8 = static_cast<int>(h.leaf8_off.size());
+        c.leaf16_off = leaf16; c.leaf8_off = leaf8; c.gather16 = g16[inv]; c.gather8 = g8[inv]; c.node_off = nodes;
+        for (int l = 0; l < 17; ++l) { c.level_begin[l] = h.level_begin[l]; c.level_cnt[l] = h.level_cnt[l]; c.pyr_off[l] = h.pyr_off[l]; }
+      }
+      it = sched_.emplace(bits, d).first;
+    }
+    *out = &it->second;
+    return RR_OK;
+  }
+
+  int get_tcos(int real_bits, const T **out)
+  {
+    auto it = tcos_.find(real_bits);
+    if (it == tcos_.end()) {
+      const T *dev = nullptr;
+      int rc = upload(cos_quarter_table<T>(real_bits), &dev);
+      if (rc) return rc;
+      it = tcos_.emplace(real_bits, dev).first;
+    }
+    *out = it->second;
+    return RR_OK;
+  }
+
+  static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+  int upload_tables()
+  {
+    int rc;
+    for (int i = 0; i < ns; ++i) {
+      const StageGeom &g = geom[i];
+      if (g.kind == RR_STAGE_HALFBAND) {
+        HalfbandParams<T> &p = half_params_[i];
+        memset(&p, 0, sizeof(p));
+        p.ncoef = g.hb_c; p.pre = design.plan.st[i].pre;
+        const double *c = half_band_coefs(g.hb_c);
+        for (int k = 0; k < g.hb_c; ++k) p.coef[k] = static_cast<T>(c[k]);
+      } else if (g.kind == RR_STAGE_POLY) {
+        PolyParams<T> &p = poly_params_[i];
+        memset(&p, 0, sizeof(p));
+        p.n = g.n; p.L = g.Lp; p.order = g.order; p.phase_bits = g.phase_bits; p.at0 = g.at0; p.step = g.pstep;
+        p.pre = design.plan.st[i].pre;
+        std::vector<T> bank(design.poly_bank.size());
+        for (size_t k = 0; k < bank.size(); ++k) bank[k] = static_cast<T>(design.poly_bank[k]);
+        if ((rc = upload(bank, &p.coefs))) return rc;
+      } else {
+        // smem budget check: the whole block lives in shared memory
+        int xs = 0, ys = 0;
+        const size_t need = sizeof(T) * dft_smem_elems<T>(g.N, 1, &xs, &ys);
+        if (need > max_smem_) {
+          set_last_error("DFT length " + std::to_string(g.N) + " exceeds the shared-memory block kernel (not implemented: global-memory multi-pass FFT)");
+          return RR_INTERNAL;
+        }
+        DftParams<T> &p = dft_params_[i];
+        memset(&p, 0, sizeof(p));
+        p.N = g.N; p.overlap = g.ov; p.L = g.L; p.step = g.step; p.in_mode = g.in_mode; p.Pf = g.Pf; p.Ni = g.Ni;
+        p.remL0 = g.remL0; p.q = g.q; p.kept = g.kept;
+        p.sqrthalf = sqrthalf_; p.c16_1 = c16_1_; p.c16_3 = c16_3_;
+        const DevSched *sf = nullptr, *si = nullptr;
+        if ((rc = get_sched(ilog2(g.Pf) - 1, &sf)) || (rc = get_sched(ilog2(g.Ni) - 1, &si))) return rc;
+        p.fwd = sf->fwd; p.pyr_f = sf->pyramid;
+        p.inv = si->inv; p.pyr_i = si->pyramid;
+        if ((rc = get_tcos(ilog2(g.Pf), &p.tcos_f)) || (rc = get_tcos(ilog2(g.Ni), &p.tcos_i))) return rc;
+        if (!dft_coef_dev_[g.filter] && (rc = make_spectrum(g.filter))) return rc;
+        p.coef = dft_coef_dev_[g.filter];
+      }
+    }
+    return be_sync(0);
+  }
+
+  // Forward real FFT of the wrapped/scaled taps, in the engine's sample type and with the engine's own
+  // transform (rate/rate_base.h:172-184 does the same with lsx_safe_rdft): one block, COPY mode, stop
+  // after the post-processing phase.
+  int make_spectrum(int instance)
+  {
+    const DftFilterDesign &f = design.dft[instance];
+    const int N = f.dft_length;
+    std::vector<T> t(static_cast<size_t>(N));
+    for (int k = 0; k < N; ++k) t[k] = static_cast<T>(f.coefs_time[k]);
+    const T *time_dev = nullptr;
+    int rc = upload(t, &time_dev);
+    if (rc) return rc;
+    void *spec = nullptr;
+    if ((rc = be_malloc(&spec, sizeof(T) * static_cast<size_t>(N) + 16))) return rc;
+    allocs_.push_back(spec);
+    DftParams<T> p;
+    memset(&p, 0, sizeof(p));
+    p.N = N; p.overlap = 0; p.L = 1; p.step = 0 /* spectrum only */; p.in_mode = DFT_IN_COPY; p.Pf = N; p.Ni = N;
+    p.q = N; p.kept = N;
+    p.sqrthalf = sqrthalf_; p.c16_1 = c16_1_; p.c16_3 = c16_3_;
+    const DevSched *sf = nullptr;
+    if ((rc = get_sched(ilog2(N) - 1, &sf))) return rc;
+    p.fwd = sf->fwd; p.pyr_f = sf->pyramid; p.inv = sf->inv; p.pyr_i = sf->pyramid;
+    if ((rc = get_tcos(ilog2(N), &p.tcos_f))) return rc;
+    p.tcos_i = p.tcos_f;
+    p.coef = nullptr;
+    LaneView v{};
+    v.origin = 0; v.mask = ~0ull; v.lo = 0; v.hi = N; v.stream_stride = 0; v.ch_stride = 0; v.elem_stride = 1; v.nch = 1;
+    p.in = v; p.in.base = const_cast<T *>(time_dev);
+    p.out = v; p.out.base = spec;
+    p.block0 = 0; p.nblocks = 1; p.nlanes = 1; p.lanes_per_cta = 1;
+    const size_t smem = sizeof(T) * dft_smem_elems<T>(N, 1, &p.xstride, &p.ystride);
+    if ((rc = Launch<T>::dft(p, false, false, 1, smem, 0))) return rc;
+    dft_coef_dev_[instance] = static_cast<T *>(spec);
+    return RR_OK;
+  }
+};
+
+// ===================================================================================================
+// Batch front-end
+// ===================================================================================================
+template <class T> class Batch : public IBatch {
+ public:
+  Engine<T> eng;
+  int nch = 0, nstreams = 0;
+  size_t frames_in_max = 0;
+  std::vector<long long> cap;        // per FIFO (1..ns-1): samples per lane
+  std::vector<T *> buf;
+  int launches_ = 0;
+
+  ~Batch() override { for (T *p : buf) be_free(p); }
+
+  int init(const RR_config &cfg, int nchannels, int nstr, size_t fmax, int device)
+  {
+    int rc = eng.init(cfg, device);
+    if (rc) return rc;
+    nch = nchannels; nstreams = nstr; frames_in_max = fmax;
+    const size_t nout = frames_out(fmax);
+    std::vector<StageRange> r(eng.ns);
+    plan_ranges(0, static_cast<long long>(nout), r.data());
+    cap.assign(eng.ns + 1, 0); buf.assign(eng.ns + 1, nullptr);
+    for (int i = 1; i < eng.ns; ++i) {
+      const StageGeom &up = eng.geom[i - 1];
+      long long slack = up.kind == RR_STAGE_DFT ? 2ll * up.N : 64;
+      cap[i] = (r[i - 1].prod_hi - r[i - 1].prod_lo) + slack;
+      void *p = nullptr;
+      const size_t bytes = sizeof(T) * static_cast<size_t>(cap[i]) * nch * nstreams;
+      if ((rc = be_malloc(&p, bytes))) return rc;
+      buf[i] = static_cast<T *>(p);
+    }
+    return RR_OK;
+  }
+
+  const Design &design() const override { return eng.design; }
+
+  size_t frames_out(size_t frames_in) const override      // rate_flush target, rate/rate_base.h:457
+  {
+    return static_cast<size_t>(static_cast<double>(frames_in) / eng.design.plan.factor + .5);
+  }
+
+  // Backward dependency pass: per-stage work for final outputs [klo, khi).
+  void plan_ranges(long long klo, long long khi, StageRange *r) const
+  {
+    for (int i = eng.ns - 1; i >= 0; --i) {
+      r[i] = stage_range_for_outputs(eng.geom[i], klo, khi);
+      const long long pre = eng.geom[i].preload;
+      klo = std::max(0ll, r[i].need_lo - pre);
+      khi = std::max(0ll, r[i].need_hi - pre);
+    }
+  }
+
+  void input_window(size_t frames_in, uint64_t out_begin, size_t out_count, uint64_t *first, uint64_t *count) const override
+  {
+    std::vector<StageRange> r(eng.ns);
+    const long long klo = static_cast<long long>(out_begin), khi = klo + static_cast<long long>(out_count);
+    plan_ranges(klo, khi, r.data());
+    const long long pre0 = eng.geom[0].preload;
+    const long long lo = std::max(0ll, r[0].need_lo - pre0);
+    const long long hi = std::min<long long>(static_cast<long long>(frames_in), std::max(0ll, r[0].need_hi - pre0));
+    if (first) *first = static_cast<uint64_t>(lo);
+    if (count) *count = static_cast<uint64_t>(std::max(0ll, hi - lo));
+  }
+
+  int process(const float *d_in, uint64_t win_first, size_t win_frames, size_t frames_in, uint64_t out_begin,
+              size_t out_count, void *d_out, bool native_out, void *stream) override
+  {
+    stream_t s = static_cast<stream_t>(stream);
+    const int ns = eng.ns, nlanes = nch * nstreams;
+    eng.launches = 0;
+    if (ns == 0) { set_last_error("identity conversion has no stages"); return RR_INVPARAM; }
+    std::vector<StageRange> r(ns);
+    const long long klo = static_cast<long long>(out_begin), khi = klo + static_cast<long long>(out_count);
+    plan_ranges(klo, khi, r.data());
+    const long long pre0 = eng.geom[0].preload;
+    if (!d_out || out_count == 0) return RR_OK;
+    {
+      uint64_t f = 0, c = 0;
+      input_window(frames_in, out_begin, out_count, &f, &c);
+      if (c && (f < win_first || f + c > win_first + win_frames)) {
+        set_last_error("input window does not cover the samples this output range depends on");
+        return RR_INVPARAM;
+      }
+    }
+
+    for (int i = 0; i < ns; ++i) {
+      LaneView in{}, out{};
+      bool in_f32, out_f32;
+      if (i == 0) {
+        in.base = const_cast<float *>(d_in);
+        in.origin = pre0 + static_cast<long long>(win_first); in.mask = ~0ull;
+        in.lo = in.origin;
+        in.hi = pre0 + std::min<long long>(static_cast<long long>(frames_in), static_cast<long long>(win_first + win_frames));
+        in.stream_stride = static_cast<long long>(win_frames) * nch; in.ch_stride = 1; in.elem_stride = nch; in.nch = nch;
+        in_f32 = true;
+      } else {
+        const long long pre = eng.geom[i].preload;
+        in.base = buf[i];
+        in.origin = pre + r[i - 1].prod_lo; in.mask = ~0ull; in.lo = pre; in.hi = pre + r[i - 1].prod_hi;
+        in.stream_stride = cap[i] * nch; in.ch_stride = static_cast<int>(cap[i]); in.elem_stride = 1; in.nch = nch;
+        if (cap[i] > 0x7fffffffll) { set_last_error("intermediate lane too long for one batch"); return RR_INVPARAM; }
+        in_f32 = false;
+      }
+      long long out_preload;
+      if (i == ns - 1) {
+        out.base = d_out;
+        out.origin = klo; out.mask = ~0ull; out.lo = klo; out.hi = khi;
+        if (native_out) { out.stream_stride = static_cast<long long>(out_count) * nch; out.ch_stride = static_cast<int>(out_count); out.elem_stride = 1; }
+        else { out.stream_stride = static_cast<long long>(out_count) * nch; out.ch_stride = 1; out.elem_stride = nch; }
+        out.nch = nch;
+        out_f32 = !native_out;
+        out_preload = 0;
+      } else {
+        const long long pre = eng.geom[i + 1].preload;
+        if (r[i].prod_hi - r[i].prod_lo > cap[i + 1]) { set_last_error("range exceeds the batch's frames_in_max"); return RR_INVPARAM; }
+        out.base = buf[i + 1];
+        out.origin = pre + r[i].prod_lo; out.mask = ~0ull; out.lo = out.origin; out.hi = pre + r[i].prod_hi;
+        out.stream_stride = cap[i + 1] * nch; out.ch_stride = static_cast<int>(cap[i + 1]); out.elem_stride = 1; out.nch = nch;
+        out_f32 = false;
+        out_preload = pre;
+      }
+      int rc = eng.run_stage(i, in, in_f32, out, out_f32, out_preload, r[i].w0, r[i].wn, nlanes, s);
+      if (rc) return rc;
+    }
+    launches_ = eng.launches;
+    return RR_OK;
+  }
+
+  int last_launches() const override { return launches_; }
+
+  double flops(size_t frames_in) const override
+  {
+    std::vector<StageRange> r(eng.ns);
+    plan_ranges(0, static_cast<long long>(frames_out(frames_in)), r.data());
+    return eng.flops_of(r.data()) * nch * nstreams;
+  }
+};
+
+// ===================================================================================================
+// Streaming front-end (RR_push / RR_pull / RR_drain on device ring buffers)
+// ===================================================================================================
+template <class T> class Stream : public IStream {
+ public:
+  Engine<T> eng;
+  int nch = 0;
+  // FIFO state, absolute coordinates (identical for every channel)
+  std::vector<long long> W;          // samples written to FIFO i (including preload)
+  std::vector<long long> done;       // stage progress: blocks (dft) or outputs (others)
+  std::vector<long long> produced;   // outputs produced by stage i
+  std::vector<long long> ring_cap;   // per-lane capacity (power of two)
+  std::vector<T *> ring;
+  long long popped = 0;              // read position of the output FIFO
+  long long out_shift = 0;           // coordinate of last-stage output 0 in the output FIFO (changes when drain trims)
+  uint64_t samples_in = 0, samples_out = 0;   // rate_t counters (rate_base.h:224-231)
+  float *stage_in = nullptr, *stage_out = nullptr;   // interleaved float staging (device)
+  size_t stage_in_cap = 0, stage_out_cap = 0;
+  T *stage_native = nullptr; size_t stage_native_cap = 0;
+
+  ~Stream() override
+  {
+    for (T *p : ring) be_free(p);
+    be_free(stage_in); be_free(stage_out); be_free(stage_native);
+  }
+
+  int init(const RR_config &cfg, int nchannels, int device)
+  {
+    int rc = eng.init(cfg, device);
+    if (rc) return rc;
+    nch = nchannels;
+    const int ns = eng.ns;
+    W.assign(ns + 1, 0); done.assign(ns + 1, 0); produced.assign(ns + 1, 0);
+    ring_cap.assign(ns + 1, 0); ring.assign(ns + 1, nullptr);
+    for (int i = 0; i < ns; ++i) W[i] = eng.geom[i].preload;
+    for (int i = 0; i <= ns; ++i)
+      if ((rc = ensure_ring(i, std::max<long long>(W[i], 1 << 14)))) return rc;
+    return RR_OK;
+  }
+
+  const Design &design() const override { return eng.design; }
+
+  LaneView ring_view(int i, long long lo, long long hi) const
+  {
+    LaneView v{};
+    v.base = ring[i]; v.origin = 0; v.mask = static_cast<unsigned long long>(ring_cap[i] - 1);
+    v.lo = lo; v.hi = hi;
+    v.stream_stride = 0; v.ch_stride = static_cast<int>(ring_cap[i]); v.elem_stride = 1; v.nch = nch;
+    return v;
+  }
+
+  // lowest coordinate of FIFO i that may still be read
+  long long keep_from(int i) const
+  {
+    if (i == eng.ns) return popped;
+    const StageGeom &g = eng.geom[i];
+    if (g.kind == RR_STAGE_HALFBAND) return 2 * done[i] + 1;
+    if (g.kind == RR_STAGE_DFT) return dft_Rb(g, done[i]);
+    return poly_q(g, done[i]);
+  }
+
+  // make ring i able to hold coordinates [keep_from(i), upto)
+  int ensure_ring(int i, long long upto)
+  {
+    const long long keep = ring[i] ? keep_from(i) : 0;
+    const long long need = upto - keep;
+    if (ring[i] && need <= ring_cap[i]) return RR_OK;
+    long long cap = std::max<long long>(ring_cap[i], 1 << 14);
+    while (cap < need) cap <<= 1;
+    if (cap > 0x40000000ll) { set_last_error("FIFO ring would exceed 2^30 samples per channel"); return RR_ENOMEM; }
+    void *p = nullptr;
+    int rc = be_malloc(&p, sizeof(T) * static_cast<size_t>(cap) * nch);
+    if (rc) return rc;
+    if (ring[i]) {                           // carry the live region over (ring -> bigger ring)
+      LaneView from = ring_view(i, keep, W[i]);
+      T *old = ring[i];
+      const long long old_cap = ring_cap[i];
+      ring[i] = static_cast<T *>(p); ring_cap[i] = cap;
+      LaneView to = ring_view(i, keep, W[i]);
+      rc = eng.copy(from, false, to, false, keep, W[i] - keep, 0, nch, 0);
+      if (!rc) rc = be_sync(0);
+      be_free(old);
+      (void)old_cap;
+      return rc;
+    }
+    ring[i] = static_cast<T *>(p); ring_cap[i] = cap;
+    // zero the preload region (fifo_write0, rate_base.h:420)
+    LaneView none{}; none.base = ring[i]; none.mask = ~0ull; none.lo = 0; none.hi = 0; none.elem_stride = 1; none.nch = nch;
+    if (W[i] > 0) {
+      LaneView to = ring_view(i, 0, W[i]);
+      rc = eng.copy(none, false, to, false, 0, W[i], 0, nch, 0);
+    }
+    return rc;
+  }
+
+  void count_input(size_t n)                 // rate_input, rate_base.h:436-441
+  {
+    samples_in += n;
+    while (samples_in > in_rate_ && samples_out > out_rate_) { samples_in -= in_rate_; samples_out -= out_rate_; }
+  }
+  uint64_t in_rate_ = 0, out_rate_ = 0;
+
+  // new totals for stage i given W[i]; returns outputs produced in total
+  void advance_counts(int i, long long *new_done, long long *new_produced) const
+  {
+    const StageGeom &g = eng.geom[i];
+    if (g.kind == RR_STAGE_HALFBAND) { *new_done = std::max(done[i], half_ready(g, W[i])); *new_produced = *new_done; }
+    else if (g.kind == RR_STAGE_DFT) { *new_done = dft_blocks_ready(g, W[i], done[i]); *new_produced = dft_kfirst(g, *new_done); }
+    else { *new_done = std::max(done[i], poly_ready(g, W[i])); *new_produced = *new_done; }
+  }
+
+  // rate_process (rate_base.h:425-432) for all channels: run every stage over what became available
+  int process_stages()
+  {
+    const int ns = eng.ns;
+    for (int i = 0; i < ns; ++i) {
+      long long nd, np;
+      advance_counts(i, &nd, &np);
+      if (nd > done[i]) {
+        const long long out_pre = i + 1 == ns ? out_shift : eng.geom[i + 1].preload;
+        const long long newW = out_pre + np;
+        int rc = ensure_ring(i + 1, newW);
+        if (rc) return rc;
+        LaneView in = ring_view(i, 0, W[i]);
+        LaneView out = ring_view(i + 1, W[i + 1], newW);
+        rc = eng.run_stage(i, in, false, out, false, out_pre, done[i], nd - done[i], nch, 0);
+        if (rc) return rc;
+        done[i] = nd; produced[i] = np; W[i + 1] = newW;
+      }
+    }
+    return RR_OK;
+  }
+
+  int push(const float *x, size_t frames) override   // RR_push_x, rate_base.h:616-636
+  {
+    if (!x || !frames) return RR_OK;
+    if (frames > eng.design.plan.isamp_max) frames = static_cast<size_t>(eng.design.plan.isamp_max);
+    count_input(frames);
+    int rc;
+    if (eng.ns == 0) return RR_OK;
+    const size_t elems = frames * static_cast<size_t>(nch);
+    if (elems > stage_in_cap) {
+      be_free(stage_in); stage_in = nullptr;
+      void *p = nullptr;
+      if ((rc = be_malloc(&p, sizeof(float) * elems))) return rc;
+      stage_in = static_cast<float *>(p); stage_in_cap = elems;
+    }
+    if ((rc = be_h2d(stage_in, x, sizeof(float) * elems, 0))) return rc;
+    if ((rc = ensure_ring(0, W[0] + static_cast<long long>(frames)))) return rc;
+    // deinterleave + convert into FIFO 0 (rate_base.h:565-569)
+    LaneView src{};
+    src.base = stage_in; src.origin = W[0]; src.mask = ~0ull; src.lo = W[0]; src.hi = W[0] + static_cast<long long>(frames);
+    src.stream_stride = 0; src.ch_stride = 1; src.elem_stride = nch; src.nch = nch;
+    LaneView dst = ring_view(0, W[0], W[0] + static_cast<long long>(frames));
+    if ((rc = eng.copy(src, true, dst, false, W[0], static_cast<long long>(frames), 0, nch, 0))) return rc;
+    W[0] += static_cast<long long>(frames);
+    if ((rc = process_stages())) return rc;
+    return be_sync(0);
+  }
+
+  int pull(float *y, void *native, size_t max_frames, size_t *got) override   // RR_pull_x, rate_base.h:638-660
+  {
+    const int last = eng.ns;
+    const long long avail = W[last] - popped;
+    const size_t n = static_cast<size_t>(std::min<long long>(avail, static_cast<long long>(max_frames)));
+    if (got) *got = n;
+    samples_out += n;                            // rate_output, rate_base.h:448
+    if (!n) return RR_OK;
+    int rc;
+    const size_t elems = n * static_cast<size_t>(nch);
+    LaneView src = ring_view(last, popped, popped + static_cast<long long>(n));
+    if (y) {
+      if (elems > stage_out_cap) {
+        be_free(stage_out); stage_out = nullptr;
+        void *p = nullptr;
+        if ((rc = be_malloc(&p, sizeof(float) * elems))) return rc;
+        stage_out = static_cast<float *>(p); stage_out_cap = elems;
+      }
+      LaneView dst{};
+      dst.base = stage_out; dst.origin = popped; dst.mask = ~0ull; dst.lo = popped; dst.hi = popped + static_cast<long long>(n);
+      dst.stream_stride = 0; dst.ch_stride = 1; dst.elem_stride = nch; dst.nch = nch;
+      if ((rc = eng.copy(src, false, dst, true, popped, static_cast<long long>(n), 0, nch, 0))) return rc;
+      if ((rc = be_d2h(y, stage_out, sizeof(float) * elems, 0))) return rc;
+    }
+    if (native) {                                // planar, engine type: out[ch * max_frames + i]
+      if (elems > stage_native_cap) {
+        be_free(stage_native); stage_native = nullptr;
+        void *p = nullptr;
+        if ((rc = be_malloc(&p, sizeof(T) * elems))) return rc;
+        stage_native = static_cast<T *>(p); stage_native_cap = elems;
+      }
+      LaneView dst{};
+      dst.base = stage_native; dst.origin = popped; dst.mask = ~0ull; dst.lo = popped; dst.hi = popped + static_cast<long long>(n);
+      dst.stream_stride = 0; dst.ch_stride = static_cast<int>(n); dst.elem_stride = 1; dst.nch = nch;
+      if ((rc = eng.copy(src, false, dst, false, popped, static_cast<long long>(n), 0, nch, 0))) return rc;
+      for (int c = 0; c < nch; ++c)
+        if ((rc = be_d2h(static_cast<T *>(native) + static_cast<size_t>(c) * max_frames, stage_native + static_cast<size_t>(c) * n,
+                         sizeof(T) * n, 0)))
+          return rc;
+    }
+    popped += static_cast<long long>(n);
+    return be_sync(0);
+  }
+
+  int drain() override                           // rate_flush, rate_base.h:454-468
+  {
+    const int last = eng.ns;
+    const uint64_t target = static_cast<uint64_t>(static_cast<double>(samples_in) / eng.design.plan.factor + .5);
+    if (target <= samples_out) return RR_OK;
+    const long long remaining = static_cast<long long>(target - samples_out);
+    if (eng.ns == 0) return RR_OK;
+    // Feed 1024-sample blocks of zeros until enough output exists. Only the counters run in the loop;
+    // the zeros are written and the stages launched once for the whole extension (same results: every
+    // stage is a pure function of absolute positions).
+    const std::vector<long long> W_save = W, done_save = done, prod_save = produced;
+    long long fed = 0;
+    while (W[last] - popped < remaining) {
+      fed += 1024; W[0] += 1024;
+      count_input(1024);
+      for (int i = 0; i < eng.ns; ++i) {
+        long long nd, np;
+        advance_counts(i, &nd, &np);
+        done[i] = nd; produced[i] = np;
+        W[i + 1] = (i + 1 == eng.ns ? out_shift : eng.geom[i + 1].preload) + np;
+      }
+    }
+    const long long W0_new = W[0];
+    W = W_save; done = done_save; produced = prod_save;
+    int rc;
+    if (fed > 0) {
+      if ((rc = ensure_ring(0, W0_new))) return rc;
+      LaneView none{}; none.base = ring[0]; none.mask = ~0ull; none.lo = 0; none.hi = 0; none.elem_stride = 1; none.nch = nch;
+      LaneView dst = ring_view(0, W[0], W0_new);
+      if ((rc = eng.copy(none, false, dst, false, W[0], fed, 0, nch, 0))) return rc;
+      W[0] = W0_new;
+      if ((rc = process_stages())) return rc;
+    }
+    // fifo_trim_to(remaining): later output continues right after the trimmed end
+    W[last] = popped + remaining;
+    out_shift = W[last] - produced[last - 1];
+    samples_in = samples_out = 0;
+    return be_sync(0);
+  }
+
+  int dft_spectrum(int instance, void *out, int max_n) const override { return eng.dft_spectrum_host(instance, out, max_n); }
+};
+
+// ===================================================================================================
+// factories
+// ===================================================================================================
+IBatch *create_batch(const RR_config &cfg, int sample_bytes, int nchannels, int nstreams, size_t frames_in_max,
+                     int device, int *err)
+{
+  int rc = RR_INVPARAM;
+  IBatch *res = nullptr;
+  if (nchannels < 1 || nstreams < 1 || frames_in_max < 1) { set_last_error("bad batch shape"); }
+  else if (sample_bytes == 4) {
+    auto *b = new Batch<float>();
+    rc = b->init(cfg, nchannels, nstreams, frames_in_max, device);
+    if (rc) delete b; else res = b;
+  } else if (sample_bytes == 8) {
+    auto *b = new Batch<double>();
+    rc = b->init(cfg, nchannels, nstreams, frames_in_max, device);
+    if (rc) delete b; else res = b;
+  }
+  if (err) *err = rc;
+  return res;
+}
+
+IStream *create_stream(const RR_config &cfg, int sample_bytes, int nchannels, int device, int *err)
+{
+  int rc = RR_INVPARAM;
+  IStream *res = nullptr;
+  if (nchannels < 1) { set_last_error("bad channel count"); }
+  else if (sample_bytes == 4) {
+    auto *s = new Stream<float>();
+    s->in_rate_ = cfg.in_rate; s->out_rate_ = cfg.out_rate;
+    rc = s->init(cfg, nchannels, device);
+    if (rc) delete s; else res = s;
+  } else if (sample_bytes == 8) {
+    auto *s = new Stream<double>();
+    s->in_rate_ = cfg.in_rate; s->out_rate_ = cfg.out_rate;
+    rc = s->init(cfg, nchannels, device);
+    if (rc) delete s; else res = s;
+  }
+  if (err) *err = rc;
+  return res;
+}
+
+}  // namespace b200rate

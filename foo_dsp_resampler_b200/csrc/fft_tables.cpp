@@ -1,0 +1,106 @@
+// fft_tables.cpp -- see fft_tables.hpp.
+#include "fft_tables.hpp"
+
+#include <cassert>
+#include <cmath>
+
+namespace b200rate {
+
+namespace {
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kSqrtHalf = 0.70710678118654752440;
+
+struct TreeWalk {
+  CfftHostSched *s;
+  std::vector<std::vector<uint16_t>> per_level;
+  void visit(int size, int off)
+  {
+    if (size == 16) { s->leaf16_off.push_back(static_cast<uint16_t>(off)); return; }
+    if (size == 8) { s->leaf8_off.push_back(static_cast<uint16_t>(off)); return; }
+    // fft(S) = fft(S/2) on the first half, fft(S/4) on each remaining quarter, then one pass
+    visit(size >> 1, off);
+    visit(size >> 2, off + (size >> 1));
+    visit(size >> 2, off + 3 * (size >> 2));
+    int lg = 0;
+    while ((1 << lg) < size) ++lg;
+    per_level[lg].push_back(static_cast<uint16_t>(off));
+  }
+};
+}  // namespace
+
+int split_radix_index(int i, int n, int inverse)
+{
+  if (n <= 2) return i & 1;
+  const int half = n >> 1, quarter = n >> 2;
+  if (!(i & half)) return 2 * split_radix_index(i, half, inverse);
+  const int sub = split_radix_index(i, quarter, inverse);
+  const int upper = (i & quarter) != 0;
+  return 4 * sub + (inverse != upper ? 1 : -1);
+}
+
+CfftHostSched build_cfft_sched(int bits)
+{
+  assert(bits >= 5 && bits <= 16);
+  CfftHostSched s;
+  s.bits = bits;
+  const int m = 1 << bits;
+  TreeWalk w{&s, std::vector<std::vector<uint16_t>>(17)};
+  w.visit(m, 0);
+  for (int lg = 5; lg <= bits; ++lg) {
+    s.level_begin[lg] = static_cast<int>(s.node_off.size());
+    s.level_cnt[lg] = static_cast<int>(w.per_level[lg].size());
+    s.node_off.insert(s.node_off.end(), w.per_level[lg].begin(), w.per_level[lg].end());
+    s.pyr_off[lg] = s.pyr_len;
+    s.pyr_len += (1 << (lg - 2)) + 1;
+  }
+  const int n16 = static_cast<int>(s.leaf16_off.size()), n8 = static_cast<int>(s.leaf8_off.size());
+  for (int inv = 0; inv < 2; ++inv) {
+    std::vector<int> natural(static_cast<size_t>(m));   // permuted[p] = natural_order[natural[p]]
+    for (int p = 0; p < m; ++p) natural[p] = (-split_radix_index(p, m, inv)) & (m - 1);
+    s.gather16[inv].assign(static_cast<size_t>(16) * n16, 0);
+    s.gather8[inv].assign(static_cast<size_t>(8) * n8, 0);
+    for (int t = 0; t < n16; ++t)
+      for (int e = 0; e < 16; ++e)
+        s.gather16[inv][static_cast<size_t>(e) * n16 + t] = static_cast<uint16_t>(natural[s.leaf16_off[t] + e]);
+    for (int t = 0; t < n8; ++t)
+      for (int e = 0; e < 8; ++e)
+        s.gather8[inv][static_cast<size_t>(e) * n8 + t] = static_cast<uint16_t>(natural[s.leaf8_off[t] + e]);
+  }
+  return s;
+}
+
+template <class T> std::vector<T> cos_quarter_table(int bits)
+{
+  const int m = 1 << bits;
+  const double freq = 2 * kPi / m;
+  std::vector<T> t(static_cast<size_t>(m / 4) + 1);
+  for (int i = 0; i <= m / 4; ++i) t[i] = static_cast<T>(std::cos(i * freq));
+  return t;
+}
+
+template <class T> std::vector<T> twiddle_pyramid(const CfftHostSched &s)
+{
+  std::vector<T> pyr(static_cast<size_t>(s.pyr_len));
+  for (int lg = 5; lg <= s.bits; ++lg) {
+    const std::vector<T> row = cos_quarter_table<T>(lg);
+    for (size_t k = 0; k < row.size(); ++k) pyr[s.pyr_off[lg] + k] = row[k];
+  }
+  return pyr;
+}
+
+template <class T> void leaf_constants(T &sqrthalf, T &c16_1, T &c16_3)
+{
+  const std::vector<T> c16 = cos_quarter_table<T>(4);
+  sqrthalf = static_cast<T>(kSqrtHalf);
+  c16_1 = c16[1];
+  c16_3 = c16[3];
+}
+
+template std::vector<float> cos_quarter_table<float>(int);
+template std::vector<double> cos_quarter_table<double>(int);
+template std::vector<float> twiddle_pyramid<float>(const CfftHostSched &);
+template std::vector<double> twiddle_pyramid<double>(const CfftHostSched &);
+template void leaf_constants<float>(float &, float &, float &);
+template void leaf_constants<double>(double &, double &, double &);
+
+}  // namespace b200rate

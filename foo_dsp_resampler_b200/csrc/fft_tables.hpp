@@ -1,0 +1,39 @@
+// fft_tables.hpp -- host-side construction of the FFT schedule and constant tables that the kernels read.
+//
+// The tables are part of the fp32 bit-exactness contract: cosines are evaluated in double
+// by the host libm and then rounded to the sample type exactly as ff_init_ff_cos_tabs does
+// (/root/reference/rate/fft-float/fft.c:50-62), and the permutation is FFmpeg's split-radix index map
+// (fft.c:82-91,156-161 with sse == 0).
+#pragma once
+
+#include <cstdint>
+#include <vector>
+
+namespace b200rate {
+
+// Schedule of a complex FFT of M = 1 << bits points (bits >= 5).
+struct CfftHostSched {
+  int bits = 0;
+  std::vector<uint16_t> leaf16_off, leaf8_off;   // permuted offsets of the register-resident leaves
+  std::vector<uint16_t> gather16[2], gather8[2]; // [inverse]: transposed [element][leaf] natural indices
+  std::vector<uint16_t> node_off;                // node offsets of sizes 32..M, concatenated
+  int level_begin[17] = {0}, level_cnt[17] = {0};
+  int pyr_off[17] = {0};                         // row offsets inside twiddle_pyramid()
+  int pyr_len = 0;
+};
+
+CfftHostSched build_cfft_sched(int bits);
+
+// Split-radix position of natural index i (FFmpeg's split_radix_permutation).
+int split_radix_index(int i, int n, int inverse);
+
+// (T)cos(2*pi*i / 2^bits) for i = 0 .. 2^bits/4, cosine evaluated in double.
+template <class T> std::vector<T> cos_quarter_table(int bits);
+
+// Rows k = 0..S/4 of cos(2*pi*k/S) for S = 32 .. 2^bits, laid out at sched.pyr_off[log2 S].
+template <class T> std::vector<T> twiddle_pyramid(const CfftHostSched &sched);
+
+// Constants of the size-8/16 leaves: sqrt(1/2), cos(2 pi/16), cos(6 pi/16) (fft.c:300,304-318).
+template <class T> void leaf_constants(T &sqrthalf, T &c16_1, T &c16_3);
+
+}  // namespace b200rate

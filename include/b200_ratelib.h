@@ -1,0 +1,154 @@
+/* b200_ratelib.h -- C ABI of libb200rate.so, the B200-native drop-in for the reference's `rate` library.
+ *
+ * Part 1 re-declares, with identical names, argument meaning and return codes, the entry points a caller of
+ * the reference binds: /root/reference/rate/ratelib.h:25-81 (public API used by chain.h:22-43 and
+ * foo_dsp_rate.cpp) and /root/reference/rate/rate_i.h:39-43 (engine constructors, needed to select the
+ * fp32 engine with Best quality -- BASELINE config 1). A translation unit written against the reference's
+ * ratelib.h links against libb200rate.so unchanged.
+ *
+ * Part 2 (RRX_*) are extensions that do not exist in the reference: device-resident batch processing so
+ * throughput can be measured with inputs already in HBM, plan/coefficient introspection for parity tests,
+ * and an un-cast tap of the fp64 engine's output for the 1e-12 contract.
+ *
+ * Every function here needs a CUDA device except those marked [host-only]; without a usable device
+ * RR_open/RR_ctor_* fail (RR_INTERNAL / NULL) -- there is no CPU fallback.
+ */
+#ifndef B200_RATELIB_H
+#define B200_RATELIB_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "rr_plan.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------ */
+/* Part 1: the reference's interface                                                                */
+/* ------------------------------------------------------------------------------------------------ */
+
+enum RR_error {          /* rate/ratelib.h:25-34 */
+  RR_OK = 0,
+  RR_ENOMEM,
+  RR_INTERNAL,           /* also: CUDA failure, no device */
+  RR_NULLHANDLE,
+  RR_RATEERROR,
+  RR_EXTUNINIT,          /* RR_open before init_ratelib */
+  RR_INVPARAM
+};
+
+enum RR_quality { RR_best = 0, RR_norm = 1 };                      /* rate/ratelib.h:36-42 */
+enum RR_phase { RR_minimum = 0, RR_linear = 50, RR_maximum = 100 }; /* rate/ratelib.h:44-49 */
+
+typedef float fb_sample_t;                                         /* rate/ratelib.h:51 */
+
+typedef struct RR_config_tag {                                     /* rate/ratelib.h:53-63 */
+  size_t in_rate;
+  size_t out_rate;
+  double phase;          /* 0..100; 50 = linear phase */
+  double bandwidth;      /* pass-band end (-3 dB point) in % of Nyquist */
+  int allow_aliasing;
+  enum RR_quality quality;
+} RR_config;
+
+typedef struct RR_handle_tag RR_handle;                            /* opaque; first member is the vtable */
+
+/* rate/rate_uni.c:210-223. Must be called once before RR_open; `oom` is invoked when a HOST allocation
+ * fails (the reference's callback contract, rate/xmalloc.c:38-43). Returns 0, or -1 if oom is NULL. */
+int init_ratelib(void (*oom)(void));
+/* rate/rate_uni.c:225-231 (defined there, not declared in ratelib.h). */
+void close_ratelib(void);
+
+/* rate/rate_uni.c:27-57: Best -> fp64 engine, Normal -> fp32 engine. Counts are FRAMES, buffers are
+ * caller-owned interleaved float32 HOST memory. */
+int RR_open(const RR_config *config, int nchannels, RR_handle **const handle);
+/* rate/rate_base.h:571-614: pull, then push, then pull again into the remaining space. */
+int RR_flow(RR_handle *h, const fb_sample_t *ibuf, fb_sample_t *obuf, size_t isamp, size_t osamp,
+            size_t *iused, size_t *ogen);
+/* rate/rate_base.h:616-636: consumes min(isamp, isamp_max) frames (silently, like the reference). */
+int RR_push(RR_handle *h, const fb_sample_t *ibuf, size_t isamp);
+/* rate/rate_base.h:638-660: writes at most osamp frames; *ogen = frames written (0: nothing ready). */
+int RR_pull(RR_handle *h, fb_sample_t *obuf, size_t osamp, size_t *ogen);
+/* rate/rate_base.h:662-672: zero-feed until round(frames_in * out_rate / in_rate) frames exist. */
+int RR_drain(RR_handle *h);
+void RR_close(RR_handle **h);                                      /* rate/rate_uni.c:83-90 */
+const char *RR_strerror(int error);                                /* rate/rate_uni.c:92-111 */
+
+/* rate/rate_i.h:39-43. The reference has one constructor per CPU flavour; here _float/_SSE create the
+ * fp32 engine and _double/_SSE3 the fp64 engine, with the quality taken from *config. NULL on failure
+ * (the reference swallows RR_INVPARAM here, rate/rate_base.h:738; this library returns NULL instead). */
+RR_handle *RR_ctor_SSE3(const RR_config *config, int nchannels);
+RR_handle *RR_ctor_double(const RR_config *config, int nchannels);
+RR_handle *RR_ctor_SSE(const RR_config *config, int nchannels);
+RR_handle *RR_ctor_float(const RR_config *config, int nchannels);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* Part 2: extensions                                                                               */
+/* ------------------------------------------------------------------------------------------------ */
+
+/* [host-only] Stage plan for a configuration: the integers of the parity contract.
+ * sample_bytes 4 or 8. Returns RR_OK or RR_INVPARAM. */
+int RRX_plan(const RR_config *config, int sample_bytes, rr_plan *out);
+/* [host-only] Designed banks, converted to the engine type (what rate_shared_t holds, rate_base.h:89-92),
+ * EXCEPT that dft coefficient banks are returned in the time domain (before the forward transform).
+ * kind 0: DFT filter 0 time-domain taps placed/scaled as rate_base.h:173-175 (dft_length doubles)
+ * kind 1: DFT filter 1 likewise; kind 2: polyphase bank [phase][tap][order..0] (doubles).
+ * Returns the number of doubles available; copies min(max_n, that). */
+int RRX_design_dump(const RR_config *config, int sample_bytes, int kind, double *out, int max_n);
+
+/* Same as the plan above but from a live handle. */
+int RRX_plan_dump(const RR_handle *h, rr_plan *out);
+/* Like RR_pull but planar and in the engine's own sample type (float for the fp32 engine, double for the
+ * fp64 engine): out[ch * osamp + i]. The fp64 "tap" for the 1e-12 check. */
+int RRX_pull_native(RR_handle *h, void *out, size_t osamp, size_t *ogen);
+/* Frequency-domain DFT coefficient bank as uploaded to the device, engine type (dft_length values). */
+int RRX_dft_spectrum(const RR_handle *h, int instance, void *out, int max_n);
+
+/* ---- device-resident batch converter ----
+ * One plan applied to nstreams independent streams of nchannels each, all of the same length, processed
+ * in one shot (push everything + drain). Buffers are DEVICE pointers:
+ *   d_in  : float32 [nstreams][frames_in ][nchannels]  (interleaved per stream)
+ *   d_out : float32 [nstreams][frames_out][nchannels]  with frames_out = RRX_batch_frames_out()
+ * Work and intermediate buffers are allocated once in RRX_batch_open for frames_in_max.
+ * `stream` is a cudaStream_t (passed as void* so this header needs no CUDA include). */
+typedef struct RRX_batch_tag RRX_batch;
+
+int RRX_batch_open(const RR_config *config, int sample_bytes, int nchannels, int nstreams,
+                   size_t frames_in_max, int device, RRX_batch **out);
+/* round(frames_in * out_rate / in_rate) computed like rate_flush (rate/rate_base.h:457). */
+size_t RRX_batch_frames_out(const RRX_batch *b, size_t frames_in);
+int RRX_batch_process(RRX_batch *b, const float *d_in, size_t frames_in, float *d_out, void *stream);
+/* Time-chunked processing (the primitive for sharding one long stream across GPUs with filter-history
+ * halos and an exactly computed start phase). Step 1: ask which input frames
+ * [*in_first, *in_first + *in_count) of a stream of frames_in_total frames the output frames
+ * [out_begin, out_begin + out_count) depend on. */
+int RRX_batch_input_window(const RRX_batch *b, size_t frames_in_total, uint64_t out_begin, size_t out_count,
+                           uint64_t *in_first, uint64_t *in_count);
+/* Step 2: d_in_window holds input frames [window_first, window_first + window_frames) of every stream
+ * (float32 [nstreams][window_frames][nchannels]) and must cover the window reported above; d_out receives
+ * output frames [out_begin, out_begin + out_count) as float32 [nstreams][out_count][nchannels]. The samples
+ * are bit-identical to the same frames of a whole-stream RRX_batch_process call. */
+int RRX_batch_process_range(RRX_batch *b, const float *d_in_window, uint64_t window_first, size_t window_frames,
+                            size_t frames_in_total, uint64_t out_begin, size_t out_count, float *d_out,
+                            void *stream);
+/* Engine-type planar output of the last stage for the same call shape as RRX_batch_process:
+ * d_out_native[(s * nchannels + c) * frames_out + i] (float or double). */
+int RRX_batch_process_native(RRX_batch *b, const float *d_in, size_t frames_in, void *d_out_native,
+                             void *stream);
+int RRX_batch_plan(const RRX_batch *b, rr_plan *out);
+/* Kernel launches issued by the most recent RRX_batch_process* call. */
+int RRX_batch_last_launches(const RRX_batch *b);
+/* Algorithmic FLOP count of one RRX_batch_process call on frames_in frames (SURVEY.md 8d accounting). */
+double RRX_batch_flops(const RRX_batch *b, size_t frames_in);
+void RRX_batch_close(RRX_batch **b);
+
+/* Last CUDA error string seen by this library on the calling thread ("" if none). */
+const char *RRX_last_error(void);
+/* [host-only] Library version string. */
+const char *RRX_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,163 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (include/b200_ratelib.h), against the
+oracle on identical bytes. Bit-exact for the fp32 engine, counts and plan integers; <= 1e-12 for the fp64
+engine at the un-cast tap (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+import oraclelib
+import signals
+
+pytestmark = pytest.mark.gpu
+
+FP64_TOL = 1e-12          # north_star: double path max |err| <= 1e-12
+FP32_TOL = 2.0 ** -22     # north_star: float path max |err| <= 2^-22 full scale (we require 0)
+
+# (in_rate, out_rate, engine, phase, bandwidth, allow_aliasing, quality, nch)
+STREAM_CASES = [
+    (44100, 48000, "float", 50, 95, 0, 0, 2),     # BASELINE config 1
+    (44100, 96000, "float", 50, 95, 0, 0, 2),     # config 2
+    (192000, 44100, "double", 25, 95, 0, 0, 8),   # config 3
+    (48000, 44100, "float", 50, 95, 0, 0, 2),     # config 4 (one stream)
+    (384000, 48000, "float", 50, 95, 0, 0, 8),    # config 5 (short)
+    (44100, 48001, "float", 50, 95, 0, 0, 1),     # vpoly2
+    (44100, 44101, "float", 50, 95, 0, 1, 1),     # vpoly1
+    (48000, 47999, "double", 50, 95, 0, 0, 1),    # vpoly3
+    (8000, 48000, "float", 50, 95, 0, 0, 1),      # zero-stuff L=3 + F-domain /2, post stage L=4
+    (48000, 32000, "float", 50, 95, 0, 0, 1),     # L=2, time-domain decimation by 3
+    (96000, 44100, "float", 75, 99, 1, 0, 1),     # phase 75, aliasing allowed
+    (44100, 48000, "float", 0, 90, 0, 1, 1),      # minimum phase, Normal quality
+    (22050, 96000, "float", 50, 95, 0, 0, 1),     # pre + arb + post stages
+    (44100, 11025, "double", 50, 95, 0, 0, 2),    # half-band + F-domain /2, fp64
+]
+
+
+def _cfgs(i, o, ph, bw, al, q):
+    import foo_dsp_resampler_b200 as pkg
+    return (pkg.make_config(i, o, ph, bw, al, q), oraclelib.make_config(i, o, ph, bw, al, q))
+
+
+@pytest.mark.parametrize("case", STREAM_CASES, ids=lambda c: "%d-%d-%s-p%d-q%d" % (c[0], c[1], c[2], c[3], c[6]))
+def test_stream_matches_oracle(case):
+    import foo_dsp_resampler_b200 as pkg
+    i, o, eng, ph, bw, al, q, nch = case
+    cfg, ocfg = _cfgs(i, o, ph, bw, al, q)
+    x = signals.sweep_noise(i, nch, int(i * 0.6) + 17)
+    y_ref, c_ref = oraclelib.resample(ocfg, x, engine=eng, chunk=7001, native=True)
+    y, c = pkg.resample(cfg, x, engine=eng, chunk=7001, native=True)
+    assert c == c_ref                                   # frames available after every push / drain
+    assert y.shape == y_ref.shape
+    if eng == "float":
+        assert np.array_equal(y, y_ref), "max diff %g" % np.abs(y - y_ref).max()
+    else:
+        assert np.abs(y - y_ref).max() <= FP64_TOL
+
+
+def test_plan_matches_oracle():
+    import foo_dsp_resampler_b200 as pkg
+    for i, o, eng, ph, bw, al, q, nch in STREAM_CASES:
+        cfg, ocfg = _cfgs(i, o, ph, bw, al, q)
+        r = pkg.RateConverter(cfg, 1, eng)
+        orc = oraclelib.OracleResampler(ocfg, 1, eng)
+        assert r.plan() == orc.plan()
+        if eng == "float":
+            for inst in (0, 1):
+                assert np.array_equal(r.dft_spectrum(inst), orc.dft_coefs(inst))
+        r.close()
+        orc.close()
+
+
+def test_chunk_size_invariance_and_float_pull():
+    import foo_dsp_resampler_b200 as pkg
+    cfg, ocfg = _cfgs(44100, 48000, 50, 95, 0, 0)
+    x = signals.sweep_noise(44100, 2, 50000)
+    ref, _ = oraclelib.resample(ocfg, x, engine="float", chunk=65536)
+    for chunk in (65536, 4096, 1000, 37 * 13):
+        y, _ = pkg.resample(cfg, x, engine="float", chunk=chunk)
+        assert np.array_equal(y, ref)
+    # RR_open(Best) selects the fp64 engine; through RR_pull both are float-rounded
+    refd, cd = oraclelib.resample(ocfg, x, engine="double", chunk=10000)
+    y, c = pkg.resample(cfg, x, engine="auto", chunk=10000)
+    assert c == cd and np.abs(y - refd).max() <= 2.0 ** -23
+
+
+def test_flow_and_edge_cases():
+    import foo_dsp_resampler_b200 as pkg
+    cfg, ocfg = _cfgs(48000, 44100, 50, 95, 0, 0)
+    x = signals.sweep_noise(48000, 2, 30000)
+    ref, _ = oraclelib.resample(ocfg, x, engine="float", chunk=65536)
+    r = pkg.RateConverter(cfg, 2, "float")
+    outs = []
+    for s in range(0, x.shape[0], 3000):
+        y, used = r.flow(x[s:s + 3000], 4000)
+        assert used == min(3000, x.shape[0] - s)
+        outs.append(y.copy())
+    r.drain()
+    while True:
+        y = r.pull(5000)
+        if not len(y):
+            break
+        outs.append(y.copy())
+    assert np.array_equal(np.concatenate(outs), ref)
+    # empty pushes / pulls are no-ops; second drain is a no-op
+    r.push(np.zeros((0, 2), np.float32))
+    r.drain()
+    assert len(r.pull(10)) == 0
+    r.close()
+    # tiny input: fewer frames than one DFT block, drain must still deliver round(n*out/in) frames
+    r = pkg.RateConverter(cfg, 2, "float")
+    r.push(x[:10])
+    assert len(r.pull(100)) == 0
+    r.drain()
+    y = r.pull(100)
+    ref10, _ = oraclelib.resample(ocfg, x[:10], engine="float")
+    assert np.array_equal(y, ref10) and len(y) == 9
+    r.close()
+
+
+def test_batch_device_resident_and_ranges():
+    import torch
+    import foo_dsp_resampler_b200 as pkg
+    cfg, ocfg = _cfgs(48000, 44100, 50, 95, 0, 0)
+    nstreams, nch, n = 5, 2, 48000
+    xs = np.stack([signals.sweep_noise(48000, nch, n, stream=s) for s in range(nstreams)])
+    b = pkg.BatchConverter(cfg, nch, nstreams, n, engine="float", device=0)
+    nout = b.frames_out(n)
+    d_in = torch.from_numpy(xs).cuda()
+    d_out = torch.zeros((nstreams, nout, nch), dtype=torch.float32, device="cuda")
+    b.process(d_in.data_ptr(), n, d_out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy()
+    for s in range(nstreams):
+        ref, _ = oraclelib.resample(ocfg, xs[s], engine="float")
+        assert ref.shape[0] == nout and np.array_equal(got[s], ref)
+    # time-chunked: every range, computed from its halo'd input window only, equals the one-shot result
+    for ob, oc in ((0, 5000), (12345, 7777), (nout - 4000, 4000)):
+        f, c = b.input_window(n, ob, oc)
+        win = d_in[:, f:f + c, :].contiguous()
+        part = torch.zeros((nstreams, oc, nch), dtype=torch.float32, device="cuda")
+        b.process_range(win.data_ptr(), f, c, n, ob, oc, part.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(part.cpu().numpy(), got[:, ob:ob + oc, :])
+    b.close()
+
+
+def test_full_size_config1_properties():
+    """BASELINE config 1 at full size (60 s stereo): frame count, bit-exactness vs the oracle, linearity of
+    the whole pipeline in the scaling-by-two sense (exact in binary floating point)."""
+    import torch
+    import foo_dsp_resampler_b200 as pkg
+    cfg, ocfg = _cfgs(44100, 48000, 50, 95, 0, 0)
+    n = 44100 * 60
+    x = signals.sweep_noise(44100, 2, n)
+    b = pkg.BatchConverter(cfg, 2, 2, n, engine="float", device=0)
+    nout = b.frames_out(n)
+    assert nout == 2880000
+    d_in = torch.from_numpy(np.stack([x, x * 2.0])).cuda()
+    d_out = torch.zeros((2, nout, 2), dtype=torch.float32, device="cuda")
+    b.process(d_in.data_ptr(), n, d_out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy()
+    ref, _ = oraclelib.resample(ocfg, x, engine="float", chunk=65536)
+    assert np.array_equal(got[0], ref)
+    assert np.array_equal(got[1], got[0] * 2.0)
+    b.close()
