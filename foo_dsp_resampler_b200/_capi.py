@@ -71,6 +71,11 @@ SYMBOLS = {
     "RRX_batch_process_range": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_size_t, C.c_size_t, C.c_uint64,
                                           C.c_size_t, C.c_void_p, C.c_void_p]),
     "RRX_batch_process_native": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "RRX_batch_process_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "RRX_batch_enable_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "RRX_batch_stage_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int]),
+    "RRX_batch_stage_work": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                       C.POINTER(C.c_double)]),
     "RRX_batch_plan": (C.c_int, [C.c_void_p, C.POINTER(Plan)]),
     "RRX_batch_last_launches": (C.c_int, [C.c_void_p]),
     "RRX_batch_flops": (C.c_double, [C.c_void_p, C.c_size_t]),

@@ -174,6 +174,27 @@ class BatchConverter:
         if rc != RR_OK:
             raise RateError(self.lib, rc, "RRX_batch_process_range")
 
+    def process_host(self, h_in, frames_in, h_out, total_streams):
+        """h_in / h_out: host addresses (ints) of float32 [total_streams][frames][nch] buffers."""
+        rc = self.lib.RRX_batch_process_host(self.b, h_in, int(frames_in), h_out, int(total_streams))
+        if rc != RR_OK:
+            raise RateError(self.lib, rc, "RRX_batch_process_host")
+
+    def enable_timing(self, on=True):
+        self.lib.RRX_batch_enable_timing(self.b, 1 if on else 0)
+
+    def stage_times(self):
+        ms = (C.c_float * 24)()
+        n = self.lib.RRX_batch_stage_times(self.b, ms, 24)
+        return [float(ms[i]) for i in range(n)]
+
+    def stage_work(self, frames_in, stage):
+        f, b, u = C.c_double(0), C.c_double(0), C.c_double(0)
+        rc = self.lib.RRX_batch_stage_work(self.b, int(frames_in), int(stage), C.byref(f), C.byref(b), C.byref(u))
+        if rc != RR_OK:
+            raise RateError(self.lib, rc, "RRX_batch_stage_work")
+        return {"flops": f.value, "bytes": b.value, "units": u.value}
+
     def last_launches(self):
         return int(self.lib.RRX_batch_last_launches(self.b))
 

@@ -330,6 +330,36 @@ int RRX_batch_process_range(RRX_batch *b, const float *d_in_window, uint64_t win
   return batch_run(b, d_in_window, window_first, window_frames, frames_in_total, out_begin, out_count, d_out, false, stream);
 }
 
+int RRX_batch_process_host(RRX_batch *b, const float *h_in, size_t frames_in, float *h_out, size_t total_streams)
+{
+  if (!b || !b->batch) return RR_NULLHANDLE;
+  if (!h_in || !h_out || !total_streams) return RR_INVPARAM;
+  struct A { RRX_batch *b; const float *in; size_t n; float *out; size_t tot; } a{b, h_in, frames_in, h_out, total_streams};
+  return guarded([](void *p) {
+    A *a = static_cast<A *>(p);
+    return a->b->batch->process_host(a->in, a->n, a->out, a->tot);
+  }, &a);
+}
+
+int RRX_batch_enable_timing(RRX_batch *b, int on)
+{
+  if (!b || !b->batch) return RR_NULLHANDLE;
+  b->batch->enable_timing(on != 0);
+  return RR_OK;
+}
+
+int RRX_batch_stage_times(RRX_batch *b, float *ms, int max_stages)
+{
+  if (!b || !b->batch || !ms) return 0;
+  return b->batch->stage_times(ms, max_stages);
+}
+
+int RRX_batch_stage_work(const RRX_batch *b, size_t frames_in, int stage, double *flops, double *bytes, double *units)
+{
+  if (!b || !b->batch) return RR_NULLHANDLE;
+  return b->batch->stage_work(frames_in, stage, flops, bytes, units);
+}
+
 int RRX_batch_plan(const RRX_batch *b, rr_plan *out)
 {
   if (!b || !b->batch) return RR_NULLHANDLE;

@@ -489,19 +489,22 @@ template <class T> class Engine {
     return N;
   }
 
-  // Algorithmic flop count of the work described by per-stage ranges (SURVEY.md 8d accounting).
-  double flops_of(const StageRange *r) const
+  // Algorithmic flop count of one stage's work range, per lane (SURVEY.md 8d accounting: split-radix
+  // 4M log2 M - 6M + 8 per M-point complex FFT, 18 per real-FFT pair, 6 per multiplied bin, 1 + 3c per
+  // half-band output, 2n (x (1 + order)) per polyphase output).
+  double stage_flops(int i, const StageRange &r) const
   {
     auto sr = [](double M) { return 4 * M * std::log2(M) - 6 * M + 8; };
+    const StageGeom &g = geom[i];
+    if (g.kind == RR_STAGE_DFT)
+      return static_cast<double>(r.wn) * (sr(g.Pf / 2.) + 18. * g.Pf / 4 + 6. * g.Ni / 2 + 18. * g.Ni / 4 + sr(g.Ni / 2.));
+    if (g.kind == RR_STAGE_HALFBAND) return static_cast<double>(r.wn) * (1 + 3. * g.hb_c);
+    return static_cast<double>(r.wn) * g.n * (2. + 2. * g.order);
+  }
+  double flops_of(const StageRange *r) const
+  {
     double total = 0;
-    for (int i = 0; i < ns; ++i) {
-      const StageGeom &g = geom[i];
-      if (g.kind == RR_STAGE_DFT)
-        total += static_cast<double>(r[i].wn) *
-                 (sr(g.Pf / 2.) + 18. * g.Pf / 4 + 6. * g.Ni / 2 + 18. * g.Ni / 4 + sr(g.Ni / 2.));
-      else if (g.kind == RR_STAGE_HALFBAND) total += static_cast<double>(r[i].wn) * (1 + 3. * g.hb_c);
-      else total += static_cast<double>(r[i].wn) * g.n * (2. + 2. * g.order);
-    }
+    for (int i = 0; i < ns; ++i) total += stage_flops(i, r[i]);
     return total;
   }
 
@@ -672,14 +675,35 @@ template <class T> class Batch : public IBatch {
   std::vector<long long> cap;        // per FIFO (1..ns-1): samples per lane
   std::vector<T *> buf;
   int launches_ = 0;
+  bool timing_ = false;
+  int active_streams_ = 0;           // streams processed by the current call (<= nstreams)
+#ifndef B200RATE_EMU
+  std::vector<cudaEvent_t> ev_;      // 2 per stage when timing is on
+  cudaStream_t hs_[3] = {nullptr, nullptr, nullptr};   // host pipeline: H2D, compute, D2H
+  cudaEvent_t h2d_done_[2] = {nullptr, nullptr}, comp_done_[2] = {nullptr, nullptr}, d2h_done_[2] = {nullptr, nullptr};
+#endif
+  float *slot_in_[2] = {nullptr, nullptr}, *slot_out_[2] = {nullptr, nullptr};
 
-  ~Batch() override { for (T *p : buf) be_free(p); }
+  ~Batch() override
+  {
+    for (T *p : buf) be_free(p);
+    for (int k = 0; k < 2; ++k) { be_free(slot_in_[k]); be_free(slot_out_[k]); }
+#ifndef B200RATE_EMU
+    for (cudaEvent_t e : ev_) cudaEventDestroy(e);
+    for (int k = 0; k < 3; ++k) if (hs_[k]) cudaStreamDestroy(hs_[k]);
+    for (int k = 0; k < 2; ++k) {
+      if (h2d_done_[k]) cudaEventDestroy(h2d_done_[k]);
+      if (comp_done_[k]) cudaEventDestroy(comp_done_[k]);
+      if (d2h_done_[k]) cudaEventDestroy(d2h_done_[k]);
+    }
+#endif
+  }
 
   int init(const RR_config &cfg, int nchannels, int nstr, size_t fmax, int device)
   {
     int rc = eng.init(cfg, device);
     if (rc) return rc;
-    nch = nchannels; nstreams = nstr; frames_in_max = fmax;
+    nch = nchannels; nstreams = nstr; frames_in_max = fmax; active_streams_ = nstr;
     const size_t nout = frames_out(fmax);
     std::vector<StageRange> r(eng.ns);
     plan_ranges(0, static_cast<long long>(nout), r.data());
@@ -730,8 +754,13 @@ template <class T> class Batch : public IBatch {
               size_t out_count, void *d_out, bool native_out, void *stream) override
   {
     stream_t s = static_cast<stream_t>(stream);
-    const int ns = eng.ns, nlanes = nch * nstreams;
+    const int ns = eng.ns, nlanes = nch * active_streams_;
     eng.launches = 0;
+#ifndef B200RATE_EMU
+    if (timing_ && ev_.size() < static_cast<size_t>(2 * ns)) {
+      while (ev_.size() < static_cast<size_t>(2 * ns)) { cudaEvent_t e; CUDA_TRY(cudaEventCreate(&e)); ev_.push_back(e); }
+    }
+#endif
     if (ns == 0) { set_last_error("identity conversion has no stages"); return RR_INVPARAM; }
     std::vector<StageRange> r(ns);
     const long long klo = static_cast<long long>(out_begin), khi = klo + static_cast<long long>(out_count);
@@ -783,14 +812,120 @@ template <class T> class Batch : public IBatch {
         out_f32 = false;
         out_preload = pre;
       }
+#ifndef B200RATE_EMU
+      if (timing_) CUDA_TRY(cudaEventRecord(ev_[2 * i], s));
+#endif
       int rc = eng.run_stage(i, in, in_f32, out, out_f32, out_preload, r[i].w0, r[i].wn, nlanes, s);
       if (rc) return rc;
+#ifndef B200RATE_EMU
+      if (timing_) CUDA_TRY(cudaEventRecord(ev_[2 * i + 1], s));
+#endif
     }
     launches_ = eng.launches;
     return RR_OK;
   }
 
+  int process_streams(const float *d_in, size_t frames_in, void *d_out, int nstreams_now, void *stream) override
+  {
+    if (nstreams_now < 1 || nstreams_now > nstreams) { set_last_error("bad active stream count"); return RR_INVPARAM; }
+    active_streams_ = nstreams_now;
+    const int rc = process(d_in, 0, frames_in, frames_in, 0, frames_out(frames_in), d_out, false, stream);
+    active_streams_ = nstreams;
+    return rc;
+  }
+
+  int process_host(const float *h_in, size_t frames_in, float *h_out, size_t total_streams) override
+  {
+    if (frames_in > frames_in_max) { set_last_error("frames_in exceeds frames_in_max"); return RR_INVPARAM; }
+    const size_t nout = frames_out(frames_in);
+    const size_t in_elems = frames_in * nch, out_elems = nout * nch;
+    int rc;
+    for (int k = 0; k < 2; ++k) {
+      if (!slot_in_[k]) {
+        void *p = nullptr;
+        if ((rc = be_malloc(&p, sizeof(float) * frames_in_max * nch * nstreams))) return rc;
+        slot_in_[k] = static_cast<float *>(p);
+        if ((rc = be_malloc(&p, sizeof(float) * (frames_out(frames_in_max) + 1) * nch * nstreams))) return rc;
+        slot_out_[k] = static_cast<float *>(p);
+      }
+    }
+#ifdef B200RATE_EMU
+    for (size_t s0 = 0; s0 < total_streams; s0 += nstreams) {
+      const int now = static_cast<int>(std::min<size_t>(nstreams, total_streams - s0));
+      memcpy(slot_in_[0], h_in + s0 * in_elems, sizeof(float) * in_elems * now);
+      if ((rc = process_streams(slot_in_[0], frames_in, slot_out_[0], now, nullptr))) return rc;
+      memcpy(h_out + s0 * out_elems, slot_out_[0], sizeof(float) * out_elems * now);
+    }
+    return RR_OK;
+#else
+    if (!hs_[0]) {
+      for (int k = 0; k < 3; ++k) CUDA_TRY(cudaStreamCreateWithFlags(&hs_[k], cudaStreamNonBlocking));
+      for (int k = 0; k < 2; ++k) {
+        CUDA_TRY(cudaEventCreateWithFlags(&h2d_done_[k], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&comp_done_[k], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&d2h_done_[k], cudaEventDisableTiming));
+      }
+    }
+    int total_launches = 0;
+    size_t k = 0;
+    for (size_t s0 = 0; s0 < total_streams; s0 += nstreams, ++k) {
+      const int slot = static_cast<int>(k & 1);
+      const int now = static_cast<int>(std::min<size_t>(nstreams, total_streams - s0));
+      if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(hs_[0], comp_done_[slot], 0));       // input slot free again
+      CUDA_TRY(cudaMemcpyAsync(slot_in_[slot], h_in + s0 * in_elems, sizeof(float) * in_elems * now,
+                               cudaMemcpyHostToDevice, hs_[0]));
+      CUDA_TRY(cudaEventRecord(h2d_done_[slot], hs_[0]));
+      CUDA_TRY(cudaStreamWaitEvent(hs_[1], h2d_done_[slot], 0));
+      if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(hs_[1], d2h_done_[slot], 0));        // output slot drained
+      if ((rc = process_streams(slot_in_[slot], frames_in, slot_out_[slot], now, hs_[1]))) return rc;
+      total_launches += launches_;
+      CUDA_TRY(cudaEventRecord(comp_done_[slot], hs_[1]));
+      CUDA_TRY(cudaStreamWaitEvent(hs_[2], comp_done_[slot], 0));
+      CUDA_TRY(cudaMemcpyAsync(h_out + s0 * out_elems, slot_out_[slot], sizeof(float) * out_elems * now,
+                               cudaMemcpyDeviceToHost, hs_[2]));
+      CUDA_TRY(cudaEventRecord(d2h_done_[slot], hs_[2]));
+    }
+    for (int q = 0; q < 3; ++q) CUDA_TRY(cudaStreamSynchronize(hs_[q]));
+    launches_ = total_launches;
+    return RR_OK;
+#endif
+  }
+
   int last_launches() const override { return launches_; }
+
+  void enable_timing(bool on) override { timing_ = on; }
+
+  int stage_times(float *ms, int max_stages) override
+  {
+    const int n = std::min(eng.ns, max_stages);
+    for (int i = 0; i < n; ++i) ms[i] = 0.f;
+#ifndef B200RATE_EMU
+    if (!timing_ || ev_.size() < static_cast<size_t>(2 * eng.ns)) return 0;
+    for (int i = 0; i < n; ++i) {
+      if (cudaEventSynchronize(ev_[2 * i + 1]) != cudaSuccess) return 0;
+      if (cudaEventElapsedTime(&ms[i], ev_[2 * i], ev_[2 * i + 1]) != cudaSuccess) return 0;
+    }
+#endif
+    return n;
+  }
+
+  int stage_work(size_t frames_in, int stage, double *flops_out, double *bytes_out, double *units_out) const override
+  {
+    if (stage < 0 || stage >= eng.ns) return RR_INVPARAM;
+    std::vector<StageRange> r(eng.ns);
+    plan_ranges(0, static_cast<long long>(frames_out(frames_in)), r.data());
+    const double lanes = static_cast<double>(nch) * nstreams;
+    const double in_bytes = stage == 0 ? 4. : sizeof(T), out_bytes = stage == eng.ns - 1 ? 4. : sizeof(T);
+    // unique input samples: the coordinates the work range reads, clipped to what really exists upstream
+    double in_samples = static_cast<double>(r[stage].need_hi - std::max<long long>(r[stage].need_lo, eng.geom[stage].preload));
+    if (stage == 0) in_samples = std::min<double>(in_samples, static_cast<double>(frames_in));
+    const double out_samples = stage == eng.ns - 1 ? static_cast<double>(frames_out(frames_in))
+                                                   : static_cast<double>(r[stage].prod_hi - r[stage].prod_lo);
+    if (flops_out) *flops_out = eng.stage_flops(stage, r[stage]) * lanes;
+    if (bytes_out) *bytes_out = (in_samples * in_bytes + out_samples * out_bytes) * lanes;
+    if (units_out) *units_out = static_cast<double>(r[stage].wn) * lanes;
+    return RR_OK;
+  }
 
   double flops(size_t frames_in) const override
   {

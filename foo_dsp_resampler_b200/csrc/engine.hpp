@@ -32,8 +32,19 @@ class IBatch {
   // instead of interleaved float.
   virtual int process(const float *d_in, uint64_t win_first, size_t win_frames, size_t frames_in, uint64_t out_begin,
                       size_t out_count, void *d_out, bool native_out, void *stream) = 0;
+  // As process() over whole streams, but with only the first `nstreams_now` streams of the batch active.
+  virtual int process_streams(const float *d_in, size_t frames_in, void *d_out, int nstreams_now, void *stream) = 0;
+  // Host-buffer variant: total_streams streams in (pinned) host memory are moved through the device in
+  // sub-batches of the batch's nstreams, H2D / compute / D2H overlapped on three CUDA streams.
+  virtual int process_host(const float *h_in, size_t frames_in, float *h_out, size_t total_streams) = 0;
   virtual int last_launches() const = 0;
   virtual double flops(size_t frames_in) const = 0;
+  // Per-stage CUDA-event timing of process() calls (events are recorded on the launching stream).
+  virtual void enable_timing(bool on) = 0;
+  virtual int stage_times(float *ms, int max_stages) = 0;          // of the most recent timed call
+  // Algorithmic work of stage i for one whole-stream call on frames_in frames, all lanes:
+  // flops (SURVEY.md 8d accounting) and bytes (unique input samples read + output samples written).
+  virtual int stage_work(size_t frames_in, int stage, double *flops, double *bytes, double *launch_units) const = 0;
 };
 
 class IStream {

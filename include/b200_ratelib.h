@@ -136,6 +136,17 @@ int RRX_batch_process_range(RRX_batch *b, const float *d_in_window, uint64_t win
  * d_out_native[(s * nchannels + c) * frames_out + i] (float or double). */
 int RRX_batch_process_native(RRX_batch *b, const float *d_in, size_t frames_in, void *d_out_native,
                              void *stream);
+/* Host-buffer batch: total_streams streams in HOST memory (float32 [total_streams][frames_in][nchannels],
+ * ideally pinned) are moved through the device in sub-batches of the batch's nstreams; H2D copy, kernels and
+ * D2H copy of consecutive sub-batches overlap on three CUDA streams. Blocking. */
+int RRX_batch_process_host(RRX_batch *b, const float *h_in, size_t frames_in, float *h_out, size_t total_streams);
+/* Per-stage device timing of RRX_batch_process* calls with CUDA events recorded on the launching stream.
+ * RRX_batch_stage_times waits for the most recent timed call and returns the number of stages written. */
+int RRX_batch_enable_timing(RRX_batch *b, int on);
+int RRX_batch_stage_times(RRX_batch *b, float *ms, int max_stages);
+/* Algorithmic work of one stage for a whole-stream call on frames_in frames over all lanes: FLOPs, bytes
+ * (unique input samples read + output samples written) and launch units (DFT blocks or output samples). */
+int RRX_batch_stage_work(const RRX_batch *b, size_t frames_in, int stage, double *flops, double *bytes, double *units);
 int RRX_batch_plan(const RRX_batch *b, rr_plan *out);
 /* Kernel launches issued by the most recent RRX_batch_process* call. */
 int RRX_batch_last_launches(const RRX_batch *b);
