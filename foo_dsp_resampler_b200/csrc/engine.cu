@@ -42,6 +42,7 @@ const char *last_error() { return g_last_error.c_str(); }
 // backend: CUDA, or host emulation for tests
 // ===================================================================================================
 #ifdef B200RATE_EMU
+constexpr int kEmulated = 1;
 typedef void *stream_t;
 static int be_set_device(int) { return RR_OK; }
 static int be_malloc(void **p, size_t n) { *p = calloc(1, n ? n : 1); return *p ? RR_OK : RR_ENOMEM; }
@@ -52,6 +53,7 @@ static int be_sync(stream_t) { return RR_OK; }
 static int be_num_sms() { return 1; }
 static size_t be_max_smem() { return 227 * 1024; }
 #else
+constexpr int kEmulated = 0;
 typedef cudaStream_t stream_t;
 static int cuda_fail(cudaError_t e, const char *what)
 {
@@ -106,6 +108,8 @@ constexpr int kTileThreads = 256;
 constexpr int kPolyTile = 2048;      // outputs per CTA tile
 constexpr int kHalfTile = 2048;
 constexpr int kCopyTile = 4096;      // elements per CTA tile (lane-fastest)
+// filter-spectrum values cached in registers per thread (phase-4 items threadIdx.x + k*blockDim.x, k < depth)
+template <class T> struct DftCacheDepth { static constexpr int value = sizeof(T) == 4 ? 8 : 4; };
 
 struct CopyParams {                  // out[coord c0 + j] = in[coord c0 + j + in_shift]
   LaneView in, out;
@@ -133,17 +137,65 @@ RR_PROG void copy_program(const CopyParams &p, long long work)
 #ifndef B200RATE_EMU
 extern __shared__ __align__(16) unsigned char rr_smem_raw[];
 
-template <class T, class InT, class OutT>
-__global__ void __launch_bounds__(kDftThreads) dft_kernel(const __grid_constant__ DftParams<T> p, long long nwork)
+// Persistent CTA: stage the twiddle / cosine tables in shared memory and the filter spectrum values this
+// thread will need in registers, once; then loop over (block, lane group) work items, prefetching the next
+// item's input tile with LDGSTS while the current one is transformed.
+template <class T, class InT, class OutT, int LPC>
+__global__ void __launch_bounds__(kDftThreads) dft_kernel(const __grid_constant__ DftParams<T> p, long long nwork, int data_bytes)
 {
-  T *smem = reinterpret_cast<T *>(rr_smem_raw);
-  for (long long w = blockIdx.x; w < nwork; w += gridDim.x) dft_stage_program<T, InT, OutT>(p, w, smem);
+  C2<T> *data = reinterpret_cast<C2<T> *>(rr_smem_raw);
+  T *t = reinterpret_cast<T *>(rr_smem_raw + data_bytes);
+  const int nf = p.fwd.pyr_len, ni = p.inv.pyr_len, tf = (p.Pf >> 2) + 1, ti = (p.Ni >> 2) + 1;
+  for (int i = threadIdx.x; i < nf; i += blockDim.x) t[i] = p.pyr_f[i];
+  for (int i = threadIdx.x; i < ni; i += blockDim.x) t[nf + i] = p.pyr_i[i];
+  for (int i = threadIdx.x; i < tf; i += blockDim.x) t[nf + ni + i] = p.tcos_f[i];
+  for (int i = threadIdx.x; i < ti; i += blockDim.x) t[nf + ni + tf + i] = p.tcos_i[i];
+  const DftTables<T> tab{t, t + nf, t + nf + ni, t + nf + ni + tf};
+  CoefCache<T, DftCacheDepth<T>::value> cc;
+  dft_load_coef_cache(p, cc);
+  if (p.zstride > 0 && (long long)blockIdx.x < nwork) {          // prime the prefetch pipeline
+    const DftItem<T> it = dft_item<T, LPC>(p, blockIdx.x);
+    dft_stage_tile<T, T, LPC, true>(p, it, data + LPC * (p.xstride + p.ystride), p.zstride);
+  }
+  __syncthreads();
+  for (long long w = blockIdx.x; w < nwork; w += gridDim.x) {
+    const long long next = w + gridDim.x < nwork ? w + gridDim.x : -1;
+    dft_stage_program<T, InT, OutT, LPC, DftCacheDepth<T>::value>(p, tab, cc, w, next, data);
+  }
 }
 template <class T, class InT, class OutT>
 __global__ void __launch_bounds__(kTileThreads) poly0_kernel(const __grid_constant__ PolyParams<T> p, long long nwork)
 {
   T *smem = reinterpret_cast<T *>(rr_smem_raw);
   for (long long w = blockIdx.x; w < nwork; w += gridDim.x) poly0_program<T, InT, OutT>(p, w, smem);
+}
+// Persistent CTA with a two-deep LDGSTS pipeline: the input windows of tile k+1 are in flight while
+// tile k is computed (when the input needs a type conversion the copy is synchronous instead).
+template <class T, class InT, class OutT, int NT>
+__global__ void __launch_bounds__(512) poly0_fast_kernel(const __grid_constant__ Poly0FastParams<T> p, long long nwork)
+{
+  T *smem = reinterpret_cast<T *>(rr_smem_raw);
+  constexpr bool kAsync = std::is_same<InT, T>::value;
+  const int set = p.win * p.CH;
+  long long w = blockIdx.x;
+  if (kAsync && p.double_buffer) {
+    if (w < nwork) poly0_fast_load<T, InT, true>(p, poly0_tile(p, w), smem);
+    for (int it = 0; w < nwork; w += gridDim.x, ++it) {
+      const int cur = it & 1;
+      const long long next = w + gridDim.x;
+      if (next < nwork) { poly0_fast_load<T, InT, true>(p, poly0_tile(p, next), smem + (cur ^ 1) * set); async_copy_wait<1>(); }
+      else async_copy_wait<0>();
+      __syncthreads();
+      poly0_fast_compute<T, OutT, NT>(p, poly0_tile(p, w), smem + cur * set);   // ends with a barrier
+    }
+  } else {
+    for (; w < nwork; w += gridDim.x) {
+      const Poly0Tile t = poly0_tile(p, w);
+      poly0_fast_load<T, InT, false>(p, t, smem);
+      __syncthreads();
+      poly0_fast_compute<T, OutT, NT>(p, t, smem);
+    }
+  }
 }
 template <class T, class InT, class OutT>
 __global__ void __launch_bounds__(kTileThreads) polyN_kernel(const __grid_constant__ PolyParams<T> p, long long nwork)
@@ -170,8 +222,9 @@ static std::map<std::pair<const void *, size_t>, LaunchInfo> &launch_cache()
   return c;
 }
 
-template <class Kernel, class Params>
-static int launch_persistent(Kernel kernel, const Params &p, long long nwork, int threads, size_t smem, stream_t s)
+template <class Kernel, class Params, class... Extra>
+static int launch_persistent(Kernel kernel, const Params &p, long long nwork, int threads, size_t smem, stream_t s,
+                             Extra... extra)
 {
   if (nwork <= 0) return RR_OK;
   const void *key = reinterpret_cast<const void *>(kernel);
@@ -190,7 +243,7 @@ static int launch_persistent(Kernel kernel, const Params &p, long long nwork, in
   }
   const long long resident = static_cast<long long>(it->second.blocks_per_sm) * be_num_sms();
   const unsigned grid = static_cast<unsigned>(std::min<long long>(nwork, resident));
-  kernel<<<grid, threads, smem, s>>>(p, nwork);
+  kernel<<<grid, threads, smem, s>>>(p, nwork, extra...);
   CUDA_TRY(cudaGetLastError());
   return RR_OK;
 }
@@ -218,16 +271,32 @@ template <class T> struct Launch {
     return CALL(T, float);                                                         \
   } while (0)
 
-  static int dft(const DftParams<T> &p, bool in_f32, bool out_f32, long long nwork, size_t smem, stream_t s)
+  // lpc: lanes per CTA (1 or 2); data_bytes: shared memory for the sample buffers, the tables follow
+  static int dft(const DftParams<T> &p, int lpc, bool in_f32, bool out_f32, long long nwork, size_t data_bytes, stream_t s)
   {
+    const size_t smem = data_bytes + sizeof(T) * static_cast<size_t>(dft_table_elems(p));
 #ifdef B200RATE_EMU
-#define RR_CALL(I, O) serial(nwork, smem, [&](long long w, T *sm) { dft_stage_program<T, I, O>(p, w, sm); })
+    const DftTables<T> tab{p.pyr_f, p.pyr_i, p.tcos_f, p.tcos_i};
+    const CoefCache<T, 0> cc{};
+    // emulation: the "asynchronous" prefetch of each item's tile is performed right before the item
+#define RR_CALLE(I, O, LPC)                                                                                   \
+  serial(nwork, smem, [&](long long w, T *sm) {                                                               \
+    C2<T> *data = reinterpret_cast<C2<T> *>(sm);                                                              \
+    if (p.zstride > 0) dft_stage_tile<T, T, LPC, true>(p, dft_item<T, LPC>(p, w), data + LPC * (p.xstride + p.ystride), p.zstride); \
+    dft_stage_program<T, I, O, LPC, 0>(p, tab, cc, w, -1, data);                                              \
+  })
+#define RR_CALL1(I, O) RR_CALLE(I, O, 1)
+#define RR_CALL2(I, O) RR_CALLE(I, O, 2)
 #else
-#define RR_CALL(I, O) launch_persistent(dft_kernel<T, I, O>, p, nwork, kDftThreads, smem, s)
+#define RR_CALL1(I, O) launch_persistent(dft_kernel<T, I, O, 1>, p, nwork, kDftThreads, smem, s, static_cast<int>(data_bytes))
+#define RR_CALL2(I, O) launch_persistent(dft_kernel<T, I, O, 2>, p, nwork, kDftThreads, smem, s, static_cast<int>(data_bytes))
 #endif
     (void)s;
-    RR_DISPATCH_IO(RR_CALL);
-#undef RR_CALL
+    if (lpc == 2) RR_DISPATCH_IO(RR_CALL2);
+    RR_DISPATCH_IO(RR_CALL1);
+#undef RR_CALL1
+#undef RR_CALL2
+#undef RR_CALLE
   }
   static int poly0(const PolyParams<T> &p, bool in_f32, bool out_f32, long long nwork, size_t smem, stream_t s)
   {
@@ -239,6 +308,32 @@ template <class T> struct Launch {
     (void)s;
     RR_DISPATCH_IO(RR_CALL);
 #undef RR_CALL
+  }
+  static int poly0_fast(const Poly0FastParams<T> &p, int threads, bool in_f32, bool out_f32, long long nwork, size_t smem,
+                        stream_t s)
+  {
+    (void)s; (void)threads;
+#ifdef B200RATE_EMU
+#define RR_CALLN(I, O, NT)                                                   \
+  serial(nwork, smem, [&](long long w, T *sm) {                              \
+    const Poly0Tile t = poly0_tile(p, w);                                    \
+    poly0_fast_load<T, I, false>(p, t, sm);                                  \
+    poly0_fast_compute<T, O, NT>(p, t, sm);                                  \
+  })
+#else
+#define RR_CALLN(I, O, NT) launch_persistent(poly0_fast_kernel<T, I, O, NT>, p, nwork, threads, smem, s)
+#endif
+#define RR_CALL16(I, O) RR_CALLN(I, O, 16)
+#define RR_CALL24(I, O) RR_CALLN(I, O, 24)
+#define RR_CALL32(I, O) RR_CALLN(I, O, 32)
+    if (p.base.n == 16) RR_DISPATCH_IO(RR_CALL16);
+    if (p.base.n == 24) RR_DISPATCH_IO(RR_CALL24);
+    if (p.base.n == 32) RR_DISPATCH_IO(RR_CALL32);
+    return RR_INTERNAL;
+#undef RR_CALL16
+#undef RR_CALL24
+#undef RR_CALL32
+#undef RR_CALLN
   }
   static int polyN(const PolyParams<T> &p, bool in_f32, bool out_f32, long long nwork, size_t smem, stream_t s)
   {
@@ -436,10 +531,18 @@ template <class T> class Engine {
       DftParams<T> p = dft_params_[i];
       p.in = in; p.out = out; p.out_preload = out_preload;
       p.block0 = w0; p.nblocks = static_cast<int>(wn); p.nlanes = nlanes;
-      p.lanes_per_cta = dft_lanes_per_cta(g, nlanes);
-      const size_t smem = sizeof(T) * dft_smem_elems<T>(g.N, p.lanes_per_cta, &p.xstride, &p.ystride);
-      const long long groups = (nlanes + p.lanes_per_cta - 1) / p.lanes_per_cta;
-      return Launch<T>::dft(p, in_f32, out_f32, wn * groups, smem, s);
+      const int lpc = dft_lanes_per_cta(g, nlanes);
+      // prefetch the next tile with LDGSTS when the input needs no conversion and the staging buffer still
+      // leaves room for two CTAs per SM
+      const bool same_type = Launch<T>::kIsF32 || !in_f32;
+      bool prefetch = same_type;
+      size_t data_bytes = dft_smem_bytes<T>(g.N, g.Pf, lpc, prefetch, &p.xstride, &p.ystride, &p.zstride);
+      if (prefetch && data_bytes + sizeof(T) * dft_table_elems(p) > 110 * 1024) {
+        prefetch = false;
+        data_bytes = dft_smem_bytes<T>(g.N, g.Pf, lpc, false, &p.xstride, &p.ystride, &p.zstride);
+      }
+      const long long groups = (nlanes + lpc - 1) / lpc;
+      return Launch<T>::dft(p, lpc, in_f32, out_f32, wn * groups, data_bytes, s);
     }
     if (g.kind == RR_STAGE_HALFBAND) {
       HalfbandParams<T> p = half_params_[i];
@@ -452,6 +555,32 @@ template <class T> class Engine {
     PolyParams<T> p = poly_params_[i];
     p.in = in; p.out = out; p.out_preload = out_preload; p.out0 = w0; p.nout = wn; p.nlanes = nlanes;
     p.tile = kPolyTile;
+    if (g.order == 0 && (g.n == 16 || g.n == 24 || g.n == 32)) {
+      // phase-stationary kernel: needs enough phases to fill a CTA and a window that fits shared memory
+      const int nch = in.nch;
+      const int CH = (nch <= 8 && nlanes % nch == 0) ? nch : 1;
+      const int ncols = (g.Lp * CH + 511) / 512;
+      const int F = (g.Lp + ncols - 1) / ncols;
+      const int threads = ((F * CH + 31) / 32) * 32;
+      const long long periods = (wn + g.Lp - 1) / g.Lp;
+      int MM = 16;
+      // per-lane window, rounded so that lanes are 16 words apart modulo 32 (no bank sharing between channels)
+      auto window = [&](int mm) {
+        long long w = ((g.Lp - 1) + static_cast<long long>(F - 1) * g.pstep) / g.Lp + static_cast<long long>(mm - 1) * g.pstep + g.n + 1;
+        const long long unit = 64 / sizeof(T);
+        return ((w + 2 * unit - 1) / (2 * unit)) * 2 * unit + unit;
+      };
+      while (MM > 2 && window(MM) * CH * sizeof(T) > 24 * 1024) MM >>= 1;
+      if (F * CH >= 64 && g.pstep < (1 << 20) && window(MM) * CH * sizeof(T) <= 48 * 1024) {
+        Poly0FastParams<T> fp;
+        fp.base = p; fp.F = F; fp.ncols = ncols; fp.MM = MM; fp.CH = CH;
+        fp.win = static_cast<int>(window(MM));
+        fp.mtiles = (periods + MM - 1) / MM;
+        fp.double_buffer = 1;
+        const long long nwork = static_cast<long long>(nlanes / CH) * ncols * fp.mtiles;
+        return Launch<T>::poly0_fast(fp, threads, in_f32, out_f32, nwork, 2 * sizeof(T) * static_cast<size_t>(fp.win) * CH, s);
+      }
+    }
     // window of one tile: worst-case start phase (L-1) plus (tile-1) steps, plus the taps
     long long win;
     if (g.order == 0) win = ((g.Lp - 1) + static_cast<long long>(p.tile - 1) * g.pstep) / g.Lp + g.n + 1;
@@ -525,9 +654,8 @@ template <class T> class Engine {
   int dft_lanes_per_cta(const StageGeom &g, int nlanes) const
   {
     if (nlanes < 2) return 1;
-    int x = 0, y = 0;
-    const size_t two = sizeof(T) * dft_smem_elems<T>(g.N, 2, &x, &y);
-    return two <= 72 * 1024 ? 2 : 1;       // keep >= 3 CTAs per SM resident
+    const size_t two = dft_smem_bytes<T>(g.N, g.Pf, 2, false, nullptr, nullptr, nullptr);
+    return two <= 100 * 1024 ? 2 : 1;      // two lanes share every table / index load; keep 2 CTAs per SM
   }
 
   template <class E> int upload(const std::vector<E> &v, const E **dev)
@@ -559,6 +687,7 @@ template <class T> class Engine {
         c.bits = bits;
         c.n16 = static_cast<int>(h.leaf16_off.size()); c.n8 = static_cast<int>(h.leaf8_off.size());
         c.leaf16_off = leaf16; c.leaf8_off = leaf8; c.gather16 = g16[inv]; c.gather8 = g8[inv]; c.node_off = nodes;
+        c.pyr_len = h.pyr_len;
         for (int l = 0; l < 17; ++l) { c.level_begin[l] = h.level_begin[l]; c.level_cnt[l] = h.level_cnt[l]; c.pyr_off[l] = h.pyr_off[l]; }
       }
       it = sched_.emplace(bits, d).first;
@@ -604,7 +733,9 @@ template <class T> class Engine {
       } else {
         // smem budget check: the whole block lives in shared memory
         int xs = 0, ys = 0;
-        const size_t need = sizeof(T) * dft_smem_elems<T>(g.N, 1, &xs, &ys);
+        DftParams<T> probe; memset(&probe, 0, sizeof(probe));
+        probe.Pf = g.Pf; probe.Ni = g.Ni; probe.fwd.pyr_len = g.Pf / 4 + 16; probe.inv.pyr_len = g.Ni / 4 + 16;
+        const size_t need = dft_smem_bytes<T>(g.N, g.Pf, 1, false, &xs, &ys, nullptr) + sizeof(T) * dft_table_elems(probe);
         if (need > max_smem_) {
           set_last_error("DFT length " + std::to_string(g.N) + " exceeds the shared-memory block kernel (not implemented: global-memory multi-pass FFT)");
           return RR_INTERNAL;
@@ -656,9 +787,9 @@ template <class T> class Engine {
     v.origin = 0; v.mask = ~0ull; v.lo = 0; v.hi = N; v.stream_stride = 0; v.ch_stride = 0; v.elem_stride = 1; v.nch = 1;
     p.in = v; p.in.base = const_cast<T *>(time_dev);
     p.out = v; p.out.base = spec;
-    p.block0 = 0; p.nblocks = 1; p.nlanes = 1; p.lanes_per_cta = 1;
-    const size_t smem = sizeof(T) * dft_smem_elems<T>(N, 1, &p.xstride, &p.ystride);
-    if ((rc = Launch<T>::dft(p, false, false, 1, smem, 0))) return rc;
+    p.block0 = 0; p.nblocks = 1; p.nlanes = 1;
+    const size_t data_bytes = dft_smem_bytes<T>(N, N, 1, false, &p.xstride, &p.ystride, &p.zstride);
+    if ((rc = Launch<T>::dft(p, 1, false, false, 1, data_bytes, 0))) return rc;
     dft_coef_dev_[instance] = static_cast<T *>(spec);
     return RR_OK;
   }

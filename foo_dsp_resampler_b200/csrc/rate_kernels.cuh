@@ -103,9 +103,40 @@ template <class E, class T> RR_HD void view_write(const LaneView &v, long long l
   static_cast<E *>(v.base)[lane_off + (long long)phys * v.elem_stride] = (E)value;
 }
 
+// Address of a coordinate for asynchronous copies; *valid = false where view_read would return zero
+// (the returned pointer is then the buffer base, never dereferenced beyond a zero-byte request).
+template <class E> RR_HD const E *view_addr(const LaneView &v, long long lane_off, long long coord, bool *valid)
+{
+  const E *base = static_cast<const E *>(v.base);
+  if (coord < v.lo || coord >= v.hi) { *valid = false; return base; }
+  const unsigned long long phys = (unsigned long long)(coord - v.origin) & v.mask;
+  *valid = true;
+  return base + lane_off + (long long)phys * v.elem_stride;
+}
+
+// LDGSTS: global -> shared without staging registers; `valid == false` zero-fills the destination.
+#if defined(__CUDA_ARCH__)
+template <class E> RR_PROG void async_copy_elem(E *smem_dst, const E *gsrc, bool valid)
+{
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? (int)sizeof(E) : 0;
+  if (sizeof(E) == 4) asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+RR_PROG void async_copy_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> RR_PROG void async_copy_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+#else
+template <class E> inline void async_copy_elem(E *dst, const E *src, bool valid) { *dst = valid ? *src : (E)0; }
+inline void async_copy_commit() {}
+template <int N> inline void async_copy_wait() {}
+#endif
+
 // ---------------------------------------------------------------------------------------------------
 // Complex FFT of size M = 1 << bits over FFmpeg's split-radix DAG (fft.c:186-346)
 // ---------------------------------------------------------------------------------------------------
+// Complex values live in shared memory as 2-element vectors so that every access is one 8/16-byte LDS/STS.
+template <class T> struct alignas(2 * sizeof(T)) C2 { T x, y; };
+
 // Device-side schedule. Node lists are per power-of-two size; the gather tables are the out-of-place
 // permutation of ff_fft_permute_c (fft.c:169-177) folded into the leaf loads and stored transposed
 // ([element][leaf]) so consecutive threads read consecutive entries.
@@ -114,16 +145,28 @@ struct CfftSched {
   int n16, n8;                   // leaves: nodes of size 16, and size-8 quarter-children of size-32 nodes
   const uint16_t *leaf16_off;    // [n16] offset of the leaf in the permuted array
   const uint16_t *leaf8_off;     // [n8]
-  const uint16_t *gather16;      // [16][n16] natural index feeding permuted element off+e
+  const uint16_t *gather16;      // [16][n16] padded slot (cslot) of the natural index feeding permuted element off+e
   const uint16_t *gather8;       // [8][n8]
   const uint16_t *node_off;      // concatenated node offsets for sizes 32 .. M
   int level_begin[17], level_cnt[17];
   int pyr_off[17];               // start of the twiddle row of each size inside the pyramid
+  int pyr_len;
 };
 
 // Bank-conflict padding of the FFT work buffer: one extra complex slot per 16.
 RR_HD int cslot(int p) { return p + (p >> 4); }
-RR_HD int cfft_buf_complex(int m) { return m + (m >> 4) + 1; }
+// Per-lane stride of a padded buffer holding m complex values: congruent to `unit` modulo 2*unit complex
+// (unit = 16 words), so two lanes never meet in a bank when accessed lane-interleaved.
+RR_HD int lane_stride_complex(int min_complex, int unit) { return ((min_complex + 2 * unit - 1) / (2 * unit)) * 2 * unit + unit; }
+
+// Read-only global loads (LDG.CONSTANT on the device).
+#if defined(__CUDA_ARCH__)
+template <class E> RR_HD E ldg(const E *p) { return __ldg(p); }
+RR_HD C2<float> ldg(const C2<float> *p) { const float2 v = __ldg(reinterpret_cast<const float2 *>(p)); return C2<float>{v.x, v.y}; }
+RR_HD C2<double> ldg(const C2<double> *p) { const double2 v = __ldg(reinterpret_cast<const double2 *>(p)); return C2<double>{v.x, v.y}; }
+#else
+template <class E> RR_HD E ldg(const E *p) { return *p; }
+#endif
 
 template <class T>
 RR_HD void sr_bfly(T &a0r, T &a0i, T &a1r, T &a1i, T &a2r, T &a2i, T &a3r, T &a3i, T wre, T wim, bool zero)
@@ -186,73 +229,88 @@ template <class T> RR_HD void leaf_fft16(T *re, T *im, T sqrthalf, T c1, T c3)  
   sr_bfly(re[3], im[3], re[7], im[7], re[11], im[11], re[15], im[15], c3, c1, false);
 }
 
-// Leaf phase for `lanes` independent transforms: gathers from linear natural-order tiles
-// (src + lane*src_stride, complex j at floats 2j,2j+1) and writes the padded work buffers
-// (dst + lane*dst_stride, complex p at floats 2*cslot(p)).
-template <class T>
-RR_PROG void cfft_leaf_task(const CfftSched &s, bool inverse_unused, int task, const T *src, T *dst, T sqrthalf,
-                          T c16_1, T c16_3)
+// Leaf task `task` for LPC transforms at once: gathers from the natural-order tiles
+// (src + lane*src_stride complex, value j stored at cslot(j)) and writes the padded work buffers
+// (dst + lane*dst_stride complex, permuted position p at cslot(p)).
+// The gather indices are loaded once and shared by the lanes.
+template <class T, int LPC>
+RR_PROG void cfft_leaf_task(const CfftSched &s, int task, int lanes, const C2<T> *src, int src_stride, C2<T> *dst,
+                            int dst_stride, T sqrthalf, T c16_1, T c16_3)
 {
-  (void)inverse_unused;
   if (task < s.n16) {
-    T re[16], im[16];
+    int g[16];
 #pragma unroll
-    for (int e = 0; e < 16; ++e) {
-      const int g = s.gather16[e * s.n16 + task];
-      re[e] = src[2 * g]; im[e] = src[2 * g + 1];
+    for (int e = 0; e < 16; ++e) g[e] = ldg(s.gather16 + e * s.n16 + task);
+    const int base = cslot(ldg(s.leaf16_off + task));             // multiples of 16: slots stay contiguous
+#pragma unroll
+    for (int l = 0; l < LPC; ++l) {
+      if (l < lanes) {
+        T re[16], im[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) { const C2<T> v = src[l * src_stride + g[e]]; re[e] = v.x; im[e] = v.y; }
+        leaf_fft16(re, im, sqrthalf, c16_1, c16_3);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) dst[l * dst_stride + base + e] = C2<T>{re[e], im[e]};
+      }
     }
-    leaf_fft16(re, im, sqrthalf, c16_1, c16_3);
-    const int base = cslot(s.leaf16_off[task]);                  // offsets are multiples of 16: slots stay contiguous
-#pragma unroll
-    for (int e = 0; e < 16; ++e) { dst[2 * (base + e)] = re[e]; dst[2 * (base + e) + 1] = im[e]; }
   } else {
     const int t8 = task - s.n16;
-    T re[8], im[8];
+    int g[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int g = s.gather8[e * s.n8 + t8];
-      re[e] = src[2 * g]; im[e] = src[2 * g + 1];
+    for (int e = 0; e < 8; ++e) g[e] = ldg(s.gather8 + e * s.n8 + t8);
+    const int base = cslot(ldg(s.leaf8_off + t8));                // multiples of 8: never straddle a pad slot
+#pragma unroll
+    for (int l = 0; l < LPC; ++l) {
+      if (l < lanes) {
+        T re[8], im[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const C2<T> v = src[l * src_stride + g[e]]; re[e] = v.x; im[e] = v.y; }
+        leaf_fft8(re, im, sqrthalf);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dst[l * dst_stride + base + e] = C2<T>{re[e], im[e]};
+      }
     }
-    leaf_fft8(re, im, sqrthalf);
-    const int base = cslot(s.leaf8_off[t8]);                     // multiples of 8: never straddle a pad slot
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { dst[2 * (base + e)] = re[e]; dst[2 * (base + e) + 1] = im[e]; }
   }
 }
 
-// One butterfly of the combining pass of size S = 1 << lg (pass(), fft.c:237-256).
-template <class T>
-RR_PROG void cfft_pass_item(const CfftSched &s, int lg, int item, T *buf, const T *pyramid)
+// One butterfly of the combining pass of size S = 1 << lg (pass(), fft.c:237-256), for every lane.
+template <class T, int LPC>
+RR_PROG void cfft_pass_item(const CfftSched &s, int lg, int item, int lanes, C2<T> *buf, int stride, const T *pyramid)
 {
   const int qbits = lg - 2, q = 1 << qbits;
   const int node = item >> qbits, k = item & (q - 1);
-  const int p0 = s.node_off[s.level_begin[lg] + node] + k;
+  const int p0 = ldg(s.node_off + s.level_begin[lg] + node) + k;
   const T *tw = pyramid + s.pyr_off[lg];
-  T *a0 = buf + 2 * cslot(p0), *a1 = buf + 2 * cslot(p0 + q), *a2 = buf + 2 * cslot(p0 + 2 * q),
-    *a3 = buf + 2 * cslot(p0 + 3 * q);
-  T a0r = a0[0], a0i = a0[1], a1r = a1[0], a1i = a1[1], a2r = a2[0], a2i = a2[1], a3r = a3[0], a3i = a3[1];
-  sr_bfly(a0r, a0i, a1r, a1i, a2r, a2i, a3r, a3i, tw[k], tw[q - k], k == 0);
-  a0[0] = a0r; a0[1] = a0i; a1[0] = a1r; a1[1] = a1i; a2[0] = a2r; a2[1] = a2i; a3[0] = a3r; a3[1] = a3i;
+  const T wre = tw[k], wim = tw[q - k];
+  const int i0 = cslot(p0), i1 = cslot(p0 + q), i2 = cslot(p0 + 2 * q), i3 = cslot(p0 + 3 * q);
+#pragma unroll
+  for (int l = 0; l < LPC; ++l) {
+    if (l < lanes) {
+      C2<T> *b = buf + l * stride;
+      C2<T> a0 = b[i0], a1 = b[i1], a2 = b[i2], a3 = b[i3];
+      sr_bfly(a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y, wre, wim, k == 0);
+      b[i0] = a0; b[i1] = a1; b[i2] = a2; b[i3] = a3;
+    }
+  }
 }
 
-// Whole complex FFT for `lanes` transforms living in one CTA.
-template <class T>
-RR_PROG void cfft_run(const CfftSched &s, int lanes, const T *src, int src_stride, T *dst, int dst_stride,
-                    const T *pyramid, T sqrthalf, T c16_1, T c16_3)
+// Whole complex FFT for the CTA's lanes: natural-order tiles `src` -> padded buffers `dst`, in two calls so
+// the caller can start refilling `src` as soon as the leaves have consumed it.
+template <class T, int LPC>
+RR_PROG void cfft_leaves(const CfftSched &s, int lanes, const C2<T> *src, int src_stride, C2<T> *dst, int dst_stride,
+                         T sqrthalf, T c16_1, T c16_3)
 {
-  const int nleaf = s.n16 + s.n8;
-  cta_for(lanes * nleaf, [&](int w) {
-    const int lane = w / nleaf, task = w - lane * nleaf;
-    cfft_leaf_task<T>(s, false, task, src + (long long)lane * src_stride, dst + (long long)lane * dst_stride, sqrthalf,
-                      c16_1, c16_3);
+  cta_for(s.n16 + s.n8, [&](int task) {
+    cfft_leaf_task<T, LPC>(s, task, lanes, src, src_stride, dst, dst_stride, sqrthalf, c16_1, c16_3);
   });
-  for (int lg = 5; lg <= s.bits; ++lg) {
-    const int per_lane = s.level_cnt[lg] << (lg - 2);
-    cta_for(lanes * per_lane, [&](int w) {
-      const int lane = w / per_lane, item = w - lane * per_lane;
-      cfft_pass_item<T>(s, lg, item, dst + (long long)lane * dst_stride, pyramid);
+}
+template <class T, int LPC>
+RR_PROG void cfft_passes(const CfftSched &s, int lanes, C2<T> *dst, int dst_stride, const T *pyramid)
+{
+  for (int lg = 5; lg <= s.bits; ++lg)
+    cta_for(s.level_cnt[lg] << (lg - 2), [&](int item) {
+      cfft_pass_item<T, LPC>(s, lg, item, lanes, dst, dst_stride, pyramid);
     });
-  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -262,7 +320,8 @@ enum DftInMode { DFT_IN_FREQ_UP = 0, DFT_IN_COPY = 1, DFT_IN_ZERO_STUFF = 2 };
 
 template <class T> struct DftParams {
   // geometry
-  int N, overlap, L, step;       // step: 1, M > 1 (time-domain decimation) or -m (F-domain decimation by 2^m)
+  int N, overlap, L, step;       // step: 1, M > 1 (time-domain decimation), -m (F-domain decimation by 2^m),
+                                 // 0 = emit the forward spectrum only (filter bank preparation)
   int in_mode;                   // DftInMode
   int Pf, Ni;                    // forward / inverse real transform sizes
   int remL0;
@@ -278,156 +337,280 @@ template <class T> struct DftParams {
   LaneView in, out;
   long long out_preload;         // coordinate of this stage's output 0 in the next FIFO
   long long block0;              // first block of this launch
-  int nblocks, nlanes, lanes_per_cta;
-  int xstride, ystride;          // per-lane smem strides (in T)
+  int nblocks, nlanes;
+  int xstride, ystride, zstride; // per-lane smem strides, in complex elements (zstride == 0: no prefetch buffer)
 };
 
-template <class T> RR_HD int dft_smem_elems(int N, int lanes_per_cta, int *xstride, int *ystride)
+// Tables the kernel stages in shared memory once per CTA (the emulation passes the global pointers).
+template <class T> struct DftTables { const T *pyr_f, *pyr_i, *tcos_f, *tcos_i; };
+
+template <class T> RR_HD int dft_table_elems(const DftParams<T> &p)
 {
-  const int xs = 2 * cfft_buf_complex(N / 2), ys = N;
+  return p.fwd.pyr_len + p.inv.pyr_len + (p.Pf >> 2) + 1 + (p.Ni >> 2) + 1 + 8;
+}
+
+// Per-lane shared-memory strides (complex elements). The natural-order tile stride is an odd multiple of
+// 8 complex (= 16 words) so that the lane-interleaved phases 0 and 7 stay bank-conflict free.
+// Buffers per lane: X (FFT work buffer), Y (natural-order input of the inverse transform) and, when the
+// next block's input is prefetched while this one is processed, Z (natural-order input of the forward
+// transform, Pf reals). Without prefetch the forward input shares Y. All use the padded cslot layout.
+template <class T> RR_HD size_t dft_smem_bytes(int N, int Pf, int lanes_per_cta, bool prefetch, int *xstride, int *ystride,
+                                               int *zstride)
+{
+  const int unit = 32 / (int)sizeof(T);                  // 16 words, in complex elements
+  const int m = N / 2, mf = Pf / 2;
+  const int xs = lane_stride_complex(m + (m >> 4) + 1, unit), ys = xs;
+  const int zs = prefetch ? lane_stride_complex(mf + (mf >> 4) + 1, unit) : 0;
   if (xstride) *xstride = xs;
   if (ystride) *ystride = ys;
-  return lanes_per_cta * (xs + ys);
+  if (zstride) *zstride = zs;
+  return sizeof(C2<T>) * (size_t)lanes_per_cta * (size_t)(xs + ys + zs);
 }
 
-// Value of the reference's `output[idx]` after the frequency-domain up-sampling block
-// (dft_filter.h:86-104), read from the packed Pf-point spectrum held in the padded buffer X.
-template <class T> RR_HD T dft_spec_freq_up(const T *X, int Pf, int idx)
+// (output[idx], output[idx+1]) for even idx of the reference's buffer after the frequency-domain
+// up-sampling block (dft_filter.h:86-104), from the packed Pf-point spectrum in the padded buffer X.
+template <class T> RR_HD C2<T> dft_spec_freq_up(const C2<T> *X, int Pf, int idx)
 {
   const int twoP = Pf << 1, r = idx & (twoP - 1);
-  if (idx >= twoP && r == 1) return (T)0;
-  if (r < Pf) { const int f = (r == 1) ? 0 : r; return X[2 * cslot(f >> 1) + (f & 1)]; }
-  if (r == Pf) return X[2 * cslot(0) + 1];
-  if (r == Pf + 1) return (T)0;
-  if (!(r & 1)) { const int f = twoP - r; return X[2 * cslot(f >> 1) + (f & 1)]; }
-  { const int f = twoP - r + 2; return -X[2 * cslot(f >> 1) + (f & 1)]; }
+  if (r == 0) { const T a0 = X[0].x; return C2<T>{a0, idx == 0 ? a0 : (T)0}; }
+  if (r < Pf) return X[cslot(r >> 1)];
+  if (r == Pf) return C2<T>{X[0].y, (T)0};
+  const C2<T> v = X[cslot((twoP - r) >> 1)];
+  return C2<T>{v.x, -v.y};
 }
 
-template <class T, class InT, class OutT>
-RR_PROG void dft_stage_program(const DftParams<T> &p, long long work, T *smem)
+// Per-thread cache of the filter spectrum values its phase-4 items need (they do not depend on the block,
+// so a persistent CTA loads them once): ca[k] / cb[k] belong to item threadIdx.x + k*blockDim.x.
+template <class T, int MAXI> struct CoefCache { C2<T> ca[MAXI > 0 ? MAXI : 1], cb[MAXI > 0 ? MAXI : 1]; };
+
+template <class T, int MAXI>
+RR_PROG void dft_load_coef_cache(const DftParams<T> &p, CoefCache<T, MAXI> &cc)
+{
+#if defined(__CUDACC__)
+  if (MAXI > 0 && p.step != 0) {
+    const C2<T> *coef = reinterpret_cast<const C2<T> *>(p.coef);
+#pragma unroll
+    for (int k = 0; k < (MAXI > 0 ? MAXI : 1); ++k) {
+      const int i = threadIdx.x + k * blockDim.x;
+      if (i >= 1 && i < (p.Ni >> 2)) { cc.ca[k] = ldg(coef + i); cc.cb[k] = ldg(coef + (p.Ni >> 1) - i); }
+    }
+  }
+#else
+  (void)p; (void)cc;
+#endif
+}
+
+// cta_for variant that also hands the per-thread iteration number to the body (device) or -1 (emulation).
+#if defined(__CUDACC__)
+template <int MAXI, class F> RR_PROG void cta_for_cached(int count, F f)
+{
+  if (MAXI > 0) {
+#pragma unroll
+    for (int k = 0; k < (MAXI > 0 ? MAXI : 1); ++k) {
+      const int i = threadIdx.x + k * blockDim.x;
+      if (i < count) f(i, k);
+    }
+    for (int i = threadIdx.x + MAXI * blockDim.x; i < count; i += blockDim.x) f(i, -1);
+  } else
+    for (int i = threadIdx.x; i < count; i += blockDim.x) f(i, -1);
+  __syncthreads();
+}
+#else
+template <int MAXI, class F> inline void cta_for_cached(int count, F f)
+{
+  for (int i = 0; i < count; ++i) f(i, -1);
+}
+#endif
+
+// Geometry of one work item (block, lane group) in absolute coordinates.
+template <class T> struct DftItem {
+  long long b, Rb, in_off0, in_off1, out_off0, out_off1;
+  int lanes, remLb;
+};
+
+template <class T, int LPC>
+RR_PROG DftItem<T> dft_item(const DftParams<T> &p, long long work)
+{
+  DftItem<T> it;
+  const int groups = (p.nlanes + LPC - 1) / LPC;
+  it.b = p.block0 + work / groups;
+  const int lane0 = (int)(work % groups) * LPC;
+  it.lanes = (p.nlanes - lane0) < LPC ? (p.nlanes - lane0) : LPC;
+  it.remLb = p.remL0;
+  if (p.in_mode == DFT_IN_ZERO_STUFF) {
+    const long long Pb = it.b * (long long)(p.N - p.overlap);
+    it.Rb = Pb <= p.remL0 ? 0 : (Pb - p.remL0 + p.L - 1) / p.L;
+    it.remLb = (int)(p.remL0 + (long long)p.L * it.Rb - Pb);
+  } else it.Rb = it.b * (long long)p.q;
+  it.in_off0 = lane_offset(p.in, lane0);
+  it.out_off0 = lane_offset(p.out, lane0);
+  const int lane1 = lane0 + (it.lanes > 1 ? 1 : 0);
+  it.in_off1 = lane_offset(p.in, lane1);
+  it.out_off1 = lane_offset(p.out, lane1);
+  return it;
+}
+
+// Phase 0: bring the input tile of a work item into a natural-order (cslot-padded) buffer, lane fastest so
+// interleaved input is read fully coalesced. ASYNC: issue LDGSTS copies and return without waiting.
+template <class T, class InT, int LPC, bool ASYNC>
+RR_PROG void dft_stage_tile(const DftParams<T> &p, const DftItem<T> &it, C2<T> *tile, int tile_stride)
+{
+  T *tr = reinterpret_cast<T *>(tile);
+  const int span = p.in_mode == DFT_IN_FREQ_UP ? p.Pf : p.N, L = p.L;
+  auto body = [&](int w) {
+    int l, j;
+    if (LPC == 1 || it.lanes == 1) { l = 0; j = w; } else { l = w & 1; j = w >> 1; }
+    long long coord = it.Rb + j;
+    bool on_grid = true;
+    if (p.in_mode == DFT_IN_ZERO_STUFF) {
+      const int d = j - it.remLb;
+      on_grid = d >= 0 && d % L == 0;
+      coord = it.Rb + (on_grid ? d / L : 0);
+    }
+    T *dst = tr + 2 * (l * tile_stride + cslot(j >> 1)) + (j & 1);
+    if (ASYNC) {
+      bool valid;
+      const T *src = reinterpret_cast<const T *>(view_addr<InT>(p.in, l ? it.in_off1 : it.in_off0, coord, &valid));
+      async_copy_elem<T>(dst, src, valid && on_grid);
+    } else *dst = on_grid ? view_read<InT, T>(p.in, l ? it.in_off1 : it.in_off0, coord) : (T)0;
+  };
+#if defined(__CUDACC__)
+  if (ASYNC) {
+    for (int w = threadIdx.x; w < it.lanes * span; w += blockDim.x) body(w);
+    async_copy_commit();
+    return;
+  }
+#endif
+  cta_for(it.lanes * span, body);
+}
+
+// `work_next` < 0: nothing to prefetch. With a prefetch buffer (p.zstride > 0) the tile of `work` must
+// already be in flight into Z (the kernel primes the first one).
+template <class T, class InT, class OutT, int LPC, int MAXI>
+RR_PROG void dft_stage_program(const DftParams<T> &p, const DftTables<T> &tab, const CoefCache<T, MAXI> &cc,
+                               long long work, long long work_next, C2<T> *smem)
 {
   typedef Arith<T> A;
-  const int LPC = p.lanes_per_cta;
-  const int groups = (p.nlanes + LPC - 1) / LPC;
-  const long long b = p.block0 + work / groups;
-  const int lane0 = (int)(work % groups) * LPC;
-  const int lanes = (p.nlanes - lane0) < LPC ? (p.nlanes - lane0) : LPC;
-  T *X = smem, *Y = smem + (long long)LPC * p.xstride;
-  const int N = p.N, L = p.L, V = N - p.overlap;
+  const DftItem<T> it = dft_item<T, LPC>(p, work);
+  const long long b = it.b;
+  const int lanes = it.lanes;
+  C2<T> *X = smem, *Y = smem + LPC * p.xstride, *Z = Y + LPC * p.ystride;
+  const int N = p.N, V = N - p.overlap;
+  const bool prefetch = p.zstride > 0;
+  const long long out_off0 = it.out_off0, out_off1 = it.out_off1;
 
-  // ---- block geometry in absolute coordinates ----
-  long long Rb; int remLb = p.remL0;
-  if (p.in_mode == DFT_IN_ZERO_STUFF) {
-    const long long Pb = b * (long long)V;
-    Rb = Pb <= p.remL0 ? 0 : (Pb - p.remL0 + L - 1) / L;
-    remLb = (int)(p.remL0 + (long long)L * Rb - Pb);
-  } else Rb = b * (long long)p.q;
-  const int span = p.in_mode == DFT_IN_FREQ_UP ? p.Pf : N;
-  long long in_off[2], out_off[2];                       // lanes_per_cta <= 2
-  for (int l = 0; l < 2; ++l) {
-    const int lane = lane0 + (l < lanes ? l : 0);
-    in_off[l] = lane_offset(p.in, lane);
-    out_off[l] = lane_offset(p.out, lane);
+  // ---- phase 0: the forward transform's input tile, natural order ----
+  if (prefetch) { async_copy_wait<0>(); cta_sync(); }
+  else dft_stage_tile<T, InT, LPC, false>(p, it, Y, p.ystride);
+  const C2<T> *fwd_in = prefetch ? Z : Y;
+  const int fwd_stride = prefetch ? p.zstride : p.ystride;
+
+  // ---- phases 1-2: forward complex FFT of Pf/2 points -> X; refill Z for the next item meanwhile ----
+  cfft_leaves<T, LPC>(p.fwd, lanes, fwd_in, fwd_stride, X, p.xstride, p.sqrthalf, p.c16_1, p.c16_3);
+  if (prefetch && work_next >= 0) {
+    const DftItem<T> nx = dft_item<T, LPC>(p, work_next);
+    dft_stage_tile<T, T, LPC, true>(p, nx, Z, p.zstride);
   }
-
-  // ---- phase 0: stage the input tile in natural order in Y ----
-  cta_for(lanes * span, [&](int w) {
-    const int l = w % lanes, j = w / lanes;
-    const long long loff = in_off[l];
-    T v;
-    if (p.in_mode == DFT_IN_ZERO_STUFF) {
-      const int d = j - remLb;
-      v = (d >= 0 && d % L == 0) ? view_read<InT, T>(p.in, loff, Rb + d / L) : (T)0;
-    } else v = view_read<InT, T>(p.in, loff, Rb + j);
-    Y[(long long)l * p.ystride + j] = v;
-  });
-
-  // ---- phases 1-2: forward complex FFT of Pf/2 points, Y -> X ----
-  cfft_run<T>(p.fwd, lanes, Y, p.ystride, X, p.xstride, p.pyr_f, p.sqrthalf, p.c16_1, p.c16_3);
+  cfft_passes<T, LPC>(p.fwd, lanes, X, p.xstride, tab.pyr_f);
 
   // ---- phase 3: real-FFT post-processing in place (ff_rdft_calc_c forward, rdft.c:46-77) ----
   {
-    const int Pf = p.Pf, per = (Pf >> 2) + 1;
-    cta_for(lanes * per, [&](int w) {
-      const int l = w / per, i = w - l * per;
-      T *d = X + (long long)l * p.xstride;
-      if (i == 0) {
-        T *z = d + 2 * cslot(0);
-        const T e = z[0];
-        z[0] = A::add(e, z[1]); z[1] = A::sub(e, z[1]);
-      } else if (i == (Pf >> 2)) {
-        T *z = d + 2 * cslot(Pf >> 2);
-        z[1] = -z[1];
-      } else {
-        T *za = d + 2 * cslot(i), *zb = d + 2 * cslot((Pf >> 1) - i);
-        const T c = p.tcos_f[i], s = p.tcos_f[(Pf >> 2) - i];
-        const T evr = A::mul((T)0.5, A::add(za[0], zb[0]));
-        const T odi = A::mul((T)0.5, A::sub(zb[0], za[0]));
-        const T evi = A::mul((T)0.5, A::sub(za[1], zb[1]));
-        const T odr = A::mul((T)0.5, A::add(za[1], zb[1]));
-        const T sr = A::add(A::mul(odr, c), A::mul(odi, s));
-        const T si = A::sub(A::mul(odi, c), A::mul(odr, s));
-        za[0] = A::add(evr, sr); za[1] = A::add(evi, si);
-        zb[0] = A::sub(evr, sr); zb[1] = A::sub(si, evi);
+    const int Pf = p.Pf;
+    cta_for((Pf >> 2) + 1, [&](int i) {
+      T c = (T)0, s = (T)0;
+      if (i > 0 && i < (Pf >> 2)) { c = tab.tcos_f[i]; s = tab.tcos_f[(Pf >> 2) - i]; }
+#pragma unroll
+      for (int l = 0; l < LPC; ++l) {
+        if (l < lanes) {
+          C2<T> *d = X + l * p.xstride;
+          if (i == 0) {
+            const C2<T> z = d[0];
+            d[0] = C2<T>{A::add(z.x, z.y), A::sub(z.x, z.y)};
+          } else if (i == (Pf >> 2)) {
+            C2<T> *z = d + cslot(Pf >> 2);
+            z->y = -z->y;
+          } else {
+            const int ia = cslot(i), ib = cslot((Pf >> 1) - i);
+            const C2<T> za = d[ia], zb = d[ib];
+            const T evr = A::mul((T)0.5, A::add(za.x, zb.x));
+            const T odi = A::mul((T)0.5, A::sub(zb.x, za.x));
+            const T evi = A::mul((T)0.5, A::sub(za.y, zb.y));
+            const T odr = A::mul((T)0.5, A::add(za.y, zb.y));
+            const T sr = A::add(A::mul(odr, c), A::mul(odi, s));
+            const T si = A::sub(A::mul(odi, c), A::mul(odr, s));
+            d[ia] = C2<T>{A::add(evr, sr), A::add(evi, si)};
+            d[ib] = C2<T>{A::sub(evr, sr), A::sub(si, evi)};
+          }
+        }
       }
     });
   }
 
   if (p.step == 0) {   // spectrum-only mode (filter bank preparation, rate_base.h:184): emit the packed spectrum
-    cta_for(lanes * p.Pf, [&](int w) {
-      const int l = w % lanes, t = w / lanes;
-      view_write<OutT, T>(p.out, out_off[l], (long long)t, X[(long long)l * p.xstride + 2 * cslot(t >> 1) + (t & 1)]);
+    cta_for(p.Pf, [&](int t) {
+      const C2<T> v = X[cslot(t >> 1)];
+      view_write<OutT, T>(p.out, out_off0, (long long)t, (t & 1) ? v.y : v.x);
     });
     return;
   }
 
   // ---- phase 4: spectrum assembly, filter multiply, inverse pre-processing, X -> Y (natural order) ----
   {
-    const int Ni = p.Ni, per = (Ni >> 2) + 1, Pf = p.Pf;
+    const int Ni = p.Ni, Pf = p.Pf;
     const bool freq_up = p.in_mode == DFT_IN_FREQ_UP;
-    cta_for(lanes * per, [&](int w) {
-      const int l = w / per, i = w - l * per;
-      const T *Xs = X + (long long)l * p.xstride;
-      T *d = Y + (long long)l * p.ystride;
-      auto spec = [&](int idx) -> T {
-        return freq_up ? dft_spec_freq_up<T>(Xs, Pf, idx) : Xs[2 * cslot(idx >> 1) + (idx & 1)];
-      };
-      auto cmul = [&](int idx, T &re, T &im) {           // dft_filter.h:140-145
-        const T t = spec(idx), o1 = spec(idx + 1), c0 = p.coef[idx], c1 = p.coef[idx + 1];
-        re = A::sub(A::mul(c0, t), A::mul(c1, o1));
-        im = A::add(A::mul(c1, t), A::mul(c0, o1));
-      };
-      if (i == 0) {
-        const T d0 = A::mul(spec(0), p.coef[0]);
-        T d1;
-        if (p.step > 0) d1 = A::mul(spec(1), p.coef[1]);
-        else d1 = A::sub(A::mul(p.coef[Ni], spec(Ni)), A::mul(p.coef[Ni + 1], spec(Ni + 1)));   // dft_filter.h:185
-        const T e0 = A::add(d0, d1), e1 = A::sub(d0, d1);       // rdft.c:44-46
-        d[0] = A::mul(e0, (T)0.5); d[1] = A::mul(e1, (T)0.5);   // rdft.c:79-80
-      } else if (i == (Ni >> 2)) {
-        T re, im;
-        cmul(Ni >> 1, re, im);
-        d[Ni >> 1] = re; d[(Ni >> 1) + 1] = -im;                // rdft.c:77
-      } else {
-        const int i1 = 2 * i, i2 = Ni - i1;
-        T ar, ai, br, bi;
-        cmul(i1, ar, ai);
-        cmul(i2, br, bi);
-        const T c = p.tcos_i[i], s = p.tcos_i[(Ni >> 2) - i];
-        const T evr = A::mul((T)0.5, A::add(ar, br));           // RDFT_UNMANGLE(-,+), k2 = -0.5
-        const T odi = A::mul((T)-0.5, A::sub(br, ar));
-        const T evi = A::mul((T)0.5, A::sub(ai, bi));
-        const T odr = A::mul((T)-0.5, A::add(ai, bi));
-        const T sr = A::sub(A::mul(odr, c), A::mul(odi, s));
-        const T si = A::add(A::mul(odi, c), A::mul(odr, s));
-        d[i1] = A::add(evr, sr); d[i1 + 1] = A::add(evi, si);
-        d[i2] = A::sub(evr, sr); d[i2 + 1] = A::sub(si, evi);
+    const C2<T> *coef = reinterpret_cast<const C2<T> *>(p.coef);
+    cta_for_cached<MAXI>((Ni >> 2) + 1, [&](int i, int k) {
+      const bool pair = i > 0 && i < (Ni >> 2);
+      C2<T> ca, cb;
+      T c = (T)0, s = (T)0;
+      if (pair) {
+        if (k >= 0) { ca = cc.ca[k]; cb = cc.cb[k]; } else { ca = ldg(coef + i); cb = ldg(coef + (Ni >> 1) - i); }
+        c = tab.tcos_i[i]; s = tab.tcos_i[(Ni >> 2) - i];
+      } else if (i == 0) {
+        ca = ldg(coef);
+        cb = p.step > 0 ? C2<T>{(T)0, (T)0} : ldg(coef + (Ni >> 1));
+      } else { ca = ldg(coef + (Ni >> 2)); cb = ca; }
+#pragma unroll
+      for (int l = 0; l < LPC; ++l) {
+        if (l < lanes) {
+          const C2<T> *Xs = X + l * p.xstride;
+          C2<T> *d = Y + l * p.ystride;
+          auto spec = [&](int bin) -> C2<T> {              // (output[2 bin], output[2 bin + 1])
+            return freq_up ? dft_spec_freq_up<T>(Xs, Pf, 2 * bin) : Xs[cslot(bin)];
+          };
+          auto cmul = [&](const C2<T> &cf, const C2<T> &v) -> C2<T> {   // dft_filter.h:140-145
+            return C2<T>{A::sub(A::mul(cf.x, v.x), A::mul(cf.y, v.y)), A::add(A::mul(cf.y, v.x), A::mul(cf.x, v.y))};
+          };
+          if (pair) {
+            const C2<T> a = cmul(ca, spec(i)), bb = cmul(cb, spec((Ni >> 1) - i));
+            const T evr = A::mul((T)0.5, A::add(a.x, bb.x));           // RDFT_UNMANGLE(-,+), k2 = -0.5
+            const T odi = A::mul((T)-0.5, A::sub(bb.x, a.x));
+            const T evi = A::mul((T)0.5, A::sub(a.y, bb.y));
+            const T odr = A::mul((T)-0.5, A::add(a.y, bb.y));
+            const T sr = A::sub(A::mul(odr, c), A::mul(odi, s));
+            const T si = A::add(A::mul(odi, c), A::mul(odr, s));
+            d[cslot(i)] = C2<T>{A::add(evr, sr), A::add(evi, si)};
+            d[cslot((Ni >> 1) - i)] = C2<T>{A::sub(evr, sr), A::sub(si, evi)};
+          } else if (i == 0) {
+            const C2<T> v0 = spec(0);
+            const T d0 = A::mul(v0.x, ca.x);
+            T d1;
+            if (p.step > 0) d1 = A::mul(v0.y, ca.y);
+            else { const C2<T> vn = spec(Ni >> 1); d1 = A::sub(A::mul(cb.x, vn.x), A::mul(cb.y, vn.y)); }  // dft_filter.h:185
+            const T e0 = A::add(d0, d1), e1 = A::sub(d0, d1);            // rdft.c:44-46
+            d[0] = C2<T>{A::mul(e0, (T)0.5), A::mul(e1, (T)0.5)};        // rdft.c:79-80
+          } else {
+            const C2<T> m = cmul(ca, spec(Ni >> 2));
+            d[cslot(Ni >> 2)] = C2<T>{m.x, -m.y};                        // rdft.c:77
+          }
+        }
       }
     });
   }
 
   // ---- phases 5-6: inverse complex FFT of Ni/2 points, Y -> X ----
-  cfft_run<T>(p.inv, lanes, Y, p.ystride, X, p.xstride, p.pyr_i, p.sqrthalf, p.c16_1, p.c16_3);
+  cfft_leaves<T, LPC>(p.inv, lanes, Y, p.ystride, X, p.xstride, p.sqrthalf, p.c16_1, p.c16_3);
+  cfft_passes<T, LPC>(p.inv, lanes, X, p.xstride, tab.pyr_i);
 
   // ---- phase 7: emit the valid samples ----
   {
@@ -440,11 +623,13 @@ RR_PROG void dft_stage_program(const DftParams<T> &p, long long work, T *smem)
       k0 = (v0 + M - 1) / M;
       count = first < V ? (V - first + M - 1) / M : 0;
     } else { count = p.kept; k0 = b * (long long)p.kept; }
+    const T *Xr = reinterpret_cast<const T *>(X);
     cta_for(lanes * count, [&](int w) {
-      const int l = w % lanes, j = w / lanes;
+      int l, j;
+      if (LPC == 1 || lanes == 1) { l = 0; j = w; } else { l = w & 1; j = w >> 1; }
       const int t = first + j * stride;
-      const T v = X[(long long)l * p.xstride + 2 * cslot(t >> 1) + (t & 1)];
-      view_write<OutT, T>(p.out, out_off[l], p.out_preload + k0 + j, v);
+      const T v = Xr[2 * (l * p.xstride + cslot(t >> 1)) + (t & 1)];
+      view_write<OutT, T>(p.out, l ? out_off1 : out_off0, p.out_preload + k0 + j, v);
     });
   }
 }
@@ -509,6 +694,110 @@ RR_PROG void poly0_program(const PolyParams<T> &p, long long work, T *smem)
     T sum = (T)0;
     for (int k = 0; k < p.n; ++k) sum = A::add(sum, A::mul(c[k], x[k]));
     view_write<OutT, T>(p.out, out_off, p.out_preload + i0 + j, sum);
+  });
+}
+
+// vpoly0, phase-stationary variant for rational ratios with enough phases: thread (slot, channel) owns the
+// outputs i = out0 + m*L + slot, m = 0, 1, ... -- they all use the same coefficient row r, which therefore
+// lives in registers for the whole tile, and consecutive m advance the input position by exactly `step`
+// (exact integer phase arithmetic: at(i + L) = at(i) + L*step, so q += step and r is unchanged).
+// The input windows of all CH channels of a stream are staged in shared memory; writes of (frame, channel)
+// pairs are contiguous for interleaved output. Taps are summed in order, un-fused (Arith<T>).
+template <class T> struct Poly0FastParams {
+  PolyParams<T> base;
+  int F, ncols, MM, CH;          // slots per CTA column, columns per period, periods per tile, lanes per CTA
+  int win;                       // shared-memory window per lane (samples; odd multiple of 16 words)
+  long long mtiles;              // tiles along m
+  int double_buffer;             // two window sets: the next tile is prefetched while this one is computed
+};
+
+// Tile geometry of one work item of the phase-stationary kernel.
+struct Poly0Tile {
+  long long i_first, q_first;
+  int lane0, nslots, mcount, r_first, win;
+};
+
+template <class T> RR_HD Poly0Tile poly0_tile(const Poly0FastParams<T> &fp, long long work)
+{
+  const PolyParams<T> &p = fp.base;
+  Poly0Tile t;
+  const int L = p.L;
+  const long long mt = work % fp.mtiles;
+  const long long rest = work / fp.mtiles;
+  const int col = (int)(rest % fp.ncols);
+  t.lane0 = (int)(rest / fp.ncols) * fp.CH;
+  const int slot0 = col * fp.F;
+  t.nslots = (L - slot0) < fp.F ? (L - slot0) : fp.F;
+  const long long periods = (p.nout + L - 1) / L;
+  const long long m0 = mt * fp.MM;
+  t.mcount = (periods - m0) < fp.MM ? (int)(periods - m0) : fp.MM;
+  // first input position touched by this tile: output out0 + m0*L + slot0
+  t.i_first = p.out0 + m0 * L + slot0;
+  const long long at_first = p.at0 + t.i_first * p.step;
+  t.q_first = at_first / L;
+  t.r_first = (int)(at_first - t.q_first * L);
+  const long long at_last = (long long)t.r_first + (long long)(t.nslots - 1) * p.step;   // relative to q_first*L
+  t.win = (int)(at_last / L) + (t.mcount - 1) * (int)p.step + p.n;
+  return t;
+}
+
+// Stage the input windows of the tile's CH lanes. ASYNC: LDGSTS, returns after committing the group.
+template <class T, class InT, bool ASYNC>
+RR_PROG void poly0_fast_load(const Poly0FastParams<T> &fp, const Poly0Tile &t, T *buf)
+{
+  const PolyParams<T> &p = fp.base;
+  for (int l = 0; l < fp.CH; ++l) {
+    const long long off = lane_offset(p.in, t.lane0 + l);
+    T *dst = buf + l * fp.win;
+    auto body = [&](int j) {
+      if (ASYNC) {
+        bool valid;
+        const T *src = reinterpret_cast<const T *>(view_addr<InT>(p.in, off, t.q_first + p.pre + j, &valid));
+        async_copy_elem<T>(dst + j, src, valid);
+      } else dst[j] = view_read<InT, T>(p.in, off, t.q_first + p.pre + j);
+    };
+#if defined(__CUDACC__)
+    for (int j = threadIdx.x; j < t.win; j += blockDim.x) body(j);
+#else
+    for (int j = 0; j < t.win; ++j) body(j);
+#endif
+  }
+  if (ASYNC) async_copy_commit();
+}
+
+template <class T, class OutT, int NT>
+RR_PROG void poly0_fast_compute(const Poly0FastParams<T> &fp, const Poly0Tile &t, const T *buf)
+{
+  typedef Arith<T> A;
+  const PolyParams<T> &p = fp.base;
+  const int CH = fp.CH, L = p.L;
+  cta_for(t.nslots * CH, [&](int tid) {
+    const int fs = tid / CH, ch = tid - fs * CH;
+    const long long at_rel = (long long)t.r_first + (long long)fs * p.step;             // < L*step: fits easily
+    const int q = (int)(at_rel / L), r = (int)(at_rel - (long long)q * L);
+    T c[NT];
+    const T *row = p.coefs + (long long)r * NT;
+#pragma unroll
+    for (int k = 0; k < NT; ++k) c[k] = ldg(row + k);
+    const T *x = buf + ch * fp.win + q;
+    const long long out_off = lane_offset(p.out, t.lane0 + ch);
+    long long i = t.i_first + fs;
+    const long long i_end = p.out0 + p.nout;
+    int m = 0;
+    for (; m + 1 < t.mcount; m += 2, x += 2 * p.step, i += 2 * L) {   // two independent accumulators
+      const T *x1 = x + p.step;
+      T s0 = (T)0, s1 = (T)0;
+#pragma unroll
+      for (int k = 0; k < NT; ++k) { s0 = A::add(s0, A::mul(c[k], x[k])); s1 = A::add(s1, A::mul(c[k], x1[k])); }
+      if (i < i_end) view_write<OutT, T>(p.out, out_off, p.out_preload + i, s0);
+      if (i + L < i_end) view_write<OutT, T>(p.out, out_off, p.out_preload + i + L, s1);
+    }
+    if (m < t.mcount) {
+      T s0 = (T)0;
+#pragma unroll
+      for (int k = 0; k < NT; ++k) s0 = A::add(s0, A::mul(c[k], x[k]));
+      if (i < i_end) view_write<OutT, T>(p.out, out_off, p.out_preload + i, s0);
+    }
   });
 }
 

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Aggregate an ncu SASS-level source page by CUDA source line.
 
-usage: ncu_by_line.py <report.ncu-rep> <cubin> <mangled kernel name> [top]
+usage: ncu_by_line.py <report.ncu-rep> <cubin> <mangled kernel name> [top] [demangled-name substring]
 Joins `ncu --page source --print-source sass --csv` (per-instruction counters) with
 `nvdisasm --print-line-info` (address -> file:line) and prints, per source line: executed warp
 instructions, shared-memory wavefronts (total / excessive) and stall samples."""
@@ -32,7 +32,12 @@ def main():
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "sass", "--csv"],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
-    hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+    want = sys.argv[5] if len(sys.argv) > 5 else None      # substring of the demangled kernel name
+    hdr_i = None
+    for i, r in enumerate(rows):
+        if r and r[0] == "Kernel Name" and (want is None or want in r[1]):
+            hdr_i = next(j for j in range(i, len(rows)) if rows[j] and rows[j][0] == "Address")
+            break
     hdr = rows[hdr_i]
     col = {n: hdr.index(n) for n in ("Address", "Source", "# Samples", "Instructions Executed", "L1 Wavefronts Shared",
                                      "L1 Wavefronts Shared Excessive", "stall_long_sb", "stall_barrier", "stall_short_sb",
@@ -40,8 +45,8 @@ def main():
     agg = defaultdict(lambda: defaultdict(float))
     first = None
     for r in rows[hdr_i + 1:]:
-        if len(r) < len(hdr) or r[0] == "Address":
-            break                                   # only the first kernel instance
+        if len(r) < len(hdr) or r[0] in ("Address", "Kernel Name"):
+            break                                   # only the first matching kernel instance
         try:
             a = int(r[col["Address"]], 16)
         except ValueError:
