@@ -114,6 +114,18 @@ template <class E> RR_HD const E *view_addr(const LaneView &v, long long lane_of
   return base + lane_off + (long long)phys * v.elem_stride;
 }
 
+// Fast path: when every coordinate of [c0, c1) is stored contiguously (no zero region, no ring wrap) the
+// per-element bounds / mask logic collapses to one pointer per lane; element j is then ptr[j * elem_stride].
+RR_HD bool view_range_direct(const LaneView &v, long long c0, long long c1)
+{
+  return c0 >= v.lo && c1 <= v.hi && c0 >= v.origin &&
+         (v.mask == ~0ull || (unsigned long long)(c1 - 1 - v.origin) <= v.mask);
+}
+template <class E> RR_HD E *view_ptr(const LaneView &v, long long lane_off, long long coord)
+{
+  return static_cast<E *>(v.base) + lane_off + (coord - v.origin) * v.elem_stride;
+}
+
 // LDGSTS: global -> shared without staging registers; `valid == false` zero-fills the destination.
 #if defined(__CUDA_ARCH__)
 template <class E> RR_PROG void async_copy_elem(E *smem_dst, const E *gsrc, bool valid)
@@ -457,9 +469,19 @@ RR_PROG void dft_stage_tile(const DftParams<T> &p, const DftItem<T> &it, C2<T> *
 {
   T *tr = reinterpret_cast<T *>(tile);
   const int span = p.in_mode == DFT_IN_FREQ_UP ? p.Pf : p.N, L = p.L;
+  const bool direct = p.in_mode != DFT_IN_ZERO_STUFF && view_range_direct(p.in, it.Rb, it.Rb + span);
+  const InT *s0 = view_ptr<const InT>(p.in, it.in_off0, it.Rb), *s1 = view_ptr<const InT>(p.in, it.in_off1, it.Rb);
+  const int es = p.in.elem_stride;
   auto body = [&](int w) {
     int l, j;
     if (LPC == 1 || it.lanes == 1) { l = 0; j = w; } else { l = w & 1; j = w >> 1; }
+    if (direct) {                                         // interior block: plain pointer arithmetic
+      T *dst = tr + 2 * (l * tile_stride + cslot(j >> 1)) + (j & 1);
+      const InT *src = (l ? s1 : s0) + j * es;
+      if (ASYNC) async_copy_elem<T>(dst, reinterpret_cast<const T *>(src), true);
+      else *dst = (T)*src;
+      return;
+    }
     long long coord = it.Rb + j;
     bool on_grid = true;
     if (p.in_mode == DFT_IN_ZERO_STUFF) {
@@ -624,12 +646,17 @@ RR_PROG void dft_stage_program(const DftParams<T> &p, const DftTables<T> &tab, c
       count = first < V ? (V - first + M - 1) / M : 0;
     } else { count = p.kept; k0 = b * (long long)p.kept; }
     const T *Xr = reinterpret_cast<const T *>(X);
+    const long long c0 = p.out_preload + k0;
+    const bool direct = view_range_direct(p.out, c0, c0 + count);
+    OutT *d0 = view_ptr<OutT>(p.out, out_off0, c0), *d1 = view_ptr<OutT>(p.out, out_off1, c0);
+    const int es = p.out.elem_stride;
     cta_for(lanes * count, [&](int w) {
       int l, j;
       if (LPC == 1 || lanes == 1) { l = 0; j = w; } else { l = w & 1; j = w >> 1; }
       const int t = first + j * stride;
       const T v = Xr[2 * (l * p.xstride + cslot(t >> 1)) + (t & 1)];
-      view_write<OutT, T>(p.out, l ? out_off1 : out_off0, p.out_preload + k0 + j, v);
+      if (direct) (l ? d1 : d0)[j * es] = (OutT)v;
+      else view_write<OutT, T>(p.out, l ? out_off1 : out_off0, c0 + j, v);
     });
   }
 }
@@ -746,11 +773,17 @@ template <class T, class InT, bool ASYNC>
 RR_PROG void poly0_fast_load(const Poly0FastParams<T> &fp, const Poly0Tile &t, T *buf)
 {
   const PolyParams<T> &p = fp.base;
+  const bool direct = view_range_direct(p.in, t.q_first + p.pre, t.q_first + p.pre + t.win);
+  const int es = p.in.elem_stride;
   for (int l = 0; l < fp.CH; ++l) {
     const long long off = lane_offset(p.in, t.lane0 + l);
     T *dst = buf + l * fp.win;
+    const InT *sp = view_ptr<const InT>(p.in, off, t.q_first + p.pre);
     auto body = [&](int j) {
-      if (ASYNC) {
+      if (direct) {
+        if (ASYNC) async_copy_elem<T>(dst + j, reinterpret_cast<const T *>(sp + j * es), true);
+        else dst[j] = (T)sp[j * es];
+      } else if (ASYNC) {
         bool valid;
         const T *src = reinterpret_cast<const T *>(view_addr<InT>(p.in, off, t.q_first + p.pre + j, &valid));
         async_copy_elem<T>(dst + j, src, valid);
@@ -783,20 +816,29 @@ RR_PROG void poly0_fast_compute(const Poly0FastParams<T> &fp, const Poly0Tile &t
     const long long out_off = lane_offset(p.out, t.lane0 + ch);
     long long i = t.i_first + fs;
     const long long i_end = p.out0 + p.nout;
+    // interior tile: every output of the tile exists and is stored contiguously -> direct stores
+    const long long i_tile_end = t.i_first + (long long)t.mcount * L;
+    const bool direct = i_tile_end <= i_end && view_range_direct(p.out, p.out_preload + t.i_first, p.out_preload + i_tile_end);
+    OutT *dp = view_ptr<OutT>(p.out, out_off, p.out_preload + i);
+    const long long dstep = (long long)L * p.out.elem_stride;
     int m = 0;
-    for (; m + 1 < t.mcount; m += 2, x += 2 * p.step, i += 2 * L) {   // two independent accumulators
+    for (; m + 1 < t.mcount; m += 2, x += 2 * p.step, i += 2 * L, dp += 2 * dstep) {   // two independent accumulators
       const T *x1 = x + p.step;
       T s0 = (T)0, s1 = (T)0;
 #pragma unroll
       for (int k = 0; k < NT; ++k) { s0 = A::add(s0, A::mul(c[k], x[k])); s1 = A::add(s1, A::mul(c[k], x1[k])); }
-      if (i < i_end) view_write<OutT, T>(p.out, out_off, p.out_preload + i, s0);
-      if (i + L < i_end) view_write<OutT, T>(p.out, out_off, p.out_preload + i + L, s1);
+      if (direct) { dp[0] = (OutT)s0; dp[dstep] = (OutT)s1; }
+      else {
+        if (i < i_end) view_write<OutT, T>(p.out, out_off, p.out_preload + i, s0);
+        if (i + L < i_end) view_write<OutT, T>(p.out, out_off, p.out_preload + i + L, s1);
+      }
     }
     if (m < t.mcount) {
       T s0 = (T)0;
 #pragma unroll
       for (int k = 0; k < NT; ++k) s0 = A::add(s0, A::mul(c[k], x[k]));
-      if (i < i_end) view_write<OutT, T>(p.out, out_off, p.out_preload + i, s0);
+      if (direct) dp[0] = (OutT)s0;
+      else if (i < i_end) view_write<OutT, T>(p.out, out_off, p.out_preload + i, s0);
     }
   });
 }
