@@ -1,0 +1,148 @@
+"""CPU tier: the product's host orchestration and CTA programs, compiled as plain C++ (tests/emu, see
+tests/emulib.py), against the oracle. This is what can be checked of the CUDA path without a GPU: stage plans,
+the absolute-coordinate bookkeeping of push/pull/drain, every index computation inside the kernels, the batch
+front-end and time-chunked ranges. fp32 bit-exact; fp64 within the 1e-12 contract (the engine's fp64 transform
+is the split-radix DAG, not Ooura's)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import emulib
+import oraclelib
+import signals
+from foo_dsp_resampler_b200 import _capi, converter
+
+FP64_TOL = 1e-12
+
+CASES = [
+    (44100, 48000, "float", 50, 95, 0, 0, 2), (44100, 96000, "float", 50, 95, 0, 0, 2),
+    (192000, 44100, "double", 25, 95, 0, 0, 3), (48000, 44100, "float", 50, 95, 0, 0, 2),
+    (384000, 48000, "float", 50, 95, 0, 0, 3), (44100, 48001, "float", 50, 95, 0, 0, 1),
+    (44100, 44101, "float", 50, 95, 0, 1, 1), (48000, 47999, "double", 50, 95, 0, 0, 1),
+    (8000, 48000, "float", 50, 95, 0, 0, 1), (48000, 32000, "float", 50, 95, 0, 0, 2),
+    (96000, 44100, "float", 75, 99, 1, 0, 1), (44100, 48000, "float", 0, 90, 0, 1, 1),
+    (22050, 96000, "float", 50, 95, 0, 0, 1), (44100, 11025, "double", 50, 95, 0, 0, 2),
+    (44100, 176400, "float", 50, 95, 0, 1, 1), (48000, 8000, "double", 50, 95, 0, 1, 1),
+]
+
+
+def ids(c):
+    return "%d-%d-%s-p%d-q%d-%dch" % (c[0], c[1], c[2], c[3], c[6], c[7])
+
+
+@pytest.mark.parametrize("case", CASES, ids=ids)
+def test_stream_front_end(case):
+    i, o, eng, ph, bw, al, q, nch = case
+    L = emulib.lib()
+    cfg, ocfg = _capi.make_config(i, o, ph, bw, al, q), oraclelib.make_config(i, o, ph, bw, al, q)
+    x = signals.sweep_noise(i, nch, int(i * 0.3) + 11)
+    yo, co = oraclelib.resample(ocfg, x, engine=eng, chunk=3001, native=True)
+    ye, ce = converter.resample(cfg, x, engine=eng, chunk=3001, native=True, lib=L)
+    assert ce == co
+    assert ye.shape == yo.shape
+    if eng == "float":
+        assert np.array_equal(ye, yo)
+    else:
+        assert np.abs(ye - yo).max() <= FP64_TOL
+
+
+@pytest.mark.parametrize("case", CASES, ids=ids)
+def test_plan_and_design(case):
+    i, o, eng, ph, bw, al, q, nch = case
+    L = emulib.lib()
+    cfg, ocfg = _capi.make_config(i, o, ph, bw, al, q), oraclelib.make_config(i, o, ph, bw, al, q)
+    p = _capi.Plan()
+    assert L.RRX_plan(C.byref(cfg), 4 if eng == "float" else 8, C.byref(p)) == 0
+    orc = oraclelib.OracleResampler(ocfg, 1, eng)
+    assert p.as_dict() == orc.plan()
+    # designed banks, before conversion to the engine type: bit-identical doubles
+    n = L.RRX_design_dump(C.byref(cfg), 4 if eng == "float" else 8, 2, None, 0)
+    if n > 0:
+        bank = np.empty(n)
+        L.RRX_design_dump(C.byref(cfg), 4 if eng == "float" else 8, 2, bank.ctypes.data, n)
+        assert np.array_equal(bank.astype(orc.dtype), orc.poly_coefs())
+    if eng == "float":                       # engine-type spectrum of the DFT filters
+        r = converter.RateConverter(cfg, 1, eng, lib=L)
+        for inst in (0, 1):
+            assert np.array_equal(r.dft_spectrum(inst), orc.dft_coefs(inst))
+        r.close()
+    orc.close()
+
+
+@pytest.mark.parametrize("case", CASES[:8], ids=ids)
+def test_batch_front_end_and_ranges(case):
+    i, o, eng, ph, bw, al, q, nch = case
+    L = emulib.lib()
+    cfg, ocfg = _capi.make_config(i, o, ph, bw, al, q), oraclelib.make_config(i, o, ph, bw, al, q)
+    nstreams, n = 3, int(i * 0.25) + 7
+    xs = np.stack([signals.sweep_noise(i, nch, n, stream=s) for s in range(nstreams)])
+    b = converter.BatchConverter(cfg, nch, nstreams, n, engine=eng, lib=L)
+    nout = b.frames_out(n)
+    out = np.zeros((nstreams, nout, nch), np.float32)
+    b.process(xs.ctypes.data, n, out.ctypes.data)
+    for s in range(nstreams):
+        ref, _ = oraclelib.resample(ocfg, xs[s], engine=eng)
+        assert ref.shape[0] == nout
+        if eng == "float":
+            assert np.array_equal(out[s], ref)
+        else:
+            assert np.abs(out[s] - ref).max() <= 2.0 ** -23
+    # time-chunked: ranges computed from their halo'd input windows equal the one-shot result bit for bit
+    for ob, oc in ((0, nout // 3), (nout // 3, nout // 2), (nout - 100, 100)):
+        f, c = b.input_window(n, ob, oc)
+        win = np.ascontiguousarray(xs[:, f:f + c, :])
+        part = np.zeros((nstreams, oc, nch), np.float32)
+        b.process_range(win.ctypes.data, f, c, n, ob, oc, part.ctypes.data)
+        assert np.array_equal(part, out[:, ob:ob + oc, :])
+    # host-buffer entry point, more streams than the batch holds
+    more = np.concatenate([xs, xs[:2] * 0.5])
+    out2 = np.zeros((5, nout, nch), np.float32)
+    b.process_host(more.ctypes.data, n, out2.ctypes.data, 5)
+    assert np.array_equal(out2[:3], out)
+    b.close()
+
+
+def test_push_pull_protocol_edges():
+    L = emulib.lib()
+    cfg, ocfg = _capi.make_config(48000, 44100), oraclelib.make_config(48000, 44100)
+    x = signals.sweep_noise(48000, 2, 20000)
+    ref, _ = oraclelib.resample(ocfg, x, engine="float")
+    # RR_flow: pull, push, pull again (rate/rate_base.h:571-614)
+    r = converter.RateConverter(cfg, 2, "float", lib=L)
+    outs = []
+    for s in range(0, x.shape[0], 2500):
+        y, used = r.flow(x[s:s + 2500], 3000)
+        assert used == min(2500, x.shape[0] - s)
+        outs.append(y.copy())
+    r.drain()
+    while True:
+        y = r.pull(4096)
+        if not len(y):
+            break
+        outs.append(y.copy())
+    assert np.array_equal(np.concatenate(outs), ref)
+    r.drain()                                   # second drain: nothing left
+    assert len(r.pull(16)) == 0
+    r.close()
+    # pushing after a drain continues the stream exactly like the reference does
+    orc = oraclelib.OracleResampler(ocfg, 2, "float")
+    r = converter.RateConverter(cfg, 2, "float", lib=L)
+    got_o, got_e = [], []
+    for blk in (x[:7000], x[7000:9000]):
+        for obj, got in ((orc, got_o), (r, got_e)):
+            obj.push(blk)
+            obj.drain()
+            got.append(obj.pull(1 << 16).copy())
+    assert [len(a) for a in got_o] == [len(a) for a in got_e]
+    assert all(np.array_equal(a, b) for a, b in zip(got_o, got_e))
+    r.close()
+    orc.close()
+    # RR_open: Best -> fp64 engine, Normal -> fp32 engine (rate/rate_uni.c:38-51)
+    assert converter.RateConverter(cfg, 1, "auto", lib=L).sample_bytes == 8
+    assert converter.RateConverter(_capi.make_config(48000, 44100, quality=1), 1, "auto", lib=L).sample_bytes == 4
+    # invalid ratio: the reference swallows RR_INVPARAM in its ctor; this library reports it
+    h = C.c_void_p()
+    bad = _capi.make_config(1, 48000)
+    assert L.RR_open(C.byref(bad), 1, C.byref(h)) == _capi.RR_INVPARAM and not h.value
+    assert L.RR_push(None, None, 0) == _capi.RR_NULLHANDLE
