@@ -153,14 +153,15 @@ __global__ void __launch_bounds__(kDftThreads) dft_kernel(const __grid_constant_
   const DftTables<T> tab{t, t + nf, t + nf + ni, t + nf + ni + tf};
   CoefCache<T, DftCacheDepth<T>::value> cc;
   dft_load_coef_cache(p, cc);
-  if (p.zstride > 0 && (long long)blockIdx.x < nwork) {          // prime the prefetch pipeline
-    const DftItem<T> it = dft_item<T, LPC>(p, blockIdx.x);
-    dft_stage_tile<T, T, LPC, true>(p, it, data + LPC * (p.xstride + p.ystride), p.zstride);
-  }
+  __shared__ DftItem<T> items[2];
+  if (threadIdx.x == 0 && (long long)blockIdx.x < nwork) items[0] = dft_item<T, LPC>(p, blockIdx.x);
   __syncthreads();
-  for (long long w = blockIdx.x; w < nwork; w += gridDim.x) {
+  if (p.zstride > 0 && (long long)blockIdx.x < nwork)             // prime the prefetch pipeline
+    dft_stage_tile<T, T, LPC, true>(p, items[0], data + LPC * (p.xstride + p.ystride), p.zstride);
+  int slot = 0;
+  for (long long w = blockIdx.x; w < nwork; w += gridDim.x, slot ^= 1) {
     const long long next = w + gridDim.x < nwork ? w + gridDim.x : -1;
-    dft_stage_program<T, InT, OutT, LPC, DftCacheDepth<T>::value>(p, tab, cc, w, next, data);
+    dft_stage_program<T, InT, OutT, LPC, DftCacheDepth<T>::value>(p, tab, cc, items, slot, next, data);
   }
 }
 template <class T, class InT, class OutT>
@@ -178,15 +179,24 @@ __global__ void __launch_bounds__(512) poly0_fast_kernel(const __grid_constant__
   constexpr bool kAsync = std::is_same<InT, T>::value;
   const int set = p.win * p.CH;
   long long w = blockIdx.x;
+  __shared__ Poly0Tile tiles[3];                     // tile geometry is computed by one thread per tile
   if (kAsync && p.double_buffer) {
-    if (w < nwork) poly0_fast_load<T, InT, true>(p, poly0_tile(p, w), smem);
+    if (threadIdx.x == 0) {
+      if (w < nwork) tiles[0] = poly0_tile(p, w);
+      if (w + gridDim.x < nwork) tiles[1] = poly0_tile(p, w + gridDim.x);
+    }
+    __syncthreads();
+    if (w < nwork) poly0_fast_load<T, InT, true>(p, tiles[0], smem);
     for (int it = 0; w < nwork; w += gridDim.x, ++it) {
-      const int cur = it & 1;
+      const int cur = it & 1, ts = it % 3, tn = (it + 1) % 3, tnn = (it + 2) % 3;
       const long long next = w + gridDim.x;
-      if (next < nwork) { poly0_fast_load<T, InT, true>(p, poly0_tile(p, next), smem + (cur ^ 1) * set); async_copy_wait<1>(); }
+      if (next < nwork) { poly0_fast_load<T, InT, true>(p, tiles[tn], smem + (cur ^ 1) * set); async_copy_wait<1>(); }
       else async_copy_wait<0>();
+      // slot tnn was the current tile of the previous iteration (all reads done before its last barrier)
+      if (threadIdx.x == 0 && next + gridDim.x < nwork) tiles[tnn] = poly0_tile(p, next + gridDim.x);
       __syncthreads();
-      poly0_fast_compute<T, OutT, NT>(p, poly0_tile(p, w), smem + cur * set);   // ends with a barrier
+      const Poly0Tile t = tiles[ts];
+      poly0_fast_compute<T, OutT, NT>(p, t, smem + cur * set);                 // ends with a barrier
     }
   } else {
     for (; w < nwork; w += gridDim.x) {
@@ -282,8 +292,10 @@ template <class T> struct Launch {
 #define RR_CALLE(I, O, LPC)                                                                                   \
   serial(nwork, smem, [&](long long w, T *sm) {                                                               \
     C2<T> *data = reinterpret_cast<C2<T> *>(sm);                                                              \
-    if (p.zstride > 0) dft_stage_tile<T, T, LPC, true>(p, dft_item<T, LPC>(p, w), data + LPC * (p.xstride + p.ystride), p.zstride); \
-    dft_stage_program<T, I, O, LPC, 0>(p, tab, cc, w, -1, data);                                              \
+    DftItem<T> items[2];                                                                                      \
+    items[0] = dft_item<T, LPC>(p, w);                                                                        \
+    if (p.zstride > 0) dft_stage_tile<T, T, LPC, true>(p, items[0], data + LPC * (p.xstride + p.ystride), p.zstride); \
+    dft_stage_program<T, I, O, LPC, 0>(p, tab, cc, items, 0, -1, data);                                       \
   })
 #define RR_CALL1(I, O) RR_CALLE(I, O, 1)
 #define RR_CALL2(I, O) RR_CALLE(I, O, 2)

@@ -63,13 +63,22 @@ template <class F> RR_PROG void cta_for(int count, F f)
   __syncthreads();
 }
 RR_PROG void cta_sync() { __syncthreads(); }
+RR_PROG bool cta_leader() { return threadIdx.x == 0; }
 #else
 template <class F> inline void cta_for(int count, F f)
 {
   for (int i = 0; i < count; ++i) f(i);
 }
 inline void cta_sync() {}
+inline bool cta_leader() { return true; }
 #endif
+
+// 64-bit / 32-bit split that avoids the slow 64-bit divide for the common case of a small dividend.
+RR_HD void divmod_ll(long long a, int b, long long &q, int &r)
+{
+  if (a >= 0 && a < 0x7fffffffll) { const unsigned ua = (unsigned)a, uq = ua / (unsigned)b; q = uq; r = (int)(ua - uq * (unsigned)b); }
+  else { q = a / b; r = (int)(a - q * b); }
+}
 
 // ---------------------------------------------------------------------------------------------------
 // Addressing of a FIFO (device ring buffer / linear intermediate) or of a caller's interleaved buffer.
@@ -445,8 +454,10 @@ RR_PROG DftItem<T> dft_item(const DftParams<T> &p, long long work)
 {
   DftItem<T> it;
   const int groups = (p.nlanes + LPC - 1) / LPC;
-  it.b = p.block0 + work / groups;
-  const int lane0 = (int)(work % groups) * LPC;
+  long long bq; int gr;
+  divmod_ll(work, groups, bq, gr);
+  it.b = p.block0 + bq;
+  const int lane0 = gr * LPC;
   it.lanes = (p.nlanes - lane0) < LPC ? (p.nlanes - lane0) : LPC;
   it.remLb = p.remL0;
   if (p.in_mode == DFT_IN_ZERO_STUFF) {
@@ -506,14 +517,17 @@ RR_PROG void dft_stage_tile(const DftParams<T> &p, const DftItem<T> &it, C2<T> *
   cta_for(it.lanes * span, body);
 }
 
-// `work_next` < 0: nothing to prefetch. With a prefetch buffer (p.zstride > 0) the tile of `work` must
-// already be in flight into Z (the kernel primes the first one).
+// `items` is a two-entry array in shared memory: items[slot] describes `work` (written by the CTA leader
+// before the previous barrier), items[slot ^ 1] receives the description of `work_next` (< 0: none) so
+// that the 64-bit coordinate arithmetic is done by one thread per item instead of by all of them. With a
+// prefetch buffer (p.zstride > 0) the tile of `work` must already be in flight into Z (the kernel primes it).
 template <class T, class InT, class OutT, int LPC, int MAXI>
 RR_PROG void dft_stage_program(const DftParams<T> &p, const DftTables<T> &tab, const CoefCache<T, MAXI> &cc,
-                               long long work, long long work_next, C2<T> *smem)
+                               DftItem<T> *items, int slot, long long work_next, C2<T> *smem)
 {
   typedef Arith<T> A;
-  const DftItem<T> it = dft_item<T, LPC>(p, work);
+  const DftItem<T> it = items[slot];
+  if (work_next >= 0 && cta_leader()) items[slot ^ 1] = dft_item<T, LPC>(p, work_next);
   const long long b = it.b;
   const int lanes = it.lanes;
   C2<T> *X = smem, *Y = smem + LPC * p.xstride, *Z = Y + LPC * p.ystride;
@@ -530,7 +544,7 @@ RR_PROG void dft_stage_program(const DftParams<T> &p, const DftTables<T> &tab, c
   // ---- phases 1-2: forward complex FFT of Pf/2 points -> X; refill Z for the next item meanwhile ----
   cfft_leaves<T, LPC>(p.fwd, lanes, fwd_in, fwd_stride, X, p.xstride, p.sqrthalf, p.c16_1, p.c16_3);
   if (prefetch && work_next >= 0) {
-    const DftItem<T> nx = dft_item<T, LPC>(p, work_next);
+    const DftItem<T> nx = items[slot ^ 1];              // published before the barrier that ended the leaves
     dft_stage_tile<T, T, LPC, true>(p, nx, Z, p.zstride);
   }
   cfft_passes<T, LPC>(p.fwd, lanes, X, p.xstride, tab.pyr_f);
@@ -749,10 +763,12 @@ template <class T> RR_HD Poly0Tile poly0_tile(const Poly0FastParams<T> &fp, long
   const PolyParams<T> &p = fp.base;
   Poly0Tile t;
   const int L = p.L;
-  const long long mt = work % fp.mtiles;
-  const long long rest = work / fp.mtiles;
-  const int col = (int)(rest % fp.ncols);
-  t.lane0 = (int)(rest / fp.ncols) * fp.CH;
+  long long mt, rest; int col;
+  if (work < 0x7fffffffll && fp.mtiles < 0x7fffffffll) {
+    const unsigned uw = (unsigned)work, um = (unsigned)fp.mtiles, ur = uw / um;
+    mt = uw - ur * um; rest = ur;
+  } else { mt = work % fp.mtiles; rest = work / fp.mtiles; }
+  { long long g; divmod_ll(rest, fp.ncols, g, col); t.lane0 = (int)g * fp.CH; }
   const int slot0 = col * fp.F;
   t.nslots = (L - slot0) < fp.F ? (L - slot0) : fp.F;
   const long long periods = (p.nout + L - 1) / L;
@@ -761,8 +777,7 @@ template <class T> RR_HD Poly0Tile poly0_tile(const Poly0FastParams<T> &fp, long
   // first input position touched by this tile: output out0 + m0*L + slot0
   t.i_first = p.out0 + m0 * L + slot0;
   const long long at_first = p.at0 + t.i_first * p.step;
-  t.q_first = at_first / L;
-  t.r_first = (int)(at_first - t.q_first * L);
+  divmod_ll(at_first, L, t.q_first, t.r_first);
   const long long at_last = (long long)t.r_first + (long long)(t.nslots - 1) * p.step;   // relative to q_first*L
   t.win = (int)(at_last / L) + (t.mcount - 1) * (int)p.step + p.n;
   return t;
@@ -806,8 +821,8 @@ RR_PROG void poly0_fast_compute(const Poly0FastParams<T> &fp, const Poly0Tile &t
   const int CH = fp.CH, L = p.L;
   cta_for(t.nslots * CH, [&](int tid) {
     const int fs = tid / CH, ch = tid - fs * CH;
-    const long long at_rel = (long long)t.r_first + (long long)fs * p.step;             // < L*step: fits easily
-    const int q = (int)(at_rel / L), r = (int)(at_rel - (long long)q * L);
+    const unsigned at_rel = (unsigned)t.r_first + (unsigned)fs * (unsigned)p.step;      // < L + 512*step < 2^30
+    const int q = (int)(at_rel / (unsigned)L), r = (int)(at_rel - (unsigned)q * (unsigned)L);
     T c[NT];
     const T *row = p.coefs + (long long)r * NT;
 #pragma unroll
