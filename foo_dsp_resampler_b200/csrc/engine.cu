@@ -141,7 +141,7 @@ extern __shared__ __align__(16) unsigned char rr_smem_raw[];
 // thread will need in registers, once; then loop over (block, lane group) work items, prefetching the next
 // item's input tile with LDGSTS while the current one is transformed.
 template <class T, class InT, class OutT, int LPC>
-__global__ void __launch_bounds__(kDftThreads) dft_kernel(const __grid_constant__ DftParams<T> p, long long nwork, int data_bytes)
+__global__ void __launch_bounds__(2 * kDftThreads) dft_kernel(const __grid_constant__ DftParams<T> p, long long nwork, int data_bytes)
 {
   C2<T> *data = reinterpret_cast<C2<T> *>(rr_smem_raw);
   T *t = reinterpret_cast<T *>(rr_smem_raw + data_bytes);
@@ -213,11 +213,11 @@ __global__ void __launch_bounds__(kTileThreads) polyN_kernel(const __grid_consta
   T *smem = reinterpret_cast<T *>(rr_smem_raw);
   for (long long w = blockIdx.x; w < nwork; w += gridDim.x) polyN_program<T, InT, OutT>(p, w, smem);
 }
-template <class T, class InT, class OutT>
+template <class T, class InT, class OutT, int NC>
 __global__ void __launch_bounds__(kTileThreads) halfband_kernel(const __grid_constant__ HalfbandParams<T> p, long long nwork)
 {
   T *smem = reinterpret_cast<T *>(rr_smem_raw);
-  for (long long w = blockIdx.x; w < nwork; w += gridDim.x) halfband_program<T, InT, OutT>(p, w, smem);
+  for (long long w = blockIdx.x; w < nwork; w += gridDim.x) halfband_program<T, InT, OutT, NC>(p, w, smem);
 }
 template <class InT, class OutT>
 __global__ void __launch_bounds__(kTileThreads) copy_kernel(const __grid_constant__ CopyParams p, long long nwork)
@@ -300,8 +300,10 @@ template <class T> struct Launch {
 #define RR_CALL1(I, O) RR_CALLE(I, O, 1)
 #define RR_CALL2(I, O) RR_CALLE(I, O, 2)
 #else
-#define RR_CALL1(I, O) launch_persistent(dft_kernel<T, I, O, 1>, p, nwork, kDftThreads, smem, s, static_cast<int>(data_bytes))
-#define RR_CALL2(I, O) launch_persistent(dft_kernel<T, I, O, 2>, p, nwork, kDftThreads, smem, s, static_cast<int>(data_bytes))
+    // a block that leaves room for only one CTA per SM gets twice the threads (same register budget per SM)
+    const int threads = smem > 113 * 1024 ? 2 * kDftThreads : kDftThreads;
+#define RR_CALL1(I, O) launch_persistent(dft_kernel<T, I, O, 1>, p, nwork, threads, smem, s, static_cast<int>(data_bytes))
+#define RR_CALL2(I, O) launch_persistent(dft_kernel<T, I, O, 2>, p, nwork, threads, smem, s, static_cast<int>(data_bytes))
 #endif
     (void)s;
     if (lpc == 2) RR_DISPATCH_IO(RR_CALL2);
@@ -360,14 +362,34 @@ template <class T> struct Launch {
   }
   static int halfband(const HalfbandParams<T> &p, bool in_f32, bool out_f32, long long nwork, size_t smem, stream_t s)
   {
-#ifdef B200RATE_EMU
-#define RR_CALL(I, O) serial(nwork, smem, [&](long long w, T *sm) { halfband_program<T, I, O>(p, w, sm); })
-#else
-#define RR_CALL(I, O) launch_persistent(halfband_kernel<T, I, O>, p, nwork, kTileThreads, smem, s)
-#endif
     (void)s;
-    RR_DISPATCH_IO(RR_CALL);
-#undef RR_CALL
+#ifdef B200RATE_EMU
+#define RR_CALLN(I, O, NC) serial(nwork, smem, [&](long long w, T *sm) { halfband_program<T, I, O, NC>(p, w, sm); })
+#else
+#define RR_CALLN(I, O, NC) launch_persistent(halfband_kernel<T, I, O, NC>, p, nwork, kTileThreads, smem, s)
+#endif
+#define RR_CALL8(I, O) RR_CALLN(I, O, 8)
+#define RR_CALL9(I, O) RR_CALLN(I, O, 9)
+#define RR_CALL10(I, O) RR_CALLN(I, O, 10)
+#define RR_CALL11(I, O) RR_CALLN(I, O, 11)
+#define RR_CALL12(I, O) RR_CALLN(I, O, 12)
+#define RR_CALL13(I, O) RR_CALLN(I, O, 13)
+    switch (p.ncoef) {
+      case 8: RR_DISPATCH_IO(RR_CALL8);
+      case 9: RR_DISPATCH_IO(RR_CALL9);
+      case 10: RR_DISPATCH_IO(RR_CALL10);
+      case 11: RR_DISPATCH_IO(RR_CALL11);
+      case 12: RR_DISPATCH_IO(RR_CALL12);
+      case 13: RR_DISPATCH_IO(RR_CALL13);
+      default: return RR_INTERNAL;
+    }
+#undef RR_CALL8
+#undef RR_CALL9
+#undef RR_CALL10
+#undef RR_CALL11
+#undef RR_CALL12
+#undef RR_CALL13
+#undef RR_CALLN
   }
   static int copy(const CopyParams &p, bool in_f32, bool out_f32, stream_t s)
   {
@@ -559,10 +581,18 @@ template <class T> class Engine {
     if (g.kind == RR_STAGE_HALFBAND) {
       HalfbandParams<T> p = half_params_[i];
       p.in = in; p.out = out; p.out_preload = out_preload; p.out0 = w0; p.nout = wn; p.nlanes = nlanes;
-      p.tile = kHalfTile;
+      // all channels of a stream per CTA when the input is interleaved (coalesced window load)
+      const int nchan = in.nch;
+      const bool group_ok = in.ch_stride == 1 && out.nch == nchan && nlanes % nchan == 0 &&
+                            (nchan == 2 || nchan == 4 || nchan == 8);
+      p.CH = group_ok ? nchan : 1;
+      p.tile = kHalfTile / p.CH;                          // power of two
+      p.qbits = 0;
+      while ((4 << p.qbits) < p.tile) ++p.qbits;
+      p.half = ((p.tile + 2 * p.ncoef + 8 + 31) / 32) * 32 + 4;
       const long long tiles = (wn + p.tile - 1) / p.tile;
-      const size_t smem = sizeof(T) * static_cast<size_t>(2 * p.tile + 4 * p.ncoef);
-      return Launch<T>::halfband(p, in_f32, out_f32, tiles * nlanes, smem, s);
+      const size_t smem = sizeof(T) * 2 * static_cast<size_t>(p.half) * p.CH;
+      return Launch<T>::halfband(p, in_f32, out_f32, tiles * ((nlanes + p.CH - 1) / p.CH), smem, s);
     }
     PolyParams<T> p = poly_params_[i];
     p.in = in; p.out = out; p.out_preload = out_preload; p.out0 = w0; p.nout = wn; p.nlanes = nlanes;
@@ -570,19 +600,25 @@ template <class T> class Engine {
     if (g.order == 0 && (g.n == 16 || g.n == 24 || g.n == 32)) {
       // phase-stationary kernel: needs enough phases to fill a CTA and a window that fits shared memory
       const int nch = in.nch;
-      const int CH = (nch <= 8 && nlanes % nch == 0) ? nch : 1;
-      const int ncols = (g.Lp * CH + 511) / 512;
-      const int F = (g.Lp + ncols - 1) / ncols;
-      const int threads = ((F * CH + 31) / 32) * 32;
-      const long long periods = (wn + g.Lp - 1) / g.Lp;
-      int MM = 16;
-      // per-lane window, rounded so that lanes are 16 words apart modulo 32 (no bank sharing between channels)
-      auto window = [&](int mm) {
-        long long w = ((g.Lp - 1) + static_cast<long long>(F - 1) * g.pstep) / g.Lp + static_cast<long long>(mm - 1) * g.pstep + g.n + 1;
+      // lanes per CTA: as many channels of a stream as still leave >= 8 periods per tile in a 24 KB window
+      // (the coefficient row load is amortised over the periods); writes stay contiguous per frame
+      int CH = (nch <= 8 && nlanes % nch == 0) ? nch : 1;
+      int ncols = 1, F = g.Lp, threads = 32, MM = 16;
+      auto window_of = [&](int f, int mm) {
+        long long w = ((g.Lp - 1) + static_cast<long long>(f - 1) * g.pstep) / g.Lp + static_cast<long long>(mm - 1) * g.pstep + g.n + 1;
         const long long unit = 64 / sizeof(T);
         return ((w + 2 * unit - 1) / (2 * unit)) * 2 * unit + unit;
       };
-      while (MM > 2 && window(MM) * CH * sizeof(T) > 24 * 1024) MM >>= 1;
+      for (;; CH >>= 1) {
+        ncols = (g.Lp * CH + 511) / 512;
+        F = (g.Lp + ncols - 1) / ncols;
+        threads = ((F * CH + 31) / 32) * 32;
+        MM = 16;
+        while (MM > 2 && window_of(F, MM) * CH * sizeof(T) > 24 * 1024) MM >>= 1;
+        if (MM >= 8 || CH == 1 || (CH & 1)) break;
+      }
+      const long long periods = (wn + g.Lp - 1) / g.Lp;
+      auto window = [&](int mm) { return window_of(F, mm); };
       if (F * CH >= 64 && g.pstep < (1 << 20) && window(MM) * CH * sizeof(T) <= 48 * 1024) {
         Poly0FastParams<T> fp;
         fp.base = p; fp.F = F; fp.ncols = ncols; fp.MM = MM; fp.CH = CH;
@@ -700,7 +736,10 @@ template <class T> class Engine {
         c.n16 = static_cast<int>(h.leaf16_off.size()); c.n8 = static_cast<int>(h.leaf8_off.size());
         c.leaf16_off = leaf16; c.leaf8_off = leaf8; c.gather16 = g16[inv]; c.gather8 = g8[inv]; c.node_off = nodes;
         c.pyr_len = h.pyr_len;
-        for (int l = 0; l < 17; ++l) { c.level_begin[l] = h.level_begin[l]; c.level_cnt[l] = h.level_cnt[l]; c.pyr_off[l] = h.pyr_off[l]; }
+        for (int l = 0; l < 17; ++l) {
+          c.level_begin[l] = h.level_begin[l]; c.level_cnt[l] = h.level_cnt[l]; c.pyr_off[l] = h.pyr_off[l];
+          c.qchild_begin[l] = h.qchild_begin[l]; c.qchild_cnt[l] = h.qchild_cnt[l];
+        }
       }
       it = sched_.emplace(bits, d).first;
     }
@@ -854,7 +893,7 @@ template <class T> class Batch : public IBatch {
     for (int i = 1; i < eng.ns; ++i) {
       const StageGeom &up = eng.geom[i - 1];
       long long slack = up.kind == RR_STAGE_DFT ? 2ll * up.N : 64;
-      cap[i] = (r[i - 1].prod_hi - r[i - 1].prod_lo) + slack;
+      cap[i] = ((r[i - 1].prod_hi - r[i - 1].prod_lo) + slack + 3) & ~3ll;   // lanes stay 16-byte aligned
       void *p = nullptr;
       const size_t bytes = sizeof(T) * static_cast<size_t>(cap[i]) * nch * nstreams;
       if ((rc = be_malloc(&p, bytes))) return rc;

@@ -15,17 +15,19 @@ constexpr double kSqrtHalf = 0.70710678118654752440;
 struct TreeWalk {
   CfftHostSched *s;
   std::vector<std::vector<uint16_t>> per_level;
-  void visit(int size, int off)
+  std::vector<std::vector<uint16_t>> quarter_children;
+  void visit(int size, int off, bool quarter = false)
   {
     if (size == 16) { s->leaf16_off.push_back(static_cast<uint16_t>(off)); return; }
     if (size == 8) { s->leaf8_off.push_back(static_cast<uint16_t>(off)); return; }
     // fft(S) = fft(S/2) on the first half, fft(S/4) on each remaining quarter, then one pass
     visit(size >> 1, off);
-    visit(size >> 2, off + (size >> 1));
-    visit(size >> 2, off + 3 * (size >> 2));
+    visit(size >> 2, off + (size >> 1), true);
+    visit(size >> 2, off + 3 * (size >> 2), true);
     int lg = 0;
     while ((1 << lg) < size) ++lg;
     per_level[lg].push_back(static_cast<uint16_t>(off));
+    if (quarter) quarter_children[lg].push_back(static_cast<uint16_t>(off));
   }
 };
 }  // namespace
@@ -46,7 +48,7 @@ CfftHostSched build_cfft_sched(int bits)
   CfftHostSched s;
   s.bits = bits;
   const int m = 1 << bits;
-  TreeWalk w{&s, std::vector<std::vector<uint16_t>>(17)};
+  TreeWalk w{&s, std::vector<std::vector<uint16_t>>(17), std::vector<std::vector<uint16_t>>(17)};
   w.visit(m, 0);
   for (int lg = 5; lg <= bits; ++lg) {
     s.level_begin[lg] = static_cast<int>(s.node_off.size());
@@ -54,6 +56,11 @@ CfftHostSched build_cfft_sched(int bits)
     s.node_off.insert(s.node_off.end(), w.per_level[lg].begin(), w.per_level[lg].end());
     s.pyr_off[lg] = s.pyr_len;
     s.pyr_len += (1 << (lg - 2)) + 1;
+  }
+  for (int lg = 5; lg <= bits; ++lg) {
+    s.qchild_begin[lg] = static_cast<int>(s.node_off.size());
+    s.qchild_cnt[lg] = static_cast<int>(w.quarter_children[lg].size());
+    s.node_off.insert(s.node_off.end(), w.quarter_children[lg].begin(), w.quarter_children[lg].end());
   }
   const int n16 = static_cast<int>(s.leaf16_off.size()), n8 = static_cast<int>(s.leaf8_off.size());
   for (int inv = 0; inv < 2; ++inv) {

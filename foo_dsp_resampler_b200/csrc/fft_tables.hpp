@@ -18,6 +18,9 @@ struct CfftHostSched {
   std::vector<uint16_t> gather16[2], gather8[2]; // [inverse]: transposed [element][leaf] padded slots of the natural indices
   std::vector<uint16_t> node_off;                // node offsets of sizes 32..M, concatenated
   int level_begin[17] = {0}, level_cnt[17] = {0};
+  // nodes of each size that are QUARTER children of a node four times their size (the others are the first
+  // halves of a node twice their size): the fused two-level passes treat the two kinds differently
+  int qchild_begin[17] = {0}, qchild_cnt[17] = {0};
   int pyr_off[17] = {0};                         // row offsets inside twiddle_pyramid()
   int pyr_len = 0;
 };

@@ -170,6 +170,7 @@ struct CfftSched {
   const uint16_t *gather8;       // [8][n8]
   const uint16_t *node_off;      // concatenated node offsets for sizes 32 .. M
   int level_begin[17], level_cnt[17];
+  int qchild_begin[17], qchild_cnt[17];   // per size: the nodes that are quarter children (fused passes)
   int pyr_off[17];               // start of the twiddle row of each size inside the pyramid
   int pyr_len;
 };
@@ -325,13 +326,82 @@ RR_PROG void cfft_leaves(const CfftSched &s, int lanes, const C2<T> *src, int sr
     cfft_leaf_task<T, LPC>(s, task, lanes, src, src_stride, dst, dst_stride, sqrthalf, c16_1, c16_3);
   });
 }
+// Two consecutive combining passes (sizes S = 1 << lg and 2S) in one shared-memory round trip. A node of size
+// 2S consists of a first half of size S (whose own pass is still due) and two finished quarters of size S/2.
+// Task (node, k), k < S/4, keeps 8 values in registers: butterfly k of the S-pass on the first half, then
+// butterflies k and k + S/4 of the 2S-pass, which consume exactly those four results plus two values of each
+// quarter. Same butterflies on the same operands as the level-by-level order (fft.c:265-272), hence the same
+// bits; one barrier and a third of the shared-memory traffic less per pair of levels.
+template <class T, int LPC>
+RR_PROG void cfft_fused_item(const CfftSched &s, int lg, int item, int lanes, C2<T> *buf, int stride, const T *pyramid)
+{
+  const int qbits = lg - 2, q = 1 << qbits;
+  const int node = item >> qbits, k = item & (q - 1);
+  const int o = ldg(s.node_off + s.level_begin[lg + 1] + node) + k;
+  const T *twa = pyramid + s.pyr_off[lg], *twb = pyramid + s.pyr_off[lg + 1];
+  const T ar = twa[k], ai = twa[q - k];
+  const T b0r = twb[k], b0i = twb[2 * q - k], b1r = twb[k + q], b1i = twb[q - k];
+  const int i0 = cslot(o), i1 = cslot(o + q), i2 = cslot(o + 2 * q), i3 = cslot(o + 3 * q);
+  const int j0 = cslot(o + 4 * q), j1 = cslot(o + 5 * q), j2 = cslot(o + 6 * q), j3 = cslot(o + 7 * q);
+#pragma unroll
+  for (int l = 0; l < LPC; ++l) {
+    if (l < lanes) {
+      C2<T> *b = buf + l * stride;
+      C2<T> a0 = b[i0], a1 = b[i1], a2 = b[i2], a3 = b[i3];
+      C2<T> c0 = b[j0], c1 = b[j1], d0 = b[j2], d1 = b[j3];
+      sr_bfly(a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y, ar, ai, k == 0);          // size S, index k
+      sr_bfly(a0.x, a0.y, a2.x, a2.y, c0.x, c0.y, d0.x, d0.y, b0r, b0i, k == 0);        // size 2S, index k
+      sr_bfly(a1.x, a1.y, a3.x, a3.y, c1.x, c1.y, d1.x, d1.y, b1r, b1i, false);         // size 2S, index k + S/4
+      b[i0] = a0; b[i1] = a1; b[i2] = a2; b[i3] = a3;
+      b[j0] = c0; b[j1] = c1; b[j2] = d0; b[j3] = d1;
+    }
+  }
+}
+
+// One butterfly of the size-S pass on a quarter-child node (not covered by a fused task).
+template <class T, int LPC>
+RR_PROG void cfft_qchild_item(const CfftSched &s, int lg, int item, int lanes, C2<T> *buf, int stride, const T *pyramid)
+{
+  const int qbits = lg - 2, q = 1 << qbits;
+  const int node = item >> qbits, k = item & (q - 1);
+  const int p0 = ldg(s.node_off + s.qchild_begin[lg] + node) + k;
+  const T *tw = pyramid + s.pyr_off[lg];
+  const T wre = tw[k], wim = tw[q - k];
+  const int i0 = cslot(p0), i1 = cslot(p0 + q), i2 = cslot(p0 + 2 * q), i3 = cslot(p0 + 3 * q);
+#pragma unroll
+  for (int l = 0; l < LPC; ++l) {
+    if (l < lanes) {
+      C2<T> *b = buf + l * stride;
+      C2<T> a0 = b[i0], a1 = b[i1], a2 = b[i2], a3 = b[i3];
+      sr_bfly(a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y, wre, wim, k == 0);
+      b[i0] = a0; b[i1] = a1; b[i2] = a2; b[i3] = a3;
+    }
+  }
+}
+
 template <class T, int LPC>
 RR_PROG void cfft_passes(const CfftSched &s, int lanes, C2<T> *dst, int dst_stride, const T *pyramid)
 {
-  for (int lg = 5; lg <= s.bits; ++lg)
+  int lg = 5;
+  if ((s.bits - 4) & 1) {                                  // odd number of levels: the smallest one goes alone
     cta_for(s.level_cnt[lg] << (lg - 2), [&](int item) {
       cfft_pass_item<T, LPC>(s, lg, item, lanes, dst, dst_stride, pyramid);
     });
+    ++lg;
+  }
+  for (; lg < s.bits; lg += 2) {
+    const int nfused = s.level_cnt[lg + 1] << (lg - 2);    // one task per (2S-node, k)
+    const int nplain = s.qchild_cnt[lg] << (lg - 2);       // single butterflies, bundled in threes (same cost)
+    const int nbundles = (nplain + 2) / 3;
+    cta_for(nfused + nbundles, [&](int t) {
+      if (t < nfused) cfft_fused_item<T, LPC>(s, lg, t, lanes, dst, dst_stride, pyramid);
+      else {
+        const int first = (t - nfused) * 3;
+        for (int j = first; j < first + 3 && j < nplain; ++j)
+          cfft_qchild_item<T, LPC>(s, lg, j, lanes, dst, dst_stride, pyramid);
+      }
+    });
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -664,6 +734,17 @@ RR_PROG void dft_stage_program(const DftParams<T> &p, const DftTables<T> &tab, c
     const bool direct = view_range_direct(p.out, c0, c0 + count);
     OutT *d0 = view_ptr<OutT>(p.out, out_off0, c0), *d1 = view_ptr<OutT>(p.out, out_off1, c0);
     const int es = p.out.elem_stride;
+    // planar same-type output of an interior block: store whole complex slots (two samples) per thread
+    const bool pairs = direct && stride == 1 && es == 1 && !(count & 1) && sizeof(OutT) == sizeof(T) &&
+                       !(((size_t)d0 | (size_t)d1) & (2 * sizeof(T) - 1));
+    if (pairs) {
+      const int half = count >> 1;
+      cta_for(lanes * half, [&](int w) {
+        int l, c;
+        if (LPC == 1 || lanes == 1) { l = 0; c = w; } else { l = w & 1; c = w >> 1; }
+        reinterpret_cast<C2<T> *>(l ? d1 : d0)[c] = X[l * p.xstride + cslot(c)];
+      });
+    } else
     cta_for(lanes * count, [&](int w) {
       int l, j;
       if (LPC == 1 || lanes == 1) { l = 0; j = w; } else { l = w & 1; j = w >> 1; }
@@ -912,31 +993,80 @@ template <class T> struct HalfbandParams {
   T coef[13];
   LaneView in, out;
   long long out_preload, out0, nout;
-  int nlanes, tile;
+  int nlanes, tile;              // tile: outputs per lane per CTA (multiple of 4)
+  int CH;                        // lanes per CTA: all channels of a stream when the input is interleaved (1, 2, 4, 8)
+  int half;                      // per-parity window capacity per lane (4 mod 32 words: no bank sharing between lanes)
+  int qbits;                     // log2(tile / 4)
 };
 
-template <class T, class InT, class OutT>
+// y[k] = 0.5 x[2k+pre] + sum_t c[t] (x[2k+pre-(2t+1)] + x[2k+pre+(2t+1)]), summed in that order.
+// The window is split by sample parity in shared memory (the centre tap reads one parity, all other taps the
+// other one), so consecutive outputs read consecutive words; each thread produces four consecutive outputs
+// from 16-byte shared loads (6.75 loaded values per output instead of 25).
+template <class T, class InT, class OutT, int NC>
 RR_PROG void halfband_program(const HalfbandParams<T> &p, long long work, T *smem)
 {
   typedef Arith<T> A;
+  const int CH = p.CH;                                   // 1, 2, 4 or 8; > 1 only for interleaved input
+  constexpr int c = NC;                                  // compile-time tap count keeps the window in registers
   const long long tiles = (p.nout + p.tile - 1) / p.tile;
-  const int lane = (int)(work / tiles);
-  const long long tix = work - lane * tiles;
-  const long long k0 = p.out0 + tix * p.tile;
+  long long group; int tix_i;
+  divmod_ll(work, (int)tiles, group, tix_i);
+  const int lane0 = (int)group * CH;
+  const long long k0 = p.out0 + (long long)tix_i * p.tile;
   const long long rest = p.out0 + p.nout - k0;
   const int cnt = rest < p.tile ? (int)rest : p.tile;
-  const int reach = 2 * p.ncoef - 1;
-  const long long x0 = 2 * k0 + p.pre - reach;           // first coordinate needed
+  const int reach = 2 * c - 1;
+  const long long x0 = 2 * k0 + p.pre - reach;           // first coordinate needed (window index u = coord - x0)
   const int win = 2 * (cnt - 1) + 2 * reach + 1;
-  const long long in_off = lane_offset(p.in, lane), out_off = lane_offset(p.out, lane);
+  T *P0 = smem, *P1 = smem + (long long)CH * p.half;     // even-u / odd-u samples, [lane][half]
+  // window index u: even u -> P0[u/2], odd u -> P1[(u+1)/2 + shift] with shift chosen so that the centre tap of
+  // output j (u = 2j + reach, odd) sits at P1[j + 4]: rows stay 16-byte aligned for the vector loads below
+  const int shift = 4 - c;
+  const int chbits = CH == 8 ? 3 : CH == 4 ? 2 : CH == 2 ? 1 : 0;
+  const long long in_off0 = lane_offset(p.in, lane0), out_off0 = lane_offset(p.out, lane0);
 
-  cta_for(win, [&](int j) { smem[j] = view_read<InT, T>(p.in, in_off, x0 + j); });
-  cta_for(cnt, [&](int j) {
-    const T *x = smem + 2 * j + reach;
-    T sum = A::mul(x[0], (T)0.5);
-    for (int k = 0; k < p.ncoef; ++k)
-      sum = A::add(sum, A::mul(A::add(x[-(2 * k + 1)], x[2 * k + 1]), p.coef[k]));
-    view_write<OutT, T>(p.out, out_off, p.out_preload + k0 + j, sum);
+  const bool direct = view_range_direct(p.in, x0, x0 + win);
+  const InT *src0 = view_ptr<const InT>(p.in, in_off0, x0);
+  cta_for(win << chbits, [&](int w) {                    // channel fastest: coalesced for interleaved input
+    const int l = w & (CH - 1), u = w >> chbits;
+    const long long off = in_off0 + (long long)l * p.in.ch_stride;
+    const T v = direct ? (T)src0[(long long)l * p.in.ch_stride + (long long)u * p.in.elem_stride]
+                       : view_read<InT, T>(p.in, off, x0 + u);
+    if (u & 1) {                                         // odd samples below the first centre tap are never read
+      const int idx = ((u + 1) >> 1) + shift;
+      if (idx >= 4) P1[l * p.half + idx] = v;
+    } else P0[l * p.half + (u >> 1)] = v;
+  });
+  const int qbits = p.qbits;                             // log2(tile / 4)
+  cta_for(CH << qbits, [&](int w) {
+    const int l = w >> qbits, j = 4 * (w & ((1 << qbits) - 1));
+    if (j >= cnt) return;
+    const T *e = P0 + l * p.half + j, *o = P1 + l * p.half + j + 4;
+    // outputs j..j+3 use P0[j .. j+2c+2] and the centres P1[j+4 .. j+7]
+    T x[2 * c + 3];
+#pragma unroll
+    for (int i = 0; i < 2 * c + 3; ++i) x[i] = e[i];
+    T y[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      T sum = A::mul(o[r], (T)0.5);
+#pragma unroll
+      for (int t = 0; t < c; ++t) sum = A::add(sum, A::mul(A::add(x[r + c - 1 - t], x[r + c + t]), p.coef[t]));
+      y[r] = sum;
+    }
+    const long long off = out_off0 + (long long)l * p.out.ch_stride;
+    const long long cbase = p.out_preload + k0 + j;
+    if (j + 4 <= cnt && view_range_direct(p.out, cbase, cbase + 4)) {
+      OutT *d = view_ptr<OutT>(p.out, off, cbase);
+      const int es = p.out.elem_stride;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) d[r * es] = (OutT)y[r];
+    } else {
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        if (j + r < cnt) view_write<OutT, T>(p.out, off, cbase + r, y[r]);
+    }
   });
 }
 
