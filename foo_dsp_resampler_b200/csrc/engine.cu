@@ -570,10 +570,10 @@ template <class T> class Engine {
       // leaves room for two CTAs per SM
       const bool same_type = Launch<T>::kIsF32 || !in_f32;
       bool prefetch = same_type;
-      size_t data_bytes = dft_smem_bytes<T>(g.N, g.Pf, lpc, prefetch, &p.xstride, &p.ystride, &p.zstride);
-      if (prefetch && data_bytes + sizeof(T) * dft_table_elems(p) > 110 * 1024) {
+      size_t data_bytes = dft_smem_bytes<T>(g.Pf, g.Ni, lpc, prefetch, &p.xstride, &p.ystride, &p.zstride);
+      if (prefetch && data_bytes + sizeof(T) * dft_table_elems(p) > 112 * 1024) {
         prefetch = false;
-        data_bytes = dft_smem_bytes<T>(g.N, g.Pf, lpc, false, &p.xstride, &p.ystride, &p.zstride);
+        data_bytes = dft_smem_bytes<T>(g.Pf, g.Ni, lpc, false, &p.xstride, &p.ystride, &p.zstride);
       }
       const long long groups = (nlanes + lpc - 1) / lpc;
       return Launch<T>::dft(p, lpc, in_f32, out_f32, wn * groups, data_bytes, s);
@@ -702,7 +702,7 @@ template <class T> class Engine {
   int dft_lanes_per_cta(const StageGeom &g, int nlanes) const
   {
     if (nlanes < 2) return 1;
-    const size_t two = dft_smem_bytes<T>(g.N, g.Pf, 2, false, nullptr, nullptr, nullptr);
+    const size_t two = dft_smem_bytes<T>(g.Pf, g.Ni, 2, false, nullptr, nullptr, nullptr);
     return two <= 100 * 1024 ? 2 : 1;      // two lanes share every table / index load; keep 2 CTAs per SM
   }
 
@@ -786,7 +786,7 @@ template <class T> class Engine {
         int xs = 0, ys = 0;
         DftParams<T> probe; memset(&probe, 0, sizeof(probe));
         probe.Pf = g.Pf; probe.Ni = g.Ni; probe.fwd.pyr_len = g.Pf / 4 + 16; probe.inv.pyr_len = g.Ni / 4 + 16;
-        const size_t need = dft_smem_bytes<T>(g.N, g.Pf, 1, false, &xs, &ys, nullptr) + sizeof(T) * dft_table_elems(probe);
+        const size_t need = dft_smem_bytes<T>(g.Pf, g.Ni, 1, false, &xs, &ys, nullptr) + sizeof(T) * dft_table_elems(probe);
         if (need > max_smem_) {
           set_last_error("DFT length " + std::to_string(g.N) + " exceeds the shared-memory block kernel (not implemented: global-memory multi-pass FFT)");
           return RR_INTERNAL;

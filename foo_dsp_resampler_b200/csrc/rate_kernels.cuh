@@ -21,6 +21,7 @@
 #pragma once
 
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define RR_HD __host__ __device__ __forceinline__   // small arithmetic / addressing helpers
@@ -183,7 +184,16 @@ RR_HD int lane_stride_complex(int min_complex, int unit) { return ((min_complex 
 
 // Read-only global loads (LDG.CONSTANT on the device).
 #if defined(__CUDA_ARCH__)
-template <class E> RR_HD E ldg(const E *p) { return __ldg(p); }
+template <class E> RR_HD E ldg(const E *p)
+{
+  if constexpr (sizeof(E) == 16 && alignof(E) == 16) {                  // any 16-byte POD: one LDG.128
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
+    E r;
+    memcpy(&r, &v, 16);
+    return r;
+  } else if constexpr (sizeof(E) <= 8 && (sizeof(E) & (sizeof(E) - 1)) == 0 && !__is_class(E)) return __ldg(p);
+  else return *p;
+}
 RR_HD C2<float> ldg(const C2<float> *p) { const float2 v = __ldg(reinterpret_cast<const float2 *>(p)); return C2<float>{v.x, v.y}; }
 RR_HD C2<double> ldg(const C2<double> *p) { const double2 v = __ldg(reinterpret_cast<const double2 *>(p)); return C2<double>{v.x, v.y}; }
 #else
@@ -445,12 +455,13 @@ template <class T> RR_HD int dft_table_elems(const DftParams<T> &p)
 // Buffers per lane: X (FFT work buffer), Y (natural-order input of the inverse transform) and, when the
 // next block's input is prefetched while this one is processed, Z (natural-order input of the forward
 // transform, Pf reals). Without prefetch the forward input shares Y. All use the padded cslot layout.
-template <class T> RR_HD size_t dft_smem_bytes(int N, int Pf, int lanes_per_cta, bool prefetch, int *xstride, int *ystride,
+template <class T> RR_HD size_t dft_smem_bytes(int Pf, int Ni, int lanes_per_cta, bool prefetch, int *xstride, int *ystride,
                                                int *zstride)
 {
   const int unit = 32 / (int)sizeof(T);                  // 16 words, in complex elements
-  const int m = N / 2, mf = Pf / 2;
-  const int xs = lane_stride_complex(m + (m >> 4) + 1, unit), ys = xs;
+  const int mf = Pf / 2, mi = Ni / 2, mx = mf > mi ? mf : mi;
+  const int xs = lane_stride_complex(mx + (mx >> 4) + 1, unit);
+  const int ys = prefetch ? lane_stride_complex(mi + (mi >> 4) + 1, unit) : xs;   // without Z, Y also takes the forward input
   const int zs = prefetch ? lane_stride_complex(mf + (mf >> 4) + 1, unit) : 0;
   if (xstride) *xstride = xs;
   if (ystride) *ystride = ys;
@@ -1028,15 +1039,39 @@ RR_PROG void halfband_program(const HalfbandParams<T> &p, long long work, T *sme
 
   const bool direct = view_range_direct(p.in, x0, x0 + win);
   const InT *src0 = view_ptr<const InT>(p.in, in_off0, x0);
+  auto put = [&](int l, int u, T v) {
+    if (u & 1) {                                         // odd samples below the first centre tap are never read
+      const int idx = ((u + 1) >> 1) + shift;
+      if (idx >= 4) P1[l * p.half + idx] = v;
+    } else P0[l * p.half + (u >> 1)] = v;
+  };
+  // interleaved frames of 4 or 8 channels: one 16-byte load brings four channels of a frame
+  const bool vec = direct && CH >= 4 && sizeof(InT) == 4 && p.in.ch_stride == 1 && p.in.elem_stride == CH &&
+                   !((size_t)src0 & 15);
+  if (vec) {
+    struct alignas(16) V4 { InT a, b, c, d; };
+    const int vbits = chbits - 2;                        // vectors per frame = CH / 4
+    const int nvec = win << vbits, nhalf = (nvec + 1) >> 1;
+    cta_for(nhalf, [&](int w) {                          // two independent 16-byte loads in flight per thread
+      const int w2 = w + nhalf;
+      const V4 va = ldg(reinterpret_cast<const V4 *>(src0) + w);
+      const V4 vb = w2 < nvec ? ldg(reinterpret_cast<const V4 *>(src0) + w2) : va;
+      {
+        const int l = 4 * (w & ((1 << vbits) - 1)), u = w >> vbits;
+        put(l, u, (T)va.a); put(l + 1, u, (T)va.b); put(l + 2, u, (T)va.c); put(l + 3, u, (T)va.d);
+      }
+      if (w2 < nvec) {
+        const int l = 4 * (w2 & ((1 << vbits) - 1)), u = w2 >> vbits;
+        put(l, u, (T)vb.a); put(l + 1, u, (T)vb.b); put(l + 2, u, (T)vb.c); put(l + 3, u, (T)vb.d);
+      }
+    });
+  } else
   cta_for(win << chbits, [&](int w) {                    // channel fastest: coalesced for interleaved input
     const int l = w & (CH - 1), u = w >> chbits;
     const long long off = in_off0 + (long long)l * p.in.ch_stride;
     const T v = direct ? (T)src0[(long long)l * p.in.ch_stride + (long long)u * p.in.elem_stride]
                        : view_read<InT, T>(p.in, off, x0 + u);
-    if (u & 1) {                                         // odd samples below the first centre tap are never read
-      const int idx = ((u + 1) >> 1) + shift;
-      if (idx >= 4) P1[l * p.half + idx] = v;
-    } else P0[l * p.half + (u >> 1)] = v;
+    put(l, u, v);
   });
   const int qbits = p.qbits;                             // log2(tile / 4)
   cta_for(CH << qbits, [&](int w) {
@@ -1044,13 +1079,26 @@ RR_PROG void halfband_program(const HalfbandParams<T> &p, long long work, T *sme
     if (j >= cnt) return;
     const T *e = P0 + l * p.half + j, *o = P1 + l * p.half + j + 4;
     // outputs j..j+3 use P0[j .. j+2c+2] and the centres P1[j+4 .. j+7]
-    T x[2 * c + 3];
+    constexpr int kPer = 16 / (int)sizeof(T);            // samples per 16-byte shared load
+    constexpr int kVecs = (2 * c + 3 + kPer - 1) / kPer;
+    struct alignas(16) Q { T v[kPer]; };
+    T x[kVecs * kPer], ctr[4];
 #pragma unroll
-    for (int i = 0; i < 2 * c + 3; ++i) x[i] = e[i];
+    for (int i = 0; i < kVecs; ++i) {
+      const Q qv = reinterpret_cast<const Q *>(e)[i];
+#pragma unroll
+      for (int k = 0; k < kPer; ++k) x[i * kPer + k] = qv.v[k];
+    }
+#pragma unroll
+    for (int i = 0; i < 4 / kPer; ++i) {
+      const Q qv = reinterpret_cast<const Q *>(o)[i];
+#pragma unroll
+      for (int k = 0; k < kPer; ++k) ctr[i * kPer + k] = qv.v[k];
+    }
     T y[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      T sum = A::mul(o[r], (T)0.5);
+      T sum = A::mul(ctr[r], (T)0.5);
 #pragma unroll
       for (int t = 0; t < c; ++t) sum = A::add(sum, A::mul(A::add(x[r + c - 1 - t], x[r + c + t]), p.coef[t]));
       y[r] = sum;
@@ -1060,8 +1108,13 @@ RR_PROG void halfband_program(const HalfbandParams<T> &p, long long work, T *sme
     if (j + 4 <= cnt && view_range_direct(p.out, cbase, cbase + 4)) {
       OutT *d = view_ptr<OutT>(p.out, off, cbase);
       const int es = p.out.elem_stride;
+      if (es == 1 && !((size_t)d & (4 * sizeof(OutT) - 1))) {          // planar, aligned: one vector store
+        struct alignas(4 * sizeof(OutT)) O4 { OutT a, b, c, d; };
+        *reinterpret_cast<O4 *>(d) = O4{(OutT)y[0], (OutT)y[1], (OutT)y[2], (OutT)y[3]};
+      } else {
 #pragma unroll
-      for (int r = 0; r < 4; ++r) d[r * es] = (OutT)y[r];
+        for (int r = 0; r < 4; ++r) d[r * es] = (OutT)y[r];
+      }
     } else {
 #pragma unroll
       for (int r = 0; r < 4; ++r)

@@ -21,8 +21,12 @@ def run(i, o, nch, nstreams, seconds, engine="float", phase=50, reps=5):
         b.process(d_in.data_ptr(), n, d_out.data_ptr(), st)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
+    b.enable_timing(True)
+    b.process(d_in.data_ptr(), n, d_out.data_ptr(), st)
+    stage_ms = [round(x, 3) for x in b.stage_times()]
+    b.enable_timing(False)
     samples = nout * nch * nstreams
-    print(f"{i}->{o} {engine} nch={nch} streams={nstreams} {seconds}s: {ms:.3f} ms/step, {samples/ms/1e6:.2f} Gsamples/s, launches={b.last_launches()}, gflops={b.flops(n)/ms/1e6:.1f}", flush=True)
+    print(f"{i}->{o} {engine} nch={nch} streams={nstreams} {seconds}s: {ms:.3f} ms/step, {samples/ms/1e6:.2f} Gsamples/s, launches={b.last_launches()}, gflops={b.flops(n)/ms/1e6:.1f}, stage_ms={stage_ms}", flush=True)
     b.close()
 
 if __name__ == "__main__":
