@@ -65,6 +65,7 @@ template <class F> RR_PROG void cta_for(int count, F f)
 }
 RR_PROG void cta_sync() { __syncthreads(); }
 RR_PROG bool cta_leader() { return threadIdx.x == 0; }
+RR_PROG int cta_threads() { return blockDim.x; }
 #else
 template <class F> inline void cta_for(int count, F f)
 {
@@ -72,6 +73,7 @@ template <class F> inline void cta_for(int count, F f)
 }
 inline void cta_sync() {}
 inline bool cta_leader() { return true; }
+inline int cta_threads() { return 256; }
 #endif
 
 // 64-bit / 32-bit split that avoids the slow 64-bit divide for the common case of a small dividend.
@@ -328,14 +330,26 @@ RR_PROG void cfft_pass_item(const CfftSched &s, int lg, int item, int lanes, C2<
 
 // Whole complex FFT for the CTA's lanes: natural-order tiles `src` -> padded buffers `dst`, in two calls so
 // the caller can start refilling `src` as soon as the leaves have consumed it.
+// When a phase has fewer work items than half the CTA, the two lanes of an item go to two threads instead
+// of one (the index / twiddle loads are then duplicated, but twice as many threads have work).
 template <class T, int LPC>
 RR_PROG void cfft_leaves(const CfftSched &s, int lanes, const C2<T> *src, int src_stride, C2<T> *dst, int dst_stride,
                          T sqrthalf, T c16_1, T c16_3)
 {
-  cta_for(s.n16 + s.n8, [&](int task) {
+  const int count = s.n16 + s.n8;
+  if (LPC == 2 && lanes == 2 && 2 * count <= cta_threads()) {
+    cta_for(2 * count, [&](int w) {
+      const int l = w & 1;
+      cfft_leaf_task<T, 1>(s, w >> 1, 1, src + l * src_stride, src_stride, dst + l * dst_stride, dst_stride, sqrthalf,
+                           c16_1, c16_3);
+    });
+    return;
+  }
+  cta_for(count, [&](int task) {
     cfft_leaf_task<T, LPC>(s, task, lanes, src, src_stride, dst, dst_stride, sqrthalf, c16_1, c16_3);
   });
 }
+
 // Two consecutive combining passes (sizes S = 1 << lg and 2S) in one shared-memory round trip. A node of size
 // 2S consists of a first half of size S (whose own pass is still due) and two finished quarters of size S/2.
 // Task (node, k), k < S/4, keeps 8 values in registers: butterfly k of the S-pass on the first half, then
@@ -392,25 +406,43 @@ RR_PROG void cfft_qchild_item(const CfftSched &s, int lg, int item, int lanes, C
 template <class T, int LPC>
 RR_PROG void cfft_passes(const CfftSched &s, int lanes, C2<T> *dst, int dst_stride, const T *pyramid)
 {
+  const bool two = LPC == 2 && lanes == 2;
+  const int nt = cta_threads();
   int lg = 5;
   if ((s.bits - 4) & 1) {                                  // odd number of levels: the smallest one goes alone
-    cta_for(s.level_cnt[lg] << (lg - 2), [&](int item) {
-      cfft_pass_item<T, LPC>(s, lg, item, lanes, dst, dst_stride, pyramid);
-    });
+    const int count = s.level_cnt[lg] << (lg - 2);
+    if (two && 2 * count <= nt)
+      cta_for(2 * count, [&](int w) {
+        cfft_pass_item<T, 1>(s, lg, w >> 1, 1, dst + (w & 1) * dst_stride, dst_stride, pyramid);
+      });
+    else
+      cta_for(count, [&](int item) { cfft_pass_item<T, LPC>(s, lg, item, lanes, dst, dst_stride, pyramid); });
     ++lg;
   }
   for (; lg < s.bits; lg += 2) {
     const int nfused = s.level_cnt[lg + 1] << (lg - 2);    // one task per (2S-node, k)
     const int nplain = s.qchild_cnt[lg] << (lg - 2);       // single butterflies, bundled in threes (same cost)
     const int nbundles = (nplain + 2) / 3;
-    cta_for(nfused + nbundles, [&](int t) {
-      if (t < nfused) cfft_fused_item<T, LPC>(s, lg, t, lanes, dst, dst_stride, pyramid);
-      else {
-        const int first = (t - nfused) * 3;
-        for (int j = first; j < first + 3 && j < nplain; ++j)
-          cfft_qchild_item<T, LPC>(s, lg, j, lanes, dst, dst_stride, pyramid);
-      }
-    });
+    const int count = nfused + nbundles;
+    if (two && 2 * count <= nt)
+      cta_for(2 * count, [&](int w) {
+        const int t = w >> 1;
+        C2<T> *b = dst + (w & 1) * dst_stride;
+        if (t < nfused) cfft_fused_item<T, 1>(s, lg, t, 1, b, dst_stride, pyramid);
+        else {
+          const int first = (t - nfused) * 3;
+          for (int j = first; j < first + 3 && j < nplain; ++j) cfft_qchild_item<T, 1>(s, lg, j, 1, b, dst_stride, pyramid);
+        }
+      });
+    else
+      cta_for(count, [&](int t) {
+        if (t < nfused) cfft_fused_item<T, LPC>(s, lg, t, lanes, dst, dst_stride, pyramid);
+        else {
+          const int first = (t - nfused) * 3;
+          for (int j = first; j < first + 3 && j < nplain; ++j)
+            cfft_qchild_item<T, LPC>(s, lg, j, lanes, dst, dst_stride, pyramid);
+        }
+      });
   }
 }
 
