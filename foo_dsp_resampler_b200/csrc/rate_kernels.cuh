@@ -356,8 +356,14 @@ RR_PROG void cfft_leaves(const CfftSched &s, int lanes, const C2<T> *src, int sr
 // butterflies k and k + S/4 of the 2S-pass, which consume exactly those four results plus two values of each
 // quarter. Same butterflies on the same operands as the level-by-level order (fft.c:265-272), hence the same
 // bits; one barrier and a third of the shared-memory traffic less per pair of levels.
-template <class T, int LPC>
-RR_PROG void cfft_fused_item(const CfftSched &s, int lg, int item, int lanes, C2<T> *buf, int stride, const T *pyramid)
+// Where the very last pass may put its results instead of shared memory: complex element c (= samples 2c,
+// 2c+1 of the block) of lane l goes to out[l][c] when c < half. Used when the block's valid samples form an
+// aligned, contiguous, same-type range, which saves a shared-memory round trip and a barrier per block.
+template <class T> struct PassSink { C2<T> *out[2]; int half; };
+
+template <class T, int LPC, bool SINK>
+RR_PROG void cfft_fused_item(const CfftSched &s, int lg, int item, int lanes, C2<T> *buf, int stride, const T *pyramid,
+                             const PassSink<T> *sink, int lane_base)
 {
   const int qbits = lg - 2, q = 1 << qbits;
   const int node = item >> qbits, k = item & (q - 1);
@@ -376,8 +382,21 @@ RR_PROG void cfft_fused_item(const CfftSched &s, int lg, int item, int lanes, C2
       sr_bfly(a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y, ar, ai, k == 0);          // size S, index k
       sr_bfly(a0.x, a0.y, a2.x, a2.y, c0.x, c0.y, d0.x, d0.y, b0r, b0i, k == 0);        // size 2S, index k
       sr_bfly(a1.x, a1.y, a3.x, a3.y, c1.x, c1.y, d1.x, d1.y, b1r, b1i, false);         // size 2S, index k + S/4
-      b[i0] = a0; b[i1] = a1; b[i2] = a2; b[i3] = a3;
-      b[j0] = c0; b[j1] = c1; b[j2] = d0; b[j3] = d1;
+      if (SINK) {
+        C2<T> *g = sink->out[lane_base + l];
+        const int h = sink->half;
+        if (o < h) g[o] = a0;
+        if (o + q < h) g[o + q] = a1;
+        if (o + 2 * q < h) g[o + 2 * q] = a2;
+        if (o + 3 * q < h) g[o + 3 * q] = a3;
+        if (o + 4 * q < h) g[o + 4 * q] = c0;
+        if (o + 5 * q < h) g[o + 5 * q] = c1;
+        if (o + 6 * q < h) g[o + 6 * q] = d0;
+        if (o + 7 * q < h) g[o + 7 * q] = d1;
+      } else {
+        b[i0] = a0; b[i1] = a1; b[i2] = a2; b[i3] = a3;
+        b[j0] = c0; b[j1] = c1; b[j2] = d0; b[j3] = d1;
+      }
     }
   }
 }
@@ -403,8 +422,10 @@ RR_PROG void cfft_qchild_item(const CfftSched &s, int lg, int item, int lanes, C
   }
 }
 
+// All combining passes. `sink` != nullptr: the final (fused, whole-array) pass stores straight to global memory.
 template <class T, int LPC>
-RR_PROG void cfft_passes(const CfftSched &s, int lanes, C2<T> *dst, int dst_stride, const T *pyramid)
+RR_PROG void cfft_passes(const CfftSched &s, int lanes, C2<T> *dst, int dst_stride, const T *pyramid,
+                         const PassSink<T> *sink = nullptr)
 {
   const bool two = LPC == 2 && lanes == 2;
   const int nt = cta_threads();
@@ -424,11 +445,20 @@ RR_PROG void cfft_passes(const CfftSched &s, int lanes, C2<T> *dst, int dst_stri
     const int nplain = s.qchild_cnt[lg] << (lg - 2);       // single butterflies, bundled in threes (same cost)
     const int nbundles = (nplain + 2) / 3;
     const int count = nfused + nbundles;
+    if (sink && lg + 1 == s.bits) {                        // top pair: every element is produced by a fused task
+      if (two && 2 * count <= nt)
+        cta_for(2 * count, [&](int w) {
+          cfft_fused_item<T, 1, true>(s, lg, w >> 1, 1, dst + (w & 1) * dst_stride, dst_stride, pyramid, sink, w & 1);
+        });
+      else
+        cta_for(count, [&](int t) { cfft_fused_item<T, LPC, true>(s, lg, t, lanes, dst, dst_stride, pyramid, sink, 0); });
+      return;
+    }
     if (two && 2 * count <= nt)
       cta_for(2 * count, [&](int w) {
         const int t = w >> 1;
         C2<T> *b = dst + (w & 1) * dst_stride;
-        if (t < nfused) cfft_fused_item<T, 1>(s, lg, t, 1, b, dst_stride, pyramid);
+        if (t < nfused) cfft_fused_item<T, 1, false>(s, lg, t, 1, b, dst_stride, pyramid, nullptr, 0);
         else {
           const int first = (t - nfused) * 3;
           for (int j = first; j < first + 3 && j < nplain; ++j) cfft_qchild_item<T, 1>(s, lg, j, 1, b, dst_stride, pyramid);
@@ -436,7 +466,7 @@ RR_PROG void cfft_passes(const CfftSched &s, int lanes, C2<T> *dst, int dst_stri
       });
     else
       cta_for(count, [&](int t) {
-        if (t < nfused) cfft_fused_item<T, LPC>(s, lg, t, lanes, dst, dst_stride, pyramid);
+        if (t < nfused) cfft_fused_item<T, LPC, false>(s, lg, t, lanes, dst, dst_stride, pyramid, nullptr, 0);
         else {
           const int first = (t - nfused) * 3;
           for (int j = first; j < first + 3 && j < nplain; ++j)
@@ -757,29 +787,39 @@ RR_PROG void dft_stage_program(const DftParams<T> &p, const DftTables<T> &tab, c
     });
   }
 
+  // ---- output geometry of this block ----
+  int first = 0, stride = 1, count; long long k0;
+  if (p.step == 1) { count = V; k0 = b * (long long)V; }
+  else if (p.step > 1) {
+    const long long v0 = b * (long long)V;
+    const int M = p.step;
+    first = (int)((M - v0 % M) % M); stride = M;
+    k0 = (v0 + M - 1) / M;
+    count = first < V ? (V - first + M - 1) / M : 0;
+  } else { count = p.kept; k0 = b * (long long)p.kept; }
+  const long long c0 = p.out_preload + k0;
+  const bool direct = view_range_direct(p.out, c0, c0 + count);
+  OutT *d0 = view_ptr<OutT>(p.out, out_off0, c0), *d1 = view_ptr<OutT>(p.out, out_off1, c0);
+  const int es = p.out.elem_stride;
+  // planar same-type output of an interior block: whole complex slots (two samples) can be stored at once
+  const bool pairs = direct && stride == 1 && es == 1 && !(count & 1) && sizeof(OutT) == sizeof(T) &&
+                     !(((size_t)d0 | (size_t)d1) & (2 * sizeof(T) - 1));
+  // ... and then the top pass of the inverse transform writes them itself (needs a fused top pair)
+  const bool sink_ok = pairs && p.inv.bits >= 6;
+
   // ---- phases 5-6: inverse complex FFT of Ni/2 points, Y -> X ----
   cfft_leaves<T, LPC>(p.inv, lanes, Y, p.ystride, X, p.xstride, p.sqrthalf, p.c16_1, p.c16_3);
+  if (sink_ok) {
+    PassSink<T> sink;
+    sink.out[0] = reinterpret_cast<C2<T> *>(d0); sink.out[1] = reinterpret_cast<C2<T> *>(d1); sink.half = count >> 1;
+    cfft_passes<T, LPC>(p.inv, lanes, X, p.xstride, tab.pyr_i, &sink);
+    return;
+  }
   cfft_passes<T, LPC>(p.inv, lanes, X, p.xstride, tab.pyr_i);
 
   // ---- phase 7: emit the valid samples ----
   {
-    int first = 0, stride = 1, count; long long k0;
-    if (p.step == 1) { count = V; k0 = b * (long long)V; }
-    else if (p.step > 1) {
-      const long long v0 = b * (long long)V;
-      const int M = p.step;
-      first = (int)((M - v0 % M) % M); stride = M;
-      k0 = (v0 + M - 1) / M;
-      count = first < V ? (V - first + M - 1) / M : 0;
-    } else { count = p.kept; k0 = b * (long long)p.kept; }
     const T *Xr = reinterpret_cast<const T *>(X);
-    const long long c0 = p.out_preload + k0;
-    const bool direct = view_range_direct(p.out, c0, c0 + count);
-    OutT *d0 = view_ptr<OutT>(p.out, out_off0, c0), *d1 = view_ptr<OutT>(p.out, out_off1, c0);
-    const int es = p.out.elem_stride;
-    // planar same-type output of an interior block: store whole complex slots (two samples) per thread
-    const bool pairs = direct && stride == 1 && es == 1 && !(count & 1) && sizeof(OutT) == sizeof(T) &&
-                       !(((size_t)d0 | (size_t)d1) & (2 * sizeof(T) - 1));
     if (pairs) {
       const int half = count >> 1;
       cta_for(lanes * half, [&](int w) {
