@@ -269,6 +269,7 @@ def main():
         import torch.distributed as dist_mod
         dist = dist_mod
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # keep NCCL's banner off stdout: one JSON line only
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
     W = max(args.warmup, 3)            # timing rule: at least 3 warm-up steps
 
