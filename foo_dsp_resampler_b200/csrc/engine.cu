@@ -24,6 +24,7 @@
 
 #include "fft_tables.hpp"
 #include "rate_kernels.cuh"
+#include "rate_kernels_pk.cuh"
 
 #ifndef B200RATE_EMU
 #include <cuda_runtime.h>
@@ -104,6 +105,7 @@ static size_t be_max_smem()
 // kernels
 // ===================================================================================================
 constexpr int kDftThreads = 256;
+constexpr int kPkGroupThreads = 128, kPkMaxGroups = 3;   // lane-pair DFT kernel: threads per group, groups per CTA
 constexpr int kTileThreads = 256;
 constexpr int kPolyTile = 2048;      // outputs per CTA tile
 constexpr int kHalfTile = 2048;
@@ -162,6 +164,37 @@ __global__ void __launch_bounds__(2 * kDftThreads) dft_kernel(const __grid_const
   for (long long w = blockIdx.x; w < nwork; w += gridDim.x, slot ^= 1) {
     const long long next = w + gridDim.x < nwork ? w + gridDim.x : -1;
     dft_stage_program<T, InT, OutT, LPC, DftCacheDepth<T>::value>(p, tab, cc, items, slot, next, data);
+  }
+}
+// Lane-pair DFT stage (rate_kernels_pk.cuh): a CTA is `groups` independent groups of `gthreads` threads, each
+// a persistent worker with its own buffers (two forward buffers, ping-pong with the LDGSTS prefetch of the
+// next item, and one inverse buffer) behind the shared twiddle tables.
+template <int MODE>
+__global__ void __launch_bounds__(kPkGroupThreads * kPkMaxGroups) dftp_kernel(const __grid_constant__ DftPkParams pp, long long nwork)
+{
+  float *tab = reinterpret_cast<float *>(rr_smem_raw);
+  const int nf = pp.fwd.pyr_len, ni = pp.inv.pyr_len;
+  for (int i = threadIdx.x; i < nf; i += blockDim.x) tab[i] = pp.base.pyr_f[i];
+  for (int i = threadIdx.x; i < ni; i += blockDim.x) tab[nf + i] = pp.base.pyr_i[i];
+  const int tab_bytes = ((nf + ni) * 4 + 15) & ~15;
+  const int gi = threadIdx.x / pp.gthreads;
+  const Grp g{(int)threadIdx.x - gi * pp.gthreads, pp.gthreads, 1 + gi};
+  CPk *F0 = reinterpret_cast<CPk *>(rr_smem_raw + tab_bytes) + (size_t)gi * (2 * pp.fslots + pp.bslots);
+  CPk *F1 = F0 + pp.fslots, *B = F1 + pp.fslots;
+  PkSpecCache cc;
+  if (MODE != PK_SPEC_GEN) pk_load_spec_cache<MODE>(pp, g, cc);
+  __shared__ PkItem items[kPkMaxGroups][2];
+  __syncthreads();
+  long long w = (long long)blockIdx.x * pp.groups + gi;
+  const long long stride = (long long)gridDim.x * pp.groups;
+  if (w < nwork) {
+    if (g.tid == 0) items[gi][0] = pk_item(pp, w);
+    grp_sync(g);
+    pk_stage_tile(pp, g, items[gi][0], F0);
+  }
+  for (int n = 0; w < nwork; w += stride, ++n) {
+    const long long next = w + stride < nwork ? w + stride : -1;
+    dftp_program<MODE, true>(pp, g, tab, tab + nf, cc, items[gi], n & 1, next, (n & 1) ? F1 : F0, (n & 1) ? F0 : F1, B);
   }
 }
 template <class T, class InT, class OutT>
@@ -258,6 +291,59 @@ static int launch_persistent(Kernel kernel, const Params &p, long long nwork, in
   return RR_OK;
 }
 #endif  // !B200RATE_EMU
+
+// Shared memory of the lane-pair DFT kernel: twiddle pyramids, then per group two forward buffers and one
+// inverse buffer of 16-byte slots.
+static size_t dftp_smem_bytes(const DftPkParams &pp)
+{
+  const size_t tab = ((static_cast<size_t>(pp.fwd.pyr_len) + pp.inv.pyr_len) * 4 + 15) & ~static_cast<size_t>(15);
+  return tab + static_cast<size_t>(pp.groups) * (2 * pp.fslots + pp.bslots) * sizeof(CPk);
+}
+
+static int launch_dftp(const DftPkParams &pp, long long nwork, stream_t s)
+{
+  if (nwork <= 0) return RR_OK;
+#ifdef B200RATE_EMU
+  (void)s;
+  if (getenv("B200RATE_TRACE")) fprintf(stderr, "dftp mode %d nwork %lld Pf %d Ni %d phases f%d i%d\n", pp.spec_mode, nwork, pp.base.Pf, pp.base.Ni, pp.fwd.nphases, pp.inv.nphases);
+  std::vector<CPk> mem(static_cast<size_t>(2 * pp.fslots + pp.bslots) + 1);
+  CPk *F0 = mem.data(), *F1 = F0 + pp.fslots, *B = F1 + pp.fslots;
+  const Grp g{0, 1, 0};
+  const PkSpecCache cc{};
+  for (long long w = 0; w < nwork; ++w) {
+    PkItem items[2];
+    items[0] = pk_item(pp, w);
+    pk_stage_tile(pp, g, items[0], F0);
+    if (pp.spec_mode == PK_SPEC_UP2) dftp_program<PK_SPEC_UP2, false>(pp, g, pp.base.pyr_f, pp.base.pyr_i, cc, items, 0, -1, F0, F1, B);
+    else if (pp.spec_mode == PK_SPEC_SAME) dftp_program<PK_SPEC_SAME, false>(pp, g, pp.base.pyr_f, pp.base.pyr_i, cc, items, 0, -1, F0, F1, B);
+    else dftp_program<PK_SPEC_GEN, false>(pp, g, pp.base.pyr_f, pp.base.pyr_i, cc, items, 0, -1, F0, F1, B);
+  }
+  return RR_OK;
+#else
+  const size_t smem = dftp_smem_bytes(pp);
+  const int threads = pp.groups * pp.gthreads;
+  auto go = [&](auto kernel) -> int {
+    const void *key = reinterpret_cast<const void *>(kernel);
+    auto &cache = launch_cache();
+    auto it = cache.find(std::make_pair(key, smem));
+    if (it == cache.end()) {
+      CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      int occ = 0;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
+      if (occ < 1) { set_last_error("lane-pair DFT kernel does not fit on an SM"); return RR_INTERNAL; }
+      it = cache.emplace(std::make_pair(key, smem), LaunchInfo{occ, smem}).first;
+    } else CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    const long long resident = static_cast<long long>(it->second.blocks_per_sm) * be_num_sms();
+    const long long ctas = (nwork + pp.groups - 1) / pp.groups;
+    kernel<<<static_cast<unsigned>(std::min(ctas, resident)), threads, smem, s>>>(pp, nwork);
+    CUDA_TRY(cudaGetLastError());
+    return RR_OK;
+  };
+  if (pp.spec_mode == PK_SPEC_UP2) return go(dftp_kernel<PK_SPEC_UP2>);
+  if (pp.spec_mode == PK_SPEC_SAME) return go(dftp_kernel<PK_SPEC_SAME>);
+  return go(dftp_kernel<PK_SPEC_GEN>);
+#endif
+}
 
 // Typed dispatch. For the fp32 engine every buffer is float; the fp64 engine reads float at the caller
 // boundary and double in between.
@@ -565,6 +651,16 @@ template <class T> class Engine {
       DftParams<T> p = dft_params_[i];
       p.in = in; p.out = out; p.out_preload = out_preload;
       p.block0 = w0; p.nblocks = static_cast<int>(wn); p.nlanes = nlanes;
+      if constexpr (std::is_same<T, float>::value) {
+        if (use_pair_kernel_ && !(nlanes & 1) && !(in.nch & 1) && !(out.nch & 1)) {
+          DftPkParams pp;
+          if (make_pair_params(i, p, pp)) {
+            last_dft_kernel_ = 1;
+            return launch_dftp(pp, wn * (nlanes / 2), s);
+          }
+        }
+      }
+      last_dft_kernel_ = 0;
       const int lpc = dft_lanes_per_cta(g, nlanes);
       // prefetch the next tile with LDGSTS when the input needs no conversion and the staging buffer still
       // leaves room for two CTAs per SM
@@ -695,7 +791,30 @@ template <class T> class Engine {
   HalfbandParams<T> half_params_[RR_MAX_STAGES];
   T *dft_coef_dev_[2] = {nullptr, nullptr};
 
-  struct DevSched { CfftSched fwd, inv; const T *pyramid; };
+  struct DevSched { CfftSched fwd, inv; const T *pyramid; PkSched pk_fwd, pk_inv; };
+  bool use_pair_kernel_ = getenv("B200RATE_NO_PAIR_KERNEL") == nullptr;   // debugging switch: generic kernel only
+  int last_dft_kernel_ = 0;
+
+  // Parameters of the lane-pair kernel for DFT stage i, or false when it does not apply (transform too
+  // large for its shared-memory layout).
+  bool make_pair_params(int i, const DftParams<float> &p, DftPkParams &pp)
+  {
+    const StageGeom &g = geom[i];
+    const int fb = ilog2(g.Pf) - 1, ib = ilog2(g.Ni) - 1;
+    if (fb < 5 || ib < 5 || fb > 13 || ib > 13) return false;
+    auto sf = sched_.find(fb), si = sched_.find(ib);
+    if (sf == sched_.end() || si == sched_.end()) return false;
+    pp.base = p;
+    pp.fwd = sf->second.pk_fwd; pp.inv = si->second.pk_inv;
+    pp.fslots = pk_buf_slots(g.Pf >> 1); pp.bslots = pk_buf_slots(g.Ni >> 1);
+    pp.gthreads = kPkGroupThreads;
+    if (g.in_mode == DFT_IN_FREQ_UP && g.L == 2 && g.step == 1) pp.spec_mode = PK_SPEC_UP2;
+    else if (g.Ni == g.Pf && g.step >= 1 && g.in_mode != DFT_IN_FREQ_UP) pp.spec_mode = PK_SPEC_SAME;
+    else pp.spec_mode = PK_SPEC_GEN;
+    for (pp.groups = kPkMaxGroups; pp.groups >= 1; --pp.groups)
+      if (dftp_smem_bytes(pp) + 1024 <= max_smem_) break;
+    return pp.groups >= 1;
+  }
   std::map<int, DevSched> sched_;          // by complex bits
   std::map<int, const T *> tcos_;          // by real bits
 
@@ -739,6 +858,26 @@ template <class T> class Engine {
         for (int l = 0; l < 17; ++l) {
           c.level_begin[l] = h.level_begin[l]; c.level_cnt[l] = h.level_cnt[l]; c.pyr_off[l] = h.pyr_off[l];
           c.qchild_begin[l] = h.qchild_begin[l]; c.qchild_cnt[l] = h.qchild_cnt[l];
+        }
+      }
+      if (std::is_same<T, float>::value && bits <= 13) {
+        const PkHostSched ph = build_pk_sched(h);
+        const uint16_t *pl16 = nullptr, *pl8 = nullptr, *perm[2] = {nullptr, nullptr};
+        if ((rc = upload(ph.leaf16_off, &pl16)) || (rc = upload(ph.leaf8_off, &pl8)) || (rc = upload(ph.perm[0], &perm[0])) ||
+            (rc = upload(ph.perm[1], &perm[1])))
+          return rc;
+        for (int inv = 0; inv < 2; ++inv) {
+          PkSched &k = inv ? d.pk_inv : d.pk_fwd;
+          k.bits = bits;
+          k.n16 = static_cast<int>(ph.leaf16_off.size()); k.n8p = ph.n8p;
+          k.leaf16_off = pl16; k.leaf8_off = pl8; k.perm = perm[inv]; k.node_off = nodes;
+          k.pyr_len = h.pyr_len;
+          for (int l = 0; l < 17; ++l) {
+            k.level_begin[l] = h.level_begin[l]; k.level_cnt[l] = h.level_cnt[l]; k.pyr_off[l] = h.pyr_off[l];
+            k.qchild_begin[l] = h.qchild_begin[l]; k.qchild_cnt[l] = h.qchild_cnt[l];
+          }
+          k.nphases = ph.nphases;
+          for (int q = 0; q < 8; ++q) { k.phase_lg[q] = ph.phase_lg[q]; k.phase_depth[q] = ph.phase_depth[q]; }
         }
       }
       it = sched_.emplace(bits, d).first;

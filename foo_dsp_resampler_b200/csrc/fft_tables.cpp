@@ -1,6 +1,7 @@
 // fft_tables.cpp -- see fft_tables.hpp.
 #include "fft_tables.hpp"
 
+#include <algorithm>
 #include <cassert>
 #include <cmath>
 
@@ -75,6 +76,65 @@ CfftHostSched build_cfft_sched(int bits)
       for (int e = 0; e < 8; ++e)
         s.gather8[inv][static_cast<size_t>(e) * n8 + t] = static_cast<uint16_t>(padded_slot(natural[s.leaf8_off[t] + e]));
   }
+  return s;
+}
+
+int pk_slot(int p) { return p + (p >> 4) + (p >> 8); }
+
+namespace {
+// Order `offs` so that every aligned run of eight entries falls into eight different 16-byte bank groups
+// (as far as the multiset allows): repeatedly take one entry from each of the fullest groups.
+std::vector<uint16_t> spread_over_bank_groups(const std::vector<uint16_t> &offs)
+{
+  std::vector<std::vector<uint16_t>> bucket(8);
+  for (uint16_t o : offs) bucket[static_cast<size_t>(pk_slot(o) & 7)].push_back(o);
+  std::vector<uint16_t> out;
+  while (out.size() < offs.size()) {
+    int order[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+    for (int a = 0; a < 8; ++a)                    // fullest buckets first (stable selection sort, 8 entries)
+      for (int b = a + 1; b < 8; ++b)
+        if (bucket[static_cast<size_t>(order[b])].size() > bucket[static_cast<size_t>(order[a])].size()) std::swap(order[a], order[b]);
+    for (int a = 0; a < 8; ++a) {
+      std::vector<uint16_t> &bk = bucket[static_cast<size_t>(order[a])];
+      if (bk.empty()) continue;
+      out.push_back(bk.back());
+      bk.pop_back();
+    }
+  }
+  return out;
+}
+}  // namespace
+
+PkHostSched build_pk_sched(const CfftHostSched &h)
+{
+  PkHostSched s;
+  const int m = 1 << h.bits;
+  s.leaf16_off = spread_over_bank_groups(h.leaf16_off);
+  const std::vector<uint16_t> l8 = spread_over_bank_groups(h.leaf8_off);
+  s.n8p = static_cast<int>((l8.size() + 1) / 2);
+  s.leaf8_off.assign(static_cast<size_t>(2 * s.n8p), 0xffff);
+  for (size_t k = 0; k < l8.size(); ++k) {         // task t: entries t and t + n8p of the spread list
+    const size_t t = k < static_cast<size_t>(s.n8p) ? k : k - static_cast<size_t>(s.n8p);
+    s.leaf8_off[2 * t + (k < static_cast<size_t>(s.n8p) ? 0 : 1)] = l8[k];
+  }
+  for (int inv = 0; inv < 2; ++inv) {
+    s.perm[inv].assign(static_cast<size_t>(m), 0);
+    for (int p = 0; p < m; ++p) {
+      const int natural = (-split_radix_index(p, m, inv)) & (m - 1);
+      s.perm[inv][static_cast<size_t>(natural)] = static_cast<uint16_t>(pk_slot(p));
+    }
+  }
+  // levels 5 .. bits in phases: three-level phases first while the transform is large enough to keep a
+  // 128-thread group busy with 16-value tasks, two-level phases otherwise; a single level only if it must
+  int lg = 5, left = h.bits - 4;
+  auto push = [&](int depth) { s.phase_lg[s.nphases] = lg; s.phase_depth[s.nphases] = depth; ++s.nphases; lg += depth; left -= depth; };
+  if (h.bits >= 11) {
+    while (left >= 3 && left != 4) push(3);
+  } else if (left & 1) {
+    if (left >= 3) push(3); else push(1);
+  }
+  while (left >= 2) push(2);
+  if (left == 1) push(1);
   return s;
 }
 

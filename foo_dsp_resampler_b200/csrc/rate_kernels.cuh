@@ -47,11 +47,16 @@ template <> struct Arith<float> {
   static RR_HD float add(float a, float b) { return a + b; }
   static RR_HD float sub(float a, float b) { return a - b; }
 #endif
+  // add / sub with a product as operand: only the packed type needs a different spelling (rate_kernels_pk.cuh)
+  static RR_HD float addp(float a, float b) { return add(a, b); }
+  static RR_HD float subp(float a, float b) { return sub(a, b); }
 };
 template <> struct Arith<double> {
   static RR_HD double mul(double a, double b) { return a * b; }
   static RR_HD double add(double a, double b) { return a + b; }
   static RR_HD double sub(double a, double b) { return a - b; }
+  static RR_HD double addp(double a, double b) { return a + b; }
+  static RR_HD double subp(double a, double b) { return a - b; }
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -209,10 +214,10 @@ RR_HD void sr_bfly(T &a0r, T &a0i, T &a1r, T &a1i, T &a2r, T &a2i, T &a3r, T &a3
   T t1, t2, t5, t6;
   if (zero) { t1 = a2r; t2 = a2i; t5 = a3r; t6 = a3i; }           // TRANSFORM_ZERO, fft.c:228-235
   else {                                                           // TRANSFORM, fft.c:222-226
-    t1 = A::add(A::mul(a2r, wre), A::mul(a2i, wim));
-    t2 = A::sub(A::mul(a2i, wre), A::mul(a2r, wim));
-    t5 = A::sub(A::mul(a3r, wre), A::mul(a3i, wim));
-    t6 = A::add(A::mul(a3r, wim), A::mul(a3i, wre));
+    t1 = A::addp(A::mul(a2r, wre), A::mul(a2i, wim));
+    t2 = A::subp(A::mul(a2i, wre), A::mul(a2r, wim));
+    t5 = A::subp(A::mul(a3r, wre), A::mul(a3i, wim));
+    t6 = A::addp(A::mul(a3r, wim), A::mul(a3i, wre));
   }
   const T t3 = A::sub(t5, t1); t5 = A::add(t5, t1);                // BUTTERFLIES, fft.c:200-207
   a2r = A::sub(a0r, t5); a0r = A::add(a0r, t5);

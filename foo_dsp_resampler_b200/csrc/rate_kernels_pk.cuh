@@ -1,0 +1,729 @@
+// rate_kernels_pk.cuh -- the overlap-save DFT stage for fp32 LANE PAIRS (two channels of one stream), the
+// dominant kernel of the fp32 engine on B200.
+//
+// Same reference behaviour as dft_stage_program in rate_kernels.cuh (dft_filter.h:60-190 over
+// fft-float/{fft.c,rdft.c}); what changes is how the work is laid on the SM:
+//
+//  * The two lanes of a pair travel together as one 64-bit register pair `Pk` and every arithmetic
+//    instruction is a packed sm_100 FMUL2 / FADD2 (PTX mul/add.rn.f32x2): one issue slot for both channels,
+//    which doubles the un-fused fp32 rate (profiles/fp_peaks.json: 36 -> 66 TFLOP/s). Each half is an IEEE
+//    round-to-nearest fp32 operation, so the bits are those of the scalar expression DAG.
+//    ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even though both carry .rn, so every add whose
+//    operand is a product is written as fma(x, one, y) with `one` read from constant memory (not foldable):
+//    one rounding of x + y, no contraction possible. The GPU parity tests (bit equality) guard this.
+//  * A complex value of the pair is one 16-byte shared-memory slot {re.a, re.b, im.a, im.b}: one LDS.128 /
+//    STS.128 per element for both lanes; two interleaved stereo frames are exactly one slot, so the input
+//    tile is brought in by 16-byte (or 8-byte) LDGSTS copies.
+//  * The out-of-place permutation of ff_fft_permute_c (fft.c:169-177) is folded into the WRITES that fill an
+//    FFT buffer (input tile copy, spectrum stage), so the leaves work in place on 16 contiguous slots.
+//  * Combining passes are fused two or three levels deep (8 or 16 values per task in registers) and
+//    instantiated per size, so every shared-memory address of a task is base + immediate.
+//  * Real-FFT post-processing, spectrum assembly, filter multiply and inverse pre-processing are one phase.
+//  * A CTA holds several independent GROUPS of 128 threads (named barriers), each with its own work item
+//    and buffers; they share the twiddle tables and hide each other's barrier stalls.
+//
+// Like rate_kernels.cuh this text also compiles as plain C++ (tests/emu): a group is then one serial
+// thread. That build is test infrastructure only.
+#pragma once
+
+#include "rate_kernels.cuh"
+
+namespace b200rate {
+
+// ---------------------------------------------------------------------------------------------------
+// Packed pair arithmetic
+// ---------------------------------------------------------------------------------------------------
+struct alignas(8) Pk { float a, b; };                     // lane 0, lane 1
+
+#if defined(__CUDACC__)
+__constant__ float rr_pk_ones[2] = {1.0f, -1.0f};          // opaque to ptxas (see header)
+#endif
+
+RR_HD Pk pk_make(float a, float b) { Pk r; r.a = a; r.b = b; return r; }
+RR_HD Pk pk_bcast(float w) { return pk_make(w, w); }
+RR_HD Pk pk_neg(Pk x) { return pk_make(-x.a, -x.b); }
+
+template <> struct Arith<Pk> {
+#if defined(__CUDA_ARCH__)
+#define RR_PK_BIN(NAME, OP)                                                                                        \
+  static __device__ __forceinline__ Pk NAME(Pk x, Pk y)                                                            \
+  {                                                                                                                \
+    Pk r;                                                                                                          \
+    asm("{\n .reg .b64 pa, pb, pc;\n mov.b64 pa, {%2, %3};\n mov.b64 pb, {%4, %5};\n " OP                         \
+        ".rn.f32x2 pc, pa, pb;\n mov.b64 {%0, %1}, pc;\n}"                                                         \
+        : "=f"(r.a), "=f"(r.b)                                                                                     \
+        : "f"(x.a), "f"(x.b), "f"(y.a), "f"(y.b));                                                                 \
+    return r;                                                                                                      \
+  }
+  RR_PK_BIN(mul, "mul")
+  RR_PK_BIN(add, "add")
+  RR_PK_BIN(sub, "sub")
+#undef RR_PK_BIN
+  // x + y / x - y where an operand is a product: fma(x, 1, y) / fma(y, -1, x), see header
+  static __device__ __forceinline__ Pk addp(Pk x, Pk y)
+  {
+    Pk r;
+    const float one = rr_pk_ones[0];
+    asm("{\n .reg .b64 pa, pb, pc, po;\n mov.b64 pa, {%2, %3};\n mov.b64 pb, {%4, %5};\n mov.b64 po, {%6, %6};\n"
+        " fma.rn.f32x2 pc, pa, po, pb;\n mov.b64 {%0, %1}, pc;\n}"
+        : "=f"(r.a), "=f"(r.b)
+        : "f"(x.a), "f"(x.b), "f"(y.a), "f"(y.b), "f"(one));
+    return r;
+  }
+  static __device__ __forceinline__ Pk subp(Pk x, Pk y)
+  {
+    Pk r;
+    const float mone = rr_pk_ones[1];
+    asm("{\n .reg .b64 pa, pb, pc, po;\n mov.b64 pa, {%2, %3};\n mov.b64 pb, {%4, %5};\n mov.b64 po, {%6, %6};\n"
+        " fma.rn.f32x2 pc, pb, po, pa;\n mov.b64 {%0, %1}, pc;\n}"
+        : "=f"(r.a), "=f"(r.b)
+        : "f"(x.a), "f"(x.b), "f"(y.a), "f"(y.b), "f"(mone));
+    return r;
+  }
+#else
+  static RR_HD Pk mul(Pk x, Pk y) { return pk_make(x.a * y.a, x.b * y.b); }   // host build: -ffp-contract=off
+  static RR_HD Pk add(Pk x, Pk y) { return pk_make(x.a + y.a, x.b + y.b); }
+  static RR_HD Pk sub(Pk x, Pk y) { return pk_make(x.a - y.a, x.b - y.b); }
+  static RR_HD Pk addp(Pk x, Pk y) { return add(x, y); }
+  static RR_HD Pk subp(Pk x, Pk y) { return sub(x, y); }
+#endif
+};
+
+typedef C2<Pk> CPk;                                        // one 16-byte slot: {re.a, re.b, im.a, im.b}
+
+// ---------------------------------------------------------------------------------------------------
+// Thread groups
+// ---------------------------------------------------------------------------------------------------
+struct Grp { int tid, size, bar; };                        // index inside the group, threads, named barrier id
+
+#if defined(__CUDACC__)
+RR_PROG void grp_sync(const Grp &g) { asm volatile("bar.sync %0, %1;" ::"r"(g.bar), "r"(g.size) : "memory"); }
+#else
+inline void grp_sync(const Grp &) {}
+#endif
+template <class F> RR_PROG void grp_for(const Grp &g, int count, F f)
+{
+  for (int i = g.tid; i < count; i += g.size) f(i);
+  grp_sync(g);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Shared-memory slot of FFT position p. Consecutive threads touch (a) consecutive positions, (b) positions
+// 16 apart (leaves) and (c) positions whose high bits differ (writes through the split-radix permutation);
+// the three terms keep all of these at most two-way conflicting for 16-byte accesses. The map is additive,
+// so slot(o + x) = slot(o) + slot(x) whenever o is a multiple of a power of two > x (node offsets).
+// ---------------------------------------------------------------------------------------------------
+RR_HD int pslot(int p) { return p + (p >> 4) + (p >> 8); }
+RR_HD int pk_buf_slots(int m) { return ((pslot(m - 1) + 1 + 7) / 8) * 8; }
+
+// Device-side schedule of one complex FFT of M = 1 << bits points.
+struct PkSched {
+  int bits;
+  int n16, n8p;                  // leaf tasks: size-16 leaves, pairs of size-8 leaves
+  const uint16_t *leaf16_off;    // [n16] offsets, ordered so that eight consecutive tasks do not share a bank group
+  const uint16_t *leaf8_off;     // [2 * n8p], 0xffff = none
+  const uint16_t *perm;          // [M] natural index -> slot of its permuted position
+  const uint16_t *node_off;      // node offsets of sizes 32 .. M, then the quarter-child lists (CfftHostSched)
+  int level_begin[17], level_cnt[17], qchild_begin[17], qchild_cnt[17], pyr_off[17];
+  int pyr_len;
+  int nphases, phase_lg[8], phase_depth[8];
+};
+
+// Where the top pass may put the block's valid samples instead of shared memory.
+struct PkSink {
+  float *d0, *d1;                // planar: lane pointers at the block's first output; interleaved: d0 only
+  int es;                        // interleaved: elements between consecutive samples of a lane; 0 = planar
+  int half;                      // complex elements to store (valid samples / 2)
+};
+
+RR_PROG void pk_sink_store(const PkSink &k, int c, const CPk &v)
+{
+  if (c >= k.half) return;
+  if (k.es == 0) {                                       // planar: (sample 2c, 2c+1) of each lane
+    reinterpret_cast<C2<float> *>(k.d0)[c] = C2<float>{v.x.a, v.y.a};
+    reinterpret_cast<C2<float> *>(k.d1)[c] = C2<float>{v.x.b, v.y.b};
+  } else {                                               // adjacent interleaved lanes: one pair per frame
+    float *f = k.d0 + (long long)(2 * c) * k.es;
+    *reinterpret_cast<Pk *>(f) = v.x;
+    *reinterpret_cast<Pk *>(f + k.es) = v.y;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Leaves (fft16 / fft8, fft.c:288-318), in place
+// ---------------------------------------------------------------------------------------------------
+// swz: the slots hold {a.re, a.im, b.re, b.im} (planar input copied 8 bytes per lane) instead of the
+// working layout; the leaf re-pairs them while the values are in registers.
+RR_PROG void pk_leaves(const PkSched &s, const Grp &g, CPk *buf, bool swz, float sqrthalf, float c16_1, float c16_3)
+{
+  const Pk sh = pk_bcast(sqrthalf), c1 = pk_bcast(c16_1), c3 = pk_bcast(c16_3);
+  grp_for(g, s.n16 + s.n8p, [&](int task) {
+    if (task < s.n16) {
+      CPk *b = buf + pslot(ldg(s.leaf16_off + task));    // multiple of 16: the 16 slots are contiguous
+      Pk re[16], im[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const CPk v = b[e];
+        re[e] = v.x; im[e] = v.y;
+        if (swz) { const float t = re[e].b; re[e].b = im[e].a; im[e].a = t; }
+      }
+      leaf_fft16<Pk>(re, im, sh, c1, c3);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) b[e] = CPk{re[e], im[e]};
+    } else {
+      for (int h = 0; h < 2; ++h) {
+        const int off = ldg(s.leaf8_off + 2 * (task - s.n16) + h);
+        if (off == 0xffff) continue;
+        CPk *b = buf + pslot(off);                        // multiple of 8: never straddles a pad slot
+        Pk re[8], im[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const CPk v = b[e];
+          re[e] = v.x; im[e] = v.y;
+          if (swz) { const float t = re[e].b; re[e].b = im[e].a; im[e].a = t; }
+        }
+        leaf_fft8<Pk>(re, im, sh);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) b[e] = CPk{re[e], im[e]};
+      }
+    }
+  });
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Combining passes (pass(), fft.c:237-256), fused 1, 2 or 3 levels deep. S = 1 << LG is the smallest size of
+// the task, q = S/4; a task (node, k < q) owns the values at o + k + j*q. slot() is additive over the node
+// offset, so with LG a template parameter every address is `base + constant`.
+// ---------------------------------------------------------------------------------------------------
+template <int LG> struct PkGeo {
+  static constexpr int q = 1 << (LG - 2);
+  static RR_HD constexpr int rel(int j) { return j * q + ((j * q) >> 4) + ((j * q) >> 8); }   // pslot(j*q)
+};
+
+RR_PROG void pk_bfly(CPk &a0, CPk &a1, CPk &a2, CPk &a3, float wre, float wim, bool zero)
+{
+  sr_bfly<Pk>(a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y, pk_bcast(wre), pk_bcast(wim), zero);
+}
+
+// one butterfly of size S on node list entry `node`
+template <int LG> RR_PROG void pk_p1_item(const PkSched &s, int list_begin, int item, CPk *buf, const float *pyr)
+{
+  typedef PkGeo<LG> G;
+  const int node = item >> (LG - 2), k = item & (G::q - 1);
+  CPk *b = buf + pslot(ldg(s.node_off + list_begin + node) + k);
+  const float *tw = pyr + s.pyr_off[LG];
+  CPk a0 = b[0], a1 = b[G::rel(1)], a2 = b[G::rel(2)], a3 = b[G::rel(3)];
+  pk_bfly(a0, a1, a2, a3, tw[k], tw[G::q - k], k == 0);
+  b[0] = a0; b[G::rel(1)] = a1; b[G::rel(2)] = a2; b[G::rel(3)] = a3;
+}
+
+// sizes S and 2S on a node of size 2S (8 values): butterfly k of the S-pass on the first half, then
+// butterflies k and k + S/4 of the 2S-pass (the two quarters of size S/2 are finished).
+template <int LG, bool SINK>
+RR_PROG void pk_l2_item(const PkSched &s, int list_begin, int item, CPk *buf, const float *pyr, const PkSink *sink)
+{
+  typedef PkGeo<LG> G;
+  constexpr int q = G::q;
+  const int node = item >> (LG - 2), k = item & (q - 1);
+  const int o = ldg(s.node_off + list_begin + node) + k;
+  CPk *b = buf + pslot(o);
+  const float *twa = pyr + s.pyr_off[LG], *twb = pyr + s.pyr_off[LG + 1];
+  CPk e[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) e[j] = b[G::rel(j)];
+  pk_bfly(e[0], e[1], e[2], e[3], twa[k], twa[q - k], k == 0);
+  pk_bfly(e[0], e[2], e[4], e[6], twb[k], twb[2 * q - k], k == 0);
+  pk_bfly(e[1], e[3], e[5], e[7], twb[k + q], twb[q - k], false);
+  if (SINK) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pk_sink_store(*sink, o + j * q, e[j]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b[G::rel(j)] = e[j];
+  }
+}
+
+// sizes S, 2S and 4S on a node of size 4S (16 values): the S-pass on the first quarter-of-the-half and on
+// both quarter children (size S), the 2S-pass on the first half, then four butterflies of the 4S-pass.
+template <int LG, bool SINK>
+RR_PROG void pk_h3_item(const PkSched &s, int list_begin, int item, CPk *buf, const float *pyr, const PkSink *sink)
+{
+  typedef PkGeo<LG> G;
+  constexpr int q = G::q;
+  const int node = item >> (LG - 2), k = item & (q - 1);
+  const int o = ldg(s.node_off + list_begin + node) + k;
+  CPk *b = buf + pslot(o);
+  const float *twa = pyr + s.pyr_off[LG], *twb = pyr + s.pyr_off[LG + 1], *twc = pyr + s.pyr_off[LG + 2];
+  CPk e[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) e[j] = b[G::rel(j)];
+  {
+    const float wr = twa[k], wi = twa[q - k];
+    pk_bfly(e[0], e[1], e[2], e[3], wr, wi, k == 0);
+    pk_bfly(e[8], e[9], e[10], e[11], wr, wi, k == 0);
+    pk_bfly(e[12], e[13], e[14], e[15], wr, wi, k == 0);
+  }
+  pk_bfly(e[0], e[2], e[4], e[6], twb[k], twb[2 * q - k], k == 0);
+  pk_bfly(e[1], e[3], e[5], e[7], twb[k + q], twb[q - k], false);
+#pragma unroll
+  for (int m = 0; m < 4; ++m) pk_bfly(e[m], e[m + 4], e[m + 8], e[m + 12], twc[k + m * q], twc[(4 - m) * q - k], m == 0 && k == 0);
+  if (SINK) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) pk_sink_store(*sink, o + j * q, e[j]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) b[G::rel(j)] = e[j];
+  }
+}
+
+// One phase: DEPTH levels starting at size 1 << LG. Light tasks are bundled in threes so that every task of
+// a phase costs about the same (3 single butterflies = one 2-level task, 3 of those = one 3-level task).
+template <int LG, int DEPTH, bool SINK>
+RR_PROG void pk_phase(const PkSched &s, const Grp &g, CPk *buf, const float *pyr, const PkSink *sink)
+{
+  constexpr int qb = LG - 2;
+  if (DEPTH == 1) {
+    grp_for(g, s.level_cnt[LG] << qb, [&](int t) { pk_p1_item<LG>(s, s.level_begin[LG], t, buf, pyr); });
+  } else if (DEPTH == 2) {
+    const int nf = s.level_cnt[LG + 1] << qb, np = s.qchild_cnt[LG] << qb, nb = (np + 2) / 3;
+    grp_for(g, nf + nb, [&](int t) {
+      if (t < nf) pk_l2_item<LG, SINK>(s, s.level_begin[LG + 1], t, buf, pyr, sink);
+      else
+        for (int j = t - nf; j < np; j += nb) pk_p1_item<LG>(s, s.qchild_begin[LG], j, buf, pyr);
+    });
+  } else {
+    const int nh = s.level_cnt[LG + 2] << qb, nl = s.qchild_cnt[LG + 1] << qb, nb = (nl + 2) / 3;
+    grp_for(g, nh + nb, [&](int t) {
+      if (t < nh) pk_h3_item<LG, SINK>(s, s.level_begin[LG + 2], t, buf, pyr, sink);
+      else
+        for (int j = t - nh; j < nl; j += nb) pk_l2_item<LG, false>(s, s.qchild_begin[LG + 1], j, buf, pyr, nullptr);
+    });
+  }
+}
+
+// Only the (size, depth) combinations build_pk_sched() (fft_tables.cpp) produces are instantiated; SINK only
+// for those that can be the top phase of a transform.
+template <bool SINK>
+RR_PROG void pk_phase_dispatch(const PkSched &s, const Grp &g, int lg, int depth, CPk *buf, const float *pyr, const PkSink *sink)
+{
+#define RR_PK_CASE(LG, D) case LG * 4 + D: pk_phase<LG, D, SINK>(s, g, buf, pyr, sink); break;
+  switch (lg * 4 + depth) {
+    RR_PK_CASE(5, 2) RR_PK_CASE(5, 3) RR_PK_CASE(7, 2) RR_PK_CASE(8, 2) RR_PK_CASE(9, 2) RR_PK_CASE(10, 2) RR_PK_CASE(11, 2)
+    RR_PK_CASE(11, 3)
+    default:
+      if (!SINK) switch (lg * 4 + depth) {
+        RR_PK_CASE(5, 1) RR_PK_CASE(8, 3)
+        default: break;
+      }
+      break;
+  }
+#undef RR_PK_CASE
+}
+
+// All combining passes. sink != nullptr: the top phase (which must be fused, i.e. cover every value with
+// 2- or 3-level tasks) stores the valid samples straight to global memory.
+RR_PROG void pk_passes(const PkSched &s, const Grp &g, CPk *buf, const float *pyr, const PkSink *sink)
+{
+  for (int ph = 0; ph < s.nphases; ++ph) {
+    const bool top = ph + 1 == s.nphases;
+    if (top && sink) pk_phase_dispatch<true>(s, g, s.phase_lg[ph], s.phase_depth[ph], buf, pyr, sink);
+    else pk_phase_dispatch<false>(s, g, s.phase_lg[ph], s.phase_depth[ph], buf, pyr, nullptr);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The stage
+// ---------------------------------------------------------------------------------------------------
+enum PkSpecMode {
+  PK_SPEC_UP2 = 0,    // F-domain up-sampling by 2, step 1: Ni = 2 Pf (44.1->48, 48->44.1, 44.1->96, ...)
+  PK_SPEC_SAME = 1,   // Ni = Pf, step >= 1 (plain / zero-stuffed input)
+  PK_SPEC_GEN = 2     // everything else: separate post-processing and spectrum phases
+};
+
+struct DftPkParams {
+  DftParams<float> base;         // geometry, views, cosine tables, filter spectrum (schedules unused)
+  PkSched fwd, inv;
+  int fslots, bslots;            // slots of one forward / inverse buffer
+  int groups, gthreads;          // groups per CTA, threads per group
+  int spec_mode;
+};
+
+// How the input tile of an item is copied: whole slots when the lanes are adjacent in an interleaved buffer,
+// 8 bytes per lane from planar lanes (re-paired by the leaves), else scalar copies with zero fill.
+enum PkTileMode { PK_TILE_SCALAR = 0, PK_TILE_INTERLEAVED = 1, PK_TILE_PLANAR = 2 };
+
+struct PkItem {
+  DftItem<float> d;
+  int tile_mode;
+};
+
+RR_PROG PkItem pk_item(const DftPkParams &pp, long long work)
+{
+  const DftParams<float> &p = pp.base;
+  PkItem it;
+  it.d = dft_item<float, 2>(p, work);
+  it.tile_mode = PK_TILE_SCALAR;
+  const int span = p.in_mode == DFT_IN_FREQ_UP ? p.Pf : p.N;
+  if (p.in_mode != DFT_IN_ZERO_STUFF && view_range_direct(p.in, it.d.Rb, it.d.Rb + span)) {
+    const float *s0 = view_ptr<const float>(p.in, it.d.in_off0, it.d.Rb), *s1 = view_ptr<const float>(p.in, it.d.in_off1, it.d.Rb);
+    const int es = p.in.elem_stride;
+    if (s1 == s0 + 1 && !(es & 1) && !((size_t)s0 & 7)) it.tile_mode = PK_TILE_INTERLEAVED;
+    else if (es == 1 && !(((size_t)s0 | (size_t)s1) & 7)) it.tile_mode = PK_TILE_PLANAR;
+  }
+  return it;
+}
+
+#if defined(__CUDA_ARCH__)
+RR_PROG void pk_async_copy8(void *smem_dst, const void *gsrc)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+RR_PROG void pk_async_copy16(void *smem_dst, const void *gsrc)
+{
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+#else
+inline void pk_async_copy8(void *dst, const void *src) { memcpy(dst, src, 8); }
+inline void pk_async_copy16(void *dst, const void *src) { memcpy(dst, src, 16); }
+#endif
+
+// Issue the (asynchronous) copy of an item's input tile into `F`, element j at the slot of its permuted
+// position. Does not wait.
+RR_PROG void pk_stage_tile(const DftPkParams &pp, const Grp &g, const PkItem &it, CPk *F)
+{
+  const DftParams<float> &p = pp.base;
+  const int span = p.in_mode == DFT_IN_FREQ_UP ? p.Pf : p.N, m = span >> 1;
+  const uint16_t *perm = pp.fwd.perm;
+  if (it.tile_mode == PK_TILE_INTERLEAVED) {
+    const float *s0 = view_ptr<const float>(p.in, it.d.in_off0, it.d.Rb);
+    const int es = p.in.elem_stride;
+    if (es == 2 && !((size_t)s0 & 15))
+      for (int j = g.tid; j < m; j += g.size) pk_async_copy16(F + ldg(perm + j), s0 + 4 * j);
+    else
+      for (int j = g.tid; j < m; j += g.size) {
+        CPk *d = F + ldg(perm + j);
+        const float *f = s0 + (long long)(2 * j) * es;
+        pk_async_copy8(&d->x, f);
+        pk_async_copy8(&d->y, f + es);
+      }
+  } else if (it.tile_mode == PK_TILE_PLANAR) {
+    const float *s0 = view_ptr<const float>(p.in, it.d.in_off0, it.d.Rb), *s1 = view_ptr<const float>(p.in, it.d.in_off1, it.d.Rb);
+    for (int j = g.tid; j < m; j += g.size) {
+      CPk *d = F + ldg(perm + j);
+      pk_async_copy8(&d->x, s0 + 2 * j);                  // {a.re, a.im}: re-paired by the leaves (swz)
+      pk_async_copy8(&d->y, s1 + 2 * j);                  // {b.re, b.im}
+    }
+  } else {
+    const int L = p.L;
+    for (int w = g.tid; w < 2 * span; w += g.size) {
+      const int l = w & 1, j = w >> 1;
+      long long coord = it.d.Rb + j;
+      bool on_grid = true;
+      if (p.in_mode == DFT_IN_ZERO_STUFF) {
+        const int d = j - it.d.remLb;
+        on_grid = d >= 0 && d % L == 0;
+        coord = it.d.Rb + (on_grid ? d / L : 0);
+      }
+      float *dst = reinterpret_cast<float *>(F + ldg(perm + (j >> 1))) + 2 * (j & 1) + l;
+      bool valid;
+      const float *src = view_addr<float>(p.in, l ? it.d.in_off1 : it.d.in_off0, coord, &valid);
+      async_copy_elem<float>(dst, src, valid && on_grid);
+    }
+  }
+  async_copy_commit();
+}
+
+// Values that do not depend on the work item and are needed by the same thread for every item: filter
+// spectrum, real-FFT cosines and the inverse transform's permuted slots of the spectrum phase. A persistent
+// group loads them once into registers (first kPkCacheRounds rounds of its strided loop).
+constexpr int kPkCacheRounds = 4;
+struct PkSpecCache {
+  C2<float> c0[kPkCacheRounds], c1[kPkCacheRounds], c2[kPkCacheRounds], c3[kPkCacheRounds];
+  float tf_c[kPkCacheRounds], tf_s[kPkCacheRounds], ti_c[kPkCacheRounds], ti_s[kPkCacheRounds];
+  unsigned s01[kPkCacheRounds], s23[kPkCacheRounds];     // two 16-bit slots each
+};
+
+// rdft.c:46-77, forward transform: (F[i], F[M-i]) -> (X[i], X[M-i])
+RR_HD void pk_post_pair(const CPk &za, const CPk &zb, float c, float s, CPk &xa, CPk &xb)
+{
+  typedef Arith<Pk> A;
+  const Pk half = pk_bcast(0.5f), pc = pk_bcast(c), ps = pk_bcast(s);
+  const Pk evr = A::mul(half, A::add(za.x, zb.x));
+  const Pk odi = A::mul(half, A::sub(zb.x, za.x));
+  const Pk evi = A::mul(half, A::sub(za.y, zb.y));
+  const Pk odr = A::mul(half, A::add(za.y, zb.y));
+  const Pk sr = A::addp(A::mul(odr, pc), A::mul(odi, ps));
+  const Pk si = A::subp(A::mul(odi, pc), A::mul(odr, ps));
+  xa = CPk{A::addp(evr, sr), A::addp(evi, si)};
+  xb = CPk{A::subp(evr, sr), A::subp(si, evi)};
+}
+
+RR_HD CPk pk_cmul(const C2<float> &cf, const CPk &v)      // dft_filter.h:140-145
+{
+  typedef Arith<Pk> A;
+  const Pk cx = pk_bcast(cf.x), cy = pk_bcast(cf.y);
+  return CPk{A::subp(A::mul(cx, v.x), A::mul(cy, v.y)), A::addp(A::mul(cy, v.x), A::mul(cx, v.y))};
+}
+
+// filter multiply of the bin pair (va = spectrum[i], vb = spectrum[Ni/2 - i]) and the inverse transform's
+// pre-processing (rdft.c:44-80 with inverse = 1) -> (d[i], d[Ni/2 - i])
+RR_HD void pk_mul_pre_pair(const CPk &va, const CPk &vb, const C2<float> &ca, const C2<float> &cb, float c, float s,
+                           CPk &da, CPk &db)
+{
+  typedef Arith<Pk> A;
+  const Pk half = pk_bcast(0.5f), mhalf = pk_bcast(-0.5f), pc = pk_bcast(c), ps = pk_bcast(s);
+  const CPk a = pk_cmul(ca, va), bb = pk_cmul(cb, vb);
+  const Pk evr = A::mul(half, A::add(a.x, bb.x));
+  const Pk odi = A::mul(mhalf, A::sub(bb.x, a.x));
+  const Pk evi = A::mul(half, A::sub(a.y, bb.y));
+  const Pk odr = A::mul(mhalf, A::add(a.y, bb.y));
+  const Pk sr = A::subp(A::mul(odr, pc), A::mul(odi, ps));
+  const Pk si = A::addp(A::mul(odi, pc), A::mul(odr, ps));
+  da = CPk{A::addp(evr, sr), A::addp(evi, si)};
+  db = CPk{A::subp(evr, sr), A::subp(si, evi)};
+}
+
+RR_HD CPk pk_conj(const CPk &v) { return CPk{v.x, pk_neg(v.y)}; }
+
+// Spectrum phase, F (forward FFT result, natural order) -> B (input of the inverse FFT, permuted order).
+// round r of thread t handles index i = t + r * g.size; `cached` rounds take their constants from `cc`.
+template <int MODE, bool CACHED>
+RR_PROG void pk_spectrum(const DftPkParams &pp, const Grp &g, const PkSpecCache &cc, const CPk *F, CPk *B)
+{
+  typedef Arith<Pk> A;
+  const DftParams<float> &p = pp.base;
+  const C2<float> *coef = reinterpret_cast<const C2<float> *>(p.coef);
+  const uint16_t *perm = pp.inv.perm;
+  const int M = p.Pf >> 1;                               // forward transform: M complex points
+  const int Mi = p.Ni >> 1;
+  const int n = M >> 1;                                   // items i = 0 .. M/2 - 1 (i = 0 also does M/2)
+  auto body = [&](int i, int r) {
+    C2<float> k0, k1, k2, k3;
+    float tfc, tfs, tic, tis;
+    int sl0, sl1, sl2, sl3;
+    if (CACHED && r >= 0) {
+      k0 = cc.c0[r]; k1 = cc.c1[r]; k2 = cc.c2[r]; k3 = cc.c3[r];
+      tfc = cc.tf_c[r]; tfs = cc.tf_s[r]; tic = cc.ti_c[r]; tis = cc.ti_s[r];
+      sl0 = cc.s01[r] & 0xffff; sl1 = cc.s01[r] >> 16; sl2 = cc.s23[r] & 0xffff; sl3 = cc.s23[r] >> 16;
+    } else {
+      const int ii = i ? i : n;                           // i == 0 loads the constants of its second job, M/2
+      tfc = ldg(p.tcos_f + ii); tfs = ldg(p.tcos_f + n - ii);
+      if (MODE == PK_SPEC_UP2) {
+        k0 = ldg(coef + ii); k1 = ldg(coef + Mi - ii); k2 = ldg(coef + M - ii); k3 = ldg(coef + M + ii);
+        tic = ldg(p.tcos_i + ii); tis = ldg(p.tcos_i + M - ii);
+        sl0 = ldg(perm + ii); sl1 = ldg(perm + Mi - ii); sl2 = ldg(perm + M - ii); sl3 = ldg(perm + M + ii);
+      } else {
+        k0 = ldg(coef + ii); k1 = ldg(coef + M - ii); k2 = k0; k3 = k0;
+        tic = tfc; tis = tfs;
+        sl0 = ldg(perm + ii); sl1 = ldg(perm + M - ii); sl2 = sl0; sl3 = sl0;
+      }
+    }
+    if (i == 0) {
+      // bins 0 and Pf/2 (packed in F[0]) and the self-paired bin M/2
+      const CPk z = F[0];
+      const CPk x0 = CPk{A::add(z.x, z.y), A::sub(z.x, z.y)};                  // rdft.c:46-48
+      CPk zm = F[pslot(n)];
+      zm.y = pk_neg(zm.y);                                                       // rdft.c:77 (forward)
+      const C2<float> cf0 = ldg(coef);
+      if (MODE == PK_SPEC_UP2) {
+        // spectrum[0] = (X0.re, X0.re); d[0] = (.5 (d0 + d1), .5 (d0 - d1)), dft_filter.h:96-98,118-119, rdft.c:44-46,79-80
+        const Pk d0 = A::mul(x0.x, pk_bcast(cf0.x)), d1 = A::mul(x0.x, pk_bcast(cf0.y));
+        B[ldg(perm)] = CPk{A::mul(A::addp(d0, d1), pk_bcast(0.5f)), A::mul(A::subp(d0, d1), pk_bcast(0.5f))};
+        // bin Ni/4 = M: spectrum = (X0.im, 0); d[M] = conj(coef[M] * spectrum)
+        const CPk mm = pk_cmul(ldg(coef + M), CPk{x0.y, pk_bcast(0.0f)});
+        B[ldg(perm + M)] = pk_conj(mm);
+        // bins M/2 and Ni/2 - M/2: spectrum[M/2] = X[M/2], spectrum[Ni/2 - M/2] = conj(X[M/2])
+        CPk da, db;
+        pk_mul_pre_pair(zm, pk_conj(zm), k0, k1, tic, tis, da, db);
+        B[sl0] = da; B[sl1] = db;
+      } else {
+        const Pk d0 = A::mul(x0.x, pk_bcast(cf0.x)), d1 = A::mul(x0.y, pk_bcast(cf0.y));
+        B[ldg(perm)] = CPk{A::mul(A::addp(d0, d1), pk_bcast(0.5f)), A::mul(A::subp(d0, d1), pk_bcast(0.5f))};
+        // bin Ni/4 = M/2: d = conj(coef * X[M/2])
+        B[sl0] = pk_conj(pk_cmul(k0, zm));
+      }
+      return;
+    }
+    const CPk za = F[pslot(i)], zb = F[pslot(M - i)];
+    CPk xa, xb;
+    pk_post_pair(za, zb, tfc, tfs, xa, xb);
+    if (MODE == PK_SPEC_UP2) {
+      // bins i / Ni/2 - i see X[i] / conj(X[i]); bins M - i / M + i see X[M-i] / conj(X[M-i])
+      CPk da, db;
+      pk_mul_pre_pair(xa, pk_conj(xa), k0, k1, tic, tis, da, db);
+      B[sl0] = da; B[sl1] = db;
+      pk_mul_pre_pair(xb, pk_conj(xb), k2, k3, tis, tic, da, db);
+      B[sl2] = da; B[sl3] = db;
+    } else {
+      CPk da, db;
+      pk_mul_pre_pair(xa, xb, k0, k1, tic, tis, da, db);
+      B[sl0] = da; B[sl1] = db;
+    }
+  };
+#if defined(__CUDACC__)
+  if (CACHED) {
+#pragma unroll
+    for (int r = 0; r < kPkCacheRounds; ++r) {
+      const int i = g.tid + r * g.size;
+      if (i < n) body(i, r);
+    }
+    for (int i = g.tid + kPkCacheRounds * g.size; i < n; i += g.size) body(i, -1);
+    grp_sync(g);
+    return;
+  }
+#endif
+  grp_for(g, n, [&](int i) { body(i, -1); });
+}
+
+template <int MODE>
+RR_PROG void pk_load_spec_cache(const DftPkParams &pp, const Grp &g, PkSpecCache &cc)
+{
+  const DftParams<float> &p = pp.base;
+  const C2<float> *coef = reinterpret_cast<const C2<float> *>(p.coef);
+  const uint16_t *perm = pp.inv.perm;
+  const int M = p.Pf >> 1, Mi = p.Ni >> 1, n = M >> 1;
+#pragma unroll
+  for (int r = 0; r < kPkCacheRounds; ++r) {
+    const int i = g.tid + r * g.size;
+    if (i >= n) continue;
+    const int ii = i ? i : n;
+    cc.tf_c[r] = ldg(p.tcos_f + ii); cc.tf_s[r] = ldg(p.tcos_f + n - ii);
+    if (MODE == PK_SPEC_UP2) {
+      cc.c0[r] = ldg(coef + ii); cc.c1[r] = ldg(coef + Mi - ii); cc.c2[r] = ldg(coef + M - ii); cc.c3[r] = ldg(coef + M + ii);
+      cc.ti_c[r] = ldg(p.tcos_i + ii); cc.ti_s[r] = ldg(p.tcos_i + M - ii);
+      cc.s01[r] = (unsigned)ldg(perm + ii) | ((unsigned)ldg(perm + Mi - ii) << 16);
+      cc.s23[r] = (unsigned)ldg(perm + M - ii) | ((unsigned)ldg(perm + M + ii) << 16);
+    } else {
+      cc.c0[r] = ldg(coef + ii); cc.c1[r] = ldg(coef + M - ii); cc.c2[r] = cc.c0[r]; cc.c3[r] = cc.c0[r];
+      cc.ti_c[r] = cc.tf_c[r]; cc.ti_s[r] = cc.tf_s[r];
+      cc.s01[r] = (unsigned)ldg(perm + ii) | ((unsigned)ldg(perm + M - ii) << 16);
+      cc.s23[r] = cc.s01[r];
+    }
+  }
+}
+
+// Generic spectrum path (any L, F-domain decimation): forward post-processing in place, then the bins of
+// the inverse transform one pair at a time through the reference's up-sampling index map (dft_filter.h:86-104).
+RR_PROG CPk pk_spec_freq_up(const CPk *X, int Pf, int idx)
+{
+  const int twoP = Pf << 1, r = idx & (twoP - 1);
+  if (r == 0) { const Pk a0 = X[0].x; return CPk{a0, idx == 0 ? a0 : pk_bcast(0.0f)}; }
+  if (r < Pf) return X[pslot(r >> 1)];
+  if (r == Pf) return CPk{X[0].y, pk_bcast(0.0f)};
+  return pk_conj(X[pslot((twoP - r) >> 1)]);
+}
+
+RR_PROG void pk_spectrum_generic(const DftPkParams &pp, const Grp &g, CPk *F, CPk *B)
+{
+  typedef Arith<Pk> A;
+  const DftParams<float> &p = pp.base;
+  const int Pf = p.Pf, Ni = p.Ni;
+  grp_for(g, (Pf >> 2) + 1, [&](int i) {
+    if (i == 0) {
+      const CPk z = F[0];
+      F[0] = CPk{A::add(z.x, z.y), A::sub(z.x, z.y)};
+    } else if (i == (Pf >> 2)) {
+      CPk *z = F + pslot(Pf >> 2);
+      z->y = pk_neg(z->y);
+    } else {
+      const int ia = pslot(i), ib = pslot((Pf >> 1) - i);
+      CPk xa, xb;
+      pk_post_pair(F[ia], F[ib], ldg(p.tcos_f + i), ldg(p.tcos_f + (Pf >> 2) - i), xa, xb);
+      F[ia] = xa; F[ib] = xb;
+    }
+  });
+  const bool freq_up = p.in_mode == DFT_IN_FREQ_UP;
+  const C2<float> *coef = reinterpret_cast<const C2<float> *>(p.coef);
+  const uint16_t *perm = pp.inv.perm;
+  grp_for(g, (Ni >> 2) + 1, [&](int i) {
+    auto spec = [&](int bin) -> CPk { return freq_up ? pk_spec_freq_up(F, Pf, 2 * bin) : F[pslot(bin)]; };
+    if (i > 0 && i < (Ni >> 2)) {
+      CPk da, db;
+      pk_mul_pre_pair(spec(i), spec((Ni >> 1) - i), ldg(coef + i), ldg(coef + (Ni >> 1) - i), ldg(p.tcos_i + i),
+                      ldg(p.tcos_i + (Ni >> 2) - i), da, db);
+      B[ldg(perm + i)] = da; B[ldg(perm + (Ni >> 1) - i)] = db;
+    } else if (i == 0) {
+      const CPk v0 = spec(0);
+      const C2<float> ca = ldg(coef);
+      const Pk d0 = A::mul(v0.x, pk_bcast(ca.x));
+      Pk d1;
+      if (p.step > 0) d1 = A::mul(v0.y, pk_bcast(ca.y));
+      else {                                              // new Nyquist bin of the decimated spectrum, dft_filter.h:185
+        const CPk vn = spec(Ni >> 1);
+        const C2<float> cb = ldg(coef + (Ni >> 1));
+        d1 = A::subp(A::mul(pk_bcast(cb.x), vn.x), A::mul(pk_bcast(cb.y), vn.y));
+      }
+      B[ldg(perm)] = CPk{A::mul(A::addp(d0, d1), pk_bcast(0.5f)), A::mul(A::subp(d0, d1), pk_bcast(0.5f))};
+    } else {
+      B[ldg(perm + (Ni >> 2))] = pk_conj(pk_cmul(ldg(coef + (Ni >> 2)), spec(Ni >> 2)));
+    }
+  });
+}
+
+// One work item (block b, lane pair). Fcur holds (or is receiving) the item's input tile; Fnext receives
+// the next item's; items[slot] describes this item, items[slot ^ 1] is filled for the next one.
+template <int MODE, bool CACHED>
+RR_PROG void dftp_program(const DftPkParams &pp, const Grp &g, const float *pyr_f, const float *pyr_i, const PkSpecCache &cc,
+                          PkItem *items, int slot, long long work_next, CPk *Fcur, CPk *Fnext, CPk *B)
+{
+  const DftParams<float> &p = pp.base;
+  async_copy_wait<0>();
+  grp_sync(g);                                            // the tile is complete; items[slot] is visible
+  const PkItem it = items[slot];
+  if (work_next >= 0 && g.tid == 0) items[slot ^ 1] = pk_item(pp, work_next);
+
+  // the forward and the inverse transform share one copy of the FFT code: a two-trip loop that is not unrolled
+  PkSink sink;
+  bool sink_ok = false, direct = false;
+  int first = 0, stride = 1, count = 0, es = 1;
+  long long c0 = 0;
+  float *d0 = nullptr, *d1 = nullptr;
+#pragma unroll 1
+  for (int dir = 0; dir < 2; ++dir) {
+    const PkSched &s = dir ? pp.inv : pp.fwd;
+    CPk *buf = dir ? B : Fcur;
+    pk_leaves(s, g, buf, dir == 0 && it.tile_mode == PK_TILE_PLANAR, p.sqrthalf, p.c16_1, p.c16_3);
+    if (dir == 0 && work_next >= 0) pk_stage_tile(pp, g, items[slot ^ 1], Fnext);   // in flight until the next item starts
+    pk_passes(s, g, buf, dir ? pyr_i : pyr_f, dir && sink_ok ? &sink : nullptr);
+    if (dir) break;
+
+    if (MODE == PK_SPEC_GEN) pk_spectrum_generic(pp, g, Fcur, B);
+    else pk_spectrum<MODE, CACHED>(pp, g, cc, Fcur, B);
+
+    // output geometry of this block (as in dft_stage_program)
+    const long long b = it.d.b;
+    const int V = p.N - p.overlap;
+    long long k0;
+    if (p.step == 1) { count = V; k0 = b * (long long)V; }
+    else if (p.step > 1) {
+      const long long v0 = b * (long long)V;
+      const int Mq = p.step;
+      first = (int)((Mq - v0 % Mq) % Mq); stride = Mq;
+      k0 = (v0 + Mq - 1) / Mq;
+      count = first < V ? (V - first + Mq - 1) / Mq : 0;
+    } else { count = p.kept; k0 = b * (long long)p.kept; }
+    c0 = p.out_preload + k0;
+    direct = view_range_direct(p.out, c0, c0 + count);
+    d0 = view_ptr<float>(p.out, it.d.out_off0, c0); d1 = view_ptr<float>(p.out, it.d.out_off1, c0);
+    es = p.out.elem_stride;
+    sink.d0 = d0; sink.d1 = d1; sink.half = count >> 1; sink.es = 0;
+    sink_ok = direct && stride == 1 && !(count & 1) && pp.inv.phase_depth[pp.inv.nphases - 1] >= 2;
+    if (sink_ok) {
+      if (es == 1 && !(((size_t)d0 | (size_t)d1) & 7)) sink.es = 0;
+      else if (d1 == d0 + 1 && !(es & 1) && !((size_t)d0 & 7)) sink.es = es;
+      else sink_ok = false;
+    }
+  }
+  if (sink_ok) return;
+
+  const float *Br = reinterpret_cast<const float *>(B);
+  grp_for(g, 2 * count, [&](int w) {
+    const int l = w & 1, j = w >> 1;
+    const int t = first + j * stride;
+    const float v = Br[4 * pslot(t >> 1) + 2 * (t & 1) + l];
+    if (direct) (l ? d1 : d0)[(long long)j * es] = v;
+    else view_write<float, float>(p.out, l ? it.d.out_off1 : it.d.out_off0, c0 + j, v);
+  });
+}
+
+}  // namespace b200rate

@@ -24,6 +24,13 @@ CASES = [
     (96000, 44100, "float", 75, 99, 1, 0, 1), (44100, 48000, "float", 0, 90, 0, 1, 1),
     (22050, 96000, "float", 50, 95, 0, 0, 1), (44100, 11025, "double", 50, 95, 0, 0, 2),
     (44100, 176400, "float", 50, 95, 0, 1, 1), (48000, 8000, "double", 50, 95, 0, 1, 1),
+    # even channel counts on the fp32 engine: the lane-pair DFT kernel (rate_kernels_pk.cuh) in all its
+    # spectrum modes, input-tile modes (interleaved / planar / zero-stuffed) and output modes
+    (96000, 44100, "float", 50, 95, 0, 0, 2), (32000, 48000, "float", 50, 95, 0, 0, 2),
+    (384000, 48000, "float", 50, 95, 0, 0, 4), (8000, 48000, "float", 50, 95, 0, 0, 2),
+    (44100, 176400, "float", 50, 95, 0, 1, 2), (48000, 8000, "float", 50, 95, 0, 1, 2),
+    (44100, 88200, "float", 25, 95, 0, 0, 6), (96000, 48000, "float", 50, 95, 1, 0, 2),
+    (44100, 22050, "float", 50, 95, 0, 1, 2), (50000, 40000, "float", 50, 95, 0, 0, 2),
 ]
 
 
@@ -70,7 +77,7 @@ def test_plan_and_design(case):
     orc.close()
 
 
-@pytest.mark.parametrize("case", CASES[:8], ids=ids)
+@pytest.mark.parametrize("case", CASES[:8] + CASES[16:20], ids=ids)
 def test_batch_front_end_and_ranges(case):
     i, o, eng, ph, bw, al, q, nch = case
     L = emulib.lib()
