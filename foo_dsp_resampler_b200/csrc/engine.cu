@@ -105,7 +105,7 @@ static size_t be_max_smem()
 // kernels
 // ===================================================================================================
 constexpr int kDftThreads = 256;
-constexpr int kPkGroupThreads = 128, kPkMaxGroups = 3;   // lane-pair DFT kernel: threads per group, groups per CTA
+constexpr int kPkGroupThreads = 128, kPkMaxGroups = 4;   // lane-pair DFT kernel: threads per group, groups per CTA
 constexpr int kTileThreads = 256;
 constexpr int kPolyTile = 2048;      // outputs per CTA tile
 constexpr int kHalfTile = 2048;
@@ -167,34 +167,44 @@ __global__ void __launch_bounds__(2 * kDftThreads) dft_kernel(const __grid_const
   }
 }
 // Lane-pair DFT stage (rate_kernels_pk.cuh): a CTA is `groups` independent groups of `gthreads` threads, each
-// a persistent worker with its own buffers (two forward buffers, ping-pong with the LDGSTS prefetch of the
-// next item, and one inverse buffer) behind the shared twiddle tables.
-template <int MODE>
+// a persistent worker with its own forward and inverse buffer behind the shared tables (twiddle pyramids,
+// task tables, forward permutation).
+// FB / IB > 0: specialised on the transform sizes (everything inlined and static); 0: any size.
+template <int MODE, int FB, int IB>
 __global__ void __launch_bounds__(kPkGroupThreads * kPkMaxGroups) dftp_kernel(const __grid_constant__ DftPkParams pp, long long nwork)
 {
-  float *tab = reinterpret_cast<float *>(rr_smem_raw);
-  const int nf = pp.fwd.pyr_len, ni = pp.inv.pyr_len;
-  for (int i = threadIdx.x; i < nf; i += blockDim.x) tab[i] = pp.base.pyr_f[i];
-  for (int i = threadIdx.x; i < ni; i += blockDim.x) tab[nf + i] = pp.base.pyr_i[i];
-  const int tab_bytes = ((nf + ni) * 4 + 15) & ~15;
+  struct { int pyr_f, pyr_i, tasks_f, tasks_i, perm_f, data, group_slots; } lay{pp.lay_pyr_f, pp.lay_pyr_i, pp.lay_tasks_f, pp.lay_tasks_i,
+                                                                                pp.lay_perm_f, pp.lay_data, pp.fslots + pp.bslots};
+  {
+    float *pf = reinterpret_cast<float *>(rr_smem_raw + lay.pyr_f), *pi = reinterpret_cast<float *>(rr_smem_raw + lay.pyr_i);
+    uint16_t *tf = reinterpret_cast<uint16_t *>(rr_smem_raw + lay.tasks_f), *ti = reinterpret_cast<uint16_t *>(rr_smem_raw + lay.tasks_i);
+    uint16_t *pm = reinterpret_cast<uint16_t *>(rr_smem_raw + lay.perm_f);
+    const int nf = pp.n_pyr_f, ni = pp.n_pyr_i, ef = pp.n_tasks_f, ei = pp.n_tasks_i, mf = 1 << pp.fb;
+    for (int i = threadIdx.x; i < nf; i += blockDim.x) pf[i] = pp.base.pyr_f[i];
+    for (int i = threadIdx.x; i < ni; i += blockDim.x) pi[i] = pp.base.pyr_i[i];
+    for (int i = threadIdx.x; i < ef; i += blockDim.x) tf[i] = pp.tasks_f[i];
+    for (int i = threadIdx.x; i < ei; i += blockDim.x) ti[i] = pp.tasks_i[i];
+    for (int i = threadIdx.x; i < mf; i += blockDim.x) pm[i] = pp.perm_f[i];
+  }
+  const PkTables tb{reinterpret_cast<const float *>(rr_smem_raw + lay.pyr_f), reinterpret_cast<const float *>(rr_smem_raw + lay.pyr_i),
+                    reinterpret_cast<const uint16_t *>(rr_smem_raw + lay.tasks_f),
+                    reinterpret_cast<const uint16_t *>(rr_smem_raw + lay.tasks_i),
+                    reinterpret_cast<const uint16_t *>(rr_smem_raw + lay.perm_f)};
   const int gi = threadIdx.x / pp.gthreads;
   const Grp g{(int)threadIdx.x - gi * pp.gthreads, pp.gthreads, 1 + gi};
-  CPk *F0 = reinterpret_cast<CPk *>(rr_smem_raw + tab_bytes) + (size_t)gi * (2 * pp.fslots + pp.bslots);
-  CPk *F1 = F0 + pp.fslots, *B = F1 + pp.fslots;
-  PkSpecCache cc;
-  if (MODE != PK_SPEC_GEN) pk_load_spec_cache<MODE>(pp, g, cc);
+  CPk *F = reinterpret_cast<CPk *>(rr_smem_raw + lay.data) + (size_t)gi * lay.group_slots, *B = F + pp.fslots;
   __shared__ PkItem items[kPkMaxGroups][2];
   __syncthreads();
   long long w = (long long)blockIdx.x * pp.groups + gi;
   const long long stride = (long long)gridDim.x * pp.groups;
   if (w < nwork) {
-    if (g.tid == 0) items[gi][0] = pk_item(pp, w);
+    if (g.tid == 0) items[gi][0] = pk_make_item(pp, w);
     grp_sync(g);
-    pk_stage_tile(pp, g, items[gi][0], F0);
+    pk_stage_tile(pp, g, items[gi][0], F, tb.perm_f);
   }
   for (int n = 0; w < nwork; w += stride, ++n) {
     const long long next = w + stride < nwork ? w + stride : -1;
-    dftp_program<MODE, true>(pp, g, tab, tab + nf, cc, items[gi], n & 1, next, (n & 1) ? F1 : F0, (n & 1) ? F0 : F1, B);
+    dftp_program<MODE, FB, IB>(pp, g, tb, items[gi], n & 1, next, F, B);
   }
 }
 template <class T, class InT, class OutT>
@@ -292,35 +302,26 @@ static int launch_persistent(Kernel kernel, const Params &p, long long nwork, in
 }
 #endif  // !B200RATE_EMU
 
-// Shared memory of the lane-pair DFT kernel: twiddle pyramids, then per group two forward buffers and one
-// inverse buffer of 16-byte slots.
-static size_t dftp_smem_bytes(const DftPkParams &pp)
-{
-  const size_t tab = ((static_cast<size_t>(pp.fwd.pyr_len) + pp.inv.pyr_len) * 4 + 15) & ~static_cast<size_t>(15);
-  return tab + static_cast<size_t>(pp.groups) * (2 * pp.fslots + pp.bslots) * sizeof(CPk);
-}
-
 static int launch_dftp(const DftPkParams &pp, long long nwork, stream_t s)
 {
   if (nwork <= 0) return RR_OK;
 #ifdef B200RATE_EMU
   (void)s;
-  if (getenv("B200RATE_TRACE")) fprintf(stderr, "dftp mode %d nwork %lld Pf %d Ni %d phases f%d i%d\n", pp.spec_mode, nwork, pp.base.Pf, pp.base.Ni, pp.fwd.nphases, pp.inv.nphases);
-  std::vector<CPk> mem(static_cast<size_t>(2 * pp.fslots + pp.bslots) + 1);
-  CPk *F0 = mem.data(), *F1 = F0 + pp.fslots, *B = F1 + pp.fslots;
+  std::vector<CPk> mem(static_cast<size_t>(pp.fslots + pp.bslots) + 1);
+  CPk *F = mem.data(), *B = F + pp.fslots;
   const Grp g{0, 1, 0};
-  const PkSpecCache cc{};
+  const PkTables tb{pp.base.pyr_f, pp.base.pyr_i, pp.tasks_f, pp.tasks_i, pp.perm_f};
   for (long long w = 0; w < nwork; ++w) {
     PkItem items[2];
-    items[0] = pk_item(pp, w);
-    pk_stage_tile(pp, g, items[0], F0);
-    if (pp.spec_mode == PK_SPEC_UP2) dftp_program<PK_SPEC_UP2, false>(pp, g, pp.base.pyr_f, pp.base.pyr_i, cc, items, 0, -1, F0, F1, B);
-    else if (pp.spec_mode == PK_SPEC_SAME) dftp_program<PK_SPEC_SAME, false>(pp, g, pp.base.pyr_f, pp.base.pyr_i, cc, items, 0, -1, F0, F1, B);
-    else dftp_program<PK_SPEC_GEN, false>(pp, g, pp.base.pyr_f, pp.base.pyr_i, cc, items, 0, -1, F0, F1, B);
+    items[0] = pk_make_item(pp, w);
+    pk_stage_tile(pp, g, items[0], F, tb.perm_f);
+    if (pp.spec_mode == PK_SPEC_UP2) dftp_program<PK_SPEC_UP2, 0, 0>(pp, g, tb, items, 0, -1, F, B);
+    else if (pp.spec_mode == PK_SPEC_SAME) dftp_program<PK_SPEC_SAME, 0, 0>(pp, g, tb, items, 0, -1, F, B);
+    else dftp_program<PK_SPEC_GEN, 0, 0>(pp, g, tb, items, 0, -1, F, B);
   }
   return RR_OK;
 #else
-  const size_t smem = dftp_smem_bytes(pp);
+  const size_t smem = pk_smem_layout(pp).total;
   const int threads = pp.groups * pp.gthreads;
   auto go = [&](auto kernel) -> int {
     const void *key = reinterpret_cast<const void *>(kernel);
@@ -339,9 +340,17 @@ static int launch_dftp(const DftPkParams &pp, long long nwork, stream_t s)
     CUDA_TRY(cudaGetLastError());
     return RR_OK;
   };
-  if (pp.spec_mode == PK_SPEC_UP2) return go(dftp_kernel<PK_SPEC_UP2>);
-  if (pp.spec_mode == PK_SPEC_SAME) return go(dftp_kernel<PK_SPEC_SAME>);
-  return go(dftp_kernel<PK_SPEC_GEN>);
+  // the common Best-quality sizes get kernels specialised on (forward, inverse) transform size
+  if (pp.spec_mode == PK_SPEC_UP2) {
+    if (pp.fb == 10 && pp.ib == 11) return go(dftp_kernel<PK_SPEC_UP2, 10, 11>);      // N = 4096, x2 (44.1 <-> 48 family)
+    return go(dftp_kernel<PK_SPEC_UP2, 0, 0>);
+  }
+  if (pp.spec_mode == PK_SPEC_SAME) {
+    if (pp.fb == 11 && pp.ib == 11) return go(dftp_kernel<PK_SPEC_SAME, 11, 11>);     // N = 4096, 1:1 pre-filter
+    return go(dftp_kernel<PK_SPEC_SAME, 0, 0>);
+  }
+  if (pp.fb == 11 && pp.ib == 10) return go(dftp_kernel<PK_SPEC_GEN, 11, 10>);        // N = 4096, F-domain / 2
+  return go(dftp_kernel<PK_SPEC_GEN, 0, 0>);
 #endif
 }
 
@@ -791,7 +800,11 @@ template <class T> class Engine {
   HalfbandParams<T> half_params_[RR_MAX_STAGES];
   T *dft_coef_dev_[2] = {nullptr, nullptr};
 
-  struct DevSched { CfftSched fwd, inv; const T *pyramid; PkSched pk_fwd, pk_inv; };
+  struct DevSched { CfftSched fwd, inv; const T *pyramid; const uint16_t *pk_tasks = nullptr, *pk_perm[2] = {nullptr, nullptr}; };
+  std::map<int, std::vector<uint16_t>> pk_perm_inv_host_;   // by complex bits
+  const PkSpecConst *pk_spec_dev_[RR_MAX_STAGES] = {nullptr};
+  std::map<int, DevSched> sched_;          // by complex bits
+  std::map<int, const T *> tcos_;          // by real bits
   bool use_pair_kernel_ = getenv("B200RATE_NO_PAIR_KERNEL") == nullptr;   // debugging switch: generic kernel only
   int last_dft_kernel_ = 0;
 
@@ -803,20 +816,71 @@ template <class T> class Engine {
     const int fb = ilog2(g.Pf) - 1, ib = ilog2(g.Ni) - 1;
     if (fb < 5 || ib < 5 || fb > 13 || ib > 13) return false;
     auto sf = sched_.find(fb), si = sched_.find(ib);
-    if (sf == sched_.end() || si == sched_.end()) return false;
+    if (sf == sched_.end() || si == sched_.end() || !sf->second.pk_tasks || !si->second.pk_tasks) return false;
     pp.base = p;
-    pp.fwd = sf->second.pk_fwd; pp.inv = si->second.pk_inv;
+    pp.fb = fb; pp.ib = ib;
+    pp.tasks_f = sf->second.pk_tasks; pp.tasks_i = si->second.pk_tasks;
+    pp.perm_f = sf->second.pk_perm[0]; pp.perm_i = si->second.pk_perm[1];
     pp.fslots = pk_buf_slots(g.Pf >> 1); pp.bslots = pk_buf_slots(g.Ni >> 1);
     pp.gthreads = kPkGroupThreads;
-    if (g.in_mode == DFT_IN_FREQ_UP && g.L == 2 && g.step == 1) pp.spec_mode = PK_SPEC_UP2;
-    else if (g.Ni == g.Pf && g.step >= 1 && g.in_mode != DFT_IN_FREQ_UP) pp.spec_mode = PK_SPEC_SAME;
-    else pp.spec_mode = PK_SPEC_GEN;
+    pp.spec_mode = pk_spec_mode(g);
+    pp.spec = pk_spec_dev_[i];
+    if (pp.spec_mode != PK_SPEC_GEN && !pp.spec) return false;
     for (pp.groups = kPkMaxGroups; pp.groups >= 1; --pp.groups)
-      if (dftp_smem_bytes(pp) + 1024 <= max_smem_) break;
-    return pp.groups >= 1;
+      if (pk_smem_layout(pp).total + 1024 <= max_smem_) break;
+    if (pp.groups < 1) return false;
+    const PkSmemLayout lay = pk_smem_layout(pp);
+    pp.lay_pyr_f = lay.pyr_f; pp.lay_pyr_i = lay.pyr_i; pp.lay_tasks_f = lay.tasks_f; pp.lay_tasks_i = lay.tasks_i;
+    pp.lay_perm_f = lay.perm_f; pp.lay_data = lay.data;
+    pp.n_pyr_f = pk_pyr_len(fb); pp.n_pyr_i = pk_pyr_len(ib); pp.n_tasks_f = pk_task_entries(fb); pp.n_tasks_i = pk_task_entries(ib);
+    return true;
   }
-  std::map<int, DevSched> sched_;          // by complex bits
-  std::map<int, const T *> tcos_;          // by real bits
+  static int pk_spec_mode(const StageGeom &g)
+  {
+    if (g.in_mode == DFT_IN_FREQ_UP && g.L == 2 && g.step == 1) return PK_SPEC_UP2;
+    if (g.Ni == g.Pf && g.step >= 1 && g.in_mode != DFT_IN_FREQ_UP) return PK_SPEC_SAME;
+    return PK_SPEC_GEN;
+  }
+
+  // Per-index constants of the fused spectrum phase of stage i (modes UP2 / SAME): record i (i = 0 stands
+  // for M/2 and also carries the two real bins). Needs the filter spectrum (make_spectrum).
+  int build_pk_spec(int i)
+  {
+    const StageGeom &g = geom[i];
+    const int mode = pk_spec_mode(g);
+    const int fb = ilog2(g.Pf) - 1, ib = ilog2(g.Ni) - 1;
+    if (mode == PK_SPEC_GEN || fb < 5 || ib < 5 || fb > 13 || ib > 13) return RR_OK;
+    const int N = g.N, M = g.Pf >> 1, Mi = g.Ni >> 1, n = M >> 1;
+    std::vector<float> spec(static_cast<size_t>(N));
+    if (dft_spectrum_host(g.filter, spec.data(), N) != N) return RR_INTERNAL;
+    const C2<float> *coef = reinterpret_cast<const C2<float> *>(spec.data());
+    const std::vector<float> tf = cos_quarter_table<float>(ilog2(g.Pf)), ti = cos_quarter_table<float>(ilog2(g.Ni));
+    const std::vector<uint16_t> &perm = pk_perm_inv_host_[ib];
+    std::vector<PkSpecConst> rec(static_cast<size_t>(n) + 1);
+    memset(rec.data(), 0, rec.size() * sizeof(PkSpecConst));
+    for (int k = 0; k < n; ++k) {
+      const int ii = k ? k : n;
+      PkSpecConst &r = rec[static_cast<size_t>(k)];
+      r.tfc = tf[static_cast<size_t>(ii)]; r.tfs = tf[static_cast<size_t>(n - ii)];
+      if (mode == PK_SPEC_UP2) {
+        r.c0 = coef[ii]; r.c1 = coef[Mi - ii]; r.c2 = coef[M - ii]; r.c3 = coef[M + ii];
+        r.tic = ti[static_cast<size_t>(ii)]; r.tis = ti[static_cast<size_t>(M - ii)];
+        r.s01 = perm[static_cast<size_t>(ii)] | (static_cast<unsigned>(perm[static_cast<size_t>(Mi - ii)]) << 16);
+        r.s23 = perm[static_cast<size_t>(M - ii)] | (static_cast<unsigned>(perm[static_cast<size_t>(M + ii)]) << 16);
+      } else {
+        r.c0 = coef[ii]; r.c1 = coef[M - ii]; r.c2 = r.c0; r.c3 = r.c0;
+        r.tic = r.tfc; r.tis = r.tfs;
+        r.s01 = perm[static_cast<size_t>(ii)] | (static_cast<unsigned>(perm[static_cast<size_t>(M - ii)]) << 16);
+        r.s23 = r.s01;
+      }
+    }
+    PkSpecConst &sp = rec[0];                      // index 0 has no use for c2, c3, s23: the two real bins go there
+    sp.c2 = coef[0];
+    sp.s23 = perm[0];
+    sp.c3 = C2<float>{0.f, 0.f};
+    if (mode == PK_SPEC_UP2) { sp.c3 = coef[M]; sp.s23 |= static_cast<unsigned>(perm[static_cast<size_t>(M)]) << 16; }
+    return upload(rec, &pk_spec_dev_[i]);
+  }
 
   int dft_lanes_per_cta(const StageGeom &g, int nlanes) const
   {
@@ -862,23 +926,9 @@ template <class T> class Engine {
       }
       if (std::is_same<T, float>::value && bits <= 13) {
         const PkHostSched ph = build_pk_sched(h);
-        const uint16_t *pl16 = nullptr, *pl8 = nullptr, *perm[2] = {nullptr, nullptr};
-        if ((rc = upload(ph.leaf16_off, &pl16)) || (rc = upload(ph.leaf8_off, &pl8)) || (rc = upload(ph.perm[0], &perm[0])) ||
-            (rc = upload(ph.perm[1], &perm[1])))
+        if ((rc = upload(ph.tasks, &d.pk_tasks)) || (rc = upload(ph.perm[0], &d.pk_perm[0])) || (rc = upload(ph.perm[1], &d.pk_perm[1])))
           return rc;
-        for (int inv = 0; inv < 2; ++inv) {
-          PkSched &k = inv ? d.pk_inv : d.pk_fwd;
-          k.bits = bits;
-          k.n16 = static_cast<int>(ph.leaf16_off.size()); k.n8p = ph.n8p;
-          k.leaf16_off = pl16; k.leaf8_off = pl8; k.perm = perm[inv]; k.node_off = nodes;
-          k.pyr_len = h.pyr_len;
-          for (int l = 0; l < 17; ++l) {
-            k.level_begin[l] = h.level_begin[l]; k.level_cnt[l] = h.level_cnt[l]; k.pyr_off[l] = h.pyr_off[l];
-            k.qchild_begin[l] = h.qchild_begin[l]; k.qchild_cnt[l] = h.qchild_cnt[l];
-          }
-          k.nphases = ph.nphases;
-          for (int q = 0; q < 8; ++q) { k.phase_lg[q] = ph.phase_lg[q]; k.phase_depth[q] = ph.phase_depth[q]; }
-        }
+        pk_perm_inv_host_[bits] = ph.perm[1];
       }
       it = sched_.emplace(bits, d).first;
     }
@@ -942,6 +992,7 @@ template <class T> class Engine {
         if ((rc = get_tcos(ilog2(g.Pf), &p.tcos_f)) || (rc = get_tcos(ilog2(g.Ni), &p.tcos_i))) return rc;
         if (!dft_coef_dev_[g.filter] && (rc = make_spectrum(g.filter))) return rc;
         p.coef = dft_coef_dev_[g.filter];
+        if constexpr (std::is_same<T, float>::value) { if ((rc = build_pk_spec(i))) return rc; }
       }
     }
     return be_sync(0);

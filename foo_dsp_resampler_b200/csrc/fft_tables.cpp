@@ -1,5 +1,6 @@
 // fft_tables.cpp -- see fft_tables.hpp.
 #include "fft_tables.hpp"
+#include "pk_plan.hpp"
 
 #include <algorithm>
 #include <cassert>
@@ -108,15 +109,31 @@ std::vector<uint16_t> spread_over_bank_groups(const std::vector<uint16_t> &offs)
 PkHostSched build_pk_sched(const CfftHostSched &h)
 {
   PkHostSched s;
-  const int m = 1 << h.bits;
-  s.leaf16_off = spread_over_bank_groups(h.leaf16_off);
-  const std::vector<uint16_t> l8 = spread_over_bank_groups(h.leaf8_off);
-  s.n8p = static_cast<int>((l8.size() + 1) / 2);
-  s.leaf8_off.assign(static_cast<size_t>(2 * s.n8p), 0xffff);
+  const int bits = h.bits, m = 1 << bits;
+  const std::vector<uint16_t> l16 = spread_over_bank_groups(h.leaf16_off), l8 = spread_over_bank_groups(h.leaf8_off);
+  assert(static_cast<int>(l16.size()) == pk_n16(bits) && static_cast<int>(l8.size()) == pk_n8(bits));
+  s.tasks = l16;
+  const int n8p = pk_n8p(bits);
+  std::vector<uint16_t> pairs(static_cast<size_t>(2 * n8p), 0xffff);
   for (size_t k = 0; k < l8.size(); ++k) {         // task t: entries t and t + n8p of the spread list
-    const size_t t = k < static_cast<size_t>(s.n8p) ? k : k - static_cast<size_t>(s.n8p);
-    s.leaf8_off[2 * t + (k < static_cast<size_t>(s.n8p) ? 0 : 1)] = l8[k];
+    const size_t t = k < static_cast<size_t>(n8p) ? k : k - static_cast<size_t>(n8p);
+    pairs[2 * t + (k < static_cast<size_t>(n8p) ? 0 : 1)] = l8[k];
   }
+  s.tasks.insert(s.tasks.end(), pairs.begin(), pairs.end());
+  const PkPhaseList pl = pk_phase_list(bits);
+  for (int ph = 0; ph < pl.n; ++ph) {
+    const int lg = pl.lg[ph], depth = pl.depth[ph], q = 1 << (lg - 2);
+    assert(static_cast<int>(s.tasks.size()) == pk_phase_base(bits, ph));
+    auto emit = [&](int begin, int count) {
+      for (int node = 0; node < count; ++node)
+        for (int k = 0; k < q; ++k) s.tasks.push_back(static_cast<uint16_t>(h.node_off[static_cast<size_t>(begin + node)] + k));
+    };
+    const int top = lg + depth - 1;                // main tasks: every node of the phase's top size
+    emit(h.level_begin[top], h.level_cnt[top]);
+    assert(static_cast<int>(s.tasks.size()) == pk_phase_base(bits, ph) + pk_phase_main(bits, lg, depth));
+    if (depth > 1) emit(h.qchild_begin[top - 1], h.qchild_cnt[top - 1]);   // light tasks: quarter children one size below
+  }
+  assert(static_cast<int>(s.tasks.size()) == pk_task_entries(bits));
   for (int inv = 0; inv < 2; ++inv) {
     s.perm[inv].assign(static_cast<size_t>(m), 0);
     for (int p = 0; p < m; ++p) {
@@ -124,17 +141,6 @@ PkHostSched build_pk_sched(const CfftHostSched &h)
       s.perm[inv][static_cast<size_t>(natural)] = static_cast<uint16_t>(pk_slot(p));
     }
   }
-  // levels 5 .. bits in phases: three-level phases first while the transform is large enough to keep a
-  // 128-thread group busy with 16-value tasks, two-level phases otherwise; a single level only if it must
-  int lg = 5, left = h.bits - 4;
-  auto push = [&](int depth) { s.phase_lg[s.nphases] = lg; s.phase_depth[s.nphases] = depth; ++s.nphases; lg += depth; left -= depth; };
-  if (h.bits >= 11) {
-    while (left >= 3 && left != 4) push(3);
-  } else if (left & 1) {
-    if (left >= 3) push(3); else push(1);
-  }
-  while (left >= 2) push(2);
-  if (left == 1) push(1);
   return s;
 }
 

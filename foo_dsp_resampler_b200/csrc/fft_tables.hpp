@@ -27,15 +27,12 @@ struct CfftHostSched {
 
 CfftHostSched build_cfft_sched(int bits);
 
-// Extra tables of the lane-pair kernel (rate_kernels_pk.cuh) for the same transform: the permutation folded
-// into the buffer-filling writes, leaf task lists ordered for bank-conflict-free 16-byte accesses, and the
-// grouping of the combining levels into phases of 1, 2 or 3 levels.
+// Tables of the lane-pair kernel (rate_kernels_pk.cuh) for the same transform: the permutation folded into
+// the buffer-filling writes and the task table in the layout pk_plan.hpp defines (leaf lists ordered for
+// bank-conflict-free 16-byte accesses, then per phase the positions o = node offset + k of its tasks).
 struct PkHostSched {
-  std::vector<uint16_t> leaf16_off;              // n16 entries
-  std::vector<uint16_t> leaf8_off;               // 2 * n8p entries: task t handles [2t] and [2t+1] (0xffff: none)
+  std::vector<uint16_t> tasks;                   // pk_task_entries(bits) entries
   std::vector<uint16_t> perm[2];                 // [inverse][natural index] -> pk_slot(permuted position)
-  int n8p = 0;
-  int nphases = 0, phase_lg[8] = {0}, phase_depth[8] = {0};
 };
 int pk_slot(int p);                              // == pslot() of rate_kernels_pk.cuh
 PkHostSched build_pk_sched(const CfftHostSched &h);

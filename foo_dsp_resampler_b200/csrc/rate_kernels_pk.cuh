@@ -26,6 +26,7 @@
 // thread. That build is test infrastructure only.
 #pragma once
 
+#include "pk_plan.hpp"
 #include "rate_kernels.cuh"
 
 namespace b200rate {
@@ -116,21 +117,8 @@ template <class F> RR_PROG void grp_for(const Grp &g, int count, F f)
 RR_HD int pslot(int p) { return p + (p >> 4) + (p >> 8); }
 RR_HD int pk_buf_slots(int m) { return ((pslot(m - 1) + 1 + 7) / 8) * 8; }
 
-// Device-side schedule of one complex FFT of M = 1 << bits points.
-struct PkSched {
-  int bits;
-  int n16, n8p;                  // leaf tasks: size-16 leaves, pairs of size-8 leaves
-  const uint16_t *leaf16_off;    // [n16] offsets, ordered so that eight consecutive tasks do not share a bank group
-  const uint16_t *leaf8_off;     // [2 * n8p], 0xffff = none
-  const uint16_t *perm;          // [M] natural index -> slot of its permuted position
-  const uint16_t *node_off;      // node offsets of sizes 32 .. M, then the quarter-child lists (CfftHostSched)
-  int level_begin[17], level_cnt[17], qchild_begin[17], qchild_cnt[17], pyr_off[17];
-  int pyr_len;
-  int nphases, phase_lg[8], phase_depth[8];
-};
-
 // Where the top pass may put the block's valid samples instead of shared memory.
-struct PkSink {
+struct PkSink {                  // passed by value: lives in registers
   float *d0, *d1;                // planar: lane pointers at the block's first output; interleaved: d0 only
   int es;                        // interleaved: elements between consecutive samples of a lane; 0 = planar
   int half;                      // complex elements to store (valid samples / 2)
@@ -150,16 +138,19 @@ RR_PROG void pk_sink_store(const PkSink &k, int c, const CPk &v)
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Leaves (fft16 / fft8, fft.c:288-318), in place
+// The FFT of M = 1 << BITS points over FFmpeg's split-radix DAG, everything about its shape a compile-time
+// constant (pk_plan.hpp); `tasks` is the task table of the transform (shared memory), `pyr` its twiddle pyramid.
 // ---------------------------------------------------------------------------------------------------
-// swz: the slots hold {a.re, a.im, b.re, b.im} (planar input copied 8 bytes per lane) instead of the
-// working layout; the leaf re-pairs them while the values are in registers.
-RR_PROG void pk_leaves(const PkSched &s, const Grp &g, CPk *buf, bool swz, float sqrthalf, float c16_1, float c16_3)
+// Leaves (fft16 / fft8, fft.c:288-318), in place. swz: the slots hold {a.re, a.im, b.re, b.im} (planar input
+// copied 8 bytes per lane) instead of the working layout; the leaf re-pairs them in registers.
+template <int BITS>
+RR_PROG void pk_fft_leaves(const Grp &g, CPk *buf, const uint16_t *tasks, bool swz, float sqrthalf, float c16_1, float c16_3)
 {
+  constexpr int n16 = pk_n16(BITS), n8p = pk_n8p(BITS);
   const Pk sh = pk_bcast(sqrthalf), c1 = pk_bcast(c16_1), c3 = pk_bcast(c16_3);
-  grp_for(g, s.n16 + s.n8p, [&](int task) {
-    if (task < s.n16) {
-      CPk *b = buf + pslot(ldg(s.leaf16_off + task));    // multiple of 16: the 16 slots are contiguous
+  grp_for(g, n16 + n8p, [&](int task) {
+    if (task < n16) {
+      CPk *b = buf + pslot(tasks[task]);                 // multiple of 16: the 16 slots are contiguous
       Pk re[16], im[16];
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
@@ -172,7 +163,7 @@ RR_PROG void pk_leaves(const PkSched &s, const Grp &g, CPk *buf, bool swz, float
       for (int e = 0; e < 16; ++e) b[e] = CPk{re[e], im[e]};
     } else {
       for (int h = 0; h < 2; ++h) {
-        const int off = ldg(s.leaf8_off + 2 * (task - s.n16) + h);
+        const int off = tasks[n16 + 2 * (task - n16) + h];
         if (off == 0xffff) continue;
         CPk *b = buf + pslot(off);                        // multiple of 8: never straddles a pad slot
         Pk re[8], im[8];
@@ -190,11 +181,9 @@ RR_PROG void pk_leaves(const PkSched &s, const Grp &g, CPk *buf, bool swz, float
   });
 }
 
-// ---------------------------------------------------------------------------------------------------
 // Combining passes (pass(), fft.c:237-256), fused 1, 2 or 3 levels deep. S = 1 << LG is the smallest size of
-// the task, q = S/4; a task (node, k < q) owns the values at o + k + j*q. slot() is additive over the node
-// offset, so with LG a template parameter every address is `base + constant`.
-// ---------------------------------------------------------------------------------------------------
+// the task, q = S/4; the task at position o = node offset + k (k < q) owns the values at o + j*q. pslot() is
+// additive over the node offset, so every address is `base + constant`.
 template <int LG> struct PkGeo {
   static constexpr int q = 1 << (LG - 2);
   static RR_HD constexpr int rel(int j) { return j * q + ((j * q) >> 4) + ((j * q) >> 8); }   // pslot(j*q)
@@ -205,129 +194,136 @@ RR_PROG void pk_bfly(CPk &a0, CPk &a1, CPk &a2, CPk &a3, float wre, float wim, b
   sr_bfly<Pk>(a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y, pk_bcast(wre), pk_bcast(wim), zero);
 }
 
-// one butterfly of size S on node list entry `node`
-template <int LG> RR_PROG void pk_p1_item(const PkSched &s, int list_begin, int item, CPk *buf, const float *pyr)
+// DEPTH 1: one butterfly of size S.  DEPTH 2: sizes S and 2S on a node of size 2S (8 values): butterfly k of the
+// S-pass on the first half, then butterflies k and k + S/4 of the 2S-pass (the quarters of size S/2 are
+// finished).  DEPTH 3: sizes S, 2S, 4S on a node of size 4S (16 values): the S-pass on the first quarter of the
+// first half and on both quarter children, the 2S-pass on the first half, four butterflies of the 4S-pass.
+// Same butterflies on the same operands as the level-by-level order of fft.c:265-272, hence the same bits.
+template <int LG, int DEPTH, bool SINK>
+RR_PROG void pk_item(int o, CPk *buf, const float *pyr, const PkSink &sink)
 {
   typedef PkGeo<LG> G;
-  const int node = item >> (LG - 2), k = item & (G::q - 1);
-  CPk *b = buf + pslot(ldg(s.node_off + list_begin + node) + k);
-  const float *tw = pyr + s.pyr_off[LG];
-  CPk a0 = b[0], a1 = b[G::rel(1)], a2 = b[G::rel(2)], a3 = b[G::rel(3)];
-  pk_bfly(a0, a1, a2, a3, tw[k], tw[G::q - k], k == 0);
-  b[0] = a0; b[G::rel(1)] = a1; b[G::rel(2)] = a2; b[G::rel(3)] = a3;
-}
-
-// sizes S and 2S on a node of size 2S (8 values): butterfly k of the S-pass on the first half, then
-// butterflies k and k + S/4 of the 2S-pass (the two quarters of size S/2 are finished).
-template <int LG, bool SINK>
-RR_PROG void pk_l2_item(const PkSched &s, int list_begin, int item, CPk *buf, const float *pyr, const PkSink *sink)
-{
-  typedef PkGeo<LG> G;
-  constexpr int q = G::q;
-  const int node = item >> (LG - 2), k = item & (q - 1);
-  const int o = ldg(s.node_off + list_begin + node) + k;
+  constexpr int q = G::q, NV = 4 << (DEPTH - 1);
+  const int k = o & (q - 1);
   CPk *b = buf + pslot(o);
-  const float *twa = pyr + s.pyr_off[LG], *twb = pyr + s.pyr_off[LG + 1];
-  CPk e[8];
+  const float *twa = pyr + pk_pyr_off(LG);
+  CPk e[NV];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) e[j] = b[G::rel(j)];
-  pk_bfly(e[0], e[1], e[2], e[3], twa[k], twa[q - k], k == 0);
-  pk_bfly(e[0], e[2], e[4], e[6], twb[k], twb[2 * q - k], k == 0);
-  pk_bfly(e[1], e[3], e[5], e[7], twb[k + q], twb[q - k], false);
-  if (SINK) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) pk_sink_store(*sink, o + j * q, e[j]);
-  } else {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) b[G::rel(j)] = e[j];
-  }
-}
-
-// sizes S, 2S and 4S on a node of size 4S (16 values): the S-pass on the first quarter-of-the-half and on
-// both quarter children (size S), the 2S-pass on the first half, then four butterflies of the 4S-pass.
-template <int LG, bool SINK>
-RR_PROG void pk_h3_item(const PkSched &s, int list_begin, int item, CPk *buf, const float *pyr, const PkSink *sink)
-{
-  typedef PkGeo<LG> G;
-  constexpr int q = G::q;
-  const int node = item >> (LG - 2), k = item & (q - 1);
-  const int o = ldg(s.node_off + list_begin + node) + k;
-  CPk *b = buf + pslot(o);
-  const float *twa = pyr + s.pyr_off[LG], *twb = pyr + s.pyr_off[LG + 1], *twc = pyr + s.pyr_off[LG + 2];
-  CPk e[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) e[j] = b[G::rel(j)];
+  for (int j = 0; j < NV; ++j) e[j] = b[G::rel(j)];
   {
     const float wr = twa[k], wi = twa[q - k];
     pk_bfly(e[0], e[1], e[2], e[3], wr, wi, k == 0);
-    pk_bfly(e[8], e[9], e[10], e[11], wr, wi, k == 0);
-    pk_bfly(e[12], e[13], e[14], e[15], wr, wi, k == 0);
+    if constexpr (DEPTH == 3) {
+      pk_bfly(e[8], e[9], e[10], e[11], wr, wi, k == 0);
+      pk_bfly(e[12], e[13], e[14], e[15], wr, wi, k == 0);
+    }
   }
-  pk_bfly(e[0], e[2], e[4], e[6], twb[k], twb[2 * q - k], k == 0);
-  pk_bfly(e[1], e[3], e[5], e[7], twb[k + q], twb[q - k], false);
+  if constexpr (DEPTH >= 2) {
+    const float *twb = pyr + pk_pyr_off(LG + 1);
+    pk_bfly(e[0], e[2], e[4], e[6], twb[k], twb[2 * q - k], k == 0);
+    pk_bfly(e[1], e[3], e[5], e[7], twb[k + q], twb[q - k], false);
+  }
+  if constexpr (DEPTH == 3) {
+    const float *twc = pyr + pk_pyr_off(LG + 2);
 #pragma unroll
-  for (int m = 0; m < 4; ++m) pk_bfly(e[m], e[m + 4], e[m + 8], e[m + 12], twc[k + m * q], twc[(4 - m) * q - k], m == 0 && k == 0);
+    for (int m = 0; m < 4; ++m)
+      pk_bfly(e[m], e[m + 4], e[m + 8], e[m + 12], twc[k + m * q], twc[(4 - m) * q - k], m == 0 && k == 0);
+  }
   if (SINK) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) pk_sink_store(*sink, o + j * q, e[j]);
+    for (int j = 0; j < NV; ++j) pk_sink_store(sink, o + j * q, e[j]);
   } else {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) b[G::rel(j)] = e[j];
+    for (int j = 0; j < NV; ++j) b[G::rel(j)] = e[j];
   }
 }
 
-// One phase: DEPTH levels starting at size 1 << LG. Light tasks are bundled in threes so that every task of
-// a phase costs about the same (3 single butterflies = one 2-level task, 3 of those = one 3-level task).
-template <int LG, int DEPTH, bool SINK>
-RR_PROG void pk_phase(const PkSched &s, const Grp &g, CPk *buf, const float *pyr, const PkSink *sink)
+// Phase PH of the transform. Light tasks (one level shallower) are bundled in threes so that every task of a
+// phase costs about the same.
+template <int BITS, int PH, bool SINK>
+RR_PROG void pk_fft_phase(const Grp &g, CPk *buf, const uint16_t *tasks, const float *pyr, const PkSink &sink)
 {
-  constexpr int qb = LG - 2;
-  if (DEPTH == 1) {
-    grp_for(g, s.level_cnt[LG] << qb, [&](int t) { pk_p1_item<LG>(s, s.level_begin[LG], t, buf, pyr); });
-  } else if (DEPTH == 2) {
-    const int nf = s.level_cnt[LG + 1] << qb, np = s.qchild_cnt[LG] << qb, nb = (np + 2) / 3;
-    grp_for(g, nf + nb, [&](int t) {
-      if (t < nf) pk_l2_item<LG, SINK>(s, s.level_begin[LG + 1], t, buf, pyr, sink);
-      else
-        for (int j = t - nf; j < np; j += nb) pk_p1_item<LG>(s, s.qchild_begin[LG], j, buf, pyr);
-    });
+  constexpr PkPhaseList pl = pk_phase_list(BITS);
+  constexpr int LG = pl.lg[PH], D = pl.depth[PH];
+  constexpr int base = pk_phase_base(BITS, PH), nmain = pk_phase_main(BITS, LG, D), nlight = pk_phase_light(BITS, LG, D);
+  constexpr int nb = (nlight + 2) / 3, DL = D > 1 ? D - 1 : 1;
+  grp_for(g, nmain + nb, [&](int t) {
+    if (t < nmain) pk_item<LG, D, SINK>(tasks[base + t], buf, pyr, sink);
+    else
+      for (int j = t - nmain; j < nlight; j += nb) pk_item<LG, DL, false>(tasks[base + nmain + j], buf, pyr, sink);
+  });
+}
+
+// Leaves and every phase but the top one / the top phase, inlined: for kernels specialised on the size.
+template <int BITS>
+RR_PROG void pk_fft_lower_impl(const Grp &g, CPk *buf, const uint16_t *tasks, const float *pyr, bool swz, float sqrthalf, float c16_1,
+                               float c16_3)
+{
+  constexpr int n = pk_phase_list(BITS).n;
+  const PkSink none{nullptr, nullptr, 0, 0};
+  pk_fft_leaves<BITS>(g, buf, tasks, swz, sqrthalf, c16_1, c16_3);
+  if constexpr (n > 1) pk_fft_phase<BITS, 0, false>(g, buf, tasks, pyr, none);
+  if constexpr (n > 2) pk_fft_phase<BITS, 1, false>(g, buf, tasks, pyr, none);
+  if constexpr (n > 3) pk_fft_phase<BITS, 2, false>(g, buf, tasks, pyr, none);
+}
+template <int BITS, bool SINK>
+RR_PROG void pk_fft_top_impl(const Grp &g, CPk *buf, const uint16_t *tasks, const float *pyr, const PkSink &sink)
+{
+  pk_fft_phase<BITS, pk_phase_list(BITS).n - 1, SINK>(g, buf, tasks, pyr, sink);
+}
+
+#if defined(__CUDACC__)
+#define RR_PK_CALL __device__ __noinline__
+#else
+#define RR_PK_CALL inline
+#endif
+
+// The same as separate, not inlined functions for the size-generic kernels: one copy per size serves the
+// forward and the inverse transform.
+template <int BITS>
+RR_PK_CALL void pk_fft_lower(Grp g, CPk *buf, const uint16_t *tasks, const float *pyr, bool swz, float sqrthalf, float c16_1, float c16_3)
+{
+  pk_fft_lower_impl<BITS>(g, buf, tasks, pyr, swz, sqrthalf, c16_1, c16_3);
+}
+template <int BITS, bool SINK>
+RR_PK_CALL void pk_fft_top(Grp g, CPk *buf, const uint16_t *tasks, const float *pyr, PkSink sink)
+{
+  pk_fft_top_impl<BITS, SINK>(g, buf, tasks, pyr, sink);
+}
+
+#define RR_PK_BITS_SWITCH(BITS_EXPR, CALL)                                                                   \
+  switch (BITS_EXPR) {                                                                                       \
+    case 5: CALL(5); break;   case 6: CALL(6); break;   case 7: CALL(7); break;                              \
+    case 8: CALL(8); break;   case 9: CALL(9); break;   case 10: CALL(10); break;                            \
+    case 11: CALL(11); break; case 12: CALL(12); break; case 13: CALL(13); break;                            \
+    default: break;                                                                                          \
+  }
+
+// BITS > 0: size known at compile time, everything inlined; BITS == 0: dispatch on the run-time size.
+template <int BITS>
+RR_PROG void pk_fft_lower_any(int bits, const Grp &g, CPk *buf, const uint16_t *tasks, const float *pyr, bool swz, float sqrthalf,
+                              float c16_1, float c16_3)
+{
+  if constexpr (BITS > 0) pk_fft_lower_impl<BITS>(g, buf, tasks, pyr, swz, sqrthalf, c16_1, c16_3);
+  else {
+#define RR_PK_LOWER(B) pk_fft_lower<B>(g, buf, tasks, pyr, swz, sqrthalf, c16_1, c16_3)
+    RR_PK_BITS_SWITCH(bits, RR_PK_LOWER)
+#undef RR_PK_LOWER
+  }
+}
+template <int BITS>
+RR_PROG void pk_fft_top_any(int bits, const Grp &g, CPk *buf, const uint16_t *tasks, const float *pyr, bool use_sink, const PkSink &sink)
+{
+  if constexpr (BITS > 0) {
+    if (use_sink) pk_fft_top_impl<BITS, true>(g, buf, tasks, pyr, sink);
+    else pk_fft_top_impl<BITS, false>(g, buf, tasks, pyr, sink);
   } else {
-    const int nh = s.level_cnt[LG + 2] << qb, nl = s.qchild_cnt[LG + 1] << qb, nb = (nl + 2) / 3;
-    grp_for(g, nh + nb, [&](int t) {
-      if (t < nh) pk_h3_item<LG, SINK>(s, s.level_begin[LG + 2], t, buf, pyr, sink);
-      else
-        for (int j = t - nh; j < nl; j += nb) pk_l2_item<LG, false>(s, s.qchild_begin[LG + 1], j, buf, pyr, nullptr);
-    });
-  }
-}
-
-// Only the (size, depth) combinations build_pk_sched() (fft_tables.cpp) produces are instantiated; SINK only
-// for those that can be the top phase of a transform.
-template <bool SINK>
-RR_PROG void pk_phase_dispatch(const PkSched &s, const Grp &g, int lg, int depth, CPk *buf, const float *pyr, const PkSink *sink)
-{
-#define RR_PK_CASE(LG, D) case LG * 4 + D: pk_phase<LG, D, SINK>(s, g, buf, pyr, sink); break;
-  switch (lg * 4 + depth) {
-    RR_PK_CASE(5, 2) RR_PK_CASE(5, 3) RR_PK_CASE(7, 2) RR_PK_CASE(8, 2) RR_PK_CASE(9, 2) RR_PK_CASE(10, 2) RR_PK_CASE(11, 2)
-    RR_PK_CASE(11, 3)
-    default:
-      if (!SINK) switch (lg * 4 + depth) {
-        RR_PK_CASE(5, 1) RR_PK_CASE(8, 3)
-        default: break;
-      }
-      break;
-  }
-#undef RR_PK_CASE
-}
-
-// All combining passes. sink != nullptr: the top phase (which must be fused, i.e. cover every value with
-// 2- or 3-level tasks) stores the valid samples straight to global memory.
-RR_PROG void pk_passes(const PkSched &s, const Grp &g, CPk *buf, const float *pyr, const PkSink *sink)
-{
-  for (int ph = 0; ph < s.nphases; ++ph) {
-    const bool top = ph + 1 == s.nphases;
-    if (top && sink) pk_phase_dispatch<true>(s, g, s.phase_lg[ph], s.phase_depth[ph], buf, pyr, sink);
-    else pk_phase_dispatch<false>(s, g, s.phase_lg[ph], s.phase_depth[ph], buf, pyr, nullptr);
+#define RR_PK_TOP_SINK(B) pk_fft_top<B, true>(g, buf, tasks, pyr, sink)
+#define RR_PK_TOP(B) pk_fft_top<B, false>(g, buf, tasks, pyr, sink)
+    if (use_sink) { RR_PK_BITS_SWITCH(bits, RR_PK_TOP_SINK) }
+    else { RR_PK_BITS_SWITCH(bits, RR_PK_TOP) }
+#undef RR_PK_TOP_SINK
+#undef RR_PK_TOP
   }
 }
 
@@ -340,13 +336,44 @@ enum PkSpecMode {
   PK_SPEC_GEN = 2     // everything else: separate post-processing and spectrum phases
 };
 
+// Constants of one index of the fused spectrum phase (modes UP2 / SAME): filter spectrum values, real-FFT
+// cosines and the inverse transform's slots. 64 bytes, fetched with four 16-byte loads.
+struct alignas(16) PkSpecConst {
+  C2<float> c0, c1, c2, c3;
+  float tfc, tfs, tic, tis;
+  unsigned s01, s23;             // two 16-bit slots each
+  unsigned pad[2];
+};
+
 struct DftPkParams {
   DftParams<float> base;         // geometry, views, cosine tables, filter spectrum (schedules unused)
-  PkSched fwd, inv;
-  int fslots, bslots;            // slots of one forward / inverse buffer
+  const uint16_t *tasks_f, *tasks_i, *perm_f, *perm_i;
+  const PkSpecConst *spec;       // [M/2] records (modes UP2 / SAME); index 0 holds those of M/2 and of the two real bins
+  int fb, ib;                    // log2 of the forward / inverse complex transform sizes
+  int fslots, bslots;            // slots of the forward / inverse buffer
   int groups, gthreads;          // groups per CTA, threads per group
   int spec_mode;
+  int lay_pyr_f, lay_pyr_i, lay_tasks_f, lay_tasks_i, lay_perm_f, lay_data;   // shared-memory byte offsets (host: pk_smem_layout)
+  int n_pyr_f, n_pyr_i, n_tasks_f, n_tasks_i;                                 // table lengths
 };
+
+// Shared memory: tables (twiddle pyramids, task tables, forward permutation), then per group F and B.
+struct PkSmemLayout { int pyr_f, pyr_i, tasks_f, tasks_i, perm_f, data, group_slots; size_t total; };
+RR_HD PkSmemLayout pk_smem_layout(const DftPkParams &pp)
+{
+  PkSmemLayout l;
+  int o = 0;
+  l.pyr_f = o; o += 4 * pk_pyr_len(pp.fb);
+  l.pyr_i = o; o += 4 * pk_pyr_len(pp.ib);
+  l.tasks_f = o; o += 2 * pk_task_entries(pp.fb);
+  l.tasks_i = o; o += 2 * pk_task_entries(pp.ib);
+  o = (o + 3) & ~3;
+  l.perm_f = o; o += 2 << pp.fb;
+  l.data = (o + 15) & ~15;
+  l.group_slots = pp.fslots + pp.bslots;
+  l.total = (size_t)l.data + (size_t)pp.groups * l.group_slots * sizeof(CPk);
+  return l;
+}
 
 // How the input tile of an item is copied: whole slots when the lanes are adjacent in an interleaved buffer,
 // 8 bytes per lane from planar lanes (re-paired by the leaves), else scalar copies with zero fill.
@@ -357,7 +384,7 @@ struct PkItem {
   int tile_mode;
 };
 
-RR_PROG PkItem pk_item(const DftPkParams &pp, long long work)
+RR_PROG PkItem pk_make_item(const DftPkParams &pp, long long work)
 {
   const DftParams<float> &p = pp.base;
   PkItem it;
@@ -388,20 +415,19 @@ inline void pk_async_copy16(void *dst, const void *src) { memcpy(dst, src, 16); 
 #endif
 
 // Issue the (asynchronous) copy of an item's input tile into `F`, element j at the slot of its permuted
-// position. Does not wait.
-RR_PROG void pk_stage_tile(const DftPkParams &pp, const Grp &g, const PkItem &it, CPk *F)
+// position (perm: the forward transform's table, shared memory). Does not wait.
+RR_PROG void pk_stage_tile(const DftPkParams &pp, const Grp &g, const PkItem &it, CPk *F, const uint16_t *perm)
 {
   const DftParams<float> &p = pp.base;
   const int span = p.in_mode == DFT_IN_FREQ_UP ? p.Pf : p.N, m = span >> 1;
-  const uint16_t *perm = pp.fwd.perm;
   if (it.tile_mode == PK_TILE_INTERLEAVED) {
     const float *s0 = view_ptr<const float>(p.in, it.d.in_off0, it.d.Rb);
     const int es = p.in.elem_stride;
     if (es == 2 && !((size_t)s0 & 15))
-      for (int j = g.tid; j < m; j += g.size) pk_async_copy16(F + ldg(perm + j), s0 + 4 * j);
+      for (int j = g.tid; j < m; j += g.size) pk_async_copy16(F + perm[j], s0 + 4 * j);
     else
       for (int j = g.tid; j < m; j += g.size) {
-        CPk *d = F + ldg(perm + j);
+        CPk *d = F + perm[j];
         const float *f = s0 + (long long)(2 * j) * es;
         pk_async_copy8(&d->x, f);
         pk_async_copy8(&d->y, f + es);
@@ -409,7 +435,7 @@ RR_PROG void pk_stage_tile(const DftPkParams &pp, const Grp &g, const PkItem &it
   } else if (it.tile_mode == PK_TILE_PLANAR) {
     const float *s0 = view_ptr<const float>(p.in, it.d.in_off0, it.d.Rb), *s1 = view_ptr<const float>(p.in, it.d.in_off1, it.d.Rb);
     for (int j = g.tid; j < m; j += g.size) {
-      CPk *d = F + ldg(perm + j);
+      CPk *d = F + perm[j];
       pk_async_copy8(&d->x, s0 + 2 * j);                  // {a.re, a.im}: re-paired by the leaves (swz)
       pk_async_copy8(&d->y, s1 + 2 * j);                  // {b.re, b.im}
     }
@@ -424,7 +450,7 @@ RR_PROG void pk_stage_tile(const DftPkParams &pp, const Grp &g, const PkItem &it
         on_grid = d >= 0 && d % L == 0;
         coord = it.d.Rb + (on_grid ? d / L : 0);
       }
-      float *dst = reinterpret_cast<float *>(F + ldg(perm + (j >> 1))) + 2 * (j & 1) + l;
+      float *dst = reinterpret_cast<float *>(F + perm[j >> 1]) + 2 * (j & 1) + l;
       bool valid;
       const float *src = view_addr<float>(p.in, l ? it.d.in_off1 : it.d.in_off0, coord, &valid);
       async_copy_elem<float>(dst, src, valid && on_grid);
@@ -433,15 +459,21 @@ RR_PROG void pk_stage_tile(const DftPkParams &pp, const Grp &g, const PkItem &it
   async_copy_commit();
 }
 
-// Values that do not depend on the work item and are needed by the same thread for every item: filter
-// spectrum, real-FFT cosines and the inverse transform's permuted slots of the spectrum phase. A persistent
-// group loads them once into registers (first kPkCacheRounds rounds of its strided loop).
-constexpr int kPkCacheRounds = 4;
-struct PkSpecCache {
-  C2<float> c0[kPkCacheRounds], c1[kPkCacheRounds], c2[kPkCacheRounds], c3[kPkCacheRounds];
-  float tf_c[kPkCacheRounds], tf_s[kPkCacheRounds], ti_c[kPkCacheRounds], ti_s[kPkCacheRounds];
-  unsigned s01[kPkCacheRounds], s23[kPkCacheRounds];     // two 16-bit slots each
-};
+RR_PROG PkSpecConst pk_load_spec(const PkSpecConst *p)
+{
+#if defined(__CUDA_ARCH__)
+  PkSpecConst r;
+  float4 v[4];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) v[k] = __ldg(reinterpret_cast<const float4 *>(p) + k);
+  const float2 w = __ldg(reinterpret_cast<const float2 *>(p) + 6);
+  v[3] = make_float4(w.x, w.y, 0.f, 0.f);
+  memcpy(&r, v, sizeof(r));
+  return r;
+#else
+  return *p;
+#endif
+}
 
 // rdft.c:46-77, forward transform: (F[i], F[M-i]) -> (X[i], X[M-i])
 RR_HD void pk_post_pair(const CPk &za, const CPk &zb, float c, float s, CPk &xa, CPk &xb)
@@ -486,120 +518,80 @@ RR_HD void pk_mul_pre_pair(const CPk &va, const CPk &vb, const C2<float> &ca, co
 RR_HD CPk pk_conj(const CPk &v) { return CPk{v.x, pk_neg(v.y)}; }
 
 // Spectrum phase, F (forward FFT result, natural order) -> B (input of the inverse FFT, permuted order).
-// round r of thread t handles index i = t + r * g.size; `cached` rounds take their constants from `cc`.
-template <int MODE, bool CACHED>
-RR_PROG void pk_spectrum(const DftPkParams &pp, const Grp &g, const PkSpecCache &cc, const CPk *F, CPk *B)
+// Round r of thread t handles index i = t + r * g.size, i < M/2 (i = 0 also does M/2 and the two real bins);
+// the first kPkSpecRounds rounds find their constants in `pre` (loaded before the previous phase).
+constexpr int kPkSpecRounds = 4;
+struct PkSpecRegs { PkSpecConst r[kPkSpecRounds]; };
+
+template <int MODE>
+RR_PROG void pk_spec_prefetch(const DftPkParams &pp, const Grp &g, PkSpecRegs &pre)
+{
+  const int n = pp.base.Pf >> 2;
+#pragma unroll
+  for (int r = 0; r < kPkSpecRounds; ++r) {
+    const int i = g.tid + r * g.size;
+    if (i < n) pre.r[r] = pk_load_spec(pp.spec + i);
+  }
+}
+
+template <int MODE>
+RR_PROG void pk_spectrum(const DftPkParams &pp, const Grp &g, const PkSpecRegs &pre, const CPk *F, CPk *B)
 {
   typedef Arith<Pk> A;
   const DftParams<float> &p = pp.base;
-  const C2<float> *coef = reinterpret_cast<const C2<float> *>(p.coef);
-  const uint16_t *perm = pp.inv.perm;
   const int M = p.Pf >> 1;                               // forward transform: M complex points
-  const int Mi = p.Ni >> 1;
-  const int n = M >> 1;                                   // items i = 0 .. M/2 - 1 (i = 0 also does M/2)
-  auto body = [&](int i, int r) {
-    C2<float> k0, k1, k2, k3;
-    float tfc, tfs, tic, tis;
-    int sl0, sl1, sl2, sl3;
-    if (CACHED && r >= 0) {
-      k0 = cc.c0[r]; k1 = cc.c1[r]; k2 = cc.c2[r]; k3 = cc.c3[r];
-      tfc = cc.tf_c[r]; tfs = cc.tf_s[r]; tic = cc.ti_c[r]; tis = cc.ti_s[r];
-      sl0 = cc.s01[r] & 0xffff; sl1 = cc.s01[r] >> 16; sl2 = cc.s23[r] & 0xffff; sl3 = cc.s23[r] >> 16;
-    } else {
-      const int ii = i ? i : n;                           // i == 0 loads the constants of its second job, M/2
-      tfc = ldg(p.tcos_f + ii); tfs = ldg(p.tcos_f + n - ii);
-      if (MODE == PK_SPEC_UP2) {
-        k0 = ldg(coef + ii); k1 = ldg(coef + Mi - ii); k2 = ldg(coef + M - ii); k3 = ldg(coef + M + ii);
-        tic = ldg(p.tcos_i + ii); tis = ldg(p.tcos_i + M - ii);
-        sl0 = ldg(perm + ii); sl1 = ldg(perm + Mi - ii); sl2 = ldg(perm + M - ii); sl3 = ldg(perm + M + ii);
-      } else {
-        k0 = ldg(coef + ii); k1 = ldg(coef + M - ii); k2 = k0; k3 = k0;
-        tic = tfc; tis = tfs;
-        sl0 = ldg(perm + ii); sl1 = ldg(perm + M - ii); sl2 = sl0; sl3 = sl0;
-      }
-    }
+  const int n = M >> 1;
+  auto body = [&](int i, const PkSpecConst &k) {
+    const int sl0 = k.s01 & 0xffff, sl1 = k.s01 >> 16, sl2 = k.s23 & 0xffff, sl3 = k.s23 >> 16;
     if (i == 0) {
       // bins 0 and Pf/2 (packed in F[0]) and the self-paired bin M/2
+      // record 0 carries the constants of M/2 in c0, c1, tic, tis, s01 and those of the real bins in the
+      // fields index 0 has no use for: c2 = coef[0], c3 = coef[M], s23 = slots of d[0] and d[M]
       const CPk z = F[0];
       const CPk x0 = CPk{A::add(z.x, z.y), A::sub(z.x, z.y)};                  // rdft.c:46-48
       CPk zm = F[pslot(n)];
       zm.y = pk_neg(zm.y);                                                       // rdft.c:77 (forward)
-      const C2<float> cf0 = ldg(coef);
       if (MODE == PK_SPEC_UP2) {
         // spectrum[0] = (X0.re, X0.re); d[0] = (.5 (d0 + d1), .5 (d0 - d1)), dft_filter.h:96-98,118-119, rdft.c:44-46,79-80
-        const Pk d0 = A::mul(x0.x, pk_bcast(cf0.x)), d1 = A::mul(x0.x, pk_bcast(cf0.y));
-        B[ldg(perm)] = CPk{A::mul(A::addp(d0, d1), pk_bcast(0.5f)), A::mul(A::subp(d0, d1), pk_bcast(0.5f))};
+        const Pk d0 = A::mul(x0.x, pk_bcast(k.c2.x)), d1 = A::mul(x0.x, pk_bcast(k.c2.y));
+        B[sl2] = CPk{A::mul(A::addp(d0, d1), pk_bcast(0.5f)), A::mul(A::subp(d0, d1), pk_bcast(0.5f))};
         // bin Ni/4 = M: spectrum = (X0.im, 0); d[M] = conj(coef[M] * spectrum)
-        const CPk mm = pk_cmul(ldg(coef + M), CPk{x0.y, pk_bcast(0.0f)});
-        B[ldg(perm + M)] = pk_conj(mm);
+        B[sl3] = pk_conj(pk_cmul(k.c3, CPk{x0.y, pk_bcast(0.0f)}));
         // bins M/2 and Ni/2 - M/2: spectrum[M/2] = X[M/2], spectrum[Ni/2 - M/2] = conj(X[M/2])
         CPk da, db;
-        pk_mul_pre_pair(zm, pk_conj(zm), k0, k1, tic, tis, da, db);
+        pk_mul_pre_pair(zm, pk_conj(zm), k.c0, k.c1, k.tic, k.tis, da, db);
         B[sl0] = da; B[sl1] = db;
       } else {
-        const Pk d0 = A::mul(x0.x, pk_bcast(cf0.x)), d1 = A::mul(x0.y, pk_bcast(cf0.y));
-        B[ldg(perm)] = CPk{A::mul(A::addp(d0, d1), pk_bcast(0.5f)), A::mul(A::subp(d0, d1), pk_bcast(0.5f))};
+        const Pk d0 = A::mul(x0.x, pk_bcast(k.c2.x)), d1 = A::mul(x0.y, pk_bcast(k.c2.y));
+        B[sl2] = CPk{A::mul(A::addp(d0, d1), pk_bcast(0.5f)), A::mul(A::subp(d0, d1), pk_bcast(0.5f))};
         // bin Ni/4 = M/2: d = conj(coef * X[M/2])
-        B[sl0] = pk_conj(pk_cmul(k0, zm));
+        B[sl0] = pk_conj(pk_cmul(k.c0, zm));
       }
       return;
     }
     const CPk za = F[pslot(i)], zb = F[pslot(M - i)];
     CPk xa, xb;
-    pk_post_pair(za, zb, tfc, tfs, xa, xb);
+    pk_post_pair(za, zb, k.tfc, k.tfs, xa, xb);
     if (MODE == PK_SPEC_UP2) {
       // bins i / Ni/2 - i see X[i] / conj(X[i]); bins M - i / M + i see X[M-i] / conj(X[M-i])
       CPk da, db;
-      pk_mul_pre_pair(xa, pk_conj(xa), k0, k1, tic, tis, da, db);
+      pk_mul_pre_pair(xa, pk_conj(xa), k.c0, k.c1, k.tic, k.tis, da, db);
       B[sl0] = da; B[sl1] = db;
-      pk_mul_pre_pair(xb, pk_conj(xb), k2, k3, tis, tic, da, db);
+      pk_mul_pre_pair(xb, pk_conj(xb), k.c2, k.c3, k.tis, k.tic, da, db);
       B[sl2] = da; B[sl3] = db;
     } else {
       CPk da, db;
-      pk_mul_pre_pair(xa, xb, k0, k1, tic, tis, da, db);
+      pk_mul_pre_pair(xa, xb, k.c0, k.c1, k.tic, k.tis, da, db);
       B[sl0] = da; B[sl1] = db;
     }
   };
-#if defined(__CUDACC__)
-  if (CACHED) {
 #pragma unroll
-    for (int r = 0; r < kPkCacheRounds; ++r) {
-      const int i = g.tid + r * g.size;
-      if (i < n) body(i, r);
-    }
-    for (int i = g.tid + kPkCacheRounds * g.size; i < n; i += g.size) body(i, -1);
-    grp_sync(g);
-    return;
-  }
-#endif
-  grp_for(g, n, [&](int i) { body(i, -1); });
-}
-
-template <int MODE>
-RR_PROG void pk_load_spec_cache(const DftPkParams &pp, const Grp &g, PkSpecCache &cc)
-{
-  const DftParams<float> &p = pp.base;
-  const C2<float> *coef = reinterpret_cast<const C2<float> *>(p.coef);
-  const uint16_t *perm = pp.inv.perm;
-  const int M = p.Pf >> 1, Mi = p.Ni >> 1, n = M >> 1;
-#pragma unroll
-  for (int r = 0; r < kPkCacheRounds; ++r) {
+  for (int r = 0; r < kPkSpecRounds; ++r) {
     const int i = g.tid + r * g.size;
-    if (i >= n) continue;
-    const int ii = i ? i : n;
-    cc.tf_c[r] = ldg(p.tcos_f + ii); cc.tf_s[r] = ldg(p.tcos_f + n - ii);
-    if (MODE == PK_SPEC_UP2) {
-      cc.c0[r] = ldg(coef + ii); cc.c1[r] = ldg(coef + Mi - ii); cc.c2[r] = ldg(coef + M - ii); cc.c3[r] = ldg(coef + M + ii);
-      cc.ti_c[r] = ldg(p.tcos_i + ii); cc.ti_s[r] = ldg(p.tcos_i + M - ii);
-      cc.s01[r] = (unsigned)ldg(perm + ii) | ((unsigned)ldg(perm + Mi - ii) << 16);
-      cc.s23[r] = (unsigned)ldg(perm + M - ii) | ((unsigned)ldg(perm + M + ii) << 16);
-    } else {
-      cc.c0[r] = ldg(coef + ii); cc.c1[r] = ldg(coef + M - ii); cc.c2[r] = cc.c0[r]; cc.c3[r] = cc.c0[r];
-      cc.ti_c[r] = cc.tf_c[r]; cc.ti_s[r] = cc.tf_s[r];
-      cc.s01[r] = (unsigned)ldg(perm + ii) | ((unsigned)ldg(perm + M - ii) << 16);
-      cc.s23[r] = cc.s01[r];
-    }
+    if (i < n) body(i, pre.r[r]);
   }
+  for (int i = g.tid + kPkSpecRounds * g.size; i < n; i += g.size) body(i, pk_load_spec(pp.spec + i));
+  grp_sync(g);
 }
 
 // Generic spectrum path (any L, F-domain decimation): forward post-processing in place, then the bins of
@@ -634,7 +626,7 @@ RR_PROG void pk_spectrum_generic(const DftPkParams &pp, const Grp &g, CPk *F, CP
   });
   const bool freq_up = p.in_mode == DFT_IN_FREQ_UP;
   const C2<float> *coef = reinterpret_cast<const C2<float> *>(p.coef);
-  const uint16_t *perm = pp.inv.perm;
+  const uint16_t *perm = pp.perm_i;
   grp_for(g, (Ni >> 2) + 1, [&](int i) {
     auto spec = [&](int bin) -> CPk { return freq_up ? pk_spec_freq_up(F, Pf, 2 * bin) : F[pslot(bin)]; };
     if (i > 0 && i < (Ni >> 2)) {
@@ -660,60 +652,61 @@ RR_PROG void pk_spectrum_generic(const DftPkParams &pp, const Grp &g, CPk *F, CP
   });
 }
 
-// One work item (block b, lane pair). Fcur holds (or is receiving) the item's input tile; Fnext receives
-// the next item's; items[slot] describes this item, items[slot ^ 1] is filled for the next one.
-template <int MODE, bool CACHED>
-RR_PROG void dftp_program(const DftPkParams &pp, const Grp &g, const float *pyr_f, const float *pyr_i, const PkSpecCache &cc,
-                          PkItem *items, int slot, long long work_next, CPk *Fcur, CPk *Fnext, CPk *B)
+// Pointers into the CTA's shared tables.
+struct PkTables { const float *pyr_f, *pyr_i; const uint16_t *tasks_f, *tasks_i, *perm_f; };
+
+// One work item (block b, lane pair). F holds (or is receiving) the item's input tile; items[slot] describes
+// this item, items[slot ^ 1] is filled for the next one, whose tile is requested as soon as F is free.
+template <int MODE, int FB, int IB>
+RR_PROG void dftp_program(const DftPkParams &pp, const Grp &g, const PkTables &tb, PkItem *items, int slot, long long work_next,
+                          CPk *F, CPk *B)
 {
   const DftParams<float> &p = pp.base;
   async_copy_wait<0>();
   grp_sync(g);                                            // the tile is complete; items[slot] is visible
   const PkItem it = items[slot];
-  if (work_next >= 0 && g.tid == 0) items[slot ^ 1] = pk_item(pp, work_next);
+  if (work_next >= 0 && g.tid == 0) items[slot ^ 1] = pk_make_item(pp, work_next);
 
-  // the forward and the inverse transform share one copy of the FFT code: a two-trip loop that is not unrolled
-  PkSink sink;
-  bool sink_ok = false, direct = false;
-  int first = 0, stride = 1, count = 0, es = 1;
-  long long c0 = 0;
-  float *d0 = nullptr, *d1 = nullptr;
-#pragma unroll 1
-  for (int dir = 0; dir < 2; ++dir) {
-    const PkSched &s = dir ? pp.inv : pp.fwd;
-    CPk *buf = dir ? B : Fcur;
-    pk_leaves(s, g, buf, dir == 0 && it.tile_mode == PK_TILE_PLANAR, p.sqrthalf, p.c16_1, p.c16_3);
-    if (dir == 0 && work_next >= 0) pk_stage_tile(pp, g, items[slot ^ 1], Fnext);   // in flight until the next item starts
-    pk_passes(s, g, buf, dir ? pyr_i : pyr_f, dir && sink_ok ? &sink : nullptr);
-    if (dir) break;
-
-    if (MODE == PK_SPEC_GEN) pk_spectrum_generic(pp, g, Fcur, B);
-    else pk_spectrum<MODE, CACHED>(pp, g, cc, Fcur, B);
-
-    // output geometry of this block (as in dft_stage_program)
-    const long long b = it.d.b;
-    const int V = p.N - p.overlap;
-    long long k0;
-    if (p.step == 1) { count = V; k0 = b * (long long)V; }
-    else if (p.step > 1) {
-      const long long v0 = b * (long long)V;
-      const int Mq = p.step;
-      first = (int)((Mq - v0 % Mq) % Mq); stride = Mq;
-      k0 = (v0 + Mq - 1) / Mq;
-      count = first < V ? (V - first + Mq - 1) / Mq : 0;
-    } else { count = p.kept; k0 = b * (long long)p.kept; }
-    c0 = p.out_preload + k0;
-    direct = view_range_direct(p.out, c0, c0 + count);
-    d0 = view_ptr<float>(p.out, it.d.out_off0, c0); d1 = view_ptr<float>(p.out, it.d.out_off1, c0);
-    es = p.out.elem_stride;
-    sink.d0 = d0; sink.d1 = d1; sink.half = count >> 1; sink.es = 0;
-    sink_ok = direct && stride == 1 && !(count & 1) && pp.inv.phase_depth[pp.inv.nphases - 1] >= 2;
-    if (sink_ok) {
-      if (es == 1 && !(((size_t)d0 | (size_t)d1) & 7)) sink.es = 0;
-      else if (d1 == d0 + 1 && !(es & 1) && !((size_t)d0 & 7)) sink.es = es;
-      else sink_ok = false;
-    }
+  PkSink sink{nullptr, nullptr, 0, 0};
+  pk_fft_lower_any<FB>(pp.fb, g, F, tb.tasks_f, tb.pyr_f, it.tile_mode == PK_TILE_PLANAR, p.sqrthalf, p.c16_1, p.c16_3);
+  if (MODE == PK_SPEC_GEN) {
+    pk_fft_top_any<FB>(pp.fb, g, F, tb.tasks_f, tb.pyr_f, false, sink);
+    pk_spectrum_generic(pp, g, F, B);
+  } else {
+    PkSpecRegs pre;
+    if (FB > 0) pk_spec_prefetch<MODE>(pp, g, pre);       // in flight while the (inlined) top forward phase runs
+    pk_fft_top_any<FB>(pp.fb, g, F, tb.tasks_f, tb.pyr_f, false, sink);
+    if (FB == 0) pk_spec_prefetch<MODE>(pp, g, pre);      // not across a call: the registers would be spilled
+    pk_spectrum<MODE>(pp, g, pre, F, B);
   }
+  if (work_next >= 0) pk_stage_tile(pp, g, items[slot ^ 1], F, tb.perm_f);   // F is free until the next item starts
+
+  // output geometry of this block (as in dft_stage_program)
+  const long long b = it.d.b;
+  const int V = p.N - p.overlap;
+  int first = 0, stride = 1, count; long long k0;
+  if (p.step == 1) { count = V; k0 = b * (long long)V; }
+  else if (p.step > 1) {
+    const long long v0 = b * (long long)V;
+    const int Mq = p.step;
+    first = (int)((Mq - v0 % Mq) % Mq); stride = Mq;
+    k0 = (v0 + Mq - 1) / Mq;
+    count = first < V ? (V - first + Mq - 1) / Mq : 0;
+  } else { count = p.kept; k0 = b * (long long)p.kept; }
+  const long long c0 = p.out_preload + k0;
+  const bool direct = view_range_direct(p.out, c0, c0 + count);
+  float *d0 = view_ptr<float>(p.out, it.d.out_off0, c0), *d1 = view_ptr<float>(p.out, it.d.out_off1, c0);
+  const int es = p.out.elem_stride;
+  sink.d0 = d0; sink.d1 = d1; sink.half = count >> 1; sink.es = 0;
+  bool sink_ok = direct && stride == 1 && !(count & 1);
+  if (sink_ok) {
+    if (es == 1 && !(((size_t)d0 | (size_t)d1) & 7)) sink.es = 0;
+    else if (d1 == d0 + 1 && !(es & 1) && !((size_t)d0 & 7)) sink.es = es;
+    else sink_ok = false;
+  }
+
+  pk_fft_lower_any<IB>(pp.ib, g, B, tb.tasks_i, tb.pyr_i, false, p.sqrthalf, p.c16_1, p.c16_3);
+  pk_fft_top_any<IB>(pp.ib, g, B, tb.tasks_i, tb.pyr_i, sink_ok, sink);
   if (sink_ok) return;
 
   const float *Br = reinterpret_cast<const float *>(B);

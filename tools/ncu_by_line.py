@@ -12,6 +12,10 @@ import sys
 from collections import defaultdict
 
 
+import os
+SORTKEY = "Instructions Executed" if os.environ.get("BY_INST") else "# Samples"
+
+
 def main():
     rep, cubin, kernel = sys.argv[1:4]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
@@ -69,7 +73,7 @@ def main():
           (tot["Instructions Executed"], tot["L1 Wavefronts Shared"], tot["L1 Wavefronts Shared Excessive"], tot["# Samples"]))
     print("%-26s %8s %6s %9s %9s %7s | %6s %6s %6s %6s %6s %6s" % ("line", "inst", "inst%", "smem_wf", "smem_exc", "smpl%",
                                                                  "longsb", "barr", "shortsb", "wait", "mio", "math"))
-    for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["# Samples"])[:top]:
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][SORTKEY])[:top]:
         print("%-26s %8.3g %5.1f%% %9.3g %9.3g %6.1f%% | %6.0f %6.0f %6.0f %6.0f %6.0f %6.0f" % (
             "%s:%d" % k, v["Instructions Executed"], 100 * v["Instructions Executed"] / max(tot["Instructions Executed"], 1),
             v["L1 Wavefronts Shared"], v["L1 Wavefronts Shared Excessive"], 100 * v["# Samples"] / max(tot["# Samples"], 1),
