@@ -173,22 +173,22 @@ __global__ void __launch_bounds__(2 * kDftThreads) dft_kernel(const __grid_const
 template <int MODE, int FB, int IB>
 __global__ void __launch_bounds__(kPkGroupThreads * kPkMaxGroups) dftp_kernel(const __grid_constant__ DftPkParams pp, long long nwork)
 {
-  struct { int pyr_f, pyr_i, tasks_f, tasks_i, perm_f, data, group_slots; } lay{pp.lay_pyr_f, pp.lay_pyr_i, pp.lay_tasks_f, pp.lay_tasks_i,
-                                                                                pp.lay_perm_f, pp.lay_data, pp.fslots + pp.bslots};
+  struct { int pyr_f, pyr_i, ltab_f, ltab_i, perm_f, data, group_slots; } lay{pp.lay_pyr_f, pp.lay_pyr_i, pp.lay_ltab_f, pp.lay_ltab_i,
+                                                                              pp.lay_perm_f, pp.lay_data, pp.fslots + pp.bslots};
   {
     float *pf = reinterpret_cast<float *>(rr_smem_raw + lay.pyr_f), *pi = reinterpret_cast<float *>(rr_smem_raw + lay.pyr_i);
-    uint16_t *tf = reinterpret_cast<uint16_t *>(rr_smem_raw + lay.tasks_f), *ti = reinterpret_cast<uint16_t *>(rr_smem_raw + lay.tasks_i);
+    uint16_t *tf = reinterpret_cast<uint16_t *>(rr_smem_raw + lay.ltab_f), *ti = reinterpret_cast<uint16_t *>(rr_smem_raw + lay.ltab_i);
     uint16_t *pm = reinterpret_cast<uint16_t *>(rr_smem_raw + lay.perm_f);
-    const int nf = pp.n_pyr_f, ni = pp.n_pyr_i, ef = pp.n_tasks_f, ei = pp.n_tasks_i, mf = 1 << pp.fb;
+    const int nf = pp.n_pyr_f, ni = pp.n_pyr_i, ef = pp.n_ltab_f, ei = pp.n_ltab_i, mf = 1 << pp.fb;
     for (int i = threadIdx.x; i < nf; i += blockDim.x) pf[i] = pp.base.pyr_f[i];
     for (int i = threadIdx.x; i < ni; i += blockDim.x) pi[i] = pp.base.pyr_i[i];
-    for (int i = threadIdx.x; i < ef; i += blockDim.x) tf[i] = pp.tasks_f[i];
-    for (int i = threadIdx.x; i < ei; i += blockDim.x) ti[i] = pp.tasks_i[i];
+    for (int i = threadIdx.x; i < ef; i += blockDim.x) tf[i] = pp.ltab_f[i];
+    for (int i = threadIdx.x; i < ei; i += blockDim.x) ti[i] = pp.ltab_i[i];
     for (int i = threadIdx.x; i < mf; i += blockDim.x) pm[i] = pp.perm_f[i];
   }
   const PkTables tb{reinterpret_cast<const float *>(rr_smem_raw + lay.pyr_f), reinterpret_cast<const float *>(rr_smem_raw + lay.pyr_i),
-                    reinterpret_cast<const uint16_t *>(rr_smem_raw + lay.tasks_f),
-                    reinterpret_cast<const uint16_t *>(rr_smem_raw + lay.tasks_i),
+                    reinterpret_cast<const uint16_t *>(rr_smem_raw + lay.ltab_f),
+                    reinterpret_cast<const uint16_t *>(rr_smem_raw + lay.ltab_i),
                     reinterpret_cast<const uint16_t *>(rr_smem_raw + lay.perm_f)};
   const int gi = threadIdx.x / pp.gthreads;
   const Grp g{(int)threadIdx.x - gi * pp.gthreads, pp.gthreads, 1 + gi};
@@ -310,7 +310,7 @@ static int launch_dftp(const DftPkParams &pp, long long nwork, stream_t s)
   std::vector<CPk> mem(static_cast<size_t>(pp.fslots + pp.bslots) + 1);
   CPk *F = mem.data(), *B = F + pp.fslots;
   const Grp g{0, 1, 0};
-  const PkTables tb{pp.base.pyr_f, pp.base.pyr_i, pp.tasks_f, pp.tasks_i, pp.perm_f};
+  const PkTables tb{pp.base.pyr_f, pp.base.pyr_i, pp.ltab_f, pp.ltab_i, pp.perm_f};
   for (long long w = 0; w < nwork; ++w) {
     PkItem items[2];
     items[0] = pk_make_item(pp, w);
@@ -800,7 +800,7 @@ template <class T> class Engine {
   HalfbandParams<T> half_params_[RR_MAX_STAGES];
   T *dft_coef_dev_[2] = {nullptr, nullptr};
 
-  struct DevSched { CfftSched fwd, inv; const T *pyramid; const uint16_t *pk_tasks = nullptr, *pk_perm[2] = {nullptr, nullptr}; };
+  struct DevSched { CfftSched fwd, inv; const T *pyramid; const uint16_t *pk_ltab = nullptr, *pk_perm[2] = {nullptr, nullptr}; };
   std::map<int, std::vector<uint16_t>> pk_perm_inv_host_;   // by complex bits
   const PkSpecConst *pk_spec_dev_[RR_MAX_STAGES] = {nullptr};
   std::map<int, DevSched> sched_;          // by complex bits
@@ -814,12 +814,12 @@ template <class T> class Engine {
   {
     const StageGeom &g = geom[i];
     const int fb = ilog2(g.Pf) - 1, ib = ilog2(g.Ni) - 1;
-    if (fb < 5 || ib < 5 || fb > 13 || ib > 13) return false;
+    if (fb < 6 || ib < 6 || fb > 13 || ib > 13) return false;
     auto sf = sched_.find(fb), si = sched_.find(ib);
-    if (sf == sched_.end() || si == sched_.end() || !sf->second.pk_tasks || !si->second.pk_tasks) return false;
+    if (sf == sched_.end() || si == sched_.end() || !sf->second.pk_ltab || !si->second.pk_ltab) return false;
     pp.base = p;
     pp.fb = fb; pp.ib = ib;
-    pp.tasks_f = sf->second.pk_tasks; pp.tasks_i = si->second.pk_tasks;
+    pp.ltab_f = sf->second.pk_ltab; pp.ltab_i = si->second.pk_ltab;
     pp.perm_f = sf->second.pk_perm[0]; pp.perm_i = si->second.pk_perm[1];
     pp.fslots = pk_buf_slots(g.Pf >> 1); pp.bslots = pk_buf_slots(g.Ni >> 1);
     pp.gthreads = kPkGroupThreads;
@@ -830,9 +830,9 @@ template <class T> class Engine {
       if (pk_smem_layout(pp).total + 1024 <= max_smem_) break;
     if (pp.groups < 1) return false;
     const PkSmemLayout lay = pk_smem_layout(pp);
-    pp.lay_pyr_f = lay.pyr_f; pp.lay_pyr_i = lay.pyr_i; pp.lay_tasks_f = lay.tasks_f; pp.lay_tasks_i = lay.tasks_i;
+    pp.lay_pyr_f = lay.pyr_f; pp.lay_pyr_i = lay.pyr_i; pp.lay_ltab_f = lay.ltab_f; pp.lay_ltab_i = lay.ltab_i;
     pp.lay_perm_f = lay.perm_f; pp.lay_data = lay.data;
-    pp.n_pyr_f = pk_pyr_len(fb); pp.n_pyr_i = pk_pyr_len(ib); pp.n_tasks_f = pk_task_entries(fb); pp.n_tasks_i = pk_task_entries(ib);
+    pp.n_pyr_f = pk_pyr_len(fb); pp.n_pyr_i = pk_pyr_len(ib); pp.n_ltab_f = pk_local_entries(fb); pp.n_ltab_i = pk_local_entries(ib);
     return true;
   }
   static int pk_spec_mode(const StageGeom &g)
@@ -849,7 +849,7 @@ template <class T> class Engine {
     const StageGeom &g = geom[i];
     const int mode = pk_spec_mode(g);
     const int fb = ilog2(g.Pf) - 1, ib = ilog2(g.Ni) - 1;
-    if (mode == PK_SPEC_GEN || fb < 5 || ib < 5 || fb > 13 || ib > 13) return RR_OK;
+    if (mode == PK_SPEC_GEN || fb < 6 || ib < 6 || fb > 13 || ib > 13) return RR_OK;
     const int N = g.N, M = g.Pf >> 1, Mi = g.Ni >> 1, n = M >> 1;
     std::vector<float> spec(static_cast<size_t>(N));
     if (dft_spectrum_host(g.filter, spec.data(), N) != N) return RR_INTERNAL;
@@ -924,9 +924,9 @@ template <class T> class Engine {
           c.qchild_begin[l] = h.qchild_begin[l]; c.qchild_cnt[l] = h.qchild_cnt[l];
         }
       }
-      if (std::is_same<T, float>::value && bits <= 13) {
+      if (std::is_same<T, float>::value && bits >= 6 && bits <= 13) {
         const PkHostSched ph = build_pk_sched(h);
-        if ((rc = upload(ph.tasks, &d.pk_tasks)) || (rc = upload(ph.perm[0], &d.pk_perm[0])) || (rc = upload(ph.perm[1], &d.pk_perm[1])))
+        if ((rc = upload(ph.local, &d.pk_ltab)) || (rc = upload(ph.perm[0], &d.pk_perm[0])) || (rc = upload(ph.perm[1], &d.pk_perm[1])))
           return rc;
         pk_perm_inv_host_[bits] = ph.perm[1];
       }

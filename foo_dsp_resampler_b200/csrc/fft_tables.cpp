@@ -134,6 +134,37 @@ PkHostSched build_pk_sched(const CfftHostSched &h)
     if (depth > 1) emit(h.qchild_begin[top - 1], h.qchild_cnt[top - 1]);   // light tasks: quarter children one size below
   }
   assert(static_cast<int>(s.tasks.size()) == pk_task_entries(bits));
+  // per-warp lists of the warp-local stages (bits >= 6: a quarter of the transform holds whole leaves)
+  if (bits >= 6) {
+    const int nlocal = pk_local_phases(bits), shift = bits - 2;
+    s.local.assign(static_cast<size_t>(pk_local_header(bits)), 0);
+    auto add_lists = [&](int stage, const std::vector<uint16_t> &mainl, const std::vector<uint16_t> &lightl, bool spread) {
+      for (int w = 0; w < kPkWarps; ++w) {
+        std::vector<uint16_t> a, b;
+        for (uint16_t o : mainl) if ((o >> shift) == w) a.push_back(o);
+        for (uint16_t o : lightl) if ((o >> shift) == w) b.push_back(o);
+        if (spread) { a = spread_over_bank_groups(a); b = spread_over_bank_groups(b); }
+        uint16_t *hd = &s.local[static_cast<size_t>(4 * (stage * kPkWarps + w))];
+        hd[0] = static_cast<uint16_t>(s.local.size()); hd[1] = static_cast<uint16_t>(a.size());
+        s.local.insert(s.local.end(), a.begin(), a.end());
+        hd = &s.local[static_cast<size_t>(4 * (stage * kPkWarps + w))];
+        hd[2] = static_cast<uint16_t>(s.local.size()); hd[3] = static_cast<uint16_t>(b.size());
+        s.local.insert(s.local.end(), b.begin(), b.end());
+      }
+    };
+    add_lists(0, h.leaf16_off, h.leaf8_off, true);
+    for (int ph = 0; ph < nlocal; ++ph) {
+      const int lg = pl.lg[ph], depth = pl.depth[ph];
+      const int base = pk_phase_base(bits, ph), nm = pk_phase_main(bits, lg, depth), nl = pk_phase_light(bits, lg, depth);
+      const std::vector<uint16_t> mainl(s.tasks.begin() + base, s.tasks.begin() + base + nm);
+      const std::vector<uint16_t> lightl(s.tasks.begin() + base + nm, s.tasks.begin() + base + nm + nl);
+      // a local task must stay inside the quarter its warp owns
+      for (uint16_t o : mainl) { assert((o >> shift) == ((o + ((4 << (depth - 1)) - 1) * (1 << (lg - 2))) >> shift)); (void)o; }
+      for (uint16_t o : lightl) { assert((o >> shift) == ((o + ((4 << (depth - 2)) - 1) * (1 << (lg - 2))) >> shift)); (void)o; }
+      add_lists(1 + ph, mainl, lightl, false);
+    }
+    assert(static_cast<int>(s.local.size()) == pk_local_entries(bits));
+  }
   for (int inv = 0; inv < 2; ++inv) {
     s.perm[inv].assign(static_cast<size_t>(m), 0);
     for (int p = 0; p < m; ++p) {

@@ -32,6 +32,7 @@ CfftHostSched build_cfft_sched(int bits);
 // bank-conflict-free 16-byte accesses, then per phase the positions o = node offset + k of its tasks).
 struct PkHostSched {
   std::vector<uint16_t> tasks;                   // pk_task_entries(bits) entries
+  std::vector<uint16_t> local;                   // pk_local_entries(bits) entries: per-warp lists of the barrier-free part
   std::vector<uint16_t> perm[2];                 // [inverse][natural index] -> pk_slot(permuted position)
 };
 int pk_slot(int p);                              // == pslot() of rate_kernels_pk.cuh

@@ -65,6 +65,29 @@ RR_PLAN_HD constexpr int pk_phase_base(int bits, int phase)
 }
 RR_PLAN_HD constexpr int pk_task_entries(int bits) { return pk_phase_base(bits, pk_phase_list(bits).n); }
 
+// Warp-local part of the schedule. A group has kPkWarps warps; warp w owns positions [w M/4, (w+1) M/4) --
+// the subtrees of size <= M/4 of the split-radix tree -- so the leaves and every phase whose top size is
+// <= M/4 run on warp-private data and need no group barrier, only __syncwarp(). The local task table starts
+// with a header of 4 uint16 per (stage, warp) -- {main begin, main count, light begin, light count}, stage 0 =
+// leaves (main: size-16, light: size-8), stage s = phase s-1 -- followed by the lists.
+constexpr int kPkWarps = 4;
+RR_PLAN_HD constexpr int pk_local_phases(int bits)
+{
+  const PkPhaseList p = pk_phase_list(bits);
+  int n = 0;
+  for (int i = 0; i < p.n; ++i)
+    if (p.lg[i] + p.depth[i] - 1 <= bits - 2) ++n;
+  return n;
+}
+RR_PLAN_HD constexpr int pk_local_header(int bits) { return 4 * kPkWarps * (1 + pk_local_phases(bits)); }
+RR_PLAN_HD constexpr int pk_local_entries(int bits)
+{
+  int e = pk_local_header(bits) + pk_n16(bits) + pk_n8(bits);
+  const PkPhaseList p = pk_phase_list(bits);
+  for (int i = 0; i < pk_local_phases(bits); ++i) e += pk_phase_main(bits, p.lg[i], p.depth[i]) + pk_phase_light(bits, p.lg[i], p.depth[i]);
+  return e;
+}
+
 // Twiddle pyramid: row of size S = 1 << lg holds cos(2 pi k / S), k = 0 .. S/4 (same layout as CfftHostSched).
 RR_PLAN_HD constexpr int pk_pyr_off(int lg)
 {

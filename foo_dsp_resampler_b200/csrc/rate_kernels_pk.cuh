@@ -141,45 +141,30 @@ RR_PROG void pk_sink_store(const PkSink &k, int c, const CPk &v)
 // The FFT of M = 1 << BITS points over FFmpeg's split-radix DAG, everything about its shape a compile-time
 // constant (pk_plan.hpp); `tasks` is the task table of the transform (shared memory), `pyr` its twiddle pyramid.
 // ---------------------------------------------------------------------------------------------------
-// Leaves (fft16 / fft8, fft.c:288-318), in place. swz: the slots hold {a.re, a.im, b.re, b.im} (planar input
-// copied 8 bytes per lane) instead of the working layout; the leaf re-pairs them in registers.
-template <int BITS>
-RR_PROG void pk_fft_leaves(const Grp &g, CPk *buf, const uint16_t *tasks, bool swz, float sqrthalf, float c16_1, float c16_3)
+// Leaves (fft16 / fft8, fft.c:288-318), in place at position `off`. swz: the slots hold {a.re, a.im, b.re, b.im}
+// (planar input copied 8 bytes per lane) instead of the working layout; the leaf re-pairs them in registers.
+template <int NV>
+RR_PROG void pk_leaf(CPk *buf, int off, bool swz, Pk sh, Pk c1, Pk c3)
 {
-  constexpr int n16 = pk_n16(BITS), n8p = pk_n8p(BITS);
-  const Pk sh = pk_bcast(sqrthalf), c1 = pk_bcast(c16_1), c3 = pk_bcast(c16_3);
-  grp_for(g, n16 + n8p, [&](int task) {
-    if (task < n16) {
-      CPk *b = buf + pslot(tasks[task]);                 // multiple of 16: the 16 slots are contiguous
-      Pk re[16], im[16];
+  CPk *b = buf + pslot(off);                             // multiple of NV: the NV slots are contiguous
+  Pk re[NV], im[NV];
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const CPk v = b[e];
-        re[e] = v.x; im[e] = v.y;
-        if (swz) { const float t = re[e].b; re[e].b = im[e].a; im[e].a = t; }
-      }
-      leaf_fft16<Pk>(re, im, sh, c1, c3);
+  for (int e = 0; e < NV; ++e) {
+    const CPk v = b[e];
+    re[e] = v.x; im[e] = v.y;
+    if (swz) { const float t = re[e].b; re[e].b = im[e].a; im[e].a = t; }
+  }
+  if constexpr (NV == 16) leaf_fft16<Pk>(re, im, sh, c1, c3);
+  else leaf_fft8<Pk>(re, im, sh);
 #pragma unroll
-      for (int e = 0; e < 16; ++e) b[e] = CPk{re[e], im[e]};
-    } else {
-      for (int h = 0; h < 2; ++h) {
-        const int off = tasks[n16 + 2 * (task - n16) + h];
-        if (off == 0xffff) continue;
-        CPk *b = buf + pslot(off);                        // multiple of 8: never straddles a pad slot
-        Pk re[8], im[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const CPk v = b[e];
-          re[e] = v.x; im[e] = v.y;
-          if (swz) { const float t = re[e].b; re[e].b = im[e].a; im[e].a = t; }
-        }
-        leaf_fft8<Pk>(re, im, sh);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) b[e] = CPk{re[e], im[e]};
-      }
-    }
-  });
+  for (int e = 0; e < NV; ++e) b[e] = CPk{re[e], im[e]};
 }
+
+#if defined(__CUDA_ARCH__)
+RR_PROG void pk_warp_sync() { __syncwarp(); }
+#else
+inline void pk_warp_sync() {}
+#endif
 
 // Combining passes (pass(), fft.c:237-256), fused 1, 2 or 3 levels deep. S = 1 << LG is the smallest size of
 // the task, q = S/4; the task at position o = node offset + k (k < q) owns the values at o + j*q. pslot() is
@@ -247,24 +232,62 @@ RR_PROG void pk_fft_phase(const Grp &g, CPk *buf, const uint16_t *tasks, const f
   constexpr int LG = pl.lg[PH], D = pl.depth[PH];
   constexpr int base = pk_phase_base(BITS, PH), nmain = pk_phase_main(BITS, LG, D), nlight = pk_phase_light(BITS, LG, D);
   constexpr int nb = (nlight + 2) / 3, DL = D > 1 ? D - 1 : 1;
-  grp_for(g, nmain + nb, [&](int t) {
-    if (t < nmain) pk_item<LG, D, SINK>(tasks[base + t], buf, pyr, sink);
+  constexpr bool top = PH == pl.n - 1;                   // one node at offset 0: task t is position t, no table needed
+  for (int t = g.tid; t < nmain + nb; t += g.size) {
+    if (t < nmain) pk_item<LG, D, SINK>(top ? t : tasks[base + t], buf, pyr, sink);
     else
       for (int j = t - nmain; j < nlight; j += nb) pk_item<LG, DL, false>(tasks[base + nmain + j], buf, pyr, sink);
-  });
+  }
+  if (!SINK) grp_sync(g);                                // a sinking top phase leaves nothing in shared memory
 }
 
-// Leaves and every phase but the top one / the top phase, inlined: for kernels specialised on the size.
+// The barrier-free part: warp w of the group runs the leaves and the local phases of the quarter of the
+// transform it owns (pk_plan.hpp), synchronising only with itself. `ltab`: the transform's local task table.
+template <int BITS, int PH>
+RR_PROG void pk_local_phase(int w, int lane, int nl, CPk *buf, const uint16_t *ltab, const float *pyr)
+{
+  constexpr PkPhaseList pl = pk_phase_list(BITS);
+  constexpr int LG = pl.lg[PH], D = pl.depth[PH], DL = D > 1 ? D - 1 : 1;
+  const uint16_t *hd = ltab + 4 * ((1 + PH) * kPkWarps + w);
+  const PkSink none{nullptr, nullptr, 0, 0};
+  const int mb = hd[0], mc = hd[1], lb = hd[2], lc = hd[3];
+  for (int t = lane; t < mc; t += nl) pk_item<LG, D, false>(ltab[mb + t], buf, pyr, none);
+  for (int t = lane; t < lc; t += nl) pk_item<LG, DL, false>(ltab[lb + t], buf, pyr, none);
+  pk_warp_sync();
+}
+
 template <int BITS>
-RR_PROG void pk_fft_lower_impl(const Grp &g, CPk *buf, const uint16_t *tasks, const float *pyr, bool swz, float sqrthalf, float c16_1,
+RR_PROG void pk_fft_local(const Grp &g, CPk *buf, const uint16_t *ltab, const float *pyr, bool swz, float sqrthalf, float c16_1,
+                          float c16_3)
+{
+  constexpr int nlocal = pk_local_phases(BITS);
+  const Pk sh = pk_bcast(sqrthalf), c1 = pk_bcast(c16_1), c3 = pk_bcast(c16_3);
+#if defined(__CUDA_ARCH__)
+  const int w0 = g.tid >> 5, w1 = w0 + 1, lane = g.tid & 31, nl = 32;
+#else
+  const int w0 = 0, w1 = kPkWarps, lane = g.tid, nl = g.size;   // emulation: one thread plays the warps in turn
+#endif
+  for (int w = w0; w < w1; ++w) {
+    const uint16_t *hd = ltab + 4 * w;
+    const int mb = hd[0], mc = hd[1], lb = hd[2], lc = hd[3];
+    for (int t = lane; t < mc; t += nl) pk_leaf<16>(buf, ltab[mb + t], swz, sh, c1, c3);
+    for (int t = lane; t < lc; t += nl) pk_leaf<8>(buf, ltab[lb + t], swz, sh, c1, c3);
+    pk_warp_sync();
+    if constexpr (nlocal > 0) pk_local_phase<BITS, 0>(w, lane, nl, buf, ltab, pyr);
+    if constexpr (nlocal > 1) pk_local_phase<BITS, 1>(w, lane, nl, buf, ltab, pyr);
+    if constexpr (nlocal > 2) pk_local_phase<BITS, 2>(w, lane, nl, buf, ltab, pyr);
+  }
+}
+
+// The warp-local part followed by the group barrier / the top phase, inlined: for kernels specialised on the size.
+template <int BITS>
+RR_PROG void pk_fft_lower_impl(const Grp &g, CPk *buf, const uint16_t *ltab, const float *pyr, bool swz, float sqrthalf, float c16_1,
                                float c16_3)
 {
-  constexpr int n = pk_phase_list(BITS).n;
-  const PkSink none{nullptr, nullptr, 0, 0};
-  pk_fft_leaves<BITS>(g, buf, tasks, swz, sqrthalf, c16_1, c16_3);
-  if constexpr (n > 1) pk_fft_phase<BITS, 0, false>(g, buf, tasks, pyr, none);
-  if constexpr (n > 2) pk_fft_phase<BITS, 1, false>(g, buf, tasks, pyr, none);
-  if constexpr (n > 3) pk_fft_phase<BITS, 2, false>(g, buf, tasks, pyr, none);
+  // every supported size (6 <= BITS <= 13) has exactly one phase above the warp-local ones: the top one
+  static_assert(BITS < 6 || pk_local_phases(BITS) + 1 == pk_phase_list(BITS).n, "one global phase expected");
+  pk_fft_local<BITS>(g, buf, ltab, pyr, swz, sqrthalf, c16_1, c16_3);
+  grp_sync(g);
 }
 template <int BITS, bool SINK>
 RR_PROG void pk_fft_top_impl(const Grp &g, CPk *buf, const uint16_t *tasks, const float *pyr, const PkSink &sink)
@@ -281,9 +304,9 @@ RR_PROG void pk_fft_top_impl(const Grp &g, CPk *buf, const uint16_t *tasks, cons
 // The same as separate, not inlined functions for the size-generic kernels: one copy per size serves the
 // forward and the inverse transform.
 template <int BITS>
-RR_PK_CALL void pk_fft_lower(Grp g, CPk *buf, const uint16_t *tasks, const float *pyr, bool swz, float sqrthalf, float c16_1, float c16_3)
+RR_PK_CALL void pk_fft_lower(Grp g, CPk *buf, const uint16_t *ltab, const float *pyr, bool swz, float sqrthalf, float c16_1, float c16_3)
 {
-  pk_fft_lower_impl<BITS>(g, buf, tasks, pyr, swz, sqrthalf, c16_1, c16_3);
+  pk_fft_lower_impl<BITS>(g, buf, ltab, pyr, swz, sqrthalf, c16_1, c16_3);
 }
 template <int BITS, bool SINK>
 RR_PK_CALL void pk_fft_top(Grp g, CPk *buf, const uint16_t *tasks, const float *pyr, PkSink sink)
@@ -293,7 +316,7 @@ RR_PK_CALL void pk_fft_top(Grp g, CPk *buf, const uint16_t *tasks, const float *
 
 #define RR_PK_BITS_SWITCH(BITS_EXPR, CALL)                                                                   \
   switch (BITS_EXPR) {                                                                                       \
-    case 5: CALL(5); break;   case 6: CALL(6); break;   case 7: CALL(7); break;                              \
+    case 6: CALL(6); break;   case 7: CALL(7); break;                                                        \
     case 8: CALL(8); break;   case 9: CALL(9); break;   case 10: CALL(10); break;                            \
     case 11: CALL(11); break; case 12: CALL(12); break; case 13: CALL(13); break;                            \
     default: break;                                                                                          \
@@ -301,12 +324,12 @@ RR_PK_CALL void pk_fft_top(Grp g, CPk *buf, const uint16_t *tasks, const float *
 
 // BITS > 0: size known at compile time, everything inlined; BITS == 0: dispatch on the run-time size.
 template <int BITS>
-RR_PROG void pk_fft_lower_any(int bits, const Grp &g, CPk *buf, const uint16_t *tasks, const float *pyr, bool swz, float sqrthalf,
+RR_PROG void pk_fft_lower_any(int bits, const Grp &g, CPk *buf, const uint16_t *ltab, const float *pyr, bool swz, float sqrthalf,
                               float c16_1, float c16_3)
 {
-  if constexpr (BITS > 0) pk_fft_lower_impl<BITS>(g, buf, tasks, pyr, swz, sqrthalf, c16_1, c16_3);
+  if constexpr (BITS > 0) pk_fft_lower_impl<BITS>(g, buf, ltab, pyr, swz, sqrthalf, c16_1, c16_3);
   else {
-#define RR_PK_LOWER(B) pk_fft_lower<B>(g, buf, tasks, pyr, swz, sqrthalf, c16_1, c16_3)
+#define RR_PK_LOWER(B) pk_fft_lower<B>(g, buf, ltab, pyr, swz, sqrthalf, c16_1, c16_3)
     RR_PK_BITS_SWITCH(bits, RR_PK_LOWER)
 #undef RR_PK_LOWER
   }
@@ -347,26 +370,26 @@ struct alignas(16) PkSpecConst {
 
 struct DftPkParams {
   DftParams<float> base;         // geometry, views, cosine tables, filter spectrum (schedules unused)
-  const uint16_t *tasks_f, *tasks_i, *perm_f, *perm_i;
+  const uint16_t *ltab_f, *ltab_i, *perm_f, *perm_i;   // local task tables (pk_plan.hpp), permutations
   const PkSpecConst *spec;       // [M/2] records (modes UP2 / SAME); index 0 holds those of M/2 and of the two real bins
   int fb, ib;                    // log2 of the forward / inverse complex transform sizes
   int fslots, bslots;            // slots of the forward / inverse buffer
   int groups, gthreads;          // groups per CTA, threads per group
   int spec_mode;
-  int lay_pyr_f, lay_pyr_i, lay_tasks_f, lay_tasks_i, lay_perm_f, lay_data;   // shared-memory byte offsets (host: pk_smem_layout)
-  int n_pyr_f, n_pyr_i, n_tasks_f, n_tasks_i;                                 // table lengths
+  int lay_pyr_f, lay_pyr_i, lay_ltab_f, lay_ltab_i, lay_perm_f, lay_data;     // shared-memory byte offsets (host: pk_smem_layout)
+  int n_pyr_f, n_pyr_i, n_ltab_f, n_ltab_i;                                   // table lengths
 };
 
 // Shared memory: tables (twiddle pyramids, task tables, forward permutation), then per group F and B.
-struct PkSmemLayout { int pyr_f, pyr_i, tasks_f, tasks_i, perm_f, data, group_slots; size_t total; };
+struct PkSmemLayout { int pyr_f, pyr_i, ltab_f, ltab_i, perm_f, data, group_slots; size_t total; };
 RR_HD PkSmemLayout pk_smem_layout(const DftPkParams &pp)
 {
   PkSmemLayout l;
   int o = 0;
   l.pyr_f = o; o += 4 * pk_pyr_len(pp.fb);
   l.pyr_i = o; o += 4 * pk_pyr_len(pp.ib);
-  l.tasks_f = o; o += 2 * pk_task_entries(pp.fb);
-  l.tasks_i = o; o += 2 * pk_task_entries(pp.ib);
+  l.ltab_f = o; o += 2 * pk_local_entries(pp.fb);
+  l.ltab_i = o; o += 2 * pk_local_entries(pp.ib);
   o = (o + 3) & ~3;
   l.perm_f = o; o += 2 << pp.fb;
   l.data = (o + 15) & ~15;
@@ -379,9 +402,16 @@ RR_HD PkSmemLayout pk_smem_layout(const DftPkParams &pp)
 // 8 bytes per lane from planar lanes (re-paired by the leaves), else scalar copies with zero fill.
 enum PkTileMode { PK_TILE_SCALAR = 0, PK_TILE_INTERLEAVED = 1, PK_TILE_PLANAR = 2 };
 
+// Everything about a work item that needs 64-bit coordinate arithmetic, computed by one thread per item.
 struct PkItem {
   DftItem<float> d;
+  const float *s0, *s1;          // lane pointers at the tile's first input sample (direct tiles)
+  float *d0, *d1;                // lane pointers at the block's first output sample
+  long long c0;                  // its coordinate
   int tile_mode;
+  int first, stride, count;      // kept samples: block sample first + j * stride, j < count
+  int direct;                    // outputs are stored contiguously (no ring wrap / clipping)
+  int sink;                      // 0: via shared memory, 1: top pass stores planar pairs, 2: interleaved frames
 };
 
 RR_PROG PkItem pk_make_item(const DftPkParams &pp, long long work)
@@ -391,11 +421,33 @@ RR_PROG PkItem pk_make_item(const DftPkParams &pp, long long work)
   it.d = dft_item<float, 2>(p, work);
   it.tile_mode = PK_TILE_SCALAR;
   const int span = p.in_mode == DFT_IN_FREQ_UP ? p.Pf : p.N;
+  it.s0 = view_ptr<const float>(p.in, it.d.in_off0, it.d.Rb); it.s1 = view_ptr<const float>(p.in, it.d.in_off1, it.d.Rb);
   if (p.in_mode != DFT_IN_ZERO_STUFF && view_range_direct(p.in, it.d.Rb, it.d.Rb + span)) {
-    const float *s0 = view_ptr<const float>(p.in, it.d.in_off0, it.d.Rb), *s1 = view_ptr<const float>(p.in, it.d.in_off1, it.d.Rb);
     const int es = p.in.elem_stride;
-    if (s1 == s0 + 1 && !(es & 1) && !((size_t)s0 & 7)) it.tile_mode = PK_TILE_INTERLEAVED;
-    else if (es == 1 && !(((size_t)s0 | (size_t)s1) & 7)) it.tile_mode = PK_TILE_PLANAR;
+    if (it.s1 == it.s0 + 1 && !(es & 1) && !((size_t)it.s0 & 7)) it.tile_mode = PK_TILE_INTERLEAVED;
+    else if (es == 1 && !(((size_t)it.s0 | (size_t)it.s1) & 7)) it.tile_mode = PK_TILE_PLANAR;
+  }
+  // output geometry of the block (as in dft_stage_program)
+  const long long b = it.d.b;
+  const int V = p.N - p.overlap;
+  long long k0;
+  it.first = 0; it.stride = 1;
+  if (p.step == 1) { it.count = V; k0 = b * (long long)V; }
+  else if (p.step > 1) {
+    const long long v0 = b * (long long)V;
+    const int Mq = p.step;
+    it.first = (int)((Mq - v0 % Mq) % Mq); it.stride = Mq;
+    k0 = (v0 + Mq - 1) / Mq;
+    it.count = it.first < V ? (V - it.first + Mq - 1) / Mq : 0;
+  } else { it.count = p.kept; k0 = b * (long long)p.kept; }
+  it.c0 = p.out_preload + k0;
+  it.direct = view_range_direct(p.out, it.c0, it.c0 + it.count);
+  it.d0 = view_ptr<float>(p.out, it.d.out_off0, it.c0); it.d1 = view_ptr<float>(p.out, it.d.out_off1, it.c0);
+  const int es = p.out.elem_stride;
+  it.sink = 0;
+  if (it.direct && it.stride == 1 && !(it.count & 1)) {
+    if (es == 1 && !(((size_t)it.d0 | (size_t)it.d1) & 7)) it.sink = 1;
+    else if (it.d1 == it.d0 + 1 && !(es & 1) && !((size_t)it.d0 & 7)) it.sink = 2;
   }
   return it;
 }
@@ -421,7 +473,7 @@ RR_PROG void pk_stage_tile(const DftPkParams &pp, const Grp &g, const PkItem &it
   const DftParams<float> &p = pp.base;
   const int span = p.in_mode == DFT_IN_FREQ_UP ? p.Pf : p.N, m = span >> 1;
   if (it.tile_mode == PK_TILE_INTERLEAVED) {
-    const float *s0 = view_ptr<const float>(p.in, it.d.in_off0, it.d.Rb);
+    const float *s0 = it.s0;
     const int es = p.in.elem_stride;
     if (es == 2 && !((size_t)s0 & 15))
       for (int j = g.tid; j < m; j += g.size) pk_async_copy16(F + perm[j], s0 + 4 * j);
@@ -433,7 +485,7 @@ RR_PROG void pk_stage_tile(const DftPkParams &pp, const Grp &g, const PkItem &it
         pk_async_copy8(&d->y, f + es);
       }
   } else if (it.tile_mode == PK_TILE_PLANAR) {
-    const float *s0 = view_ptr<const float>(p.in, it.d.in_off0, it.d.Rb), *s1 = view_ptr<const float>(p.in, it.d.in_off1, it.d.Rb);
+    const float *s0 = it.s0, *s1 = it.s1;
     for (int j = g.tid; j < m; j += g.size) {
       CPk *d = F + perm[j];
       pk_async_copy8(&d->x, s0 + 2 * j);                  // {a.re, a.im}: re-paired by the leaves (swz)
@@ -462,13 +514,16 @@ RR_PROG void pk_stage_tile(const DftPkParams &pp, const Grp &g, const PkItem &it
 RR_PROG PkSpecConst pk_load_spec(const PkSpecConst *p)
 {
 #if defined(__CUDA_ARCH__)
+  // field-by-field from three 16-byte and one 8-byte load (no memcpy: the record must stay in registers)
+  const float4 *q = reinterpret_cast<const float4 *>(p);
+  const float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+  const uint2 d = __ldg(reinterpret_cast<const uint2 *>(p) + 6);
   PkSpecConst r;
-  float4 v[4];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) v[k] = __ldg(reinterpret_cast<const float4 *>(p) + k);
-  const float2 w = __ldg(reinterpret_cast<const float2 *>(p) + 6);
-  v[3] = make_float4(w.x, w.y, 0.f, 0.f);
-  memcpy(&r, v, sizeof(r));
+  r.c0 = C2<float>{a.x, a.y}; r.c1 = C2<float>{a.z, a.w};
+  r.c2 = C2<float>{b.x, b.y}; r.c3 = C2<float>{b.z, b.w};
+  r.tfc = c.x; r.tfs = c.y; r.tic = c.z; r.tis = c.w;
+  r.s01 = d.x; r.s23 = d.y;
+  r.pad[0] = 0; r.pad[1] = 0;
   return r;
 #else
   return *p;
@@ -519,8 +574,10 @@ RR_HD CPk pk_conj(const CPk &v) { return CPk{v.x, pk_neg(v.y)}; }
 
 // Spectrum phase, F (forward FFT result, natural order) -> B (input of the inverse FFT, permuted order).
 // Round r of thread t handles index i = t + r * g.size, i < M/2 (i = 0 also does M/2 and the two real bins);
-// the first kPkSpecRounds rounds find their constants in `pre` (loaded before the previous phase).
-constexpr int kPkSpecRounds = 4;
+// the first kPkSpecRounds rounds find their constants in `pre` (loaded before the previous phase), the next
+// kPkSpecLate rounds load theirs when the phase starts, ahead of the arithmetic of the first rounds.
+constexpr int kPkSpecRounds = 1, kPkSpecLate = 3;
+constexpr bool kPkPrefetchAcrossTop = true;
 struct PkSpecRegs { PkSpecConst r[kPkSpecRounds]; };
 
 template <int MODE>
@@ -585,12 +642,18 @@ RR_PROG void pk_spectrum(const DftPkParams &pp, const Grp &g, const PkSpecRegs &
       B[sl0] = da; B[sl1] = db;
     }
   };
-#pragma unroll
-  for (int r = 0; r < kPkSpecRounds; ++r) {
-    const int i = g.tid + r * g.size;
-    if (i < n) body(i, pre.r[r]);
-  }
-  for (int i = g.tid + kPkSpecRounds * g.size; i < n; i += g.size) body(i, pk_load_spec(pp.spec + i));
+  // software pipeline, two records live: the record of the next round is requested before a round is computed
+  static_assert(kPkSpecRounds == 1 && kPkSpecLate == 3, "pipeline below is written for 1 + 3 rounds");
+  const int i0 = g.tid, i1 = i0 + g.size, i2 = i1 + g.size, i3 = i2 + g.size;
+  PkSpecConst ra = pre.r[0], rb;
+  if (i1 < n) rb = pk_load_spec(pp.spec + i1);
+  if (i0 < n) body(i0, ra);
+  if (i2 < n) ra = pk_load_spec(pp.spec + i2);
+  if (i1 < n) body(i1, rb);
+  if (i3 < n) rb = pk_load_spec(pp.spec + i3);
+  if (i2 < n) body(i2, ra);
+  if (i3 < n) body(i3, rb);
+  for (int i = g.tid + (kPkSpecRounds + kPkSpecLate) * g.size; i < n; i += g.size) body(i, pk_load_spec(pp.spec + i));
   grp_sync(g);
 }
 
@@ -653,7 +716,7 @@ RR_PROG void pk_spectrum_generic(const DftPkParams &pp, const Grp &g, CPk *F, CP
 }
 
 // Pointers into the CTA's shared tables.
-struct PkTables { const float *pyr_f, *pyr_i; const uint16_t *tasks_f, *tasks_i, *perm_f; };
+struct PkTables { const float *pyr_f, *pyr_i; const uint16_t *ltab_f, *ltab_i, *perm_f; };
 
 // One work item (block b, lane pair). F holds (or is receiving) the item's input tile; items[slot] describes
 // this item, items[slot ^ 1] is filled for the next one, whose tile is requested as soon as F is free.
@@ -664,51 +727,32 @@ RR_PROG void dftp_program(const DftPkParams &pp, const Grp &g, const PkTables &t
   const DftParams<float> &p = pp.base;
   async_copy_wait<0>();
   grp_sync(g);                                            // the tile is complete; items[slot] is visible
-  const PkItem it = items[slot];
+  const PkItem &it = items[slot];                        // stays valid for the whole item; fields are read where needed
   if (work_next >= 0 && g.tid == 0) items[slot ^ 1] = pk_make_item(pp, work_next);
 
   PkSink sink{nullptr, nullptr, 0, 0};
-  pk_fft_lower_any<FB>(pp.fb, g, F, tb.tasks_f, tb.pyr_f, it.tile_mode == PK_TILE_PLANAR, p.sqrthalf, p.c16_1, p.c16_3);
+  pk_fft_lower_any<FB>(pp.fb, g, F, tb.ltab_f, tb.pyr_f, it.tile_mode == PK_TILE_PLANAR, p.sqrthalf, p.c16_1, p.c16_3);
   if (MODE == PK_SPEC_GEN) {
-    pk_fft_top_any<FB>(pp.fb, g, F, tb.tasks_f, tb.pyr_f, false, sink);
+    pk_fft_top_any<FB>(pp.fb, g, F, nullptr, tb.pyr_f, false, sink);
     pk_spectrum_generic(pp, g, F, B);
   } else {
     PkSpecRegs pre;
-    if (FB > 0) pk_spec_prefetch<MODE>(pp, g, pre);       // in flight while the (inlined) top forward phase runs
-    pk_fft_top_any<FB>(pp.fb, g, F, tb.tasks_f, tb.pyr_f, false, sink);
-    if (FB == 0) pk_spec_prefetch<MODE>(pp, g, pre);      // not across a call: the registers would be spilled
+    if (FB > 0 && kPkPrefetchAcrossTop) pk_spec_prefetch<MODE>(pp, g, pre);   // in flight while the (inlined) top forward phase runs
+    pk_fft_top_any<FB>(pp.fb, g, F, nullptr, tb.pyr_f, false, sink);
+    if (FB == 0 || !kPkPrefetchAcrossTop) pk_spec_prefetch<MODE>(pp, g, pre);   // not across a call: the registers would be spilled
     pk_spectrum<MODE>(pp, g, pre, F, B);
   }
   if (work_next >= 0) pk_stage_tile(pp, g, items[slot ^ 1], F, tb.perm_f);   // F is free until the next item starts
 
-  // output geometry of this block (as in dft_stage_program)
-  const long long b = it.d.b;
-  const int V = p.N - p.overlap;
-  int first = 0, stride = 1, count; long long k0;
-  if (p.step == 1) { count = V; k0 = b * (long long)V; }
-  else if (p.step > 1) {
-    const long long v0 = b * (long long)V;
-    const int Mq = p.step;
-    first = (int)((Mq - v0 % Mq) % Mq); stride = Mq;
-    k0 = (v0 + Mq - 1) / Mq;
-    count = first < V ? (V - first + Mq - 1) / Mq : 0;
-  } else { count = p.kept; k0 = b * (long long)p.kept; }
-  const long long c0 = p.out_preload + k0;
-  const bool direct = view_range_direct(p.out, c0, c0 + count);
-  float *d0 = view_ptr<float>(p.out, it.d.out_off0, c0), *d1 = view_ptr<float>(p.out, it.d.out_off1, c0);
-  const int es = p.out.elem_stride;
-  sink.d0 = d0; sink.d1 = d1; sink.half = count >> 1; sink.es = 0;
-  bool sink_ok = direct && stride == 1 && !(count & 1);
-  if (sink_ok) {
-    if (es == 1 && !(((size_t)d0 | (size_t)d1) & 7)) sink.es = 0;
-    else if (d1 == d0 + 1 && !(es & 1) && !((size_t)d0 & 7)) sink.es = es;
-    else sink_ok = false;
-  }
+  sink.d0 = it.d0; sink.d1 = it.d1; sink.half = it.count >> 1; sink.es = it.sink == 2 ? p.out.elem_stride : 0;
+  pk_fft_lower_any<IB>(pp.ib, g, B, tb.ltab_i, tb.pyr_i, false, p.sqrthalf, p.c16_1, p.c16_3);
+  pk_fft_top_any<IB>(pp.ib, g, B, nullptr, tb.pyr_i, it.sink != 0, sink);
+  if (it.sink) return;
 
-  pk_fft_lower_any<IB>(pp.ib, g, B, tb.tasks_i, tb.pyr_i, false, p.sqrthalf, p.c16_1, p.c16_3);
-  pk_fft_top_any<IB>(pp.ib, g, B, tb.tasks_i, tb.pyr_i, sink_ok, sink);
-  if (sink_ok) return;
-
+  const int first = it.first, stride = it.stride, count = it.count, es = p.out.elem_stride;
+  const bool direct = it.direct != 0;
+  float *d0 = it.d0, *d1 = it.d1;
+  const long long c0 = it.c0;
   const float *Br = reinterpret_cast<const float *>(B);
   grp_for(g, 2 * count, [&](int w) {
     const int l = w & 1, j = w >> 1;
@@ -717,6 +761,128 @@ RR_PROG void dftp_program(const DftPkParams &pp, const Grp &g, const PkTables &t
     if (direct) (l ? d1 : d0)[(long long)j * es] = v;
     else view_write<float, float>(p.out, l ? it.d.out_off1 : it.d.out_off0, c0 + j, v);
   });
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// vpoly0 for lane pairs (rate_filters_generic.h:272-305): the phase-stationary scheme of poly0_fast_kernel with
+// both channels of a pair in one thread -- the input window is staged pair-interleaved (one LDS.64 per tap
+// feeds both channels), products and sums are FMUL2 / FFMA2(x, 1, y) -- and with the slots of a period dealt to
+// the threads so that the sixteen lanes of a half-warp read sixteen different 8-byte banks.
+// ---------------------------------------------------------------------------------------------------
+struct Poly0PairParams {
+  Poly0FastParams<float> fast;   // tile geometry (CH = lanes per CTA, even), window, tiling
+  int P;                         // pairs per CTA = CH / 2
+  int PG;                        // period groups: thread (slot, pair, g) takes periods g, g + PG, ...
+  int tslots;                    // threads along the slot dimension (multiple of 16, >= slots per column)
+  int spread;                    // deal the slots over the banks (needs one column per period)
+};
+
+// thread slot ts -> slot of the column (or 0xffff): slot_of[j * 16 + b] = the j-th slot whose first input
+// sample falls into bank pair b. cnt: 16 counters, zero on entry.
+RR_PROG void poly0_pair_deal(const Poly0PairParams &pp, const Poly0Tile &t, uint16_t *slot_of, int *cnt, int tid, int nthreads)
+{
+  const PolyParams<float> &p = pp.fast.base;
+  for (int fs = tid; fs < t.nslots; fs += nthreads) {
+    const unsigned at_rel = (unsigned)t.r_first + (unsigned)fs * (unsigned)p.step;
+    const int b = (int)((at_rel / (unsigned)p.L) & 15);
+#if defined(__CUDA_ARCH__)
+    const int j = atomicAdd(cnt + b, 1);
+#else
+    const int j = cnt[b]++;
+#endif
+    if (j * 16 + b < pp.tslots) slot_of[j * 16 + b] = (uint16_t)fs;
+  }
+}
+
+// Stage the pair-interleaved input windows of a tile. Does not wait.
+RR_PROG void poly0_pair_load(const Poly0PairParams &pp, const Poly0Tile &t, Pk *buf, int tid, int nthreads)
+{
+  const Poly0FastParams<float> &fp = pp.fast;
+  const PolyParams<float> &p = fp.base;
+  const long long c0 = t.q_first + p.pre;
+  const bool direct = view_range_direct(p.in, c0, c0 + t.win);
+  const int es = p.in.elem_stride;
+  for (int pr = 0; pr < pp.P; ++pr) {
+    const long long off0 = lane_offset(p.in, t.lane0 + 2 * pr), off1 = lane_offset(p.in, t.lane0 + 2 * pr + 1);
+    Pk *dst = buf + pr * fp.win;
+    const float *s0 = view_ptr<const float>(p.in, off0, c0), *s1 = view_ptr<const float>(p.in, off1, c0);
+    if (direct && s1 == s0 + 1 && !(es & 1) && !((size_t)s0 & 7)) {
+      for (int j = tid; j < t.win; j += nthreads) pk_async_copy8(dst + j, s0 + (long long)j * es);
+    } else if (direct) {
+      for (int w = tid; w < 2 * t.win; w += nthreads) {
+        const int l = w & 1, j = w >> 1;
+        async_copy_elem<float>(&dst[j].a + l, (l ? s1 : s0) + (long long)j * es, true);
+      }
+    } else {
+      for (int w = tid; w < 2 * t.win; w += nthreads) {
+        const int l = w & 1, j = w >> 1;
+        bool valid;
+        const float *src = view_addr<float>(p.in, l ? off1 : off0, c0 + j, &valid);
+        async_copy_elem<float>(&dst[j].a + l, src, valid);
+      }
+    }
+  }
+  async_copy_commit();
+}
+
+template <int NT>
+RR_PROG void poly0_pair_compute(const Poly0PairParams &pp, const Poly0Tile &t, const Pk *buf, const uint16_t *slot_of, int tid,
+                                int nthreads)
+{
+  typedef Arith<Pk> A;
+  const Poly0FastParams<float> &fp = pp.fast;
+  const PolyParams<float> &p = fp.base;
+  const int L = p.L, per_group = pp.tslots * pp.P;
+  for (int w = tid; w < per_group * pp.PG; w += nthreads) {
+    const int g = w / per_group, rest = w - g * per_group;
+    const int pr = rest / pp.tslots, ts = rest - pr * pp.tslots;
+    const int fs = pp.spread ? slot_of[ts] : ts;
+    if (fs >= t.nslots) continue;                         // hole of the deal (0xffff) or padding
+    const unsigned at_rel = (unsigned)t.r_first + (unsigned)fs * (unsigned)p.step;
+    const int q = (int)(at_rel / (unsigned)L), r = (int)(at_rel - (unsigned)q * (unsigned)L);
+    float c[NT];
+    const float *row = p.coefs + (long long)r * NT;
+#pragma unroll
+    for (int k = 0; k < NT; ++k) c[k] = ldg(row + k);
+    const int lane_a = t.lane0 + 2 * pr;
+    const long long off0 = lane_offset(p.out, lane_a), off1 = lane_offset(p.out, lane_a + 1);
+    const long long i_end = p.out0 + p.nout, i_tile_end = t.i_first + (long long)t.mcount * L;
+    const bool direct = i_tile_end <= i_end && view_range_direct(p.out, p.out_preload + t.i_first, p.out_preload + i_tile_end);
+    float *d0 = view_ptr<float>(p.out, off0, p.out_preload + t.i_first + fs), *d1 = view_ptr<float>(p.out, off1, p.out_preload + t.i_first + fs);
+    const long long dstep = (long long)L * p.out.elem_stride;
+    const bool packed_out = direct && d1 == d0 + 1 && !((size_t)d0 & 7) && !(dstep & 1);
+    auto emit = [&](int m, Pk s) {
+      const long long i = t.i_first + fs + (long long)m * L;
+      if (packed_out) *reinterpret_cast<Pk *>(d0 + m * dstep) = s;
+      else if (direct) { d0[m * dstep] = s.a; d1[m * dstep] = s.b; }
+      else if (i < i_end) {
+        view_write<float, float>(p.out, off0, p.out_preload + i, s.a);
+        view_write<float, float>(p.out, off1, p.out_preload + i, s.b);
+      }
+    };
+    const Pk *x = buf + pr * fp.win + q;
+    const int step = (int)p.step;
+    int m = g;
+    for (; m + pp.PG < t.mcount; m += 2 * pp.PG) {       // two periods at a time: two independent chains
+      const Pk *xa = x + m * step, *xb = xa + pp.PG * step;
+      Pk sa = pk_bcast(0.0f), sb = pk_bcast(0.0f);
+#pragma unroll
+      for (int k = 0; k < NT; ++k) {
+        const Pk ck = pk_bcast(c[k]);
+        sa = A::addp(sa, A::mul(ck, xa[k]));
+        sb = A::addp(sb, A::mul(ck, xb[k]));
+      }
+      emit(m, sa); emit(m + pp.PG, sb);
+    }
+    if (m < t.mcount) {
+      const Pk *xa = x + m * step;
+      Pk sa = pk_bcast(0.0f);
+#pragma unroll
+      for (int k = 0; k < NT; ++k) sa = A::addp(sa, A::mul(pk_bcast(c[k]), xa[k]));
+      emit(m, sa);
+    }
+  }
 }
 
 }  // namespace b200rate
