@@ -190,21 +190,22 @@ __global__ void __launch_bounds__(kPkGroupThreads * kPkMaxGroups) dftp_kernel(co
                     reinterpret_cast<const uint16_t *>(rr_smem_raw + lay.ltab_f),
                     reinterpret_cast<const uint16_t *>(rr_smem_raw + lay.ltab_i),
                     reinterpret_cast<const uint16_t *>(rr_smem_raw + lay.perm_f)};
-  const int gi = threadIdx.x / pp.gthreads;
-  const Grp g{(int)threadIdx.x - gi * pp.gthreads, pp.gthreads, 1 + gi};
+  const int gi = threadIdx.x / kPkGroupThreads;          // pp.gthreads == kPkGroupThreads: a literal keeps it out of registers
+  const Grp g{(int)threadIdx.x % kPkGroupThreads, kPkGroupThreads, 1 + gi};
   CPk *F = reinterpret_cast<CPk *>(rr_smem_raw + lay.data) + (size_t)gi * lay.group_slots, *B = F + pp.fslots;
   __shared__ PkItem items[kPkMaxGroups][2];
   __syncthreads();
-  long long w = (long long)blockIdx.x * pp.groups + gi;
-  const long long stride = (long long)gridDim.x * pp.groups;
-  if (w < nwork) {
+  // 32-bit work counters (the host splits launches of more than 2^30 items)
+  int w = (int)blockIdx.x * pp.groups + gi;
+  const int stride = (int)gridDim.x * pp.groups, nw = (int)nwork;
+  if (w < nw) {
     if (g.tid == 0) items[gi][0] = pk_make_item(pp, w);
     grp_sync(g);
     pk_stage_tile(pp, g, items[gi][0], F, tb.perm_f);
   }
-  for (int n = 0; w < nwork; w += stride, ++n) {
-    const long long next = w + stride < nwork ? w + stride : -1;
-    dftp_program<MODE, FB, IB>(pp, g, tb, items[gi], n & 1, next, F, B);
+  for (int n = 0; w < nw; w += stride, n ^= 1) {
+    const int next = w + stride < nw ? w + stride : -1;
+    dftp_program<MODE, FB, IB>(pp, g, tb, items[gi], n, next, F, B);
   }
 }
 template <class T, class InT, class OutT>
@@ -248,6 +249,42 @@ __global__ void __launch_bounds__(512) poly0_fast_kernel(const __grid_constant__
       __syncthreads();
       poly0_fast_compute<T, OutT, NT>(p, t, smem);
     }
+  }
+}
+// vpoly0 for lane pairs (rate_kernels_pk.cuh): persistent CTA, two-deep LDGSTS pipeline over the tiles like
+// poly0_fast_kernel; the slots of a period are dealt to the threads once per CTA.
+template <int NT>
+__global__ void __launch_bounds__(512, 2) poly0_pair_kernel(const __grid_constant__ Poly0PairParams pp, long long nwork)
+{
+  const Poly0FastParams<float> &p = pp.fast;
+  Pk *smem = reinterpret_cast<Pk *>(rr_smem_raw);
+  const int set = p.win * pp.P;
+  uint16_t *slot_of = reinterpret_cast<uint16_t *>(smem + 2 * set);
+  __shared__ Poly0Tile tiles[3];
+  __shared__ int cnt[16];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  long long w = blockIdx.x;
+  for (int i = tid; i < pp.tslots; i += nt) slot_of[i] = 0xffff;
+  if (tid < 16) cnt[tid] = 0;
+  if (tid == 0) {
+    if (w < nwork) tiles[0] = poly0_tile(p, w);
+    if (w + gridDim.x < nwork) tiles[1] = poly0_tile(p, w + gridDim.x);
+  }
+  __syncthreads();
+  if (w >= nwork) return;
+  if (pp.spread) poly0_pair_deal(pp, tiles[0], slot_of, cnt, tid, nt);     // one column: the deal holds for every tile
+  poly0_pair_load(pp, tiles[0], smem, tid, nt);
+  __syncthreads();
+  const Poly0PairThread<NT> st = poly0_pair_setup<NT>(pp, tiles[0], slot_of, tid);
+  for (int it = 0; w < nwork; w += gridDim.x, ++it) {
+    const int cur = it & 1, ts = it % 3, tn = (it + 1) % 3, tnn = (it + 2) % 3;
+    const long long next = w + gridDim.x;
+    if (next < nwork) { poly0_pair_load(pp, tiles[tn], smem + (cur ^ 1) * set, tid, nt); async_copy_wait<1>(); }
+    else async_copy_wait<0>();
+    if (tid == 0 && next + gridDim.x < nwork) tiles[tnn] = poly0_tile(p, next + gridDim.x);
+    __syncthreads();
+    poly0_pair_tile<NT>(pp, tiles[ts], smem + cur * set, st);
+    __syncthreads();
   }
 }
 template <class T, class InT, class OutT>
@@ -351,6 +388,39 @@ static int launch_dftp(const DftPkParams &pp, long long nwork, stream_t s)
   }
   if (pp.fb == 11 && pp.ib == 10) return go(dftp_kernel<PK_SPEC_GEN, 11, 10>);        // N = 4096, F-domain / 2
   return go(dftp_kernel<PK_SPEC_GEN, 0, 0>);
+#endif
+}
+
+static size_t poly0_pair_smem(const Poly0PairParams &pp)
+{
+  return 2 * sizeof(Pk) * static_cast<size_t>(pp.fast.win) * pp.P + 2 * static_cast<size_t>(pp.tslots) + 16;
+}
+static int launch_poly0_pair(const Poly0PairParams &pp, int threads, long long nwork, stream_t s)
+{
+  if (nwork <= 0) return RR_OK;
+#ifdef B200RATE_EMU
+  (void)s; (void)threads;
+  if (getenv("B200RATE_TRACE")) fprintf(stderr, "poly0pair L %d n %d step %lld P %d PG %d tslots %d spread %d MM %d win %d nwork %lld\n", pp.fast.base.L, pp.fast.base.n, pp.fast.base.step, pp.P, pp.PG, pp.tslots, pp.spread, pp.fast.MM, pp.fast.win, nwork);
+  std::vector<Pk> buf(static_cast<size_t>(pp.fast.win) * pp.P + 1);
+  std::vector<uint16_t> slot_of(static_cast<size_t>(pp.tslots) + 1);
+  for (long long w = 0; w < nwork; ++w) {
+    const Poly0Tile t = poly0_tile(pp.fast, w);
+    int cnt[16] = {0};
+    std::fill(slot_of.begin(), slot_of.end(), static_cast<uint16_t>(0xffff));
+    if (pp.spread) poly0_pair_deal(pp, t, slot_of.data(), cnt, 0, 1);
+    poly0_pair_load(pp, t, buf.data(), 0, 1);
+    for (int th = 0; th < pp.tslots * pp.P * pp.PG; ++th) {
+      if (pp.fast.base.n == 16) poly0_pair_tile<16>(pp, t, buf.data(), poly0_pair_setup<16>(pp, t, slot_of.data(), th));
+      else if (pp.fast.base.n == 24) poly0_pair_tile<24>(pp, t, buf.data(), poly0_pair_setup<24>(pp, t, slot_of.data(), th));
+      else poly0_pair_tile<32>(pp, t, buf.data(), poly0_pair_setup<32>(pp, t, slot_of.data(), th));
+    }
+  }
+  return RR_OK;
+#else
+  const size_t smem = poly0_pair_smem(pp);
+  if (pp.fast.base.n == 16) return launch_persistent(poly0_pair_kernel<16>, pp, nwork, threads, smem, s);
+  if (pp.fast.base.n == 24) return launch_persistent(poly0_pair_kernel<24>, pp, nwork, threads, smem, s);
+  return launch_persistent(poly0_pair_kernel<32>, pp, nwork, threads, smem, s);
 #endif
 }
 
@@ -661,7 +731,7 @@ template <class T> class Engine {
       p.in = in; p.out = out; p.out_preload = out_preload;
       p.block0 = w0; p.nblocks = static_cast<int>(wn); p.nlanes = nlanes;
       if constexpr (std::is_same<T, float>::value) {
-        if (use_pair_kernel_ && !(nlanes & 1) && !(in.nch & 1) && !(out.nch & 1)) {
+        if (use_pair_kernel_ && !(nlanes & 1) && !(in.nch & 1) && !(out.nch & 1) && wn * (nlanes / 2) < (1ll << 30)) {
           DftPkParams pp;
           if (make_pair_params(i, p, pp)) {
             last_dft_kernel_ = 1;
@@ -702,6 +772,39 @@ template <class T> class Engine {
     PolyParams<T> p = poly_params_[i];
     p.in = in; p.out = out; p.out_preload = out_preload; p.out0 = w0; p.nout = wn; p.nlanes = nlanes;
     p.tile = kPolyTile;
+    if constexpr (std::is_same<T, float>::value) {
+      if (use_pair_kernel_ && g.order == 0 && (g.n == 16 || g.n == 24 || g.n == 32) && !(nlanes & 1) && !(in.nch & 1) &&
+          !(out.nch & 1) && g.Lp >= 48 && g.Lp <= 512 && g.pstep < (1 << 16)) {
+        // lane-pair kernel: one column per period (L <= 512 slots), P pairs of a stream and PG period groups per CTA
+        Poly0PairParams pp;
+        pp.fast.base = p;
+        const int L = g.Lp, step = static_cast<int>(g.pstep);
+        const int r_first = static_cast<int>((((g.at0 + static_cast<i128>(w0) * g.pstep) % L) + L) % L);
+        int bucket[16] = {0}, maxb = 0;
+        for (int fs = 0; fs < L; ++fs) maxb = std::max(maxb, ++bucket[((r_first + static_cast<long long>(fs) * step) / L) & 15]);
+        pp.spread = 1; pp.tslots = 16 * maxb;
+        if (pp.tslots > 2 * L) { pp.spread = 0; pp.tslots = ((L + 15) / 16) * 16; }   // few distinct banks (steep up-sampling): keep order
+        pp.P = 1;
+        while (2 * pp.P < in.nch && in.nch % (4 * pp.P) == 0 && pp.tslots * 2 * pp.P <= 256) pp.P *= 2;
+        pp.PG = std::max(1, std::min(4, 512 / (pp.tslots * pp.P)));
+        int MM = 4 * pp.PG;
+        auto window_of = [&](int mm) {
+          const long long wd = ((L - 1) + static_cast<long long>(L - 1) * step) / L + static_cast<long long>(mm - 1) * step + g.n + 1;
+          return ((wd + 15) / 16) * 16 + 8;
+        };
+        while (MM > 2 && window_of(MM) * pp.P * sizeof(Pk) > 44 * 1024) MM >>= 1;
+        if (window_of(MM) * pp.P * sizeof(Pk) <= 44 * 1024 && nlanes % (2 * pp.P) == 0) {
+          pp.PG = std::min(pp.PG, std::max(1, MM / 2));
+          const long long periods = (wn + L - 1) / L;
+          pp.fast.F = L; pp.fast.ncols = 1; pp.fast.MM = MM; pp.fast.CH = 2 * pp.P;
+          pp.fast.win = static_cast<int>(window_of(MM));
+          pp.fast.mtiles = (periods + MM - 1) / MM;
+          pp.fast.double_buffer = 1;
+          const long long nwork = static_cast<long long>(nlanes / (2 * pp.P)) * pp.fast.mtiles;
+          return launch_poly0_pair(pp, pp.tslots * pp.P * pp.PG, nwork, s);
+        }
+      }
+    }
     if (g.order == 0 && (g.n == 16 || g.n == 24 || g.n == 32)) {
       // phase-stationary kernel: needs enough phases to fill a CTA and a window that fits shared memory
       const int nch = in.nch;

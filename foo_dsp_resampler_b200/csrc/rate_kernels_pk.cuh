@@ -744,8 +744,8 @@ RR_PROG void dftp_program(const DftPkParams &pp, const Grp &g, const PkTables &t
   }
   if (work_next >= 0) pk_stage_tile(pp, g, items[slot ^ 1], F, tb.perm_f);   // F is free until the next item starts
 
-  sink.d0 = it.d0; sink.d1 = it.d1; sink.half = it.count >> 1; sink.es = it.sink == 2 ? p.out.elem_stride : 0;
   pk_fft_lower_any<IB>(pp.ib, g, B, tb.ltab_i, tb.pyr_i, false, p.sqrthalf, p.c16_1, p.c16_3);
+  sink.d0 = it.d0; sink.d1 = it.d1; sink.half = it.count >> 1; sink.es = it.sink == 2 ? p.out.elem_stride : 0;
   pk_fft_top_any<IB>(pp.ib, g, B, nullptr, tb.pyr_i, it.sink != 0, sink);
   if (it.sink) return;
 
@@ -826,62 +826,90 @@ RR_PROG void poly0_pair_load(const Poly0PairParams &pp, const Poly0Tile &t, Pk *
   async_copy_commit();
 }
 
+// What a thread keeps for the whole launch: its slot (hence phase r and first-sample offset q: one column per
+// period, so neither depends on the tile), pair, period group and the coefficient row of the phase.
+template <int NT> struct Poly0PairThread {
+  int fs, q, pr, g;              // fs < 0: no work (hole of the deal / padding)
+  float c[NT];
+};
+
 template <int NT>
-RR_PROG void poly0_pair_compute(const Poly0PairParams &pp, const Poly0Tile &t, const Pk *buf, const uint16_t *slot_of, int tid,
-                                int nthreads)
+RR_PROG Poly0PairThread<NT> poly0_pair_setup(const Poly0PairParams &pp, const Poly0Tile &t, const uint16_t *slot_of, int w)
+{
+  const PolyParams<float> &p = pp.fast.base;
+  Poly0PairThread<NT> st;
+  const int per_group = pp.tslots * pp.P;
+  st.g = w / per_group;
+  const int rest = w - st.g * per_group;
+  st.pr = rest / pp.tslots;
+  const int ts = rest - st.pr * pp.tslots;
+  const int fs = st.g < pp.PG ? (pp.spread ? (int)slot_of[ts] : ts) : 0xffff;
+  st.fs = fs < t.nslots ? fs : -1;
+  const unsigned at_rel = (unsigned)t.r_first + (unsigned)(st.fs < 0 ? 0 : st.fs) * (unsigned)p.step;
+  st.q = (int)(at_rel / (unsigned)p.L);
+  const int r = (int)(at_rel - (unsigned)st.q * (unsigned)p.L);
+  const float *row = p.coefs + (long long)r * NT;
+#pragma unroll
+  for (int k = 0; k < NT; ++k) st.c[k] = ldg(row + k);
+  return st;
+}
+
+RR_PROG Pk pk_load8(const Pk *p)                         // one 8-byte shared / global load
+{
+#if defined(__CUDA_ARCH__)
+  const float2 v = *reinterpret_cast<const float2 *>(p);
+  return pk_make(v.x, v.y);
+#else
+  return *p;
+#endif
+}
+
+template <int NT>
+RR_PROG void poly0_pair_tile(const Poly0PairParams &pp, const Poly0Tile &t, const Pk *buf, const Poly0PairThread<NT> &st)
 {
   typedef Arith<Pk> A;
+  if (st.fs < 0) return;
   const Poly0FastParams<float> &fp = pp.fast;
   const PolyParams<float> &p = fp.base;
-  const int L = p.L, per_group = pp.tslots * pp.P;
-  for (int w = tid; w < per_group * pp.PG; w += nthreads) {
-    const int g = w / per_group, rest = w - g * per_group;
-    const int pr = rest / pp.tslots, ts = rest - pr * pp.tslots;
-    const int fs = pp.spread ? slot_of[ts] : ts;
-    if (fs >= t.nslots) continue;                         // hole of the deal (0xffff) or padding
-    const unsigned at_rel = (unsigned)t.r_first + (unsigned)fs * (unsigned)p.step;
-    const int q = (int)(at_rel / (unsigned)L), r = (int)(at_rel - (unsigned)q * (unsigned)L);
-    float c[NT];
-    const float *row = p.coefs + (long long)r * NT;
-#pragma unroll
-    for (int k = 0; k < NT; ++k) c[k] = ldg(row + k);
-    const int lane_a = t.lane0 + 2 * pr;
-    const long long off0 = lane_offset(p.out, lane_a), off1 = lane_offset(p.out, lane_a + 1);
-    const long long i_end = p.out0 + p.nout, i_tile_end = t.i_first + (long long)t.mcount * L;
-    const bool direct = i_tile_end <= i_end && view_range_direct(p.out, p.out_preload + t.i_first, p.out_preload + i_tile_end);
-    float *d0 = view_ptr<float>(p.out, off0, p.out_preload + t.i_first + fs), *d1 = view_ptr<float>(p.out, off1, p.out_preload + t.i_first + fs);
-    const long long dstep = (long long)L * p.out.elem_stride;
-    const bool packed_out = direct && d1 == d0 + 1 && !((size_t)d0 & 7) && !(dstep & 1);
-    auto emit = [&](int m, Pk s) {
-      const long long i = t.i_first + fs + (long long)m * L;
-      if (packed_out) *reinterpret_cast<Pk *>(d0 + m * dstep) = s;
-      else if (direct) { d0[m * dstep] = s.a; d1[m * dstep] = s.b; }
-      else if (i < i_end) {
-        view_write<float, float>(p.out, off0, p.out_preload + i, s.a);
-        view_write<float, float>(p.out, off1, p.out_preload + i, s.b);
-      }
-    };
-    const Pk *x = buf + pr * fp.win + q;
-    const int step = (int)p.step;
-    int m = g;
-    for (; m + pp.PG < t.mcount; m += 2 * pp.PG) {       // two periods at a time: two independent chains
-      const Pk *xa = x + m * step, *xb = xa + pp.PG * step;
-      Pk sa = pk_bcast(0.0f), sb = pk_bcast(0.0f);
-#pragma unroll
-      for (int k = 0; k < NT; ++k) {
-        const Pk ck = pk_bcast(c[k]);
-        sa = A::addp(sa, A::mul(ck, xa[k]));
-        sb = A::addp(sb, A::mul(ck, xb[k]));
-      }
-      emit(m, sa); emit(m + pp.PG, sb);
+  const int L = p.L, PG = pp.PG;
+  const int lane_a = t.lane0 + 2 * st.pr;
+  const long long off0 = lane_offset(p.out, lane_a), off1 = lane_offset(p.out, lane_a + 1);
+  const long long i_end = p.out0 + p.nout, i_tile_end = t.i_first + (long long)t.mcount * L;
+  const bool direct = i_tile_end <= i_end && view_range_direct(p.out, p.out_preload + t.i_first, p.out_preload + i_tile_end);
+  const long long i0 = t.i_first + st.fs + (long long)st.g * L;               // first output of this thread in the tile
+  float *d0 = view_ptr<float>(p.out, off0, p.out_preload + i0), *d1 = view_ptr<float>(p.out, off1, p.out_preload + i0);
+  const long long dstep = (long long)PG * L * p.out.elem_stride;              // between this thread's consecutive outputs
+  const bool packed_out = direct && d1 == d0 + 1 && !((size_t)d0 & 7) && !(dstep & 1);
+  const int xstep = PG * (int)p.step;
+  const Pk *x = buf + st.pr * fp.win + st.q + st.g * (int)p.step;
+  long long i = i0;
+  const long long istep = (long long)PG * L;
+  auto emit = [&](Pk s) {
+    if (packed_out) *reinterpret_cast<Pk *>(d0) = s;
+    else if (direct) { *d0 = s.a; *d1 = s.b; }
+    else if (i < i_end) {
+      view_write<float, float>(p.out, off0, p.out_preload + i, s.a);
+      view_write<float, float>(p.out, off1, p.out_preload + i, s.b);
     }
-    if (m < t.mcount) {
-      const Pk *xa = x + m * step;
-      Pk sa = pk_bcast(0.0f);
+    d0 += dstep; d1 += dstep; i += istep;
+  };
+  int m = st.g;
+  for (; m + PG < t.mcount; m += 2 * PG, x += 2 * xstep) {                    // two periods at a time: two independent chains
+    const Pk *xb = x + xstep;
+    Pk sa = pk_bcast(0.0f), sb = pk_bcast(0.0f);
 #pragma unroll
-      for (int k = 0; k < NT; ++k) sa = A::addp(sa, A::mul(pk_bcast(c[k]), xa[k]));
-      emit(m, sa);
+    for (int k = 0; k < NT; ++k) {
+      const Pk ck = pk_bcast(st.c[k]);
+      sa = A::addp(sa, A::mul(ck, pk_load8(x + k)));
+      sb = A::addp(sb, A::mul(ck, pk_load8(xb + k)));
     }
+    emit(sa); emit(sb);
+  }
+  if (m < t.mcount) {
+    Pk sa = pk_bcast(0.0f);
+#pragma unroll
+    for (int k = 0; k < NT; ++k) sa = A::addp(sa, A::mul(pk_bcast(st.c[k]), pk_load8(x + k)));
+    emit(sa);
   }
 }
 
