@@ -1197,6 +1197,16 @@ template <class T> class Batch : public IBatch {
 
   const Design &design() const override { return eng.design; }
 
+  // FIFO i (input of stage i) is stored pair-interleaved -- [pair of lanes][sample][2], i.e. a view of two-channel
+  // "streams" -- when the lane-pair kernels sit on both sides of it: the DFT stage then stores whole 16-byte
+  // slots and the polyphase stage stages its window with 16-byte copies. Planar otherwise.
+  bool pair_fifo(int i) const
+  {
+    if (!std::is_same<T, float>::value || (nch & 1) || i < 1 || i >= eng.ns || getenv("B200RATE_NO_PAIR_KERNEL")) return false;
+    const StageGeom &prod = eng.geom[i - 1], &cons = eng.geom[i];
+    return prod.kind == RR_STAGE_DFT && (cons.kind == RR_STAGE_DFT || (cons.kind == RR_STAGE_POLY && cons.order == 0));
+  }
+
   size_t frames_out(size_t frames_in) const override      // rate_flush target, rate/rate_base.h:457
   {
     return static_cast<size_t>(static_cast<double>(frames_in) / eng.design.plan.factor + .5);
@@ -1266,6 +1276,7 @@ template <class T> class Batch : public IBatch {
         in.base = buf[i];
         in.origin = pre + r[i - 1].prod_lo; in.mask = ~0ull; in.lo = pre; in.hi = pre + r[i - 1].prod_hi;
         in.stream_stride = cap[i] * nch; in.ch_stride = static_cast<int>(cap[i]); in.elem_stride = 1; in.nch = nch;
+        if (pair_fifo(i)) { in.stream_stride = 2 * cap[i]; in.ch_stride = 1; in.elem_stride = 2; in.nch = 2; }
         if (cap[i] > 0x7fffffffll) { set_last_error("intermediate lane too long for one batch"); return RR_INVPARAM; }
         in_f32 = false;
       }
@@ -1284,6 +1295,7 @@ template <class T> class Batch : public IBatch {
         out.base = buf[i + 1];
         out.origin = pre + r[i].prod_lo; out.mask = ~0ull; out.lo = out.origin; out.hi = pre + r[i].prod_hi;
         out.stream_stride = cap[i + 1] * nch; out.ch_stride = static_cast<int>(cap[i + 1]); out.elem_stride = 1; out.nch = nch;
+        if (pair_fifo(i + 1)) { out.stream_stride = 2 * cap[i + 1]; out.ch_stride = 1; out.elem_stride = 2; out.nch = 2; }
         out_f32 = false;
         out_preload = pre;
       }

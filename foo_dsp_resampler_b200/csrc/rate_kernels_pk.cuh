@@ -132,8 +132,11 @@ RR_PROG void pk_sink_store(const PkSink &k, int c, const CPk &v)
     reinterpret_cast<C2<float> *>(k.d1)[c] = C2<float>{v.x.b, v.y.b};
   } else {                                               // adjacent interleaved lanes: one pair per frame
     float *f = k.d0 + (long long)(2 * c) * k.es;
-    *reinterpret_cast<Pk *>(f) = v.x;
-    *reinterpret_cast<Pk *>(f + k.es) = v.y;
+    if (k.es == 2 && !((size_t)k.d0 & 15)) *reinterpret_cast<CPk *>(f) = v;   // two stereo frames = one slot
+    else {
+      *reinterpret_cast<Pk *>(f) = v.x;
+      *reinterpret_cast<Pk *>(f + k.es) = v.y;
+    }
   }
 }
 
@@ -807,7 +810,17 @@ RR_PROG void poly0_pair_load(const Poly0PairParams &pp, const Poly0Tile &t, Pk *
     const long long off0 = lane_offset(p.in, t.lane0 + 2 * pr), off1 = lane_offset(p.in, t.lane0 + 2 * pr + 1);
     Pk *dst = buf + pr * fp.win;
     const float *s0 = view_ptr<const float>(p.in, off0, c0), *s1 = view_ptr<const float>(p.in, off1, c0);
-    if (direct && s1 == s0 + 1 && !(es & 1) && !((size_t)s0 & 7)) {
+    if (direct && s1 == s0 + 1 && es == 2 && !((size_t)s0 & 7)) {
+      // adjacent stereo frames: 16-byte copies of two frames between an optional odd head and tail
+      // (window rows are 16-byte aligned: win is even and the buffers start aligned)
+      const int head = (int)(((size_t)s0 >> 3) & 1), body = (t.win - head) >> 1;
+      if (tid == 0 && head) pk_async_copy8(dst, s0);
+      if (tid == 1 && ((t.win - head) & 1)) pk_async_copy8(dst + t.win - 1, s0 + 2 * (t.win - 1));
+      if (!head)
+        for (int j = tid; j < body; j += nthreads) pk_async_copy16(dst + 2 * j, s0 + 4 * j);
+      else                                                // source odd: destination pairs are then misaligned for 16 bytes
+        for (int j = tid; j < 2 * body; j += nthreads) pk_async_copy8(dst + head + j, s0 + 2 * (head + j));
+    } else if (direct && s1 == s0 + 1 && !(es & 1) && !((size_t)s0 & 7)) {
       for (int j = tid; j < t.win; j += nthreads) pk_async_copy8(dst + j, s0 + (long long)j * es);
     } else if (direct) {
       for (int w = tid; w < 2 * t.win; w += nthreads) {
