@@ -258,33 +258,47 @@ __global__ void __launch_bounds__(512, 2) poly0_pair_kernel(const __grid_constan
 {
   const Poly0FastParams<float> &p = pp.fast;
   Pk *smem = reinterpret_cast<Pk *>(rr_smem_raw);
-  const int set = p.win * pp.P;
-  uint16_t *slot_of = reinterpret_cast<uint16_t *>(smem + 2 * set);
-  __shared__ Poly0Tile tiles[3];
+  const int set = p.win * pp.P, nbuf = p.double_buffer ? 2 : 1;
+  uint16_t *slot_of = reinterpret_cast<uint16_t *>(smem + nbuf * set);
+  __shared__ Poly0PairTile tiles[3];
   __shared__ int cnt[16];
   const int tid = threadIdx.x, nt = blockDim.x;
   long long w = blockIdx.x;
+  if (w >= nwork) return;
   for (int i = tid; i < pp.tslots; i += nt) slot_of[i] = 0xffff;
   if (tid < 16) cnt[tid] = 0;
   if (tid == 0) {
-    if (w < nwork) tiles[0] = poly0_tile(p, w);
-    if (w + gridDim.x < nwork) tiles[1] = poly0_tile(p, w + gridDim.x);
+    tiles[0] = poly0_pair_make_tile(pp, w);
+    if (w + gridDim.x < nwork) tiles[1] = poly0_pair_make_tile(pp, w + gridDim.x);
   }
   __syncthreads();
-  if (w >= nwork) return;
-  if (pp.spread) poly0_pair_deal(pp, tiles[0], slot_of, cnt, tid, nt);     // one column: the deal holds for every tile
-  poly0_pair_load(pp, tiles[0], smem, tid, nt);
+  if (pp.spread) poly0_pair_deal(pp, tiles[0].t, slot_of, cnt, tid, nt);   // one column: the deal holds for every tile
+  poly0_pair_load(pp, tiles[0].t, smem, tid, nt);
   __syncthreads();
-  const Poly0PairThread<NT> st = poly0_pair_setup<NT>(pp, tiles[0], slot_of, tid);
-  for (int it = 0; w < nwork; w += gridDim.x, ++it) {
-    const int cur = it & 1, ts = it % 3, tn = (it + 1) % 3, tnn = (it + 2) % 3;
-    const long long next = w + gridDim.x;
-    if (next < nwork) { poly0_pair_load(pp, tiles[tn], smem + (cur ^ 1) * set, tid, nt); async_copy_wait<1>(); }
-    else async_copy_wait<0>();
-    if (tid == 0 && next + gridDim.x < nwork) tiles[tnn] = poly0_tile(p, next + gridDim.x);
-    __syncthreads();
-    poly0_pair_tile<NT>(pp, tiles[ts], smem + cur * set, st);
-    __syncthreads();
+  const Poly0PairThread<NT> st = poly0_pair_setup<NT>(pp, tiles[0].t, slot_of, tid);
+  if (p.double_buffer) {
+    for (int it = 0; w < nwork; w += gridDim.x, ++it) {
+      const int cur = it & 1, ts = it % 3, tn = (it + 1) % 3, tnn = (it + 2) % 3;
+      const long long next = w + gridDim.x;
+      if (next < nwork) { poly0_pair_load(pp, tiles[tn].t, smem + (cur ^ 1) * set, tid, nt); async_copy_wait<1>(); }
+      else async_copy_wait<0>();
+      if (tid == 0 && next + gridDim.x < nwork) tiles[tnn] = poly0_pair_make_tile(pp, next + gridDim.x);
+      __syncthreads();
+      poly0_pair_tile<NT>(pp, tiles[ts], smem + cur * set, st);
+      __syncthreads();
+    }
+  } else {
+    // one window buffer: with several CTAs per SM the others cover this one's load
+    for (int it = 0; w < nwork; w += gridDim.x, ++it) {
+      const int ts = it & 1;
+      const long long next = w + gridDim.x;
+      if (tid == 0 && next < nwork) tiles[ts ^ 1] = poly0_pair_make_tile(pp, next);
+      async_copy_wait<0>();
+      __syncthreads();
+      poly0_pair_tile<NT>(pp, tiles[ts], smem, st);
+      __syncthreads();
+      if (next < nwork) poly0_pair_load(pp, tiles[ts ^ 1].t, smem, tid, nt);
+    }
   }
 }
 template <class T, class InT, class OutT>
@@ -393,7 +407,7 @@ static int launch_dftp(const DftPkParams &pp, long long nwork, stream_t s)
 
 static size_t poly0_pair_smem(const Poly0PairParams &pp)
 {
-  return 2 * sizeof(Pk) * static_cast<size_t>(pp.fast.win) * pp.P + 2 * static_cast<size_t>(pp.tslots) + 16;
+  return (pp.fast.double_buffer ? 2 : 1) * sizeof(Pk) * static_cast<size_t>(pp.fast.win) * pp.P + 2 * static_cast<size_t>(pp.tslots) + 16;
 }
 static int launch_poly0_pair(const Poly0PairParams &pp, int threads, long long nwork, stream_t s)
 {
@@ -404,15 +418,16 @@ static int launch_poly0_pair(const Poly0PairParams &pp, int threads, long long n
   std::vector<Pk> buf(static_cast<size_t>(pp.fast.win) * pp.P + 1);
   std::vector<uint16_t> slot_of(static_cast<size_t>(pp.tslots) + 1);
   for (long long w = 0; w < nwork; ++w) {
-    const Poly0Tile t = poly0_tile(pp.fast, w);
+    const Poly0PairTile pt = poly0_pair_make_tile(pp, w);
+    const Poly0Tile &t = pt.t;
     int cnt[16] = {0};
     std::fill(slot_of.begin(), slot_of.end(), static_cast<uint16_t>(0xffff));
     if (pp.spread) poly0_pair_deal(pp, t, slot_of.data(), cnt, 0, 1);
     poly0_pair_load(pp, t, buf.data(), 0, 1);
     for (int th = 0; th < pp.tslots * pp.P * pp.PG; ++th) {
-      if (pp.fast.base.n == 16) poly0_pair_tile<16>(pp, t, buf.data(), poly0_pair_setup<16>(pp, t, slot_of.data(), th));
-      else if (pp.fast.base.n == 24) poly0_pair_tile<24>(pp, t, buf.data(), poly0_pair_setup<24>(pp, t, slot_of.data(), th));
-      else poly0_pair_tile<32>(pp, t, buf.data(), poly0_pair_setup<32>(pp, t, slot_of.data(), th));
+      if (pp.fast.base.n == 16) poly0_pair_tile<16>(pp, pt, buf.data(), poly0_pair_setup<16>(pp, t, slot_of.data(), th));
+      else if (pp.fast.base.n == 24) poly0_pair_tile<24>(pp, pt, buf.data(), poly0_pair_setup<24>(pp, t, slot_of.data(), th));
+      else poly0_pair_tile<32>(pp, pt, buf.data(), poly0_pair_setup<32>(pp, t, slot_of.data(), th));
     }
   }
   return RR_OK;
@@ -786,20 +801,24 @@ template <class T> class Engine {
         if (pp.tslots > 2 * L) { pp.spread = 0; pp.tslots = ((L + 15) / 16) * 16; }   // few distinct banks (steep up-sampling): keep order
         pp.P = 1;
         while (2 * pp.P < in.nch && in.nch % (4 * pp.P) == 0 && pp.tslots * 2 * pp.P <= 256) pp.P *= 2;
-        pp.PG = std::max(1, std::min(4, 512 / (pp.tslots * pp.P)));
-        int MM = 4 * pp.PG;
+        // one period group; as many CTAs per SM as 64 registers per thread allow (1024 threads), each with one
+        // window buffer of an even number of periods (the other CTAs cover its load)
+        pp.PG = 1;
+        const int threads = pp.tslots * pp.P;
+        const int ctas = std::max(1, std::min(16, 1024 / threads));
+        const size_t budget = std::min<size_t>(64 * 1024, (max_smem_ - 2048) / ctas - 1024);
         auto window_of = [&](int mm) {
           const long long wd = ((L - 1) + static_cast<long long>(L - 1) * step) / L + static_cast<long long>(mm - 1) * step + g.n + 1;
           return ((wd + 15) / 16) * 16 + 8;
         };
-        while (MM > 2 && window_of(MM) * pp.P * sizeof(Pk) > 44 * 1024) MM >>= 1;
-        if (window_of(MM) * pp.P * sizeof(Pk) <= 44 * 1024 && nlanes % (2 * pp.P) == 0) {
-          pp.PG = std::min(pp.PG, std::max(1, MM / 2));
+        int MM = 32;
+        while (MM > 2 && window_of(MM) * pp.P * sizeof(Pk) > budget) MM -= 2;
+        if (window_of(MM) * pp.P * sizeof(Pk) <= budget && nlanes % (2 * pp.P) == 0) {
           const long long periods = (wn + L - 1) / L;
           pp.fast.F = L; pp.fast.ncols = 1; pp.fast.MM = MM; pp.fast.CH = 2 * pp.P;
           pp.fast.win = static_cast<int>(window_of(MM));
           pp.fast.mtiles = (periods + MM - 1) / MM;
-          pp.fast.double_buffer = 1;
+          pp.fast.double_buffer = 0;
           const long long nwork = static_cast<long long>(nlanes / (2 * pp.P)) * pp.fast.mtiles;
           return launch_poly0_pair(pp, pp.tslots * pp.P * pp.PG, nwork, s);
         }

@@ -877,36 +877,58 @@ RR_PROG Pk pk_load8(const Pk *p)                         // one 8-byte shared / 
 #endif
 }
 
+// Tile description for the pair kernel: the generic tile plus everything about its output that needs 64-bit
+// arithmetic, computed by one thread per tile.
+struct Poly0PairTile {
+  Poly0Tile t;
+  float *d_base;                 // first output sample of the tile (slot 0, period 0) of lane t.lane0
+  long long i_end;               // outputs at or beyond this index do not exist
+  int direct;                    // every output of the tile exists and is stored contiguously
+};
+
+RR_PROG Poly0PairTile poly0_pair_make_tile(const Poly0PairParams &pp, long long work)
+{
+  const PolyParams<float> &p = pp.fast.base;
+  Poly0PairTile pt;
+  pt.t = poly0_tile(pp.fast, work);
+  pt.i_end = p.out0 + p.nout;
+  const long long i_tile_end = pt.t.i_first + (long long)pt.t.mcount * p.L;
+  pt.direct = i_tile_end <= pt.i_end && view_range_direct(p.out, p.out_preload + pt.t.i_first, p.out_preload + i_tile_end);
+  pt.d_base = view_ptr<float>(p.out, lane_offset(p.out, pt.t.lane0), p.out_preload + pt.t.i_first);
+  return pt;
+}
+
 template <int NT>
-RR_PROG void poly0_pair_tile(const Poly0PairParams &pp, const Poly0Tile &t, const Pk *buf, const Poly0PairThread<NT> &st)
+RR_PROG void poly0_pair_tile(const Poly0PairParams &pp, const Poly0PairTile &pt, const Pk *buf, const Poly0PairThread<NT> &st)
 {
   typedef Arith<Pk> A;
   if (st.fs < 0) return;
+  const Poly0Tile &t = pt.t;
   const Poly0FastParams<float> &fp = pp.fast;
   const PolyParams<float> &p = fp.base;
-  const int L = p.L, PG = pp.PG;
-  const int lane_a = t.lane0 + 2 * st.pr;
-  const long long off0 = lane_offset(p.out, lane_a), off1 = lane_offset(p.out, lane_a + 1);
-  const long long i_end = p.out0 + p.nout, i_tile_end = t.i_first + (long long)t.mcount * L;
-  const bool direct = i_tile_end <= i_end && view_range_direct(p.out, p.out_preload + t.i_first, p.out_preload + i_tile_end);
-  const long long i0 = t.i_first + st.fs + (long long)st.g * L;               // first output of this thread in the tile
-  float *d0 = view_ptr<float>(p.out, off0, p.out_preload + i0), *d1 = view_ptr<float>(p.out, off1, p.out_preload + i0);
-  const long long dstep = (long long)PG * L * p.out.elem_stride;              // between this thread's consecutive outputs
-  const bool packed_out = direct && d1 == d0 + 1 && !((size_t)d0 & 7) && !(dstep & 1);
+  const int L = p.L, PG = pp.PG, es = p.out.elem_stride, cs = p.out.ch_stride;
+  // the P pairs of a CTA are channels of one stream: lane offsets differ by multiples of the channel stride
+  const int rel = (st.fs + st.g * L) * es + 2 * st.pr * cs;
+  float *d0 = pt.d_base + rel, *d1 = d0 + cs;
+  const int dstep = PG * L * es;                          // between this thread's consecutive outputs
+  const bool direct = pt.direct != 0;
+  const bool packed_out = direct && cs == 1 && !((size_t)d0 & 7) && !(dstep & 1);
   const int xstep = PG * (int)p.step;
   const Pk *x = buf + st.pr * fp.win + st.q + st.g * (int)p.step;
-  long long i = i0;
-  const long long istep = (long long)PG * L;
-  auto emit = [&](Pk s) {
+  int m = st.g;
+  auto emit = [&](int mm, Pk s) {
     if (packed_out) *reinterpret_cast<Pk *>(d0) = s;
     else if (direct) { *d0 = s.a; *d1 = s.b; }
-    else if (i < i_end) {
-      view_write<float, float>(p.out, off0, p.out_preload + i, s.a);
-      view_write<float, float>(p.out, off1, p.out_preload + i, s.b);
+    else {
+      const long long i = t.i_first + st.fs + (long long)mm * L;
+      if (i < pt.i_end) {
+        const int lane_a = t.lane0 + 2 * st.pr;
+        view_write<float, float>(p.out, lane_offset(p.out, lane_a), p.out_preload + i, s.a);
+        view_write<float, float>(p.out, lane_offset(p.out, lane_a + 1), p.out_preload + i, s.b);
+      }
     }
-    d0 += dstep; d1 += dstep; i += istep;
+    d0 += dstep; d1 += dstep;
   };
-  int m = st.g;
   for (; m + PG < t.mcount; m += 2 * PG, x += 2 * xstep) {                    // two periods at a time: two independent chains
     const Pk *xb = x + xstep;
     Pk sa = pk_bcast(0.0f), sb = pk_bcast(0.0f);
@@ -916,13 +938,13 @@ RR_PROG void poly0_pair_tile(const Poly0PairParams &pp, const Poly0Tile &t, cons
       sa = A::addp(sa, A::mul(ck, pk_load8(x + k)));
       sb = A::addp(sb, A::mul(ck, pk_load8(xb + k)));
     }
-    emit(sa); emit(sb);
+    emit(m, sa); emit(m + PG, sb);
   }
   if (m < t.mcount) {
     Pk sa = pk_bcast(0.0f);
 #pragma unroll
     for (int k = 0; k < NT; ++k) sa = A::addp(sa, A::mul(pk_bcast(st.c[k]), pk_load8(x + k)));
-    emit(sa);
+    emit(m, sa);
   }
 }
 
