@@ -424,6 +424,14 @@ static int launch_poly0_pair(const Poly0PairParams &pp, int threads, long long n
     std::fill(slot_of.begin(), slot_of.end(), static_cast<uint16_t>(0xffff));
     if (pp.spread) poly0_pair_deal(pp, t, slot_of.data(), cnt, 0, 1);
     poly0_pair_load(pp, t, buf.data(), 0, 1);
+    if (getenv("B200RATE_CHECKWIN")) {
+      const PolyParams<float> &bp = pp.fast.base;
+      for (int j = 0; j < t.win; ++j) {
+        const float a = view_read<float, float>(bp.in, lane_offset(bp.in, t.lane0), t.q_first + bp.pre + j);
+        const float b2 = view_read<float, float>(bp.in, lane_offset(bp.in, t.lane0 + 1), t.q_first + bp.pre + j);
+        if (a != buf[j].a || b2 != buf[j].b) { fprintf(stderr, "window mismatch w %lld j %d of %d (%g %g) vs (%g %g) q_first %lld\n", w, j, t.win, buf[j].a, buf[j].b, a, b2, t.q_first); break; }
+      }
+    }
     for (int th = 0; th < pp.tslots * pp.P * pp.PG; ++th) {
       if (pp.fast.base.n == 16) poly0_pair_tile<16>(pp, pt, buf.data(), poly0_pair_setup<16>(pp, t, slot_of.data(), th));
       else if (pp.fast.base.n == 24) poly0_pair_tile<24>(pp, pt, buf.data(), poly0_pair_setup<24>(pp, t, slot_of.data(), th));
@@ -746,7 +754,7 @@ template <class T> class Engine {
       p.in = in; p.out = out; p.out_preload = out_preload;
       p.block0 = w0; p.nblocks = static_cast<int>(wn); p.nlanes = nlanes;
       if constexpr (std::is_same<T, float>::value) {
-        if (use_pair_kernel_ && !(nlanes & 1) && !(in.nch & 1) && !(out.nch & 1) && wn * (nlanes / 2) < (1ll << 30)) {
+        if (use_pair_kernel_ && use_pair_dft_ && !(nlanes & 1) && !(in.nch & 1) && !(out.nch & 1) && wn * (nlanes / 2) < (1ll << 30)) {
           DftPkParams pp;
           if (make_pair_params(i, p, pp)) {
             last_dft_kernel_ = 1;
@@ -788,7 +796,7 @@ template <class T> class Engine {
     p.in = in; p.out = out; p.out_preload = out_preload; p.out0 = w0; p.nout = wn; p.nlanes = nlanes;
     p.tile = kPolyTile;
     if constexpr (std::is_same<T, float>::value) {
-      if (use_pair_kernel_ && g.order == 0 && (g.n == 16 || g.n == 24 || g.n == 32) && !(nlanes & 1) && !(in.nch & 1) &&
+      if (use_pair_kernel_ && use_pair_poly_ && g.order == 0 && (g.n == 16 || g.n == 24 || g.n == 32) && !(nlanes & 1) && !(in.nch & 1) &&
           !(out.nch & 1) && g.Lp >= 48 && g.Lp <= 512 && g.pstep < (1 << 16)) {
         // lane-pair kernel: one column per period (L <= 512 slots), P pairs of a stream and PG period groups per CTA
         Poly0PairParams pp;
@@ -927,7 +935,9 @@ template <class T> class Engine {
   const PkSpecConst *pk_spec_dev_[RR_MAX_STAGES] = {nullptr};
   std::map<int, DevSched> sched_;          // by complex bits
   std::map<int, const T *> tcos_;          // by real bits
-  bool use_pair_kernel_ = getenv("B200RATE_NO_PAIR_KERNEL") == nullptr;   // debugging switch: generic kernel only
+  // debugging switches: generic kernels only / per stage kind
+  bool use_pair_kernel_ = getenv("B200RATE_NO_PAIR_KERNEL") == nullptr;
+  bool use_pair_dft_ = getenv("B200RATE_NO_PAIR_DFT") == nullptr, use_pair_poly_ = getenv("B200RATE_NO_PAIR_POLY") == nullptr;
   int last_dft_kernel_ = 0;
 
   // Parameters of the lane-pair kernel for DFT stage i, or false when it does not apply (transform too

@@ -815,7 +815,7 @@ RR_PROG void poly0_pair_load(const Poly0PairParams &pp, const Poly0Tile &t, Pk *
       // (window rows are 16-byte aligned: win is even and the buffers start aligned)
       const int head = (int)(((size_t)s0 >> 3) & 1), body = (t.win - head) >> 1;
       if (tid == 0 && head) pk_async_copy8(dst, s0);
-      if (tid == 1 && ((t.win - head) & 1)) pk_async_copy8(dst + t.win - 1, s0 + 2 * (t.win - 1));
+      if (tid == 0 && ((t.win - head) & 1)) pk_async_copy8(dst + t.win - 1, s0 + 2 * (t.win - 1));
       if (!head)
         for (int j = tid; j < body; j += nthreads) pk_async_copy16(dst + 2 * j, s0 + 4 * j);
       else                                                // source odd: destination pairs are then misaligned for 16 bytes

@@ -31,6 +31,7 @@ CASES = [
     (44100, 176400, "float", 50, 95, 0, 1, 2), (48000, 8000, "float", 50, 95, 0, 1, 2),
     (44100, 88200, "float", 25, 95, 0, 0, 6), (96000, 48000, "float", 50, 95, 1, 0, 2),
     (44100, 22050, "float", 50, 95, 0, 1, 2), (50000, 40000, "float", 50, 95, 0, 0, 2),
+    (48000, 44100, "float", 50, 95, 0, 0, 8), (44100, 48000, "float", 50, 95, 0, 1, 6),
 ]
 
 
@@ -77,7 +78,7 @@ def test_plan_and_design(case):
     orc.close()
 
 
-@pytest.mark.parametrize("case", CASES[:8] + CASES[16:20], ids=ids)
+@pytest.mark.parametrize("case", CASES[:8] + CASES[16:20] + CASES[26:28], ids=ids)
 def test_batch_front_end_and_ranges(case):
     i, o, eng, ph, bw, al, q, nch = case
     L = emulib.lib()

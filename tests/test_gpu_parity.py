@@ -28,6 +28,25 @@ STREAM_CASES = [
     (44100, 48000, "float", 0, 90, 0, 1, 1),      # minimum phase, Normal quality
     (22050, 96000, "float", 50, 95, 0, 0, 1),     # pre + arb + post stages
     (44100, 11025, "double", 50, 95, 0, 0, 2),    # half-band + F-domain /2, fp64
+    # even channel counts on the fp32 engine run the lane-pair kernels (rate_kernels_pk.cuh): every spectrum
+    # mode (x2 up / same size / generic), tile mode (interleaved, planar, zero-stuffed) and output mode
+    (96000, 44100, "float", 50, 95, 0, 0, 2),     # half-band -> 1:1 DFT (same-size mode, planar tiles) -> vpoly0
+    (32000, 48000, "float", 50, 95, 0, 0, 2),     # zero-stuffed tiles (L = 3)
+    (384000, 48000, "float", 50, 95, 0, 0, 4),    # F-domain /2 as last stage, interleaved sink with 4 channels
+    (8000, 48000, "float", 50, 95, 0, 0, 2),      # two DFT stages, post stage L = 4 (generic spectrum mode)
+    (44100, 176400, "float", 50, 95, 0, 1, 2),    # Normal quality, x4
+    (48000, 8000, "float", 50, 95, 0, 1, 2),      # half-bands + time-domain decimation
+    (44100, 88200, "float", 25, 95, 0, 0, 6),     # intermediate phase, 6 channels, DFT only
+    (96000, 48000, "float", 50, 95, 1, 0, 2),     # aliasing allowed
+    (50000, 40000, "float", 50, 95, 0, 0, 2),     # L = 4 / M = 5
+    (48000, 44100, "float", 50, 95, 0, 0, 3),     # odd channel count: generic kernels
+]
+
+# batches (device-resident entry point: pair-interleaved intermediate FIFOs between DFT and polyphase stages)
+BATCH_CASES = [
+    (44100, 48000, 50, 95, 0, 0, 2, 3), (48000, 44100, 50, 95, 0, 0, 8, 2), (44100, 96000, 50, 95, 0, 0, 4, 2),
+    (96000, 44100, 50, 95, 0, 0, 2, 3), (384000, 48000, 50, 95, 0, 0, 8, 1), (22050, 96000, 50, 95, 0, 0, 2, 2),
+    (44100, 48000, 50, 95, 0, 1, 6, 1), (48000, 44100, 50, 95, 0, 0, 3, 2),
 ]
 
 
@@ -138,6 +157,36 @@ def test_batch_device_resident_and_ranges():
         b.process_range(win.data_ptr(), f, c, n, ob, oc, part.data_ptr(), torch.cuda.current_stream().cuda_stream)
         torch.cuda.synchronize()
         assert np.array_equal(part.cpu().numpy(), got[:, ob:ob + oc, :])
+    b.close()
+
+
+@pytest.mark.parametrize("case", BATCH_CASES, ids=lambda c: "%d-%d-q%d-%dch-x%d" % (c[0], c[1], c[5], c[6], c[7]))
+def test_batch_cases_match_oracle(case):
+    import torch
+    import foo_dsp_resampler_b200 as pkg
+    i, o, ph, bw, al, q, nch, nstreams = case
+    cfg, ocfg = _cfgs(i, o, ph, bw, al, q)
+    n = int(i * 0.4) + 13
+    xs = np.stack([signals.sweep_noise(i, nch, n, stream=s) for s in range(nstreams)])
+    b = pkg.BatchConverter(cfg, nch, nstreams, n, engine="float", device=0)
+    nout = b.frames_out(n)
+    d_in = torch.from_numpy(xs).cuda()
+    d_out = torch.zeros((nstreams, nout, nch), dtype=torch.float32, device="cuda")
+    b.process(d_in.data_ptr(), n, d_out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy()
+    for s in range(nstreams):
+        ref, _ = oraclelib.resample(ocfg, xs[s], engine="float")
+        assert ref.shape[0] == nout
+        assert np.array_equal(got[s], ref), "stream %d max diff %g" % (s, np.abs(got[s] - ref).max())
+    # a range in the middle from its halo'd window only (time-chunk primitive)
+    ob, oc = nout // 3, nout // 4
+    f, c = b.input_window(n, ob, oc)
+    win = d_in[:, f:f + c, :].contiguous()
+    part = torch.zeros((nstreams, oc, nch), dtype=torch.float32, device="cuda")
+    b.process_range(win.data_ptr(), f, c, n, ob, oc, part.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(part.cpu().numpy(), got[:, ob:ob + oc, :])
     b.close()
 
 
