@@ -369,24 +369,43 @@ def main():
         dur_ms = stage_ms_acc[dom] / args.steps
         work = b.stage_work(frames, dom)
         peak, how = load_peaks()
-        kinds = {0: "halfband_kernel", 1: "dft_kernel", 2: "poly_kernel"}
+        kname = b.stage_kernel(dom) or "?"
+        kfamily = kname.split(" ")[0]
         # DRAM traffic of this launch from the committed ncu capture (bytes per launch unit x units launched);
-        # only the fp32 captures exist so far, other engines report null
+        # captures exist for the cfg4 plan (48 -> 44.1 kHz fp32), other workloads report null
         traffic = None
         tp = os.path.join(ROOT, "profiles", "dram_traffic.json")
-        if os.path.exists(tp) and engine == "float":
+        if os.path.exists(tp) and engine == "float" and args.workload == "cfg4":
             with open(tp) as f:
-                ent = json.load(f).get(kinds[plan["stages"][dom]["kind"]])
-            if ent and args.workload == "cfg4":          # the capture is of this plan (48 -> 44.1 kHz)
+                ent = json.load(f).get(kfamily)
+            if ent:
                 traffic = ent["bytes_per_unit"] * work["units"]
-        roofline = {"bound": "hbm", "kernel": kinds[plan["stages"][dom]["kind"]], "stage": dom,
+        # arithmetic peaks measured on this pool's B200 by tools/peak_fp.cu (profiles/fp_peaks.json): the
+        # bit-faithful fp32 kernels issue un-fused multiplies and adds, packed two lanes per instruction in the
+        # lane-pair kernels (FMUL2 / FADD2), scalar (FMUL / FADD) in the generic ones
+        fpp = {}
+        fp_path = os.path.join(ROOT, "profiles", "fp_peaks.json")
+        if os.path.exists(fp_path):
+            with open(fp_path) as f:
+                fpp = json.load(f)
+        packed = kfamily in ("dftp_kernel", "poly0_pair_kernel")
+        if engine == "float":
+            alu_peak = fpp.get("fp32_fmul2_fadd2_tflops" if packed else "fp32_fmul_fadd_tflops")
+            alu_how = ("measured, un-fused packed FMUL2+FADD2" if packed else "measured, un-fused FMUL+FADD") + " (profiles/fp_peaks.json)"
+        else:
+            alu_peak = fpp.get("fp64_dfma_tflops")
+            alu_how = "measured, DFMA (profiles/fp_peaks.json)"
+        ach_tflops = work["flops"] / dur_ms / 1e9
+        roofline = {"bound": "hbm", "kernel": kname, "stage": dom,
                     "achieved": work["bytes"] / dur_ms / 1e6, "peak": peak, "unit": "GB/s",
                     "frac": work["bytes"] / dur_ms / 1e6 / peak, "traffic": traffic, "peak_source": how,
                     "ms_per_launch": dur_ms, "algorithmic_bytes_per_launch": work["bytes"],
                     "share_of_step": dur_ms / ms_step,
-                    "fp32_alu": {"achieved_tflops": work["flops"] / dur_ms / 1e9,
-                                 "peak_tflops_nominal_ffma": 74.4 if engine == "float" else 37.2,
-                                 "note": "bit-faithful fp32 issues FMUL+FADD, so half the FFMA peak is attainable"},
+                    "alu": {"achieved_tflops": ach_tflops, "peak_tflops": alu_peak,
+                            "frac": (ach_tflops / alu_peak) if alu_peak else None, "peak_source": alu_how,
+                            "note": "algorithmic flops (SURVEY.md 8d accounting) / kernel time; the kernel is bound by "
+                                    "shared-memory bandwidth and latency, not by HBM (see profiles/README.md)"},
+                    "stage_kernels": [b.stage_kernel(i) for i in range(len(stage_ms_acc))],
                     "stage_ms": [m / args.steps for m in stage_ms_acc]}
 
     # ---- end to end through the host-buffer entry point (H2D + kernels + D2H inside the timed region) ----

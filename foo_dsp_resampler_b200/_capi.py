@@ -76,6 +76,7 @@ SYMBOLS = {
     "RRX_batch_stage_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int]),
     "RRX_batch_stage_work": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                        C.POINTER(C.c_double)]),
+    "RRX_batch_stage_kernel": (C.c_char_p, [C.c_void_p, C.c_int]),
     "RRX_batch_plan": (C.c_int, [C.c_void_p, C.POINTER(Plan)]),
     "RRX_batch_last_launches": (C.c_int, [C.c_void_p]),
     "RRX_batch_flops": (C.c_double, [C.c_void_p, C.c_size_t]),

@@ -188,6 +188,9 @@ class BatchConverter:
         n = self.lib.RRX_batch_stage_times(self.b, ms, 24)
         return [float(ms[i]) for i in range(n)]
 
+    def stage_kernel(self, stage):
+        return (self.lib.RRX_batch_stage_kernel(self.b, int(stage)) or b"").decode()
+
     def stage_work(self, frames_in, stage):
         f, b, u = C.c_double(0), C.c_double(0), C.c_double(0)
         rc = self.lib.RRX_batch_stage_work(self.b, int(frames_in), int(stage), C.byref(f), C.byref(b), C.byref(u))

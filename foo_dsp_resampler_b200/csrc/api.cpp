@@ -360,6 +360,12 @@ int RRX_batch_stage_work(const RRX_batch *b, size_t frames_in, int stage, double
   return b->batch->stage_work(frames_in, stage, flops, bytes, units);
 }
 
+const char *RRX_batch_stage_kernel(const RRX_batch *b, int stage)
+{
+  if (!b || !b->batch) return "";
+  return b->batch->stage_kernel(stage);
+}
+
 int RRX_batch_plan(const RRX_batch *b, rr_plan *out)
 {
   if (!b || !b->batch) return RR_NULLHANDLE;

@@ -705,6 +705,7 @@ template <class T> class Engine {
   int ns = 0;
   StageGeom geom[RR_MAX_STAGES];
   int launches = 0;
+  const char *kernel_name[RR_MAX_STAGES] = {nullptr};   // what run_stage launched last for each stage
 
   ~Engine() { for (void *p : allocs_) be_free(p); }
 
@@ -758,11 +759,16 @@ template <class T> class Engine {
           DftPkParams pp;
           if (make_pair_params(i, p, pp)) {
             last_dft_kernel_ = 1;
+            const bool spec = (pp.spec_mode == PK_SPEC_UP2 && pp.fb == 10 && pp.ib == 11) ||
+                              (pp.spec_mode == PK_SPEC_SAME && pp.fb == 11 && pp.ib == 11) ||
+                              (pp.spec_mode == PK_SPEC_GEN && pp.fb == 11 && pp.ib == 10);
+            kernel_name[i] = spec ? "dftp_kernel (lane pairs, size-specialised)" : "dftp_kernel (lane pairs)";
             return launch_dftp(pp, wn * (nlanes / 2), s);
           }
         }
       }
       last_dft_kernel_ = 0;
+      kernel_name[i] = "dft_kernel";
       const int lpc = dft_lanes_per_cta(g, nlanes);
       // prefetch the next tile with LDGSTS when the input needs no conversion and the staging buffer still
       // leaves room for two CTAs per SM
@@ -790,6 +796,7 @@ template <class T> class Engine {
       p.half = ((p.tile + 2 * p.ncoef + 8 + 31) / 32) * 32 + 4;
       const long long tiles = (wn + p.tile - 1) / p.tile;
       const size_t smem = sizeof(T) * 2 * static_cast<size_t>(p.half) * p.CH;
+      kernel_name[i] = "halfband_kernel";
       return Launch<T>::halfband(p, in_f32, out_f32, tiles * ((nlanes + p.CH - 1) / p.CH), smem, s);
     }
     PolyParams<T> p = poly_params_[i];
@@ -828,6 +835,7 @@ template <class T> class Engine {
           pp.fast.mtiles = (periods + MM - 1) / MM;
           pp.fast.double_buffer = 0;
           const long long nwork = static_cast<long long>(nlanes / (2 * pp.P)) * pp.fast.mtiles;
+          kernel_name[i] = "poly0_pair_kernel";
           return launch_poly0_pair(pp, pp.tslots * pp.P * pp.PG, nwork, s);
         }
       }
@@ -861,6 +869,7 @@ template <class T> class Engine {
         fp.mtiles = (periods + MM - 1) / MM;
         fp.double_buffer = 1;
         const long long nwork = static_cast<long long>(nlanes / CH) * ncols * fp.mtiles;
+        kernel_name[i] = "poly0_fast_kernel";
         return Launch<T>::poly0_fast(fp, threads, in_f32, out_f32, nwork, 2 * sizeof(T) * static_cast<size_t>(fp.win) * CH, s);
       }
     }
@@ -876,6 +885,7 @@ template <class T> class Engine {
     p.win_cap = static_cast<int>(win);
     const long long tiles = (wn + p.tile - 1) / p.tile;
     const size_t smem = sizeof(T) * static_cast<size_t>(win);
+    kernel_name[i] = g.order == 0 ? "poly0_kernel" : "polyN_kernel";
     if (g.order == 0) return Launch<T>::poly0(p, in_f32, out_f32, tiles * nlanes, smem, s);
     return Launch<T>::polyN(p, in_f32, out_f32, tiles * nlanes, smem, s);
   }
@@ -1225,6 +1235,10 @@ template <class T> class Batch : public IBatch {
   }
 
   const Design &design() const override { return eng.design; }
+  const char *stage_kernel(int stage) const override
+  {
+    return stage >= 0 && stage < eng.ns && eng.kernel_name[stage] ? eng.kernel_name[stage] : "";
+  }
 
   // FIFO i (input of stage i) is stored pair-interleaved -- [pair of lanes][sample][2], i.e. a view of two-channel
   // "streams" -- when the lane-pair kernels sit on both sides of it: the DFT stage then stores whole 16-byte

@@ -45,6 +45,8 @@ class IBatch {
   // Algorithmic work of stage i for one whole-stream call on frames_in frames, all lanes:
   // flops (SURVEY.md 8d accounting) and bytes (unique input samples read + output samples written).
   virtual int stage_work(size_t frames_in, int stage, double *flops, double *bytes, double *launch_units) const = 0;
+  // Name of the kernel the most recent call launched for stage i ("" before the first call).
+  virtual const char *stage_kernel(int stage) const = 0;
 };
 
 class IStream {

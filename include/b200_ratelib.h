@@ -147,6 +147,8 @@ int RRX_batch_stage_times(RRX_batch *b, float *ms, int max_stages);
 /* Algorithmic work of one stage for a whole-stream call on frames_in frames over all lanes: FLOPs, bytes
  * (unique input samples read + output samples written) and launch units (DFT blocks or output samples). */
 int RRX_batch_stage_work(const RRX_batch *b, size_t frames_in, int stage, double *flops, double *bytes, double *units);
+/* Name of the kernel the most recent RRX_batch_process* call launched for `stage` (static string, "" if none). */
+const char *RRX_batch_stage_kernel(const RRX_batch *b, int stage);
 int RRX_batch_plan(const RRX_batch *b, rr_plan *out);
 /* Kernel launches issued by the most recent RRX_batch_process* call. */
 int RRX_batch_last_launches(const RRX_batch *b);
