@@ -1,0 +1,24 @@
+import sys, torch, numpy as np
+sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+import foo_dsp_resampler_b200 as pkg
+def probe(i, o, nch, nstreams, secs, engine="float", **kw):
+    cfg = pkg.make_config(i, o, **kw)
+    n = int(i * secs)
+    b = pkg.BatchConverter(cfg, nch, nstreams, n, engine=engine, device=0)
+    x = (torch.rand((nstreams, n, nch), device="cuda") - 0.5)
+    nout = b.frames_out(n)
+    y = torch.zeros((nstreams, nout, nch), device="cuda")
+    b.enable_timing(True)
+    for _ in range(3):
+        b.process(x.data_ptr(), n, y.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        ms = b.stage_times()
+    tot = sum(ms)
+    print("%d->%d %dch x%d %s: %s ms, kernels %s, %.1f Gs/s out, in %.2f GB" % (i, o, nch, nstreams, engine, ["%.3f" % m for m in ms],
+          [b.stage_kernel(k) for k in range(len(ms))], nout * nch * nstreams / tot / 1e6, x.numel() * 4 / 1e9))
+    for k in range(len(ms)):
+        w = b.stage_work(n, k)
+        print("   stage %d: %.1f GB/s algorithmic, %.2f TFLOP/s" % (k, w["bytes"] / ms[k] / 1e6, w["flops"] / ms[k] / 1e9))
+    b.close()
+probe(384000, 48000, 8, 8, 20)
+probe(192000, 44100, 8, 16, 20, engine="double", phase=25)
+probe(48000, 44100, 2, 256, 10)
