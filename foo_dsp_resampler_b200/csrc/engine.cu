@@ -313,6 +313,26 @@ __global__ void __launch_bounds__(kTileThreads) halfband_kernel(const __grid_con
   T *smem = reinterpret_cast<T *>(rr_smem_raw);
   for (long long w = blockIdx.x; w < nwork; w += gridDim.x) halfband_program<T, InT, OutT, NC>(p, w, smem);
 }
+template <int NC>
+__global__ void __launch_bounds__(kTileThreads) halfband_pair_kernel(const __grid_constant__ HalfbandPairParams p, long long nwork)
+{
+  Pk *smem = reinterpret_cast<Pk *>(rr_smem_raw);
+  float cf[NC];                                          // coefficients in registers for the whole launch
+#pragma unroll
+  for (int t = 0; t < NC; ++t) cf[t] = p.base.coef[t];
+  // two window buffers: the next tile's LDGSTS copies are in flight while this one is computed
+  const int set = 2 * p.base.half * p.G + 8;
+  long long w = blockIdx.x;
+  if (w < nwork) halfband_pair_load<NC>(p, w, smem, threadIdx.x, blockDim.x);
+  for (int it = 0; w < nwork; w += gridDim.x, ++it) {
+    const long long next = w + gridDim.x;
+    if (next < nwork) { halfband_pair_load<NC>(p, next, smem + ((it + 1) & 1) * set, threadIdx.x, blockDim.x); async_copy_wait<1>(); }
+    else async_copy_wait<0>();
+    __syncthreads();
+    halfband_pair_compute<NC>(p, cf, w, smem + (it & 1) * set, threadIdx.x, blockDim.x);
+    __syncthreads();
+  }
+}
 template <class InT, class OutT>
 __global__ void __launch_bounds__(kTileThreads) copy_kernel(const __grid_constant__ CopyParams p, long long nwork)
 {
@@ -403,6 +423,30 @@ static int launch_dftp(const DftPkParams &pp, long long nwork, stream_t s)
   if (pp.fb == 11 && pp.ib == 10) return go(dftp_kernel<PK_SPEC_GEN, 11, 10>);        // N = 4096, F-domain / 2
   return go(dftp_kernel<PK_SPEC_GEN, 0, 0>);
 #endif
+}
+
+static int launch_halfband_pair(const HalfbandPairParams &hp, long long nwork, size_t smem, stream_t s)
+{
+  if (nwork <= 0) return RR_OK;
+#ifdef B200RATE_EMU
+  (void)s;
+  std::vector<Pk> mem(smem / sizeof(Pk) + 2);
+#define RR_HBP(NC) { float cf[NC]; for (int t = 0; t < NC; ++t) cf[t] = hp.base.coef[t]; \
+                     for (long long w = 0; w < nwork; ++w) { halfband_pair_load<NC>(hp, w, mem.data(), 0, 1); \
+                                                             halfband_pair_compute<NC>(hp, cf, w, mem.data(), 0, 1); } return RR_OK; }
+#else
+#define RR_HBP(NC) return launch_persistent(halfband_pair_kernel<NC>, hp, nwork, kTileThreads, smem, s)
+#endif
+  switch (hp.base.ncoef) {
+    case 8: RR_HBP(8);
+    case 9: RR_HBP(9);
+    case 10: RR_HBP(10);
+    case 11: RR_HBP(11);
+    case 12: RR_HBP(12);
+    case 13: RR_HBP(13);
+    default: return RR_INTERNAL;
+  }
+#undef RR_HBP
 }
 
 static size_t poly0_pair_smem(const Poly0PairParams &pp)
@@ -785,6 +829,26 @@ template <class T> class Engine {
     if (g.kind == RR_STAGE_HALFBAND) {
       HalfbandParams<T> p = half_params_[i];
       p.in = in; p.out = out; p.out_preload = out_preload; p.out0 = w0; p.nout = wn; p.nlanes = nlanes;
+      if constexpr (std::is_same<T, float>::value) {
+        if (use_pair_kernel_ && use_pair_half_ && !(nlanes & 1) && !(in.nch & 1) && !(out.nch & 1)) {
+          // lane-pair kernel: all pairs of a stream per CTA when its frames are interleaved (coalesced window load)
+          HalfbandPairParams hp;
+          hp.base = p;
+          const int nchan = in.nch;
+          const bool group_ok = in.ch_stride == 1 && out.nch == nchan && nlanes % nchan == 0 && (nchan == 2 || nchan == 4 || nchan == 8);
+          hp.G = group_ok ? nchan / 2 : 1;
+          hp.base.CH = 2 * hp.G;
+          hp.base.tile = kHalfTile / (2 * hp.G);             // outputs per pair per CTA, power of two
+          hp.base.qbits = 0;
+          while ((4 << hp.base.qbits) < hp.base.tile) ++hp.base.qbits;
+          // rows of 8-byte values: 16-byte aligned (even) and 4 mod 16, so the pairs of a frame land 8 banks apart
+          hp.base.half = ((hp.base.tile + 2 * p.ncoef + 8 + 15) / 16) * 16 + 4;
+          const long long tiles = (wn + hp.base.tile - 1) / hp.base.tile;
+          const size_t smem = 2 * sizeof(Pk) * (2 * static_cast<size_t>(hp.base.half) * hp.G + 8);   // two window buffers
+          kernel_name[i] = "halfband_pair_kernel";
+          return launch_halfband_pair(hp, tiles * (nlanes / (2 * hp.G)), smem, s);
+        }
+      }
       // all channels of a stream per CTA when the input is interleaved (coalesced window load)
       const int nchan = in.nch;
       const bool group_ok = in.ch_stride == 1 && out.nch == nchan && nlanes % nchan == 0 &&
@@ -948,6 +1012,7 @@ template <class T> class Engine {
   // debugging switches: generic kernels only / per stage kind
   bool use_pair_kernel_ = getenv("B200RATE_NO_PAIR_KERNEL") == nullptr;
   bool use_pair_dft_ = getenv("B200RATE_NO_PAIR_DFT") == nullptr, use_pair_poly_ = getenv("B200RATE_NO_PAIR_POLY") == nullptr;
+  bool use_pair_half_ = getenv("B200RATE_NO_PAIR_HALF") == nullptr;
   int last_dft_kernel_ = 0;
 
   // Parameters of the lane-pair kernel for DFT stage i, or false when it does not apply (transform too

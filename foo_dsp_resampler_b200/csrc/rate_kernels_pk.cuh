@@ -948,4 +948,150 @@ RR_PROG void poly0_pair_tile(const Poly0PairParams &pp, const Poly0PairTile &pt,
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Half-band 2:1 decimator (h8..h13, rate_filters_generic.h:80-249) for lane pairs: the scheme of
+// halfband_program (window split by sample parity, four consecutive outputs per thread from 16-byte shared
+// loads) with both channels of a pair in every value, so each add / multiply is one FADD2 / FMUL2.
+// y[k] = 0.5 x[2k+pre] + sum_t c[t] (x[2k+pre-(2t+1)] + x[2k+pre+(2t+1)]), summed in that order.
+// ---------------------------------------------------------------------------------------------------
+struct HalfbandPairParams {
+  HalfbandParams<float> base;    // coefficients, views, ranges; tile = outputs per pair per CTA (multiple of 4), half, qbits
+  int G;                         // pairs per CTA: all channels of a stream when the input is interleaved, else 1
+};
+
+// Geometry of one tile: `tile` outputs of the G pairs of one stream (or of one pair).
+struct HalfbandPairTile {
+  int lane0, cnt, win;
+  long long k0, x0;              // first output / first input coordinate (window index u = coord - x0)
+};
+template <int NC>
+RR_PROG HalfbandPairTile halfband_pair_tile(const HalfbandPairParams &hp, long long work)
+{
+  const HalfbandParams<float> &p = hp.base;
+  HalfbandPairTile t;
+  const long long tiles = (p.nout + p.tile - 1) / p.tile;
+  long long group; int tix_i;
+  divmod_ll(work, (int)tiles, group, tix_i);
+  t.lane0 = (int)group * 2 * hp.G;
+  t.k0 = p.out0 + (long long)tix_i * p.tile;
+  const long long rest = p.out0 + p.nout - t.k0;
+  t.cnt = rest < p.tile ? (int)rest : p.tile;
+  const int reach = 2 * NC - 1;
+  t.x0 = 2 * t.k0 + p.pre - reach;
+  t.win = 2 * (t.cnt - 1) + 2 * reach + 1;
+  return t;
+}
+
+// Stage the window of a tile, split by sample parity: even u -> P0[g][u/2]; odd u -> P1[g][(u+1)/2 + shift], so
+// that the centre tap of output j (u = 2j + reach) sits at P1[j + 4]; odd samples below the first centre tap
+// (index < 4) are never read and not stored. Asynchronous (LDGSTS): returns after committing the copies.
+template <int NC>
+RR_PROG void halfband_pair_load(const HalfbandPairParams &hp, long long work, Pk *smem, int tid, int nthreads)
+{
+  const HalfbandParams<float> &p = hp.base;
+  const HalfbandPairTile t = halfband_pair_tile<NC>(hp, work);
+  const int G = hp.G, gbits = G == 4 ? 2 : G == 2 ? 1 : 0;      // G is 1, 2 or 4
+  // the odd array starts 8 values (16 banks) further so that the even and the odd sample of a frame pair never
+  // share a bank
+  Pk *P0 = smem, *P1 = smem + (long long)G * p.half + 8;
+  const int shift = 4 - NC, win = t.win;
+  const long long in_off0 = lane_offset(p.in, t.lane0);
+  const int ics = p.in.ch_stride, ies = p.in.elem_stride;
+  const bool direct = view_range_direct(p.in, t.x0, t.x0 + win);
+  const float *src0 = view_ptr<const float>(p.in, in_off0, t.x0);
+  const int npairs_u = (win + 1) >> 1;                   // frame pairs (u = 2f, 2f + 1)
+  if (direct && ics == 1 && !(ies & 1) && !((size_t)src0 & 7)) {
+    // interleaved frames: the pairs of a frame are consecutive 8-byte words; one thread takes both frames of a
+    // frame pair for one lane pair
+    for (int w = tid; w < (npairs_u << gbits); w += nthreads) {
+      const int g = w & (G - 1), f = w >> gbits;
+      const float *sp = src0 + (2 * f) * ies + 2 * g;
+      pk_async_copy8(P0 + g * p.half + f, sp);
+      const int io = f + 1 + shift;
+      if (2 * f + 1 < win && io >= 4) pk_async_copy8(P1 + g * p.half + io, sp + ies);
+    }
+  } else if (direct) {
+    // planar lanes (or any regular strides): lane by lane, frame pairs fastest
+    for (int l = 0; l < 2 * G; ++l) {
+      const float *sl = src0 + (long long)l * ics;
+      float *d0 = &P0[(l >> 1) * p.half].a + (l & 1), *d1 = &P1[(l >> 1) * p.half].a + (l & 1);
+      for (int f = tid; f < npairs_u; f += nthreads) {
+        async_copy_elem<float>(d0 + 2 * f, sl + (long long)(2 * f) * ies, true);
+        const int io = f + 1 + shift;
+        if (2 * f + 1 < win && io >= 4) async_copy_elem<float>(d1 + 2 * io, sl + (long long)(2 * f + 1) * ies, true);
+      }
+    }
+  } else {
+    for (int w = tid; w < 2 * win * G; w += nthreads) {
+      const int u = w % win, l = w / win, g = l >> 1;
+      bool valid;
+      const float *src = view_addr<float>(p.in, in_off0 + (long long)l * ics, t.x0 + u, &valid);
+      if (u & 1) {
+        const int io = ((u + 1) >> 1) + shift;
+        if (io >= 4) async_copy_elem<float>(&P1[g * p.half + io].a + (l & 1), src, valid);
+      } else async_copy_elem<float>(&P0[g * p.half + (u >> 1)].a + (l & 1), src, valid);
+    }
+  }
+  async_copy_commit();
+}
+
+template <int NC>
+RR_PROG void halfband_pair_compute(const HalfbandPairParams &hp, const float (&cf)[NC], long long work, const Pk *smem, int tid,
+                                   int nthreads)
+{
+  typedef Arith<Pk> A;
+  const HalfbandParams<float> &p = hp.base;
+  constexpr int c = NC;
+  const HalfbandPairTile t = halfband_pair_tile<NC>(hp, work);
+  const int G = hp.G, cnt = t.cnt;
+  const Pk *P0 = smem, *P1 = smem + (long long)G * p.half + 8;
+  const long long out_off0 = lane_offset(p.out, t.lane0), k0 = t.k0;
+  const int qbits = p.qbits;                             // log2(tile / 4)
+  const int ocs = p.out.ch_stride, oes = p.out.elem_stride;
+  for (int w = tid; w < (G << qbits); w += nthreads) {
+    const int g = w >> qbits, j = 4 * (w & ((1 << qbits) - 1));
+    if (j >= cnt) continue;
+    const Pk *e = P0 + g * p.half + j, *o = P1 + g * p.half + j + 4;
+    // outputs j..j+3 use P0[j .. j+2c+2] and the centres P1[j+4 .. j+7]; rows are 16-byte aligned
+    constexpr int kVecs = (2 * c + 3 + 1) / 2;
+    Pk x[2 * kVecs], ctr[4];
+#pragma unroll
+    for (int i = 0; i < kVecs; ++i) { const CPk v = reinterpret_cast<const CPk *>(e)[i]; x[2 * i] = v.x; x[2 * i + 1] = v.y; }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { const CPk v = reinterpret_cast<const CPk *>(o)[i]; ctr[2 * i] = v.x; ctr[2 * i + 1] = v.y; }
+    Pk y[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      Pk sum = A::mul(ctr[r], pk_bcast(0.5f));
+#pragma unroll
+      for (int tt = 0; tt < c; ++tt) sum = A::addp(sum, A::mul(A::add(x[r + c - 1 - tt], x[r + c + tt]), pk_bcast(cf[tt])));
+      y[r] = sum;
+    }
+    const long long off_a = out_off0 + (long long)(2 * g) * ocs, off_b = off_a + ocs;
+    const long long cbase = p.out_preload + k0 + j;
+    if (j + 4 <= cnt && view_range_direct(p.out, cbase, cbase + 4)) {
+      float *da = view_ptr<float>(p.out, off_a, cbase), *db = view_ptr<float>(p.out, off_b, cbase);
+      if (ocs == 1 && !(oes & 1) && !((size_t)da & 7)) {                  // interleaved: one pair per frame
+#pragma unroll
+        for (int r = 0; r < 4; ++r) *reinterpret_cast<Pk *>(da + (long long)r * oes) = y[r];
+      } else if (oes == 1 && !(((size_t)da | (size_t)db) & 15)) {         // planar, aligned: one vector store per lane
+        struct alignas(16) O4 { float a, b, c, d; };
+        *reinterpret_cast<O4 *>(da) = O4{y[0].a, y[1].a, y[2].a, y[3].a};
+        *reinterpret_cast<O4 *>(db) = O4{y[0].b, y[1].b, y[2].b, y[3].b};
+      } else {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { da[(long long)r * oes] = y[r].a; db[(long long)r * oes] = y[r].b; }
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        if (j + r < cnt) {
+          view_write<float, float>(p.out, off_a, cbase + r, y[r].a);
+          view_write<float, float>(p.out, off_b, cbase + r, y[r].b);
+        }
+    }
+  }
+}
+
 }  // namespace b200rate
