@@ -261,20 +261,22 @@ __global__ void __launch_bounds__(512, 2) poly0_pair_kernel(const __grid_constan
   const int set = p.win * pp.P, nbuf = p.double_buffer ? 2 : 1;
   uint16_t *slot_of = reinterpret_cast<uint16_t *>(smem + nbuf * set);
   __shared__ Poly0PairTile tiles[3];
-  __shared__ int cnt[16];
+  __shared__ int cnt[17];
+  __shared__ uint16_t ovf[kPolyDealOverflow];
   const int tid = threadIdx.x, nt = blockDim.x;
   long long w = blockIdx.x;
   if (w >= nwork) return;
   for (int i = tid; i < pp.tslots; i += nt) slot_of[i] = 0xffff;
-  if (tid < 16) cnt[tid] = 0;
+  if (tid < 17) cnt[tid] = 0;
   if (tid == 0) {
     tiles[0] = poly0_pair_make_tile(pp, w);
     if (w + gridDim.x < nwork) tiles[1] = poly0_pair_make_tile(pp, w + gridDim.x);
   }
   __syncthreads();
-  if (pp.spread) poly0_pair_deal(pp, tiles[0].t, slot_of, cnt, tid, nt);   // one column: the deal holds for every tile
+  if (pp.spread) poly0_pair_deal(pp, tiles[0].t, slot_of, cnt, ovf, tid, nt);   // one column: the deal holds for every tile
   poly0_pair_load(pp, tiles[0].t, smem, tid, nt);
   __syncthreads();
+  if (pp.spread) { poly0_pair_deal_overflow(pp, slot_of, cnt, ovf, tid); __syncthreads(); }
   const Poly0PairThread<NT> st = poly0_pair_setup<NT>(pp, tiles[0].t, slot_of, tid);
   if (p.double_buffer) {
     for (int it = 0; w < nwork; w += gridDim.x, ++it) {
@@ -296,6 +298,57 @@ __global__ void __launch_bounds__(512, 2) poly0_pair_kernel(const __grid_constan
       async_copy_wait<0>();
       __syncthreads();
       poly0_pair_tile<NT>(pp, tiles[ts], smem, st);
+      __syncthreads();
+      if (next < nwork) poly0_pair_load(pp, tiles[ts ^ 1].t, smem, tid, nt);
+    }
+  }
+}
+// Two adjacent slots per thread (poly0_pair2_*): same skeleton.
+template <int NT, int DLO>
+__global__ void __launch_bounds__(256, 3) poly0_pair2_kernel(const __grid_constant__ Poly0PairParams pp, long long nwork)
+{
+  const Poly0FastParams<float> &p = pp.fast;
+  Pk *smem = reinterpret_cast<Pk *>(rr_smem_raw);
+  const int set = p.win * pp.P, nbuf = p.double_buffer ? 2 : 1;
+  uint16_t *slot_of = reinterpret_cast<uint16_t *>(smem + nbuf * set);
+  __shared__ Poly0PairTile tiles[3];
+  __shared__ int cnt[17];
+  __shared__ uint16_t ovf[kPolyDealOverflow];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  long long w = blockIdx.x;
+  if (w >= nwork) return;
+  for (int i = tid; i < pp.tslots; i += nt) slot_of[i] = 0xffff;
+  if (tid < 17) cnt[tid] = 0;
+  if (tid == 0) {
+    tiles[0] = poly0_pair_make_tile(pp, w);
+    if (w + gridDim.x < nwork) tiles[1] = poly0_pair_make_tile(pp, w + gridDim.x);
+  }
+  __syncthreads();
+  if (pp.spread) poly0_pair_deal(pp, tiles[0].t, slot_of, cnt, ovf, tid, nt);   // one column: the deal holds for every tile
+  poly0_pair_load(pp, tiles[0].t, smem, tid, nt);
+  __syncthreads();
+  if (pp.spread) { poly0_pair_deal_overflow(pp, slot_of, cnt, ovf, tid); __syncthreads(); }
+  const Poly0Pair2Thread<NT, DLO> st = poly0_pair2_setup<NT, DLO>(pp, tiles[0].t, slot_of, tid);
+  if (p.double_buffer) {
+    for (int it = 0; w < nwork; w += gridDim.x, ++it) {
+      const int cur = it & 1, ts = it % 3, tn = (it + 1) % 3, tnn = (it + 2) % 3;
+      const long long next = w + gridDim.x;
+      if (next < nwork) { poly0_pair_load(pp, tiles[tn].t, smem + (cur ^ 1) * set, tid, nt); async_copy_wait<1>(); }
+      else async_copy_wait<0>();
+      if (tid == 0 && next + gridDim.x < nwork) tiles[tnn] = poly0_pair_make_tile(pp, next + gridDim.x);
+      __syncthreads();
+      poly0_pair2_tile<NT, DLO>(pp, tiles[ts], smem + cur * set, st);
+      __syncthreads();
+    }
+  } else {
+    // one window buffer: with several CTAs per SM the others cover this one's load
+    for (int it = 0; w < nwork; w += gridDim.x, ++it) {
+      const int ts = it & 1;
+      const long long next = w + gridDim.x;
+      if (tid == 0 && next < nwork) tiles[ts ^ 1] = poly0_pair_make_tile(pp, next);
+      async_copy_wait<0>();
+      __syncthreads();
+      poly0_pair2_tile<NT, DLO>(pp, tiles[ts], smem, st);
       __syncthreads();
       if (next < nwork) poly0_pair_load(pp, tiles[ts ^ 1].t, smem, tid, nt);
     }
@@ -458,15 +511,16 @@ static int launch_poly0_pair(const Poly0PairParams &pp, int threads, long long n
   if (nwork <= 0) return RR_OK;
 #ifdef B200RATE_EMU
   (void)s; (void)threads;
-  if (getenv("B200RATE_TRACE")) fprintf(stderr, "poly0pair L %d n %d step %lld P %d PG %d tslots %d spread %d MM %d win %d nwork %lld\n", pp.fast.base.L, pp.fast.base.n, pp.fast.base.step, pp.P, pp.PG, pp.tslots, pp.spread, pp.fast.MM, pp.fast.win, nwork);
+  if (getenv("B200RATE_TRACE")) fprintf(stderr, "poly0pair L %d n %d step %lld P %d PG %d CL %d tslots %d spread %d MM %d win %d nwork %lld\n", pp.fast.base.L, pp.fast.base.n, pp.fast.base.step, pp.P, pp.PG, pp.CL, pp.tslots, pp.spread, pp.fast.MM, pp.fast.win, nwork);
   std::vector<Pk> buf(static_cast<size_t>(pp.fast.win) * pp.P + 1);
   std::vector<uint16_t> slot_of(static_cast<size_t>(pp.tslots) + 1);
   for (long long w = 0; w < nwork; ++w) {
     const Poly0PairTile pt = poly0_pair_make_tile(pp, w);
     const Poly0Tile &t = pt.t;
-    int cnt[16] = {0};
+    int cnt[17] = {0};
+    uint16_t ovf[kPolyDealOverflow];
     std::fill(slot_of.begin(), slot_of.end(), static_cast<uint16_t>(0xffff));
-    if (pp.spread) poly0_pair_deal(pp, t, slot_of.data(), cnt, 0, 1);
+    if (pp.spread) { poly0_pair_deal(pp, t, slot_of.data(), cnt, ovf, 0, 1); poly0_pair_deal_overflow(pp, slot_of.data(), cnt, ovf, 0); }
     poly0_pair_load(pp, t, buf.data(), 0, 1);
     if (getenv("B200RATE_CHECKWIN")) {
       const PolyParams<float> &bp = pp.fast.base;
@@ -475,6 +529,15 @@ static int launch_poly0_pair(const Poly0PairParams &pp, int threads, long long n
         const float b2 = view_read<float, float>(bp.in, lane_offset(bp.in, t.lane0 + 1), t.q_first + bp.pre + j);
         if (a != buf[j].a || b2 != buf[j].b) { fprintf(stderr, "window mismatch w %lld j %d of %d (%g %g) vs (%g %g) q_first %lld\n", w, j, t.win, buf[j].a, buf[j].b, a, b2, t.q_first); break; }
       }
+    }
+    if (pp.CL == 2) {
+      const int dlo = static_cast<int>(pp.fast.base.step / pp.fast.base.L);
+      for (int th = 0; th < pp.tslots * pp.P; ++th) {
+#define RR_P2(NT, D) if (pp.fast.base.n == NT && dlo == D) poly0_pair2_tile<NT, D>(pp, pt, buf.data(), poly0_pair2_setup<NT, D>(pp, t, slot_of.data(), th))
+        RR_P2(16, 0); RR_P2(16, 1); RR_P2(16, 2); RR_P2(24, 0); RR_P2(24, 1); RR_P2(24, 2); RR_P2(32, 0); RR_P2(32, 1); RR_P2(32, 2);
+#undef RR_P2
+      }
+      continue;
     }
     for (int th = 0; th < pp.tslots * pp.P * pp.PG; ++th) {
       if (pp.fast.base.n == 16) poly0_pair_tile<16>(pp, pt, buf.data(), poly0_pair_setup<16>(pp, t, slot_of.data(), th));
@@ -485,6 +548,13 @@ static int launch_poly0_pair(const Poly0PairParams &pp, int threads, long long n
   return RR_OK;
 #else
   const size_t smem = poly0_pair_smem(pp);
+  if (pp.CL == 2) {
+    const int dlo = static_cast<int>(pp.fast.base.step / pp.fast.base.L);
+#define RR_P2(NT, D) if (pp.fast.base.n == NT && dlo == D) return launch_persistent(poly0_pair2_kernel<NT, D>, pp, nwork, threads, smem, s)
+    RR_P2(16, 0); RR_P2(16, 1); RR_P2(16, 2); RR_P2(24, 0); RR_P2(24, 1); RR_P2(24, 2); RR_P2(32, 0); RR_P2(32, 1); RR_P2(32, 2);
+#undef RR_P2
+    return RR_INTERNAL;
+  }
   if (pp.fast.base.n == 16) return launch_persistent(poly0_pair_kernel<16>, pp, nwork, threads, smem, s);
   if (pp.fast.base.n == 24) return launch_persistent(poly0_pair_kernel<24>, pp, nwork, threads, smem, s);
   return launch_persistent(poly0_pair_kernel<32>, pp, nwork, threads, smem, s);
@@ -874,10 +944,16 @@ template <class T> class Engine {
         pp.fast.base = p;
         const int L = g.Lp, step = static_cast<int>(g.pstep);
         const int r_first = static_cast<int>((((g.at0 + static_cast<i128>(w0) * g.pstep) % L) + L) % L);
+        // two adjacent slots per thread when their windows overlap almost entirely (step / L < 3) and a period
+        // still has enough slot pairs for a CTA
+        pp.CL = (use_pair_poly2_ && step / L <= 2 && L >= 96) ? 2 : 1;
         int bucket[16] = {0}, maxb = 0;
-        for (int fs = 0; fs < L; ++fs) maxb = std::max(maxb, ++bucket[((r_first + static_cast<long long>(fs) * step) / L) & 15]);
-        pp.spread = 1; pp.tslots = 16 * maxb;
-        if (pp.tslots > 2 * L) { pp.spread = 0; pp.tslots = ((L + 15) / 16) * 16; }   // few distinct banks (steep up-sampling): keep order
+        for (int fs = 0; fs < L; fs += pp.CL) maxb = std::max(maxb, ++bucket[((r_first + static_cast<long long>(fs) * step) / L) & 15]);
+        const int ncl = (L + pp.CL - 1) / pp.CL, rows = (ncl + 15) / 16;
+        pp.spread = 1; pp.tslots = 16 * rows;               // overfull banks spill into the holes (poly0_pair_deal_overflow)
+        int spill = 0;
+        for (int b2 = 0; b2 < 16; ++b2) spill += std::max(0, bucket[b2] - rows);
+        if (maxb > 2 * rows || spill > kPolyDealOverflow) pp.spread = 0;   // few distinct banks (steep up-sampling): keep order
         pp.P = 1;
         while (2 * pp.P < in.nch && in.nch % (4 * pp.P) == 0 && pp.tslots * 2 * pp.P <= 256) pp.P *= 2;
         // one period group; as many CTAs per SM as 64 registers per thread allow (1024 threads), each with one
@@ -887,7 +963,7 @@ template <class T> class Engine {
         const int ctas = std::max(1, std::min(16, 1024 / threads));
         const size_t budget = std::min<size_t>(64 * 1024, (max_smem_ - 2048) / ctas - 1024);
         auto window_of = [&](int mm) {
-          const long long wd = ((L - 1) + static_cast<long long>(L - 1) * step) / L + static_cast<long long>(mm - 1) * step + g.n + 1;
+          const long long wd = ((L - 1) + static_cast<long long>(L - 1) * step) / L + static_cast<long long>(mm - 1) * step + g.n + 1 + 4;
           return ((wd + 15) / 16) * 16 + 8;
         };
         int MM = 32;
@@ -1012,7 +1088,7 @@ template <class T> class Engine {
   // debugging switches: generic kernels only / per stage kind
   bool use_pair_kernel_ = getenv("B200RATE_NO_PAIR_KERNEL") == nullptr;
   bool use_pair_dft_ = getenv("B200RATE_NO_PAIR_DFT") == nullptr, use_pair_poly_ = getenv("B200RATE_NO_PAIR_POLY") == nullptr;
-  bool use_pair_half_ = getenv("B200RATE_NO_PAIR_HALF") == nullptr;
+  bool use_pair_half_ = getenv("B200RATE_NO_PAIR_HALF") == nullptr, use_pair_poly2_ = getenv("B200RATE_NO_PAIR_POLY2") == nullptr;
   int last_dft_kernel_ = 0;
 
   // Parameters of the lane-pair kernel for DFT stage i, or false when it does not apply (transform too
