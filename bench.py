@@ -42,6 +42,20 @@ WORKLOADS = {
 }
 
 
+_JSON_FD = None     # saved stdout when the process-level stdout has been redirected (multi-rank runs)
+
+
+def emit_json(line):
+    """The one JSON line of the contract, on the real stdout."""
+    text = json.dumps(line) + "\n"
+    if _JSON_FD is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, text.encode())
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -206,7 +220,7 @@ def run_reference_arm(args, rank):
         "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_json(line)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -269,7 +283,13 @@ def main():
         import torch.distributed as dist_mod
         dist = dist_mod
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # keep NCCL's banner off stdout: one JSON line only
+        # NCCL prints its version banner to file descriptor 1 on the first collective; stdout must carry exactly
+        # one JSON line, so the process-level stdout is pointed at stderr and the line is written to the saved fd
+        global _JSON_FD
+        if _JSON_FD is None:
+            sys.stdout.flush()
+            _JSON_FD = os.dup(1)
+            os.dup2(2, 1)
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
     W = max(args.warmup, 3)            # timing rule: at least 3 warm-up steps
 
@@ -481,7 +501,7 @@ def main():
         }
         if gather:
             line["gather"] = gather
-        print(json.dumps(line), flush=True)
+        emit_json(line)
     if dist:
         dist.barrier()
         dist.destroy_process_group()
