@@ -166,6 +166,25 @@ __global__ void __launch_bounds__(2 * kDftThreads) dft_kernel(const __grid_const
     dft_stage_program<T, InT, OutT, LPC, DftCacheDepth<T>::value>(p, tab, cc, items, slot, next, data);
   }
 }
+// DFT blocks that do not fit shared memory (N > 16384 fp32 / 8192 fp64: transition bands below ~1 % of Nyquist):
+// the same CTA program with its work buffers in a per-CTA slice of global scratch (L2-resident) and the tables
+// read from global memory. One lane per CTA, no prefetch buffer. Slow path, there for coverage of RR_config.
+template <class T, class InT, class OutT>
+__global__ void __launch_bounds__(2 * kDftThreads) dft_big_kernel(const __grid_constant__ DftParams<T> p, long long nwork,
+                                                                   C2<T> *scratch, unsigned long long per_cta)
+{
+  C2<T> *data = scratch + (size_t)blockIdx.x * per_cta;
+  const DftTables<T> tab{p.pyr_f, p.pyr_i, p.tcos_f, p.tcos_i};
+  const CoefCache<T, 0> cc{};
+  __shared__ DftItem<T> items[2];
+  for (long long w = blockIdx.x; w < nwork; w += gridDim.x) {
+    if (threadIdx.x == 0) items[0] = dft_item<T, 1>(p, w);
+    __syncthreads();
+    dft_stage_program<T, InT, OutT, 1, 0>(p, tab, cc, items, 0, -1, data);
+    __syncthreads();
+  }
+}
+
 // Lane-pair DFT stage (rate_kernels_pk.cuh): a CTA is `groups` independent groups of `gthreads` threads, each
 // a persistent worker with its own forward and inverse buffer behind the shared tables (twiddle pyramids,
 // task tables, forward permutation).
@@ -584,9 +603,24 @@ template <class T> struct Launch {
   } while (0)
 
   // lpc: lanes per CTA (1 or 2); data_bytes: shared memory for the sample buffers, the tables follow
-  static int dft(const DftParams<T> &p, int lpc, bool in_f32, bool out_f32, long long nwork, size_t data_bytes, stream_t s)
+  // big != nullptr: the block does not fit shared memory; *big is a global scratch area of big_ctas slices
+  static int dft(const DftParams<T> &p, int lpc, bool in_f32, bool out_f32, long long nwork, size_t data_bytes, stream_t s,
+                 void *big = nullptr, int big_ctas = 0)
   {
     const size_t smem = data_bytes + sizeof(T) * static_cast<size_t>(dft_table_elems(p));
+#ifndef B200RATE_EMU
+    if (big) {
+      if (nwork <= 0) return RR_OK;
+      const unsigned long long per_cta = data_bytes / sizeof(C2<T>);
+      const unsigned grid = static_cast<unsigned>(std::min<long long>(nwork, big_ctas));
+#define RR_CALLB(I, O) (dft_big_kernel<T, I, O><<<grid, 2 * kDftThreads, 0, s>>>(p, nwork, static_cast<C2<T> *>(big), per_cta), \
+                        cudaGetLastError() == cudaSuccess ? RR_OK : RR_INTERNAL)
+      RR_DISPATCH_IO(RR_CALLB);
+#undef RR_CALLB
+    }
+#else
+    (void)big; (void)big_ctas;
+#endif
 #ifdef B200RATE_EMU
     const DftTables<T> tab{p.pyr_f, p.pyr_i, p.tcos_f, p.tcos_i};
     const CoefCache<T, 0> cc{};
@@ -893,6 +927,13 @@ template <class T> class Engine {
         prefetch = false;
         data_bytes = dft_smem_bytes<T>(g.Pf, g.Ni, lpc, false, &p.xstride, &p.ystride, &p.zstride);
       }
+      if (dft_big_[i]) {
+        data_bytes = dft_smem_bytes<T>(g.Pf, g.Ni, 1, false, &p.xstride, &p.ystride, &p.zstride);
+        int rc = ensure_big_scratch(data_bytes);
+        if (rc != RR_OK) return rc;
+        kernel_name[i] = "dft_big_kernel (global-memory work buffers)";
+        return Launch<T>::dft(p, 1, in_f32, out_f32, wn * nlanes, data_bytes, s, big_scratch_, kBigCtas);
+      }
       const long long groups = (nlanes + lpc - 1) / lpc;
       return Launch<T>::dft(p, lpc, in_f32, out_f32, wn * groups, data_bytes, s);
     }
@@ -1079,6 +1120,21 @@ template <class T> class Engine {
   PolyParams<T> poly_params_[RR_MAX_STAGES];
   HalfbandParams<T> half_params_[RR_MAX_STAGES];
   T *dft_coef_dev_[2] = {nullptr, nullptr};
+  bool dft_big_[RR_MAX_STAGES] = {false};
+  void *big_scratch_ = nullptr;              // global work buffers of dft_big_kernel, kBigCtas slices of big_slice_ bytes
+  size_t big_slice_ = 0;
+  static constexpr int kBigCtas = 296;
+
+  int ensure_big_scratch(size_t slice_bytes)
+  {
+    if (big_scratch_ && big_slice_ >= slice_bytes) return RR_OK;
+    void *p = nullptr;
+    int rc = be_malloc(&p, slice_bytes * kBigCtas + 256);
+    if (rc != RR_OK) return rc;
+    allocs_.push_back(p);                    // an outgrown area stays allocated until the engine goes (launches may be in flight)
+    big_scratch_ = p; big_slice_ = slice_bytes;
+    return RR_OK;
+  }
 
   struct DevSched { CfftSched fwd, inv; const T *pyramid; const uint16_t *pk_ltab = nullptr, *pk_perm[2] = {nullptr, nullptr}; };
   std::map<int, std::vector<uint16_t>> pk_perm_inv_host_;   // by complex bits
@@ -1259,10 +1315,11 @@ template <class T> class Engine {
         DftParams<T> probe; memset(&probe, 0, sizeof(probe));
         probe.Pf = g.Pf; probe.Ni = g.Ni; probe.fwd.pyr_len = g.Pf / 4 + 16; probe.inv.pyr_len = g.Ni / 4 + 16;
         const size_t need = dft_smem_bytes<T>(g.Pf, g.Ni, 1, false, &xs, &ys, nullptr) + sizeof(T) * dft_table_elems(probe);
-        if (need > max_smem_) {
-          set_last_error("DFT length " + std::to_string(g.N) + " exceeds the shared-memory block kernel (not implemented: global-memory multi-pass FFT)");
+        if (ilog2(g.Pf) - 1 > 15 || ilog2(g.Ni) - 1 > 15) {
+          set_last_error("DFT length " + std::to_string(g.N) + " exceeds the 65536-point limit of the FFT schedule tables");
           return RR_INTERNAL;
         }
+        dft_big_[i] = need > max_smem_;             // work buffers in global scratch instead of shared memory
         DftParams<T> &p = dft_params_[i];
         memset(&p, 0, sizeof(p));
         p.N = g.N; p.overlap = g.ov; p.L = g.L; p.step = g.step; p.in_mode = g.in_mode; p.Pf = g.Pf; p.Ni = g.Ni;
@@ -1313,7 +1370,12 @@ template <class T> class Engine {
     p.out = v; p.out.base = spec;
     p.block0 = 0; p.nblocks = 1; p.nlanes = 1;
     const size_t data_bytes = dft_smem_bytes<T>(N, N, 1, false, &p.xstride, &p.ystride, &p.zstride);
-    if ((rc = Launch<T>::dft(p, 1, false, false, 1, data_bytes, 0))) return rc;
+    void *big = nullptr;
+    if (data_bytes + sizeof(T) * dft_table_elems(p) > max_smem_) {
+      if ((rc = ensure_big_scratch(data_bytes))) return rc;
+      big = big_scratch_;
+    }
+    if ((rc = Launch<T>::dft(p, 1, false, false, 1, data_bytes, 0, big, kBigCtas))) return rc;
     dft_coef_dev_[instance] = static_cast<T *>(spec);
     return RR_OK;
   }

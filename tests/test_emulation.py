@@ -32,6 +32,9 @@ CASES = [
     (44100, 88200, "float", 25, 95, 0, 0, 6), (96000, 48000, "float", 50, 95, 1, 0, 2),
     (44100, 22050, "float", 50, 95, 0, 1, 2), (50000, 40000, "float", 50, 95, 0, 0, 2),
     (48000, 44100, "float", 50, 95, 0, 0, 8), (44100, 48000, "float", 50, 95, 0, 1, 6),
+    # narrow transition bands: DFT blocks beyond the shared-memory kernels (work buffers in global scratch)
+    (44100, 48000, "float", 50, 99.5, 0, 0, 2), (44100, 48000, "double", 50, 99, 0, 0, 1),
+    (192000, 44100, "double", 50, 99, 0, 0, 1),
 ]
 
 

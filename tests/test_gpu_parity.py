@@ -40,6 +40,12 @@ STREAM_CASES = [
     (96000, 48000, "float", 50, 95, 1, 0, 2),     # aliasing allowed
     (50000, 40000, "float", 50, 95, 0, 0, 2),     # L = 4 / M = 5
     (48000, 44100, "float", 50, 95, 0, 0, 3),     # odd channel count: generic kernels
+    # narrow transition bands (bandwidth 99 % is within the plugin's UI range): DFT blocks of 16384 ... 65536
+    # points, beyond the shared-memory kernels -> dft_big_kernel (work buffers in global scratch)
+    (44100, 48000, "float", 50, 99.5, 0, 0, 2),   # N = 32768, fp32
+    (44100, 48000, "double", 50, 99, 0, 0, 2),    # N = 16384, fp64 (what RR_open selects for Best quality)
+    (192000, 44100, "double", 50, 99, 0, 0, 1),   # N = 32768 after a half-band stage
+    (48000, 44100, "float", 50, 99.7, 0, 0, 1),   # N = 65536
 ]
 
 # batches (device-resident entry point: pair-interleaved intermediate FIFOs between DFT and polyphase stages)
