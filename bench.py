@@ -66,15 +66,48 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML in a thread every 10 ms (starts at
+    once, so even a 100 ms region is covered); `nvidia-smi -lms` as the fallback when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:                                   # CUDA index -> physical index
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if index < len(ids) and ids[index].isdigit():
+                index = int(ids[index])
         self.index, self.proc, self.lines = index, None, []
+        self.nvml, self.samples, self.stop_flag, self.t = None, [], False, None
+
+    def _nvml_loop(self):
+        n, h = self.nvml
+        bits = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+                try:
+                    r = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((float(sm), {k for k, b in bits.items() if r & b}))
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def start(self):
+        try:
+            import pynvml as n
+            n.nvmlInit()
+            h = n.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM))
+            self.nvml = (n, h)
+            self.t = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -89,6 +122,15 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml:
+            self.stop_flag = True
+            self.t.join(timeout=1)
+            sm = sorted(s for s, _ in self.samples)
+            reasons = set()
+            for _, r in self.samples:
+                reasons |= r
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(reasons),
+                    "samples": len(sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -111,7 +153,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------------
