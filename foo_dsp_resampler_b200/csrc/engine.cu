@@ -541,14 +541,6 @@ static int launch_poly0_pair(const Poly0PairParams &pp, int threads, long long n
     std::fill(slot_of.begin(), slot_of.end(), static_cast<uint16_t>(0xffff));
     if (pp.spread) { poly0_pair_deal(pp, t, slot_of.data(), cnt, ovf, 0, 1); poly0_pair_deal_overflow(pp, slot_of.data(), cnt, ovf, 0); }
     poly0_pair_load(pp, t, buf.data(), 0, 1);
-    if (getenv("B200RATE_CHECKWIN")) {
-      const PolyParams<float> &bp = pp.fast.base;
-      for (int j = 0; j < t.win; ++j) {
-        const float a = view_read<float, float>(bp.in, lane_offset(bp.in, t.lane0), t.q_first + bp.pre + j);
-        const float b2 = view_read<float, float>(bp.in, lane_offset(bp.in, t.lane0 + 1), t.q_first + bp.pre + j);
-        if (a != buf[j].a || b2 != buf[j].b) { fprintf(stderr, "window mismatch w %lld j %d of %d (%g %g) vs (%g %g) q_first %lld\n", w, j, t.win, buf[j].a, buf[j].b, a, b2, t.q_first); break; }
-      }
-    }
     if (pp.CL == 2) {
       const int dlo = static_cast<int>(pp.fast.base.step / pp.fast.base.L);
       for (int th = 0; th < pp.tslots * pp.P; ++th) {
