@@ -982,11 +982,12 @@ template <class T> class Engine {
         pp.CL = (use_pair_poly2_ && step / L <= 2 && L >= 96) ? 2 : 1;
         int bucket[16] = {0}, maxb = 0;
         for (int fs = 0; fs < L; fs += pp.CL) maxb = std::max(maxb, ++bucket[((r_first + static_cast<long long>(fs) * step) / L) & 15]);
-        const int ncl = (L + pp.CL - 1) / pp.CL, rows = (ncl + 15) / 16;
+        const int ncl = (L + pp.CL - 1) / pp.CL;
+        int rows = (ncl + 15) / 16;
+        auto spill_of = [&](int r) { int sp = 0; for (int b2 = 0; b2 < 16; ++b2) sp += std::max(0, bucket[b2] - r); return sp; };
+        if (spill_of(rows) > ncl / 10) ++rows;               // a few idle lanes cost less than two-way conflicts in most half-warps
         pp.spread = 1; pp.tslots = 16 * rows;               // overfull banks spill into the holes (poly0_pair_deal_overflow)
-        int spill = 0;
-        for (int b2 = 0; b2 < 16; ++b2) spill += std::max(0, bucket[b2] - rows);
-        if (maxb > 2 * rows || spill > kPolyDealOverflow) pp.spread = 0;   // few distinct banks (steep up-sampling): keep order
+        if (maxb > 2 * rows || spill_of(rows) > kPolyDealOverflow) pp.spread = 0;   // few distinct banks (steep up-sampling): keep order
         pp.P = 1;
         while (2 * pp.P < in.nch && in.nch % (4 * pp.P) == 0 && pp.tslots * 2 * pp.P <= 256) pp.P *= 2;
         // one period group; as many CTAs per SM as 64 registers per thread allow (1024 threads), each with one
