@@ -196,6 +196,30 @@ def test_batch_cases_match_oracle(case):
     b.close()
 
 
+@pytest.mark.parametrize("rates", [(48000, 44100, 2), (44100, 96000, 2), (384000, 48000, 8)], ids=lambda r: "%d-%d-%dch" % r)
+def test_many_identical_streams_agree(rates):
+    """Stress for the persistent multi-group kernels (named barriers, warp-local FFT phases, LDGSTS pipelines):
+    hundreds of work items in flight on every SM, all fed the same input -- every stream must come out
+    bit-identical to the oracle, twice in a row. (compute-sanitizer is not available on this pool.)"""
+    import torch
+    import foo_dsp_resampler_b200 as pkg
+    i, o, nch = rates
+    cfg, ocfg = _cfgs(i, o, 50, 95, 0, 0)
+    nstreams, n = (600 if nch == 2 else 150), int(i * 0.5)
+    x = signals.sweep_noise(i, nch, n)
+    ref, _ = oraclelib.resample(ocfg, x, engine="float")
+    b = pkg.BatchConverter(cfg, nch, nstreams, n, engine="float", device=0)
+    nout = b.frames_out(n)
+    d_in = torch.from_numpy(x).cuda().unsqueeze(0).repeat(nstreams, 1, 1).contiguous()
+    d_ref = torch.from_numpy(ref).cuda()
+    for _ in range(2):
+        d_out = torch.full((nstreams, nout, nch), 7.0, dtype=torch.float32, device="cuda")
+        b.process(d_in.data_ptr(), n, d_out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert bool((d_out == d_ref.unsqueeze(0)).all())
+    b.close()
+
+
 def test_full_size_config1_properties():
     """BASELINE config 1 at full size (60 s stereo): frame count, bit-exactness vs the oracle, linearity of
     the whole pipeline in the scaling-by-two sense (exact in binary floating point)."""
