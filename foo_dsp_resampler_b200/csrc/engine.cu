@@ -148,11 +148,19 @@ __global__ void __launch_bounds__(2 * kDftThreads) dft_kernel(const __grid_const
   C2<T> *data = reinterpret_cast<C2<T> *>(rr_smem_raw);
   T *t = reinterpret_cast<T *>(rr_smem_raw + data_bytes);
   const int nf = p.fwd.pyr_len, ni = p.inv.pyr_len, tf = (p.Pf >> 2) + 1, ti = (p.Ni >> 2) + 1;
-  for (int i = threadIdx.x; i < nf; i += blockDim.x) t[i] = p.pyr_f[i];
-  for (int i = threadIdx.x; i < ni; i += blockDim.x) t[nf + i] = p.pyr_i[i];
-  for (int i = threadIdx.x; i < tf; i += blockDim.x) t[nf + ni + i] = p.tcos_f[i];
-  for (int i = threadIdx.x; i < ti; i += blockDim.x) t[nf + ni + tf + i] = p.tcos_i[i];
-  const DftTables<T> tab{t, t + nf, t + nf + ni, t + nf + ni + tf};
+  DftTables<T> tab;
+  if (p.lean_tables) {                                   // pyramids only (shared when both sizes agree), cosines stay in global memory
+    const bool same = p.fwd.bits == p.inv.bits;
+    for (int i = threadIdx.x; i < nf; i += blockDim.x) t[i] = p.pyr_f[i];
+    if (!same) for (int i = threadIdx.x; i < ni; i += blockDim.x) t[nf + i] = p.pyr_i[i];
+    tab = DftTables<T>{t, same ? t : t + nf, p.tcos_f, p.tcos_i};
+  } else {
+    for (int i = threadIdx.x; i < nf; i += blockDim.x) t[i] = p.pyr_f[i];
+    for (int i = threadIdx.x; i < ni; i += blockDim.x) t[nf + i] = p.pyr_i[i];
+    for (int i = threadIdx.x; i < tf; i += blockDim.x) t[nf + ni + i] = p.tcos_f[i];
+    for (int i = threadIdx.x; i < ti; i += blockDim.x) t[nf + ni + tf + i] = p.tcos_i[i];
+    tab = DftTables<T>{t, t + nf, t + nf + ni, t + nf + ni + tf};
+  }
   CoefCache<T, DftCacheDepth<T>::value> cc;
   dft_load_coef_cache(p, cc);
   __shared__ DftItem<T> items[2];
@@ -915,9 +923,18 @@ template <class T> class Engine {
       const bool same_type = Launch<T>::kIsF32 || !in_f32;
       bool prefetch = same_type;
       size_t data_bytes = dft_smem_bytes<T>(g.Pf, g.Ni, lpc, prefetch, &p.xstride, &p.ystride, &p.zstride);
+      p.lean_tables = 0;
       if (prefetch && data_bytes + sizeof(T) * dft_table_elems(p) > 112 * 1024) {
-        prefetch = false;
-        data_bytes = dft_smem_bytes<T>(g.Pf, g.Ni, lpc, false, &p.xstride, &p.ystride, &p.zstride);
+        // no room for two CTAs per SM with a prefetch buffer. One CTA per SM exposes the tile load entirely, so
+        // rather keep the buffer and shrink the tables (pyramids only, cosines from global memory) if that fits
+        p.lean_tables = 1;
+        if (lpc == 1 && data_bytes + sizeof(T) * dft_table_elems(p) + 1024 <= max_smem_) {
+          // keep prefetch
+        } else {
+          p.lean_tables = 0;
+          prefetch = false;
+          data_bytes = dft_smem_bytes<T>(g.Pf, g.Ni, lpc, false, &p.xstride, &p.ystride, &p.zstride);
+        }
       }
       if (dft_big_[i]) {
         data_bytes = dft_smem_bytes<T>(g.Pf, g.Ni, 1, false, &p.xstride, &p.ystride, &p.zstride);

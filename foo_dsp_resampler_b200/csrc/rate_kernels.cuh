@@ -507,6 +507,7 @@ template <class T> struct DftParams {
   long long block0;              // first block of this launch
   int nblocks, nlanes;
   int xstride, ystride, zstride; // per-lane smem strides, in complex elements (zstride == 0: no prefetch buffer)
+  int lean_tables;               // only the twiddle pyramids in shared memory (once if both transforms have one size), cosines from global
 };
 
 // Tables the kernel stages in shared memory once per CTA (the emulation passes the global pointers).
@@ -514,6 +515,7 @@ template <class T> struct DftTables { const T *pyr_f, *pyr_i, *tcos_f, *tcos_i; 
 
 template <class T> RR_HD int dft_table_elems(const DftParams<T> &p)
 {
+  if (p.lean_tables) return p.fwd.pyr_len + (p.fwd.bits == p.inv.bits ? 0 : p.inv.pyr_len) + 8;
   return p.fwd.pyr_len + p.inv.pyr_len + (p.Pf >> 2) + 1 + (p.Ni >> 2) + 1 + 8;
 }
 
