@@ -157,3 +157,42 @@ def test_push_pull_protocol_edges():
     bad = _capi.make_config(1, 48000)
     assert L.RR_open(C.byref(bad), 1, C.byref(h)) == _capi.RR_INVPARAM and not h.value
     assert L.RR_push(None, None, 0) == _capi.RR_NULLHANDLE
+
+
+FUZZ_RATES = [8000, 11025, 16000, 22050, 24000, 32000, 44100, 48000, 50000, 64000, 88200, 96000, 176400, 192000, 352800,
+              384000, 47999, 44101]
+
+
+def fuzz_cases(seed, count):
+    """Seeded random configurations with an even channel count (lane-pair kernels): rates, phase, bandwidth,
+    aliasing, quality, channels, length, chunk size."""
+    import random
+    rng = random.Random(seed)
+    out = []
+    while len(out) < count:
+        i, o = rng.choice(FUZZ_RATES), rng.choice(FUZZ_RATES)
+        if i == o:
+            continue
+        out.append((i, o, rng.choice([0, 25, 50, 50, 50, 75, 100]), rng.choice([90, 93, 95, 95, 97, 99]), rng.choice([0, 0, 1]),
+                    rng.choice([0, 0, 1]), rng.choice([2, 2, 4, 6, 8]),
+                    max(int(i * rng.choice([0.05, 0.11, 0.23])) + rng.randrange(0, 50), 64), rng.choice([977, 4096, 30011])))
+    return out
+
+
+@pytest.mark.parametrize("case", fuzz_cases(7, 24), ids=lambda c: "%d-%d-p%d-b%d-a%d-q%d-%dch" % c[:7])
+def test_fuzz_stream_and_batch(case):
+    i, o, ph, bw, al, q, nch, n, chunk = case
+    L = emulib.lib()
+    cfg, ocfg = _capi.make_config(i, o, ph, bw, al, q), oraclelib.make_config(i, o, ph, bw, al, q)
+    x = signals.sweep_noise(i, nch, n)
+    yo, co = oraclelib.resample(ocfg, x, engine="float", chunk=chunk, native=True)
+    ye, ce = converter.resample(cfg, x, engine="float", chunk=chunk, native=True, lib=L)
+    assert ce == co and ye.shape == yo.shape and np.array_equal(ye, yo)
+    b = converter.BatchConverter(cfg, nch, 2, n, engine="float", lib=L)
+    nout = b.frames_out(n)
+    xs = np.stack([x, x * 0.5])
+    out = np.zeros((2, nout, nch), np.float32)
+    b.process(xs.ctypes.data, n, out.ctypes.data)
+    ref, _ = oraclelib.resample(ocfg, x, engine="float")
+    assert ref.shape[0] == nout and np.array_equal(out[0], ref)
+    b.close()
