@@ -903,7 +903,8 @@ template <class T> class Engine {
       p.in = in; p.out = out; p.out_preload = out_preload;
       p.block0 = w0; p.nblocks = static_cast<int>(wn); p.nlanes = nlanes;
       if constexpr (std::is_same<T, float>::value) {
-        if (use_pair_kernel_ && use_pair_dft_ && !(nlanes & 1) && !(in.nch & 1) && !(out.nch & 1) && wn * (nlanes / 2) < (1ll << 30)) {
+        // any two lanes form a pair (channels of a stream, or different streams of a mono / odd-channel batch)
+        if (use_pair_kernel_ && use_pair_dft_ && !(nlanes & 1) && wn * (nlanes / 2) < (1ll << 30)) {
           DftPkParams pp;
           if (make_pair_params(i, p, pp)) {
             last_dft_kernel_ = 1;
@@ -950,12 +951,13 @@ template <class T> class Engine {
       HalfbandParams<T> p = half_params_[i];
       p.in = in; p.out = out; p.out_preload = out_preload; p.out0 = w0; p.nout = wn; p.nlanes = nlanes;
       if constexpr (std::is_same<T, float>::value) {
-        if (use_pair_kernel_ && use_pair_half_ && !(nlanes & 1) && !(in.nch & 1) && !(out.nch & 1)) {
+        if (use_pair_kernel_ && use_pair_half_ && !(nlanes & 1)) {
           // lane-pair kernel: all pairs of a stream per CTA when its frames are interleaved (coalesced window load)
           HalfbandPairParams hp;
           hp.base = p;
           const int nchan = in.nch;
-          const bool group_ok = in.ch_stride == 1 && out.nch == nchan && nlanes % nchan == 0 && (nchan == 2 || nchan == 4 || nchan == 8);
+          const bool group_ok = in.ch_stride == 1 && out.nch == nchan && nlanes % nchan == 0 && (nchan == 2 || nchan == 4 || nchan == 8) &&
+                                !(out.nch & 1);
           hp.G = group_ok ? nchan / 2 : 1;
           hp.base.CH = 2 * hp.G;
           hp.base.tile = kHalfTile / (2 * hp.G);             // outputs per pair per CTA, power of two
@@ -987,8 +989,8 @@ template <class T> class Engine {
     p.in = in; p.out = out; p.out_preload = out_preload; p.out0 = w0; p.nout = wn; p.nlanes = nlanes;
     p.tile = kPolyTile;
     if constexpr (std::is_same<T, float>::value) {
-      if (use_pair_kernel_ && use_pair_poly_ && g.order == 0 && (g.n == 16 || g.n == 24 || g.n == 32) && !(nlanes & 1) && !(in.nch & 1) &&
-          !(out.nch & 1) && g.Lp >= 48 && g.Lp <= 512 && g.pstep < (1 << 16)) {
+      if (use_pair_kernel_ && use_pair_poly_ && g.order == 0 && (g.n == 16 || g.n == 24 || g.n == 32) && !(nlanes & 1) &&
+          g.Lp >= 48 && g.Lp <= 512 && g.pstep < (1 << 16)) {
         // lane-pair kernel: one column per period (L <= 512 slots), P pairs of a stream and PG period groups per CTA
         Poly0PairParams pp;
         pp.fast.base = p;
@@ -1006,7 +1008,9 @@ template <class T> class Engine {
         pp.spread = 1; pp.tslots = 16 * rows;               // overfull banks spill into the holes (poly0_pair_deal_overflow)
         if (maxb > 2 * rows || spill_of(rows) > kPolyDealOverflow) pp.spread = 0;   // few distinct banks (steep up-sampling): keep order
         pp.P = 1;
-        while (2 * pp.P < in.nch && in.nch % (4 * pp.P) == 0 && pp.tslots * 2 * pp.P <= 256) pp.P *= 2;
+        while (!(in.nch & 1) && !(out.nch & 1) && in.nch == out.nch && 2 * pp.P < in.nch && in.nch % (4 * pp.P) == 0 &&
+               pp.tslots * 2 * pp.P <= 256)
+          pp.P *= 2;                                          // several pairs per CTA only as channels of one stream
         // one period group; as many CTAs per SM as 64 registers per thread allow (1024 threads), each with one
         // window buffer of an even number of periods (the other CTAs cover its load)
         pp.PG = 1;

@@ -905,6 +905,7 @@ RR_PROG Pk pk_load8(const Pk *p)                         // one 8-byte shared / 
 struct Poly0PairTile {
   Poly0Tile t;
   float *d_base;                 // first output sample of the tile (slot 0, period 0) of lane t.lane0
+  long long lane1;               // elements from a pair's first lane to its second (the two need not share a stream)
   long long i_end;               // outputs at or beyond this index do not exist
   int direct;                    // every output of the tile exists and is stored contiguously
 };
@@ -918,6 +919,7 @@ RR_PROG Poly0PairTile poly0_pair_make_tile(const Poly0PairParams &pp, long long 
   const long long i_tile_end = pt.t.i_first + (long long)pt.t.mcount * p.L;
   pt.direct = i_tile_end <= pt.i_end && view_range_direct(p.out, p.out_preload + pt.t.i_first, p.out_preload + i_tile_end);
   pt.d_base = view_ptr<float>(p.out, lane_offset(p.out, pt.t.lane0), p.out_preload + pt.t.i_first);
+  pt.lane1 = lane_offset(p.out, pt.t.lane0 + 1) - lane_offset(p.out, pt.t.lane0);
   return pt;
 }
 
@@ -931,11 +933,11 @@ RR_PROG void poly0_pair_tile(const Poly0PairParams &pp, const Poly0PairTile &pt,
   const PolyParams<float> &p = fp.base;
   const int L = p.L, PG = pp.PG, es = p.out.elem_stride, cs = p.out.ch_stride;
   // the P pairs of a CTA are channels of one stream: lane offsets differ by multiples of the channel stride
-  const int rel = (st.fs + st.g * L) * es + 2 * st.pr * cs;
-  float *d0 = pt.d_base + rel, *d1 = d0 + cs;
+  const int rel = (st.fs + st.g * L) * es + 2 * st.pr * cs;   // P > 1 only for pairs of one stream
+  float *d0 = pt.d_base + rel, *d1 = d0 + pt.lane1;
   const int dstep = PG * L * es;                          // between this thread's consecutive outputs
   const bool direct = pt.direct != 0;
-  const bool packed_out = direct && cs == 1 && !((size_t)d0 & 7) && !(dstep & 1);
+  const bool packed_out = direct && d1 == d0 + 1 && !((size_t)d0 & 7) && !(dstep & 1);
   const int xstep = PG * (int)p.step;
   const Pk *x = buf + st.pr * fp.win + st.q + st.g * (int)p.step;
   int m = st.g;
@@ -1019,11 +1021,11 @@ RR_PROG void poly0_pair2_tile(const Poly0PairParams &pp, const Poly0PairTile &pt
   const Poly0FastParams<float> &fp = pp.fast;
   const PolyParams<float> &p = fp.base;
   const int L = p.L, es = p.out.elem_stride, cs = p.out.ch_stride;
-  const int rel = st.fs * es + 2 * st.pr * cs;
-  float *d0 = pt.d_base + rel, *d1 = d0 + cs;
+  const int rel = st.fs * es + 2 * st.pr * cs;               // P > 1 only for pairs of one stream
+  float *d0 = pt.d_base + rel, *d1 = d0 + pt.lane1;
   const int dstep = L * es;
   const bool direct = pt.direct != 0;
-  const bool packed_out = direct && cs == 1 && !((size_t)d0 & 7) && !(dstep & 1) && !(es & 1);
+  const bool packed_out = direct && d1 == d0 + 1 && !((size_t)d0 & 7) && !(dstep & 1) && !(es & 1);
   const int xstep = (int)p.step;
   const Pk *x = buf + st.pr * fp.win + st.q;
   const bool dlo = st.d_lo, two = st.two;
@@ -1107,10 +1109,12 @@ RR_PROG void halfband_pair_load(const HalfbandPairParams &hp, long long work, Pk
   const int shift = 4 - NC, win = t.win;
   const long long in_off0 = lane_offset(p.in, t.lane0);
   const int ics = p.in.ch_stride, ies = p.in.elem_stride;
+  // lane l of the tile relative to its first lane: channels of one stream when G > 1, any two lanes when G == 1
+  auto lane_rel = [&](int l) -> long long { return G > 1 ? (long long)l * ics : lane_offset(p.in, t.lane0 + l) - in_off0; };
   const bool direct = view_range_direct(p.in, t.x0, t.x0 + win);
   const float *src0 = view_ptr<const float>(p.in, in_off0, t.x0);
   const int npairs_u = (win + 1) >> 1;                   // frame pairs (u = 2f, 2f + 1)
-  if (direct && ics == 1 && !(ies & 1) && !((size_t)src0 & 7)) {
+  if (direct && lane_rel(1) == 1 && !(ies & 1) && !((size_t)src0 & 7)) {
     // interleaved frames: the pairs of a frame are consecutive 8-byte words; one thread takes both frames of a
     // frame pair for one lane pair
     for (int w = tid; w < (npairs_u << gbits); w += nthreads) {
@@ -1123,7 +1127,7 @@ RR_PROG void halfband_pair_load(const HalfbandPairParams &hp, long long work, Pk
   } else if (direct) {
     // planar lanes (or any regular strides): lane by lane, frame pairs fastest
     for (int l = 0; l < 2 * G; ++l) {
-      const float *sl = src0 + (long long)l * ics;
+      const float *sl = src0 + lane_rel(l);
       float *d0 = &P0[(l >> 1) * p.half].a + (l & 1), *d1 = &P1[(l >> 1) * p.half].a + (l & 1);
       for (int f = tid; f < npairs_u; f += nthreads) {
         async_copy_elem<float>(d0 + 2 * f, sl + (long long)(2 * f) * ies, true);
@@ -1135,7 +1139,7 @@ RR_PROG void halfband_pair_load(const HalfbandPairParams &hp, long long work, Pk
     for (int w = tid; w < 2 * win * G; w += nthreads) {
       const int u = w % win, l = w / win, g = l >> 1;
       bool valid;
-      const float *src = view_addr<float>(p.in, in_off0 + (long long)l * ics, t.x0 + u, &valid);
+      const float *src = view_addr<float>(p.in, in_off0 + lane_rel(l), t.x0 + u, &valid);
       if (u & 1) {
         const int io = ((u + 1) >> 1) + shift;
         if (io >= 4) async_copy_elem<float>(&P1[g * p.half + io].a + (l & 1), src, valid);
@@ -1177,11 +1181,12 @@ RR_PROG void halfband_pair_compute(const HalfbandPairParams &hp, const float (&c
       for (int tt = 0; tt < c; ++tt) sum = A::addp(sum, A::mul(A::add(x[r + c - 1 - tt], x[r + c + tt]), pk_bcast(cf[tt])));
       y[r] = sum;
     }
-    const long long off_a = out_off0 + (long long)(2 * g) * ocs, off_b = off_a + ocs;
+    const long long off_a = G > 1 ? out_off0 + (long long)(2 * g) * ocs : out_off0;
+    const long long off_b = G > 1 ? off_a + ocs : lane_offset(p.out, t.lane0 + 1);
     const long long cbase = p.out_preload + k0 + j;
     if (j + 4 <= cnt && view_range_direct(p.out, cbase, cbase + 4)) {
       float *da = view_ptr<float>(p.out, off_a, cbase), *db = view_ptr<float>(p.out, off_b, cbase);
-      if (ocs == 1 && !(oes & 1) && !((size_t)da & 7)) {                  // interleaved: one pair per frame
+      if (db == da + 1 && !(oes & 1) && !((size_t)da & 7)) {                // interleaved: one pair per frame
 #pragma unroll
         for (int r = 0; r < 4; ++r) *reinterpret_cast<Pk *>(da + (long long)r * oes) = y[r];
       } else if (oes == 1 && !(((size_t)da | (size_t)db) & 15)) {         // planar, aligned: one vector store per lane

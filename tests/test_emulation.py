@@ -159,6 +159,32 @@ def test_push_pull_protocol_edges():
     assert L.RR_push(None, None, 0) == _capi.RR_NULLHANDLE
 
 
+# Any two lanes can share the lane-pair kernels, also lanes of different streams: mono and odd-channel batches
+# with an even number of lanes.
+@pytest.mark.parametrize("case", [(48000, 44100, 1, 4, 0), (384000, 48000, 3, 2, 0), (96000, 44100, 1, 2, 0), (44100, 96000, 5, 2, 1),
+                                  (44100, 48000, 1, 6, 0)], ids=lambda c: "%d-%d-%dch-x%d-q%d" % c)
+def test_batch_pairs_across_streams(case):
+    i, o, nch, nstreams, q = case
+    L = emulib.lib()
+    cfg, ocfg = _capi.make_config(i, o, 50, 95, 0, q), oraclelib.make_config(i, o, 50, 95, 0, q)
+    n = int(i * 0.2) + 5
+    xs = np.stack([signals.sweep_noise(i, nch, n, stream=s) for s in range(nstreams)])
+    b = converter.BatchConverter(cfg, nch, nstreams, n, engine="float", lib=L)
+    nout = b.frames_out(n)
+    out = np.zeros((nstreams, nout, nch), np.float32)
+    b.process(xs.ctypes.data, n, out.ctypes.data)
+    for s in range(nstreams):
+        ref, _ = oraclelib.resample(ocfg, xs[s], engine="float")
+        assert ref.shape[0] == nout and np.array_equal(out[s], ref)
+    ob, oc = nout // 3, nout // 2
+    f, c = b.input_window(n, ob, oc)
+    win = np.ascontiguousarray(xs[:, f:f + c, :])
+    part = np.zeros((nstreams, oc, nch), np.float32)
+    b.process_range(win.ctypes.data, f, c, n, ob, oc, part.ctypes.data)
+    assert np.array_equal(part, out[:, ob:ob + oc, :])
+    b.close()
+
+
 FUZZ_RATES = [8000, 11025, 16000, 22050, 24000, 32000, 44100, 48000, 50000, 64000, 88200, 96000, 176400, 192000, 352800,
               384000, 47999, 44101]
 

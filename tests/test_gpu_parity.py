@@ -53,6 +53,9 @@ BATCH_CASES = [
     (44100, 48000, 50, 95, 0, 0, 2, 3), (48000, 44100, 50, 95, 0, 0, 8, 2), (44100, 96000, 50, 95, 0, 0, 4, 2),
     (96000, 44100, 50, 95, 0, 0, 2, 3), (384000, 48000, 50, 95, 0, 0, 8, 1), (22050, 96000, 50, 95, 0, 0, 2, 2),
     (44100, 48000, 50, 95, 0, 1, 6, 1), (48000, 44100, 50, 95, 0, 0, 3, 2),
+    # pairs of lanes from different streams: mono and odd-channel batches with an even number of lanes
+    (48000, 44100, 50, 95, 0, 0, 1, 4), (384000, 48000, 50, 95, 0, 0, 3, 2), (96000, 44100, 50, 95, 0, 0, 1, 2),
+    (44100, 96000, 50, 95, 0, 1, 5, 2), (44100, 48000, 50, 95, 0, 0, 1, 6),
 ]
 
 
