@@ -400,16 +400,26 @@ __global__ void __launch_bounds__(kTileThreads) halfband_pair_kernel(const __gri
   float cf[NC];                                          // coefficients in registers for the whole launch
 #pragma unroll
   for (int t = 0; t < NC; ++t) cf[t] = p.base.coef[t];
-  // two window buffers: the next tile's LDGSTS copies are in flight while this one is computed
+  // two window buffers: the next tile's LDGSTS copies are in flight while this one is computed; tile geometry
+  // comes from one thread per tile
   const int set = 2 * p.base.half * p.G + 8;
+  __shared__ HalfbandPairTile tiles[3];
   long long w = blockIdx.x;
-  if (w < nwork) halfband_pair_load<NC>(p, w, smem, threadIdx.x, blockDim.x);
+  if (w >= nwork) return;
+  if (threadIdx.x == 0) {
+    tiles[0] = halfband_pair_tile<NC>(p, w);
+    if (w + gridDim.x < nwork) tiles[1] = halfband_pair_tile<NC>(p, w + gridDim.x);
+  }
+  __syncthreads();
+  halfband_pair_load<NC>(p, tiles[0], smem, threadIdx.x, blockDim.x);
   for (int it = 0; w < nwork; w += gridDim.x, ++it) {
+    const int ts = it % 3, tn = (it + 1) % 3, tnn = (it + 2) % 3;
     const long long next = w + gridDim.x;
-    if (next < nwork) { halfband_pair_load<NC>(p, next, smem + ((it + 1) & 1) * set, threadIdx.x, blockDim.x); async_copy_wait<1>(); }
+    if (next < nwork) { halfband_pair_load<NC>(p, tiles[tn], smem + ((it + 1) & 1) * set, threadIdx.x, blockDim.x); async_copy_wait<1>(); }
     else async_copy_wait<0>();
+    if (threadIdx.x == 0 && next + gridDim.x < nwork) tiles[tnn] = halfband_pair_tile<NC>(p, next + gridDim.x);
     __syncthreads();
-    halfband_pair_compute<NC>(p, cf, w, smem + (it & 1) * set, threadIdx.x, blockDim.x);
+    halfband_pair_compute<NC>(p, cf, tiles[ts], smem + (it & 1) * set, threadIdx.x, blockDim.x);
     __syncthreads();
   }
 }
@@ -512,8 +522,9 @@ static int launch_halfband_pair(const HalfbandPairParams &hp, long long nwork, s
   (void)s;
   std::vector<Pk> mem(smem / sizeof(Pk) + 2);
 #define RR_HBP(NC) { float cf[NC]; for (int t = 0; t < NC; ++t) cf[t] = hp.base.coef[t]; \
-                     for (long long w = 0; w < nwork; ++w) { halfband_pair_load<NC>(hp, w, mem.data(), 0, 1); \
-                                                             halfband_pair_compute<NC>(hp, cf, w, mem.data(), 0, 1); } return RR_OK; }
+                     for (long long w = 0; w < nwork; ++w) { const HalfbandPairTile t = halfband_pair_tile<NC>(hp, w); \
+                                                             halfband_pair_load<NC>(hp, t, mem.data(), 0, 1); \
+                                                             halfband_pair_compute<NC>(hp, cf, t, mem.data(), 0, 1); } return RR_OK; }
 #else
 #define RR_HBP(NC) return launch_persistent(halfband_pair_kernel<NC>, hp, nwork, kTileThreads, smem, s)
 #endif

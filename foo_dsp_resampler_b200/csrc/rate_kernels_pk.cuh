@@ -1071,10 +1071,16 @@ struct HalfbandPairParams {
   int G;                         // pairs per CTA: all channels of a stream when the input is interleaved, else 1
 };
 
-// Geometry of one tile: `tile` outputs of the G pairs of one stream (or of one pair).
+// Geometry of one tile -- `tile` outputs of the G pairs of one stream (or of one pair) -- with everything that
+// needs divisions or 64-bit coordinate arithmetic, computed by one thread per tile.
 struct HalfbandPairTile {
   int lane0, cnt, win;
   long long k0, x0;              // first output / first input coordinate (window index u = coord - x0)
+  const float *src0;             // input sample x0 of lane0 (valid when in_direct)
+  float *dst0;                   // output sample k0 of lane0 (valid when out_direct)
+  long long in_lane1, out_lane1; // elements from a pair's first lane to its second
+  long long in_off0, out_off0;   // lane offsets of lane0 (for the clipped / ring paths)
+  int in_direct, out_direct;     // the whole window / output range of the tile is stored contiguously
 };
 template <int NC>
 RR_PROG HalfbandPairTile halfband_pair_tile(const HalfbandPairParams &hp, long long work)
@@ -1091,6 +1097,14 @@ RR_PROG HalfbandPairTile halfband_pair_tile(const HalfbandPairParams &hp, long l
   const int reach = 2 * NC - 1;
   t.x0 = 2 * t.k0 + p.pre - reach;
   t.win = 2 * (t.cnt - 1) + 2 * reach + 1;
+  t.in_off0 = lane_offset(p.in, t.lane0); t.out_off0 = lane_offset(p.out, t.lane0);
+  t.in_lane1 = lane_offset(p.in, t.lane0 + 1) - t.in_off0;
+  t.out_lane1 = lane_offset(p.out, t.lane0 + 1) - t.out_off0;
+  t.in_direct = view_range_direct(p.in, t.x0, t.x0 + t.win);
+  const long long c0 = p.out_preload + t.k0;
+  t.out_direct = view_range_direct(p.out, c0, c0 + t.cnt);
+  t.src0 = view_ptr<const float>(p.in, t.in_off0, t.x0);
+  t.dst0 = view_ptr<float>(p.out, t.out_off0, c0);
   return t;
 }
 
@@ -1098,21 +1112,19 @@ RR_PROG HalfbandPairTile halfband_pair_tile(const HalfbandPairParams &hp, long l
 // that the centre tap of output j (u = 2j + reach) sits at P1[j + 4]; odd samples below the first centre tap
 // (index < 4) are never read and not stored. Asynchronous (LDGSTS): returns after committing the copies.
 template <int NC>
-RR_PROG void halfband_pair_load(const HalfbandPairParams &hp, long long work, Pk *smem, int tid, int nthreads)
+RR_PROG void halfband_pair_load(const HalfbandPairParams &hp, const HalfbandPairTile &t, Pk *smem, int tid, int nthreads)
 {
   const HalfbandParams<float> &p = hp.base;
-  const HalfbandPairTile t = halfband_pair_tile<NC>(hp, work);
   const int G = hp.G, gbits = G == 4 ? 2 : G == 2 ? 1 : 0;      // G is 1, 2 or 4
   // the odd array starts 8 values (16 banks) further so that the even and the odd sample of a frame pair never
   // share a bank
   Pk *P0 = smem, *P1 = smem + (long long)G * p.half + 8;
   const int shift = 4 - NC, win = t.win;
-  const long long in_off0 = lane_offset(p.in, t.lane0);
   const int ics = p.in.ch_stride, ies = p.in.elem_stride;
   // lane l of the tile relative to its first lane: channels of one stream when G > 1, any two lanes when G == 1
-  auto lane_rel = [&](int l) -> long long { return G > 1 ? (long long)l * ics : lane_offset(p.in, t.lane0 + l) - in_off0; };
-  const bool direct = view_range_direct(p.in, t.x0, t.x0 + win);
-  const float *src0 = view_ptr<const float>(p.in, in_off0, t.x0);
+  auto lane_rel = [&](int l) -> long long { return G > 1 ? (long long)l * ics : (long long)l * t.in_lane1; };
+  const bool direct = t.in_direct != 0;
+  const float *src0 = t.src0;
   const int npairs_u = (win + 1) >> 1;                   // frame pairs (u = 2f, 2f + 1)
   if (direct && lane_rel(1) == 1 && !(ies & 1) && !((size_t)src0 & 7)) {
     // interleaved frames: the pairs of a frame are consecutive 8-byte words; one thread takes both frames of a
@@ -1139,7 +1151,7 @@ RR_PROG void halfband_pair_load(const HalfbandPairParams &hp, long long work, Pk
     for (int w = tid; w < 2 * win * G; w += nthreads) {
       const int u = w % win, l = w / win, g = l >> 1;
       bool valid;
-      const float *src = view_addr<float>(p.in, in_off0 + lane_rel(l), t.x0 + u, &valid);
+      const float *src = view_addr<float>(p.in, t.in_off0 + lane_rel(l), t.x0 + u, &valid);
       if (u & 1) {
         const int io = ((u + 1) >> 1) + shift;
         if (io >= 4) async_copy_elem<float>(&P1[g * p.half + io].a + (l & 1), src, valid);
@@ -1150,18 +1162,17 @@ RR_PROG void halfband_pair_load(const HalfbandPairParams &hp, long long work, Pk
 }
 
 template <int NC>
-RR_PROG void halfband_pair_compute(const HalfbandPairParams &hp, const float (&cf)[NC], long long work, const Pk *smem, int tid,
-                                   int nthreads)
+RR_PROG void halfband_pair_compute(const HalfbandPairParams &hp, const float (&cf)[NC], const HalfbandPairTile &t, const Pk *smem,
+                                   int tid, int nthreads)
 {
   typedef Arith<Pk> A;
   const HalfbandParams<float> &p = hp.base;
   constexpr int c = NC;
-  const HalfbandPairTile t = halfband_pair_tile<NC>(hp, work);
   const int G = hp.G, cnt = t.cnt;
   const Pk *P0 = smem, *P1 = smem + (long long)G * p.half + 8;
-  const long long out_off0 = lane_offset(p.out, t.lane0), k0 = t.k0;
   const int qbits = p.qbits;                             // log2(tile / 4)
   const int ocs = p.out.ch_stride, oes = p.out.elem_stride;
+  const long long lane1 = G > 1 ? ocs : t.out_lane1;
   for (int w = tid; w < (G << qbits); w += nthreads) {
     const int g = w >> qbits, j = 4 * (w & ((1 << qbits) - 1));
     if (j >= cnt) continue;
@@ -1181,23 +1192,22 @@ RR_PROG void halfband_pair_compute(const HalfbandPairParams &hp, const float (&c
       for (int tt = 0; tt < c; ++tt) sum = A::addp(sum, A::mul(A::add(x[r + c - 1 - tt], x[r + c + tt]), pk_bcast(cf[tt])));
       y[r] = sum;
     }
-    const long long off_a = G > 1 ? out_off0 + (long long)(2 * g) * ocs : out_off0;
-    const long long off_b = G > 1 ? off_a + ocs : lane_offset(p.out, t.lane0 + 1);
-    const long long cbase = p.out_preload + k0 + j;
-    if (j + 4 <= cnt && view_range_direct(p.out, cbase, cbase + 4)) {
-      float *da = view_ptr<float>(p.out, off_a, cbase), *db = view_ptr<float>(p.out, off_b, cbase);
-      if (db == da + 1 && !(oes & 1) && !((size_t)da & 7)) {                // interleaved: one pair per frame
+    if (j + 4 <= cnt && t.out_direct) {
+      float *da = t.dst0 + (G > 1 ? (2 * g) * ocs : 0) + j * oes, *db = da + lane1;
+      if (lane1 == 1 && !(oes & 1) && !((size_t)da & 7)) {                // interleaved: one pair per frame
 #pragma unroll
-        for (int r = 0; r < 4; ++r) *reinterpret_cast<Pk *>(da + (long long)r * oes) = y[r];
+        for (int r = 0; r < 4; ++r) *reinterpret_cast<Pk *>(da + r * oes) = y[r];
       } else if (oes == 1 && !(((size_t)da | (size_t)db) & 15)) {         // planar, aligned: one vector store per lane
         struct alignas(16) O4 { float a, b, c, d; };
         *reinterpret_cast<O4 *>(da) = O4{y[0].a, y[1].a, y[2].a, y[3].a};
         *reinterpret_cast<O4 *>(db) = O4{y[0].b, y[1].b, y[2].b, y[3].b};
       } else {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) { da[(long long)r * oes] = y[r].a; db[(long long)r * oes] = y[r].b; }
+        for (int r = 0; r < 4; ++r) { da[r * oes] = y[r].a; db[r * oes] = y[r].b; }
       }
     } else {
+      const long long off_a = t.out_off0 + (G > 1 ? (long long)(2 * g) * ocs : 0), off_b = off_a + lane1;
+      const long long cbase = p.out_preload + t.k0 + j;
 #pragma unroll
       for (int r = 0; r < 4; ++r)
         if (j + r < cnt) {
