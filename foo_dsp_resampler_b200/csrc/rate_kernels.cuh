@@ -1099,25 +1099,49 @@ RR_PROG void halfband_program(const HalfbandParams<T> &p, long long work, T *sme
   typedef Arith<T> A;
   const int CH = p.CH;                                   // 1, 2, 4 or 8; > 1 only for interleaved input
   constexpr int c = NC;                                  // compile-time tap count keeps the window in registers
-  const long long tiles = (p.nout + p.tile - 1) / p.tile;
-  long long group; int tix_i;
-  divmod_ll(work, (int)tiles, group, tix_i);
-  const int lane0 = (int)group * CH;
-  const long long k0 = p.out0 + (long long)tix_i * p.tile;
-  const long long rest = p.out0 + p.nout - k0;
-  const int cnt = rest < p.tile ? (int)rest : p.tile;
-  const int reach = 2 * c - 1;
-  const long long x0 = 2 * k0 + p.pre - reach;           // first coordinate needed (window index u = coord - x0)
-  const int win = 2 * (cnt - 1) + 2 * reach + 1;
+  // tile geometry (divisions, 64-bit coordinates) once per tile, by the CTA leader
+  struct Tile {
+    long long k0, x0, in_off0, out_off0;
+    const InT *src0; OutT *dst0;
+    int cnt, win, in_direct, out_direct;
+  };
+  auto make_tile = [&]() {
+    Tile t;
+    const long long tiles = (p.nout + p.tile - 1) / p.tile;
+    long long group; int tix_i;
+    divmod_ll(work, (int)tiles, group, tix_i);
+    const int lane0 = (int)group * CH;
+    t.k0 = p.out0 + (long long)tix_i * p.tile;
+    const long long rest = p.out0 + p.nout - t.k0;
+    t.cnt = rest < p.tile ? (int)rest : p.tile;
+    t.x0 = 2 * t.k0 + p.pre - (2 * c - 1);               // first coordinate needed (window index u = coord - x0)
+    t.win = 2 * (t.cnt - 1) + 2 * (2 * c - 1) + 1;
+    t.in_off0 = lane_offset(p.in, lane0); t.out_off0 = lane_offset(p.out, lane0);
+    t.in_direct = view_range_direct(p.in, t.x0, t.x0 + t.win);
+    t.out_direct = view_range_direct(p.out, p.out_preload + t.k0, p.out_preload + t.k0 + t.cnt);
+    t.src0 = view_ptr<const InT>(p.in, t.in_off0, t.x0);
+    t.dst0 = view_ptr<OutT>(p.out, t.out_off0, p.out_preload + t.k0);
+    return t;
+  };
+#if defined(__CUDA_ARCH__)
+  __shared__ Tile tile_s;
+  if (threadIdx.x == 0) tile_s = make_tile();
+  __syncthreads();
+  const Tile tl = tile_s;                                // the program's last phase ends with a barrier: safe to reuse
+#else
+  const Tile tl = make_tile();
+#endif
+  const long long k0 = tl.k0, x0 = tl.x0;
+  const int cnt = tl.cnt, win = tl.win;
   T *P0 = smem, *P1 = smem + (long long)CH * p.half;     // even-u / odd-u samples, [lane][half]
   // window index u: even u -> P0[u/2], odd u -> P1[(u+1)/2 + shift] with shift chosen so that the centre tap of
   // output j (u = 2j + reach, odd) sits at P1[j + 4]: rows stay 16-byte aligned for the vector loads below
   const int shift = 4 - c;
   const int chbits = CH == 8 ? 3 : CH == 4 ? 2 : CH == 2 ? 1 : 0;
-  const long long in_off0 = lane_offset(p.in, lane0), out_off0 = lane_offset(p.out, lane0);
+  const long long in_off0 = tl.in_off0, out_off0 = tl.out_off0;
 
-  const bool direct = view_range_direct(p.in, x0, x0 + win);
-  const InT *src0 = view_ptr<const InT>(p.in, in_off0, x0);
+  const bool direct = tl.in_direct != 0;
+  const InT *src0 = tl.src0;
   auto put = [&](int l, int u, T v) {
     if (u & 1) {                                         // odd samples below the first centre tap are never read
       const int idx = ((u + 1) >> 1) + shift;
@@ -1184,9 +1208,9 @@ RR_PROG void halfband_program(const HalfbandParams<T> &p, long long work, T *sme
     }
     const long long off = out_off0 + (long long)l * p.out.ch_stride;
     const long long cbase = p.out_preload + k0 + j;
-    if (j + 4 <= cnt && view_range_direct(p.out, cbase, cbase + 4)) {
-      OutT *d = view_ptr<OutT>(p.out, off, cbase);
+    if (j + 4 <= cnt && tl.out_direct) {
       const int es = p.out.elem_stride;
+      OutT *d = tl.dst0 + (long long)l * p.out.ch_stride + j * es;
       if (es == 1 && !((size_t)d & (4 * sizeof(OutT) - 1))) {          // planar, aligned: one vector store
         struct alignas(4 * sizeof(OutT)) O4 { OutT a, b, c, d; };
         *reinterpret_cast<O4 *>(d) = O4{(OutT)y[0], (OutT)y[1], (OutT)y[2], (OutT)y[3]};
