@@ -450,7 +450,7 @@ def main():
         if os.path.exists(fp_path):
             with open(fp_path) as f:
                 fpp = json.load(f)
-        packed = kfamily in ("dftp_kernel", "poly0_pair_kernel")
+        packed = kfamily in ("dftp_kernel", "poly0_pair_kernel", "poly0_pair2_kernel", "halfband_pair_kernel")
         if engine == "float":
             alu_peak = fpp.get("fp32_fmul2_fadd2_tflops" if packed else "fp32_fmul_fadd_tflops")
             alu_how = ("measured, un-fused packed FMUL2+FADD2" if packed else "measured, un-fused FMUL+FADD") + " (profiles/fp_peaks.json)"

@@ -1041,7 +1041,7 @@ template <class T> class Engine {
           pp.fast.mtiles = (periods + MM - 1) / MM;
           pp.fast.double_buffer = 0;
           const long long nwork = static_cast<long long>(nlanes / (2 * pp.P)) * pp.fast.mtiles;
-          kernel_name[i] = "poly0_pair_kernel";
+          kernel_name[i] = pp.CL == 2 ? "poly0_pair2_kernel" : "poly0_pair_kernel";
           return launch_poly0_pair(pp, pp.tslots * pp.P * pp.PG, nwork, s);
         }
       }
