@@ -1015,7 +1015,8 @@ template <class T> class Engine {
         const int ncl = (L + pp.CL - 1) / pp.CL;
         int rows = (ncl + 15) / 16;
         auto spill_of = [&](int r) { int sp = 0; for (int b2 = 0; b2 < 16; ++b2) sp += std::max(0, bucket[b2] - r); return sp; };
-        if (spill_of(rows) > ncl / 10) ++rows;               // a few idle lanes cost less than two-way conflicts in most half-warps
+        const int max_threads = pp.CL == 2 ? 256 : 512;      // launch bounds of poly0_pair2_kernel / poly0_pair_kernel
+        if (spill_of(rows) > ncl / 10 && 16 * (rows + 1) <= max_threads) ++rows;   // a few idle lanes cost less than two-way conflicts
         pp.spread = 1; pp.tslots = 16 * rows;               // overfull banks spill into the holes (poly0_pair_deal_overflow)
         if (maxb > 2 * rows || spill_of(rows) > kPolyDealOverflow) pp.spread = 0;   // few distinct banks (steep up-sampling): keep order
         pp.P = 1;
@@ -1034,7 +1035,7 @@ template <class T> class Engine {
         };
         int MM = 32;
         while (MM > 2 && window_of(MM) * pp.P * sizeof(Pk) > budget) MM -= 2;
-        if (window_of(MM) * pp.P * sizeof(Pk) <= budget && nlanes % (2 * pp.P) == 0) {
+        if (window_of(MM) * pp.P * sizeof(Pk) <= budget && nlanes % (2 * pp.P) == 0 && threads <= max_threads) {
           const long long periods = (wn + L - 1) / L;
           pp.fast.F = L; pp.fast.ncols = 1; pp.fast.MM = MM; pp.fast.CH = 2 * pp.P;
           pp.fast.win = static_cast<int>(window_of(MM));

@@ -162,7 +162,7 @@ def test_push_pull_protocol_edges():
 # Any two lanes can share the lane-pair kernels, also lanes of different streams: mono and odd-channel batches
 # with an even number of lanes.
 @pytest.mark.parametrize("case", [(48000, 44100, 1, 4, 0), (384000, 48000, 3, 2, 0), (96000, 44100, 1, 2, 0), (44100, 96000, 5, 2, 1),
-                                  (44100, 48000, 1, 6, 0)], ids=lambda c: "%d-%d-%dch-x%d-q%d" % c)
+                                  (44100, 48000, 1, 6, 0), (50000, 44100, 2, 1, 0), (44100, 50000, 2, 2, 0)], ids=lambda c: "%d-%d-%dch-x%d-q%d" % c)
 def test_batch_pairs_across_streams(case):
     i, o, nch, nstreams, q = case
     L = emulib.lib()

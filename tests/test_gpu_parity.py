@@ -56,6 +56,8 @@ BATCH_CASES = [
     # pairs of lanes from different streams: mono and odd-channel batches with an even number of lanes
     (48000, 44100, 50, 95, 0, 0, 1, 4), (384000, 48000, 50, 95, 0, 0, 3, 2), (96000, 44100, 50, 95, 0, 0, 1, 2),
     (44100, 96000, 50, 95, 0, 1, 5, 2), (44100, 48000, 50, 95, 0, 0, 1, 6),
+    # polyphase banks with many phases (L = 441, 250): CTA sizes near the kernels' launch bounds
+    (50000, 44100, 50, 95, 0, 0, 2, 2), (44100, 50000, 50, 95, 0, 0, 2, 2),
 ]
 
 
