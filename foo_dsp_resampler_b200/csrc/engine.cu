@@ -445,13 +445,13 @@ static int launch_persistent(Kernel kernel, const Params &p, long long nwork, in
   auto &cache = launch_cache();
   auto it = cache.find(std::make_pair(key, smem));
   if (it == cache.end()) {
-    if (smem > 48 * 1024)
+    if (smem > 32 * 1024)   // static shared memory counts against the 48 KB default too
       CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     int occ = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
     if (occ < 1) { set_last_error("kernel does not fit on an SM"); return RR_INTERNAL; }
     it = cache.emplace(std::make_pair(key, smem), LaunchInfo{occ, smem}).first;
-  } else if (smem > 48 * 1024) {
+  } else if (smem > 32 * 1024) {
     // the attribute is per function, the largest request so far wins; re-arm when this one is larger
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   }
