@@ -185,8 +185,8 @@ def test_batch_pairs_across_streams(case):
     b.close()
 
 
-FUZZ_RATES = [8000, 11025, 16000, 22050, 24000, 32000, 44100, 48000, 50000, 64000, 88200, 96000, 176400, 192000, 352800,
-              384000, 47999, 44101]
+FUZZ_RATES = [8000, 11025, 12000, 16000, 22050, 24000, 32000, 37800, 44100, 48000, 50000, 64000, 88200, 96000, 176400, 192000,
+              352800, 384000, 47999, 44101]
 
 
 def fuzz_cases(seed, count):

@@ -227,7 +227,7 @@ def test_many_identical_streams_agree(rates):
 
 def _fuzz_cases():
     import test_emulation
-    return test_emulation.fuzz_cases(11, 20)
+    return test_emulation.fuzz_cases(11, 20) + test_emulation.fuzz_cases(13, 30)
 
 
 @pytest.mark.parametrize("case", _fuzz_cases(), ids=lambda c: "%d-%d-p%d-b%d-a%d-q%d-%dch" % c[:7])
