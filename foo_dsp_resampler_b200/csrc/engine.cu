@@ -51,6 +51,8 @@ static void be_free(void *p) { free(p); }
 static int be_h2d(void *d, const void *h, size_t n, stream_t) { memcpy(d, h, n); return RR_OK; }
 static int be_d2h(void *h, const void *d, size_t n, stream_t) { memcpy(h, d, n); return RR_OK; }
 static int be_sync(stream_t) { return RR_OK; }
+static int be_stream_create(stream_t *s) { *s = nullptr; return RR_OK; }
+static void be_stream_destroy(stream_t) {}
 static int be_num_sms() { return 1; }
 static size_t be_max_smem() { return 227 * 1024; }
 #else
@@ -87,6 +89,8 @@ static int be_d2h(void *h, const void *d, size_t n, stream_t s)
   return RR_OK;
 }
 static int be_sync(stream_t s) { CUDA_TRY(cudaStreamSynchronize(s)); return RR_OK; }
+static int be_stream_create(stream_t *s) { CUDA_TRY(cudaStreamCreateWithFlags(s, cudaStreamNonBlocking)); return RR_OK; }
+static void be_stream_destroy(stream_t s) { if (s) cudaStreamDestroy(s); }
 static int be_num_sms()
 {
   int dev = 0, n = 148;
@@ -1713,17 +1717,21 @@ template <class T> class Stream : public IStream {
   float *stage_in = nullptr, *stage_out = nullptr;   // interleaved float staging (device)
   size_t stage_in_cap = 0, stage_out_cap = 0;
   T *stage_native = nullptr; size_t stage_native_cap = 0;
+  stream_t s_ = nullptr;             // this handle's own (non-blocking) stream: handles on different host threads overlap
 
   ~Stream() override
   {
+    if (s_) be_sync(s_);
     for (T *p : ring) be_free(p);
     be_free(stage_in); be_free(stage_out); be_free(stage_native);
+    be_stream_destroy(s_);
   }
 
   int init(const RR_config &cfg, int nchannels, int device)
   {
     int rc = eng.init(cfg, device);
     if (rc) return rc;
+    if ((rc = be_stream_create(&s_))) return rc;
     nch = nchannels;
     const int ns = eng.ns;
     W.assign(ns + 1, 0); done.assign(ns + 1, 0); produced.assign(ns + 1, 0);
@@ -1773,8 +1781,8 @@ template <class T> class Stream : public IStream {
       const long long old_cap = ring_cap[i];
       ring[i] = static_cast<T *>(p); ring_cap[i] = cap;
       LaneView to = ring_view(i, keep, W[i]);
-      rc = eng.copy(from, false, to, false, keep, W[i] - keep, 0, nch, 0);
-      if (!rc) rc = be_sync(0);
+      rc = eng.copy(from, false, to, false, keep, W[i] - keep, 0, nch, s_);
+      if (!rc) rc = be_sync(s_);
       be_free(old);
       (void)old_cap;
       return rc;
@@ -1784,7 +1792,7 @@ template <class T> class Stream : public IStream {
     LaneView none{}; none.base = ring[i]; none.mask = ~0ull; none.lo = 0; none.hi = 0; none.elem_stride = 1; none.nch = nch;
     if (W[i] > 0) {
       LaneView to = ring_view(i, 0, W[i]);
-      rc = eng.copy(none, false, to, false, 0, W[i], 0, nch, 0);
+      rc = eng.copy(none, false, to, false, 0, W[i], 0, nch, s_);
     }
     return rc;
   }
@@ -1819,7 +1827,7 @@ template <class T> class Stream : public IStream {
         if (rc) return rc;
         LaneView in = ring_view(i, 0, W[i]);
         LaneView out = ring_view(i + 1, W[i + 1], newW);
-        rc = eng.run_stage(i, in, false, out, false, out_pre, done[i], nd - done[i], nch, 0);
+        rc = eng.run_stage(i, in, false, out, false, out_pre, done[i], nd - done[i], nch, s_);
         if (rc) return rc;
         done[i] = nd; produced[i] = np; W[i + 1] = newW;
       }
@@ -1841,17 +1849,18 @@ template <class T> class Stream : public IStream {
       if ((rc = be_malloc(&p, sizeof(float) * elems))) return rc;
       stage_in = static_cast<float *>(p); stage_in_cap = elems;
     }
-    if ((rc = be_h2d(stage_in, x, sizeof(float) * elems, 0))) return rc;
+    if ((rc = be_h2d(stage_in, x, sizeof(float) * elems, s_))) return rc;
     if ((rc = ensure_ring(0, W[0] + static_cast<long long>(frames)))) return rc;
     // deinterleave + convert into FIFO 0 (rate_base.h:565-569)
     LaneView src{};
     src.base = stage_in; src.origin = W[0]; src.mask = ~0ull; src.lo = W[0]; src.hi = W[0] + static_cast<long long>(frames);
     src.stream_stride = 0; src.ch_stride = 1; src.elem_stride = nch; src.nch = nch;
     LaneView dst = ring_view(0, W[0], W[0] + static_cast<long long>(frames));
-    if ((rc = eng.copy(src, true, dst, false, W[0], static_cast<long long>(frames), 0, nch, 0))) return rc;
+    if ((rc = eng.copy(src, true, dst, false, W[0], static_cast<long long>(frames), 0, nch, s_))) return rc;
     W[0] += static_cast<long long>(frames);
-    if ((rc = process_stages())) return rc;
-    return be_sync(0);
+    // no synchronisation here: the copy from the caller's (pageable) buffer is complete when cudaMemcpyAsync
+    // returns, the kernels run on this handle's stream while the caller prepares its next buffer; RR_pull waits
+    return process_stages();
   }
 
   int pull(float *y, void *native, size_t max_frames, size_t *got) override   // RR_pull_x, rate_base.h:638-660
@@ -1875,8 +1884,8 @@ template <class T> class Stream : public IStream {
       LaneView dst{};
       dst.base = stage_out; dst.origin = popped; dst.mask = ~0ull; dst.lo = popped; dst.hi = popped + static_cast<long long>(n);
       dst.stream_stride = 0; dst.ch_stride = 1; dst.elem_stride = nch; dst.nch = nch;
-      if ((rc = eng.copy(src, false, dst, true, popped, static_cast<long long>(n), 0, nch, 0))) return rc;
-      if ((rc = be_d2h(y, stage_out, sizeof(float) * elems, 0))) return rc;
+      if ((rc = eng.copy(src, false, dst, true, popped, static_cast<long long>(n), 0, nch, s_))) return rc;
+      if ((rc = be_d2h(y, stage_out, sizeof(float) * elems, s_))) return rc;
     }
     if (native) {                                // planar, engine type: out[ch * max_frames + i]
       if (elems > stage_native_cap) {
@@ -1888,14 +1897,14 @@ template <class T> class Stream : public IStream {
       LaneView dst{};
       dst.base = stage_native; dst.origin = popped; dst.mask = ~0ull; dst.lo = popped; dst.hi = popped + static_cast<long long>(n);
       dst.stream_stride = 0; dst.ch_stride = static_cast<int>(n); dst.elem_stride = 1; dst.nch = nch;
-      if ((rc = eng.copy(src, false, dst, false, popped, static_cast<long long>(n), 0, nch, 0))) return rc;
+      if ((rc = eng.copy(src, false, dst, false, popped, static_cast<long long>(n), 0, nch, s_))) return rc;
       for (int c = 0; c < nch; ++c)
         if ((rc = be_d2h(static_cast<T *>(native) + static_cast<size_t>(c) * max_frames, stage_native + static_cast<size_t>(c) * n,
-                         sizeof(T) * n, 0)))
+                         sizeof(T) * n, s_)))
           return rc;
     }
     popped += static_cast<long long>(n);
-    return be_sync(0);
+    return be_sync(s_);
   }
 
   int drain() override                           // rate_flush, rate_base.h:454-468
@@ -1927,7 +1936,7 @@ template <class T> class Stream : public IStream {
       if ((rc = ensure_ring(0, W0_new))) return rc;
       LaneView none{}; none.base = ring[0]; none.mask = ~0ull; none.lo = 0; none.hi = 0; none.elem_stride = 1; none.nch = nch;
       LaneView dst = ring_view(0, W[0], W0_new);
-      if ((rc = eng.copy(none, false, dst, false, W[0], fed, 0, nch, 0))) return rc;
+      if ((rc = eng.copy(none, false, dst, false, W[0], fed, 0, nch, s_))) return rc;
       W[0] = W0_new;
       if ((rc = process_stages())) return rc;
     }
@@ -1935,7 +1944,7 @@ template <class T> class Stream : public IStream {
     W[last] = popped + remaining;
     out_shift = W[last] - produced[last - 1];
     samples_in = samples_out = 0;
-    return be_sync(0);
+    return be_sync(s_);
   }
 
   int dft_spectrum(int instance, void *out, int max_n) const override { return eng.dft_spectrum_host(instance, out, max_n); }

@@ -254,6 +254,28 @@ def test_fuzz_batch_matches_oracle(case):
     assert np.array_equal(y, ref)
 
 
+def test_handles_on_concurrent_host_threads():
+    """Distinct handles driven from distinct host threads (the reference's threading contract, rate_uni.c:210):
+    each handle has its own CUDA stream; every thread's output equals the oracle."""
+    import threading
+    import foo_dsp_resampler_b200 as pkg
+    cfg, ocfg = _cfgs(44100, 48000, 50, 95, 0, 0)
+    x = signals.sweep_noise(44100, 2, 44100 * 3)
+    ref, _ = oraclelib.resample(ocfg, x, engine="float", chunk=8192)
+    out = [None] * 6
+
+    def work(k):
+        out[k], _ = pkg.resample(cfg, x * (1.0 if k % 2 == 0 else 0.5), engine="float", chunk=8192 + 512 * k)
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(len(out))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for k, y in enumerate(out):
+        assert y is not None and np.array_equal(y, ref if k % 2 == 0 else ref * 0.5)
+
+
 def test_full_size_config1_properties():
     """BASELINE config 1 at full size (60 s stereo): frame count, bit-exactness vs the oracle, linearity of
     the whole pipeline in the scaling-by-two sense (exact in binary floating point)."""
