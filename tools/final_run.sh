@@ -7,4 +7,4 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:'dftp_kernel|poly0_pair' -c 2 -s 8 -o gpurun_out/r1b/prof_cfg4x256 -f python bench.py --workload cfg4 --streams 256 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r1b/ncu_f.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'halfband_pair' -c 2 -s 4 -o gpurun_out/r1b/prof_cfg5_halfband -f python tools/stage_probe.py > gpurun_out/r1b/ncu_h.log 2>&1
 python tools/stage_probe.py > gpurun_out/r1b/stage_probe.txt 2>&1
-tail -3 gpurun_out/r1b/*.err | tail -30
+for f in gpurun_out/r1b/*.err; do tail -n 2 "$f"; done | tail -n 30
