@@ -22,3 +22,5 @@ def probe(i, o, nch, nstreams, secs, engine="float", **kw):
 probe(384000, 48000, 8, 8, 20)
 probe(192000, 44100, 8, 16, 20, engine="double", phase=25)
 probe(48000, 44100, 2, 256, 10)
+probe(44100, 48000, 2, 256, 10, engine="double")      # what RR_open selects for Best quality (plugin default)
+probe(48000, 44100, 1, 512, 10)                        # mono batch: lanes of different streams paired
