@@ -60,6 +60,7 @@ SYMBOLS = {
     "RRX_plan": (C.c_int, [C.POINTER(RRConfig), C.c_int, C.POINTER(Plan)]),
     "RRX_design_dump": (C.c_int, [C.POINTER(RRConfig), C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "RRX_plan_dump": (C.c_int, [C.c_void_p, C.POINTER(Plan)]),
+    "RRX_enable_native_tap": (C.c_int, [C.c_void_p]),
     "RRX_pull_native": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "RRX_dft_spectrum": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "RRX_batch_open": (C.c_int, [C.POINTER(RRConfig), C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int,
@@ -109,6 +110,15 @@ def product():
     """The CUDA library. No fallback: a missing or unloadable extension is an error."""
     global _product
     if _product is None:
+        # B200RATE_VARIANT=<name> loads libb200rate_<name>.so, a differently compiled build of the same CUDA sources
+        # (measurement variants, csrc/Makefile); still the product, still no fallback
+        variant = os.environ.get("B200RATE_VARIANT")
+        if variant:
+            path = os.path.join(PKG_DIR, "libb200rate_%s.so" % variant)
+            if not os.path.exists(path):
+                raise RuntimeError("variant library %s is not built" % path)
+            _product = bind(path)
+            return _product
         if not os.path.exists(PRODUCT_SO):
             raise RuntimeError(
                 "libb200rate.so is not built; run `python -c 'import __graft_entry__ as g; g.build()'` "

@@ -16,7 +16,7 @@ class RateConverter:
     """engine: 'auto' = RR_open (Best -> fp64 engine, Normal -> fp32 engine, rate/rate_uni.c:38-51);
     'float' / 'double' = RR_ctor_float / RR_ctor_double with the config's quality (rate/rate_i.h:39-43)."""
 
-    def __init__(self, cfg, nchannels, engine="auto", lib=None):
+    def __init__(self, cfg, nchannels, engine="auto", lib=None, native_tap=False):
         self.lib = lib or _capi.product()
         self.nch = int(nchannels)
         self.h = C.c_void_p()
@@ -32,6 +32,10 @@ class RateConverter:
                 raise RateError(self.lib, _capi.RR_INTERNAL, "RR_ctor_" + engine)
         self.sample_bytes = self.plan()["sample_bytes"]
         self.dtype = np.float32 if self.sample_bytes == 4 else np.float64
+        if native_tap:                      # keep the last FIFO un-cast (fp64 engine): before the first push
+            rc = self.lib.RRX_enable_native_tap(self.h)
+            if rc != RR_OK:
+                raise RateError(self.lib, rc, "RRX_enable_native_tap")
 
     def plan(self):
         p = Plan()
@@ -101,7 +105,7 @@ def resample(cfg, x, engine="float", chunk=65536, native=False, pull_chunk=None,
     """Push ``x`` ([frames, nch] float32) in ``chunk``-frame pieces, pulling everything after each push,
     then drain: the driving pattern of foo_dsp_rate.cpp:165-187,218-313. Returns (y, counts)."""
     nch = x.shape[1]
-    r = RateConverter(cfg, nch, engine, lib=lib)
+    r = RateConverter(cfg, nch, engine, lib=lib, native_tap=native)
     pull_chunk = pull_chunk or max(chunk * 4, 1 << 16)
     outs, counts = [], []
 

@@ -91,24 +91,11 @@ int h_flow(RR_handle *h, const fb_sample_t *ibuf, fb_sample_t *obuf, size_t isam
 {
   if (!h) return RR_NULLHANDLE;
   if (!h->stream) return RR_INVPARAM;
-  size_t dummy = 0, got = 0, got2 = 0;
-  if (!iused) iused = &dummy;
-  if (!ibuf) isamp = 0;
-  const size_t isamp_max = static_cast<size_t>(h->stream->design().plan.isamp_max);
-  if (isamp > isamp_max) isamp = isamp_max;
-  *iused = 0;
-  int rc = RR_OK;
-  if (obuf && osamp) rc = h_pull(h, obuf, osamp, &got);
-  if (rc) return rc;
-  if (isamp) {
-    if ((rc = h_push(h, ibuf, isamp))) return rc;
-    *iused = isamp;
-  }
-  if (obuf && got < osamp) {
-    if ((rc = h_pull(h, obuf + got * static_cast<size_t>(h->nchannels), osamp - got, &got2))) return rc;
-  }
-  if (ogen) *ogen = got + got2;
-  return RR_OK;
+  struct A { RR_handle *h; const float *x; float *y; size_t ni, no; size_t *iu, *og; } a{h, ibuf, obuf, isamp, osamp, iused, ogen};
+  return guarded([](void *p) {
+    A *a = static_cast<A *>(p);
+    return a->h->stream->flow(a->x, a->ni, a->y, a->no, a->iu, a->og);
+  }, &a);
 }
 
 void h_close(RR_handle *h)
@@ -260,6 +247,13 @@ int RRX_pull_native(RR_handle *h, void *out, size_t osamp, size_t *ogen)
   if (!out || !osamp) { if (ogen) *ogen = 0; return RR_OK; }
   struct A { RR_handle *h; void *y; size_t n; size_t *g; } a{h, out, osamp, ogen};
   return guarded([](void *p) { A *a = static_cast<A *>(p); return a->h->stream->pull(nullptr, a->y, a->n, a->g); }, &a);
+}
+
+int RRX_enable_native_tap(RR_handle *h)
+{
+  if (!h) return RR_NULLHANDLE;
+  if (!h->stream) return RR_INVPARAM;
+  return guarded([](void *p) { return static_cast<RR_handle *>(p)->stream->enable_native_tap(); }, h);
 }
 
 int RRX_dft_spectrum(const RR_handle *h, int instance, void *out, int max_n)

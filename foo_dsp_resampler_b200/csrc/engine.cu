@@ -19,6 +19,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <type_traits>
 #include <vector>
 
@@ -55,6 +56,17 @@ static int be_stream_create(stream_t *s) { *s = nullptr; return RR_OK; }
 static void be_stream_destroy(stream_t) {}
 static int be_num_sms() { return 1; }
 static size_t be_max_smem() { return 227 * 1024; }
+static int be_current_device() { return 0; }
+struct DeviceScope { explicit DeviceScope(int) {} bool ok() const { return true; } };
+typedef int event_t;
+static int be_host_alloc(void **p, size_t n) { *p = malloc(n ? n : 1); return *p ? RR_OK : RR_ENOMEM; }
+static void be_host_free(void *p) { free(p); }
+static bool be_host_is_pinned(const void *) { return false; }
+static int be_memset(void *d, int v, size_t n, stream_t) { memset(d, v, n); return RR_OK; }
+static int be_event_create(event_t *e) { *e = 1; return RR_OK; }
+static void be_event_destroy(event_t) {}
+static int be_event_record(event_t, stream_t) { return RR_OK; }
+static int be_event_sync(event_t) { return RR_OK; }
 #else
 constexpr int kEmulated = 0;
 typedef cudaStream_t stream_t;
@@ -103,7 +115,48 @@ static size_t be_max_smem()
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   return static_cast<size_t>(n);
 }
+static int be_current_device()
+{
+  int dev = 0;
+  return cudaGetDevice(&dev) == cudaSuccess ? dev : 0;
+}
+// A handle / batch lives on the device it was opened on; every public entry point selects that device for the
+// duration of the call (the caller may drive it from any host thread, whose current device is arbitrary) and
+// restores the caller's device on return.
+struct DeviceScope {
+  int prev_ = -1, want_;
+  bool ok_ = true;
+  explicit DeviceScope(int device) : want_(device)
+  {
+    if (cudaGetDevice(&prev_) != cudaSuccess) { ok_ = false; return; }
+    if (prev_ != want_ && cudaSetDevice(want_) != cudaSuccess) ok_ = false;
+  }
+  ~DeviceScope() { if (ok_ && prev_ != want_) cudaSetDevice(prev_); }
+  bool ok() const { return ok_; }
+};
 #endif
+#ifndef B200RATE_EMU
+typedef cudaEvent_t event_t;
+// page-locked host memory for the staging buffers of the host-facing entry points
+static int be_host_alloc(void **p, size_t n) { CUDA_TRY(cudaHostAlloc(p, n ? n : 1, cudaHostAllocDefault)); return RR_OK; }
+static void be_host_free(void *p) { if (p) cudaFreeHost(p); }
+// true when `p` is page-locked host memory CUDA knows about (cudaHostAlloc / cudaHostRegister): an asynchronous
+// copy from / to it really is asynchronous, so it can be used directly instead of the library's staging buffer
+static bool be_host_is_pinned(const void *p)
+{
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+static int be_memset(void *d, int v, size_t n, stream_t s) { CUDA_TRY(cudaMemsetAsync(d, v, n, s)); return RR_OK; }
+static int be_event_create(event_t *e) { CUDA_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming)); return RR_OK; }
+static void be_event_destroy(event_t e) { if (e) cudaEventDestroy(e); }
+static int be_event_record(event_t e, stream_t s) { CUDA_TRY(cudaEventRecord(e, s)); return RR_OK; }
+static int be_event_sync(event_t e) { CUDA_TRY(cudaEventSynchronize(e)); return RR_OK; }
+#endif
+#define RR_DEVICE_SCOPE(dev)                                                               \
+  DeviceScope device_scope_(dev);                                                          \
+  if (!device_scope_.ok()) { set_last_error("cannot select the handle's device"); return RR_INTERNAL; }
 
 // ===================================================================================================
 // kernels
@@ -231,8 +284,7 @@ __global__ void __launch_bounds__(kPkGroupThreads * kPkMaxGroups) dftp_kernel(co
   const int stride = (int)gridDim.x * pp.groups, nw = (int)nwork;
   if (w < nw) {
     if (g.tid == 0) items[gi][0] = pk_make_item(pp, w);
-    grp_sync(g);
-    pk_stage_tile(pp, g, items[gi][0], F, tb.perm_f);
+    if (!pp.tile_regs) { grp_sync(g); pk_stage_tile(pp, g, items[gi][0], F, tb.perm_f); }
   }
   for (int n = 0; w < nw; w += stride, n ^= 1) {
     const int next = w + stride < nw ? w + stride : -1;
@@ -433,11 +485,69 @@ __global__ void __launch_bounds__(kTileThreads) copy_kernel(const __grid_constan
   for (long long w = blockIdx.x; w < nwork; w += gridDim.x) copy_program<InT, OutT>(p, w);
 }
 
-struct LaunchInfo { int blocks_per_sm; size_t smem_set; };
-static std::map<std::pair<const void *, size_t>, LaunchInfo> &launch_cache()
+// Launch bookkeeping shared by every handle of the process: distinct handles may be driven from distinct host
+// threads (the reference's threading contract, rate/rate_uni.c:210), so the cache is guarded by a mutex. The
+// opt-in dynamic shared-memory limit of a kernel is raised ONCE per (device, kernel) to the device maximum and
+// never lowered, so launches of one kernel with different shared-memory sizes cannot disturb each other.
+struct LaunchKey {
+  int device; const void *fn; int threads; size_t smem;
+  bool operator<(const LaunchKey &o) const
+  {
+    if (device != o.device) return device < o.device;
+    if (fn != o.fn) return fn < o.fn;
+    if (threads != o.threads) return threads < o.threads;
+    return smem < o.smem;
+  }
+};
+struct LaunchCache {
+  std::mutex mu;
+  std::map<std::pair<int, const void *>, int> armed;   // (device, kernel) -> largest dynamic shared memory it may use
+  std::map<LaunchKey, int> blocks_per_sm;
+  std::map<int, int> sms;                               // device -> SM count
+};
+static LaunchCache &launch_cache()
 {
-  static std::map<std::pair<const void *, size_t>, LaunchInfo> c;
+  static LaunchCache c;
   return c;
+}
+
+// Resident CTAs of `kernel` on the current device for (threads, smem), and the device's SM count.
+template <class Kernel>
+static int launch_geometry(Kernel kernel, int threads, size_t smem, long long *resident)
+{
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  const void *fn = reinterpret_cast<const void *>(kernel);
+  LaunchCache &c = launch_cache();
+  std::lock_guard<std::mutex> lock(c.mu);
+  auto sm = c.sms.find(dev);
+  if (sm == c.sms.end()) {
+    int n = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    sm = c.sms.emplace(dev, n).first;
+  }
+  auto arm = c.armed.find(std::make_pair(dev, fn));
+  if (arm == c.armed.end()) {
+    cudaFuncAttributes fa;
+    CUDA_TRY(cudaFuncGetAttributes(&fa, kernel));
+    int optin = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const int max_dyn = optin - static_cast<int>(fa.sharedSizeBytes);
+    if (max_dyn > 48 * 1024 - static_cast<int>(fa.sharedSizeBytes))
+      CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+    arm = c.armed.emplace(std::make_pair(dev, fn), max_dyn).first;
+  }
+  if (static_cast<long long>(smem) > arm->second) { set_last_error("kernel needs more shared memory than an SM has"); return RR_INTERNAL; }
+  const LaunchKey key{dev, fn, threads, smem};
+  auto it = c.blocks_per_sm.find(key);
+  if (it == c.blocks_per_sm.end()) {
+    int occ = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
+    if (occ < 1) { set_last_error("kernel does not fit on an SM"); return RR_INTERNAL; }
+    it = c.blocks_per_sm.emplace(key, occ).first;
+  }
+  *resident = static_cast<long long>(it->second) * sm->second;
+  return RR_OK;
 }
 
 template <class Kernel, class Params, class... Extra>
@@ -445,21 +555,9 @@ static int launch_persistent(Kernel kernel, const Params &p, long long nwork, in
                              Extra... extra)
 {
   if (nwork <= 0) return RR_OK;
-  const void *key = reinterpret_cast<const void *>(kernel);
-  auto &cache = launch_cache();
-  auto it = cache.find(std::make_pair(key, smem));
-  if (it == cache.end()) {
-    if (smem > 32 * 1024)   // static shared memory counts against the 48 KB default too
-      CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    int occ = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
-    if (occ < 1) { set_last_error("kernel does not fit on an SM"); return RR_INTERNAL; }
-    it = cache.emplace(std::make_pair(key, smem), LaunchInfo{occ, smem}).first;
-  } else if (smem > 32 * 1024) {
-    // the attribute is per function, the largest request so far wins; re-arm when this one is larger
-    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  }
-  const long long resident = static_cast<long long>(it->second.blocks_per_sm) * be_num_sms();
+  long long resident = 0;
+  const int rc = launch_geometry(kernel, threads, smem, &resident);
+  if (rc != RR_OK) return rc;
   const unsigned grid = static_cast<unsigned>(std::min<long long>(nwork, resident));
   kernel<<<grid, threads, smem, s>>>(p, nwork, extra...);
   CUDA_TRY(cudaGetLastError());
@@ -479,7 +577,7 @@ static int launch_dftp(const DftPkParams &pp, long long nwork, stream_t s)
   for (long long w = 0; w < nwork; ++w) {
     PkItem items[2];
     items[0] = pk_make_item(pp, w);
-    pk_stage_tile(pp, g, items[0], F, tb.perm_f);
+    if (!pp.tile_regs) pk_stage_tile(pp, g, items[0], F, tb.perm_f);
     if (pp.spec_mode == PK_SPEC_UP2) dftp_program<PK_SPEC_UP2, 0, 0>(pp, g, tb, items, 0, -1, F, B);
     else if (pp.spec_mode == PK_SPEC_SAME) dftp_program<PK_SPEC_SAME, 0, 0>(pp, g, tb, items, 0, -1, F, B);
     else dftp_program<PK_SPEC_GEN, 0, 0>(pp, g, tb, items, 0, -1, F, B);
@@ -489,17 +587,9 @@ static int launch_dftp(const DftPkParams &pp, long long nwork, stream_t s)
   const size_t smem = pk_smem_layout(pp).total;
   const int threads = pp.groups * pp.gthreads;
   auto go = [&](auto kernel) -> int {
-    const void *key = reinterpret_cast<const void *>(kernel);
-    auto &cache = launch_cache();
-    auto it = cache.find(std::make_pair(key, smem));
-    if (it == cache.end()) {
-      CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-      int occ = 0;
-      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
-      if (occ < 1) { set_last_error("lane-pair DFT kernel does not fit on an SM"); return RR_INTERNAL; }
-      it = cache.emplace(std::make_pair(key, smem), LaunchInfo{occ, smem}).first;
-    } else CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    const long long resident = static_cast<long long>(it->second.blocks_per_sm) * be_num_sms();
+    long long resident = 0;
+    const int rc = launch_geometry(kernel, threads, smem, &resident);
+    if (rc != RR_OK) return rc;
     const long long ctas = (nwork + pp.groups - 1) / pp.groups;
     kernel<<<static_cast<unsigned>(std::min(ctas, resident)), threads, smem, s>>>(pp, nwork);
     CUDA_TRY(cudaGetLastError());
@@ -868,6 +958,7 @@ template <class T> class Engine {
   int ns = 0;
   StageGeom geom[RR_MAX_STAGES];
   int launches = 0;
+  int device_id = 0;                                      // the device every buffer, stream and launch of this engine lives on
   const char *kernel_name[RR_MAX_STAGES] = {nullptr};   // what run_stage launched last for each stage
 
   ~Engine() { for (void *p : allocs_) be_free(p); }
@@ -877,6 +968,7 @@ template <class T> class Engine {
     int rc = build_design(cfg, static_cast<int>(sizeof(T)), design);
     if (rc != RR_OK) { set_last_error("invalid resampler configuration"); return rc; }
     if ((rc = be_set_device(device)) != RR_OK) return rc;
+    device_id = be_current_device();
     ns = design.plan.num_stages;
     num_sms_ = be_num_sms();
     max_smem_ = be_max_smem();
@@ -1166,7 +1258,7 @@ template <class T> class Engine {
     return RR_OK;
   }
 
-  struct DevSched { CfftSched fwd, inv; const T *pyramid; const uint16_t *pk_ltab = nullptr, *pk_perm[2] = {nullptr, nullptr}; };
+  struct DevSched { CfftSched fwd, inv; const T *pyramid; const uint16_t *pk_ltab = nullptr, *pk_perm[2] = {nullptr, nullptr}; int pk_ltab_len = 0; };
   std::map<int, std::vector<uint16_t>> pk_perm_inv_host_;   // by complex bits
   const PkSpecConst *pk_spec_dev_[RR_MAX_STAGES] = {nullptr};
   std::map<int, DevSched> sched_;          // by complex bits
@@ -1175,6 +1267,7 @@ template <class T> class Engine {
   bool use_pair_kernel_ = getenv("B200RATE_NO_PAIR_KERNEL") == nullptr;
   bool use_pair_dft_ = getenv("B200RATE_NO_PAIR_DFT") == nullptr, use_pair_poly_ = getenv("B200RATE_NO_PAIR_POLY") == nullptr;
   bool use_pair_half_ = getenv("B200RATE_NO_PAIR_HALF") == nullptr, use_pair_poly2_ = getenv("B200RATE_NO_PAIR_POLY2") == nullptr;
+  bool tile_regs_ = getenv("B200RATE_TILE_LDGSTS") == nullptr;   // measurement switch: LDGSTS prefetch of the input tiles instead
   int last_dft_kernel_ = 0;
 
   // Parameters of the lane-pair kernel for DFT stage i, or false when it does not apply (transform too
@@ -1193,15 +1286,16 @@ template <class T> class Engine {
     pp.fslots = pk_buf_slots(g.Pf >> 1); pp.bslots = pk_buf_slots(g.Ni >> 1);
     pp.gthreads = kPkGroupThreads;
     pp.spec_mode = pk_spec_mode(g);
+    pp.tile_regs = tile_regs_ ? 1 : 0;
     pp.spec = pk_spec_dev_[i];
     if (pp.spec_mode != PK_SPEC_GEN && !pp.spec) return false;
+    pp.n_pyr_f = pk_pyr_len(fb); pp.n_pyr_i = pk_pyr_len(ib); pp.n_ltab_f = sf->second.pk_ltab_len; pp.n_ltab_i = si->second.pk_ltab_len;
     for (pp.groups = kPkMaxGroups; pp.groups >= 1; --pp.groups)
       if (pk_smem_layout(pp).total + 1024 <= max_smem_) break;
     if (pp.groups < 1) return false;
     const PkSmemLayout lay = pk_smem_layout(pp);
     pp.lay_pyr_f = lay.pyr_f; pp.lay_pyr_i = lay.pyr_i; pp.lay_ltab_f = lay.ltab_f; pp.lay_ltab_i = lay.ltab_i;
     pp.lay_perm_f = lay.perm_f; pp.lay_data = lay.data;
-    pp.n_pyr_f = pk_pyr_len(fb); pp.n_pyr_i = pk_pyr_len(ib); pp.n_ltab_f = pk_local_entries(fb); pp.n_ltab_i = pk_local_entries(ib);
     return true;
   }
   static int pk_spec_mode(const StageGeom &g)
@@ -1297,6 +1391,7 @@ template <class T> class Engine {
         const PkHostSched ph = build_pk_sched(h);
         if ((rc = upload(ph.local, &d.pk_ltab)) || (rc = upload(ph.perm[0], &d.pk_perm[0])) || (rc = upload(ph.perm[1], &d.pk_perm[1])))
           return rc;
+        d.pk_ltab_len = static_cast<int>(ph.local.size());
         pk_perm_inv_host_[bits] = ph.perm[1];
       }
       it = sched_.emplace(bits, d).first;
@@ -1433,6 +1528,7 @@ template <class T> class Batch : public IBatch {
 
   ~Batch() override
   {
+    DeviceScope scope(eng.device_id);
     for (T *p : buf) be_free(p);
     for (int k = 0; k < 2; ++k) { be_free(slot_in_[k]); be_free(slot_out_[k]); }
 #ifndef B200RATE_EMU
@@ -1448,7 +1544,9 @@ template <class T> class Batch : public IBatch {
 
   int init(const RR_config &cfg, int nchannels, int nstr, size_t fmax, int device)
   {
-    int rc = eng.init(cfg, device);
+    const int dev = device >= 0 ? device : be_current_device();
+    RR_DEVICE_SCOPE(dev);
+    int rc = eng.init(cfg, dev);
     if (rc) return rc;
     nch = nchannels; nstreams = nstr; frames_in_max = fmax; active_streams_ = nstr;
     const size_t nout = frames_out(fmax);
@@ -1501,6 +1599,12 @@ template <class T> class Batch : public IBatch {
 
   void input_window(size_t frames_in, uint64_t out_begin, size_t out_count, uint64_t *first, uint64_t *count) const override
   {
+    if (eng.ns == 0) {                       // identity: output frame k is input frame k
+      const uint64_t lo = std::min<uint64_t>(out_begin, frames_in), hi = std::min<uint64_t>(out_begin + out_count, frames_in);
+      if (first) *first = lo;
+      if (count) *count = hi - lo;
+      return;
+    }
     std::vector<StageRange> r(eng.ns);
     const long long klo = static_cast<long long>(out_begin), khi = klo + static_cast<long long>(out_count);
     plan_ranges(klo, khi, r.data());
@@ -1514,6 +1618,7 @@ template <class T> class Batch : public IBatch {
   int process(const float *d_in, uint64_t win_first, size_t win_frames, size_t frames_in, uint64_t out_begin,
               size_t out_count, void *d_out, bool native_out, void *stream) override
   {
+    RR_DEVICE_SCOPE(eng.device_id);
     stream_t s = static_cast<stream_t>(stream);
     const int ns = eng.ns, nlanes = nch * active_streams_;
     eng.launches = 0;
@@ -1522,9 +1627,24 @@ template <class T> class Batch : public IBatch {
       while (ev_.size() < static_cast<size_t>(2 * ns)) { cudaEvent_t e; CUDA_TRY(cudaEventCreate(&e)); ev_.push_back(e); }
     }
 #endif
-    if (ns == 0) { set_last_error("identity conversion has no stages"); return RR_INVPARAM; }
-    std::vector<StageRange> r(ns);
     const long long klo = static_cast<long long>(out_begin), khi = klo + static_cast<long long>(out_count);
+    if (ns == 0) {
+      // in_rate == out_rate: no stages, FIFO 0 is the output FIFO (rate_base.h:445-447) -- the frames pass through
+      if (!d_out || out_count == 0) return RR_OK;
+      LaneView in{}, out{};
+      in.base = const_cast<float *>(d_in);
+      in.origin = static_cast<long long>(win_first); in.mask = ~0ull; in.lo = in.origin;
+      in.hi = std::min<long long>(static_cast<long long>(frames_in), static_cast<long long>(win_first + win_frames));
+      in.stream_stride = static_cast<long long>(win_frames) * nch; in.ch_stride = 1; in.elem_stride = nch; in.nch = nch;
+      out.base = d_out; out.origin = klo; out.mask = ~0ull; out.lo = klo; out.hi = khi; out.nch = nch;
+      out.stream_stride = static_cast<long long>(out_count) * nch;
+      if (native_out) { out.ch_stride = static_cast<int>(out_count); out.elem_stride = 1; }
+      else { out.ch_stride = 1; out.elem_stride = nch; }
+      const int rc = eng.copy(in, true, out, !native_out, klo, static_cast<long long>(out_count), 0, nlanes, s);
+      launches_ = eng.launches;
+      return rc;
+    }
+    std::vector<StageRange> r(ns);
     plan_ranges(klo, khi, r.data());
     const long long pre0 = eng.geom[0].preload;
     if (!d_out || out_count == 0) return RR_OK;
@@ -1599,15 +1719,18 @@ template <class T> class Batch : public IBatch {
 
   int process_host(const float *h_in, size_t frames_in, float *h_out, size_t total_streams) override
   {
+    RR_DEVICE_SCOPE(eng.device_id);
     if (frames_in > frames_in_max) { set_last_error("frames_in exceeds frames_in_max"); return RR_INVPARAM; }
     const size_t nout = frames_out(frames_in);
     const size_t in_elems = frames_in * nch, out_elems = nout * nch;
     int rc;
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < 2; ++k) {              // the four staging slots are allocated independently (a failure leaves the rest usable)
+      void *p = nullptr;
       if (!slot_in_[k]) {
-        void *p = nullptr;
         if ((rc = be_malloc(&p, sizeof(float) * frames_in_max * nch * nstreams))) return rc;
         slot_in_[k] = static_cast<float *>(p);
+      }
+      if (!slot_out_[k]) {
         if ((rc = be_malloc(&p, sizeof(float) * (frames_out(frames_in_max) + 1) * nch * nstreams))) return rc;
         slot_out_[k] = static_cast<float *>(p);
       }
@@ -1630,27 +1753,37 @@ template <class T> class Batch : public IBatch {
       }
     }
     int total_launches = 0;
-    size_t k = 0;
-    for (size_t s0 = 0; s0 < total_streams; s0 += nstreams, ++k) {
-      const int slot = static_cast<int>(k & 1);
-      const int now = static_cast<int>(std::min<size_t>(nstreams, total_streams - s0));
-      if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(hs_[0], comp_done_[slot], 0));       // input slot free again
-      CUDA_TRY(cudaMemcpyAsync(slot_in_[slot], h_in + s0 * in_elems, sizeof(float) * in_elems * now,
-                               cudaMemcpyHostToDevice, hs_[0]));
-      CUDA_TRY(cudaEventRecord(h2d_done_[slot], hs_[0]));
-      CUDA_TRY(cudaStreamWaitEvent(hs_[1], h2d_done_[slot], 0));
-      if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(hs_[1], d2h_done_[slot], 0));        // output slot drained
-      if ((rc = process_streams(slot_in_[slot], frames_in, slot_out_[slot], now, hs_[1]))) return rc;
-      total_launches += launches_;
-      CUDA_TRY(cudaEventRecord(comp_done_[slot], hs_[1]));
-      CUDA_TRY(cudaStreamWaitEvent(hs_[2], comp_done_[slot], 0));
-      CUDA_TRY(cudaMemcpyAsync(h_out + s0 * out_elems, slot_out_[slot], sizeof(float) * out_elems * now,
-                               cudaMemcpyDeviceToHost, hs_[2]));
-      CUDA_TRY(cudaEventRecord(d2h_done_[slot], hs_[2]));
+    // H2D, kernels and D2H of consecutive sub-batches overlap on three streams; on any failure the streams are
+    // drained before returning, so the caller's host buffers are never still in flight
+    auto pipeline = [&]() -> int {
+      size_t k = 0;
+      for (size_t s0 = 0; s0 < total_streams; s0 += nstreams, ++k) {
+        const int slot = static_cast<int>(k & 1);
+        const int now = static_cast<int>(std::min<size_t>(nstreams, total_streams - s0));
+        if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(hs_[0], comp_done_[slot], 0));       // input slot free again
+        CUDA_TRY(cudaMemcpyAsync(slot_in_[slot], h_in + s0 * in_elems, sizeof(float) * in_elems * now,
+                                 cudaMemcpyHostToDevice, hs_[0]));
+        CUDA_TRY(cudaEventRecord(h2d_done_[slot], hs_[0]));
+        CUDA_TRY(cudaStreamWaitEvent(hs_[1], h2d_done_[slot], 0));
+        if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(hs_[1], d2h_done_[slot], 0));        // output slot drained
+        const int prc = process_streams(slot_in_[slot], frames_in, slot_out_[slot], now, hs_[1]);
+        if (prc) return prc;
+        total_launches += launches_;
+        CUDA_TRY(cudaEventRecord(comp_done_[slot], hs_[1]));
+        CUDA_TRY(cudaStreamWaitEvent(hs_[2], comp_done_[slot], 0));
+        CUDA_TRY(cudaMemcpyAsync(h_out + s0 * out_elems, slot_out_[slot], sizeof(float) * out_elems * now,
+                                 cudaMemcpyDeviceToHost, hs_[2]));
+        CUDA_TRY(cudaEventRecord(d2h_done_[slot], hs_[2]));
+      }
+      return RR_OK;
+    };
+    rc = pipeline();
+    for (int q = 0; q < 3; ++q) {
+      const cudaError_t e = cudaStreamSynchronize(hs_[q]);
+      if (e != cudaSuccess && rc == RR_OK) rc = cuda_fail(e, "cudaStreamSynchronize");
     }
-    for (int q = 0; q < 3; ++q) CUDA_TRY(cudaStreamSynchronize(hs_[q]));
     launches_ = total_launches;
-    return RR_OK;
+    return rc;
 #endif
   }
 
@@ -1660,6 +1793,7 @@ template <class T> class Batch : public IBatch {
 
   int stage_times(float *ms, int max_stages) override
   {
+    DeviceScope scope(eng.device_id);
     const int n = std::min(eng.ns, max_stages);
     for (int i = 0; i < n; ++i) ms[i] = 0.f;
 #ifndef B200RATE_EMU
@@ -1699,7 +1833,17 @@ template <class T> class Batch : public IBatch {
 };
 
 // ===================================================================================================
-// Streaming front-end (RR_push / RR_pull / RR_drain on device ring buffers)
+// Streaming front-end (RR_push / RR_pull / RR_drain / RR_flow on device ring buffers)
+//
+// FIFO 0 and the output FIFO are rings of INTERLEAVED FLOAT frames -- the caller's own layout -- so a push is a
+// plain host-to-device copy into ring 0 and a pull a plain device-to-host copy out of the last ring: the
+// (de)interleave and the float <-> sample type conversion of rate/rate_base.h:559-569 happen inside the first /
+// last stage kernel, there is no separate copy pass. Host buffers are staged through page-locked memory owned
+// by the handle (two input slots, so the copy-in of push k+1 overlaps the transfer and the kernels of push k);
+// caller buffers that are themselves page-locked are used directly. RR_push returns as soon as the caller's
+// buffer has been consumed (never while a copy from it is in flight); the kernels run on the handle's own
+// non-blocking stream and RR_pull / RR_drain wait for them, so a failure of a kernel launched by RR_push is
+// reported by the next RR_pull / RR_drain.
 // ===================================================================================================
 template <class T> class Stream : public IStream {
  public:
@@ -1710,28 +1854,47 @@ template <class T> class Stream : public IStream {
   std::vector<long long> done;       // stage progress: blocks (dft) or outputs (others)
   std::vector<long long> produced;   // outputs produced by stage i
   std::vector<long long> ring_cap;   // per-lane capacity (power of two)
-  std::vector<T *> ring;
+  std::vector<void *> ring;          // 0 and ns: interleaved float; 1 .. ns-1 (and ns with the native tap): planar T
+  bool native_tap_ = false;          // last FIFO kept in the engine type (RRX_pull_native of the fp64 engine)
   long long popped = 0;              // read position of the output FIFO
   long long out_shift = 0;           // coordinate of last-stage output 0 in the output FIFO (changes when drain trims)
   uint64_t samples_in = 0, samples_out = 0;   // rate_t counters (rate_base.h:224-231)
-  float *stage_in = nullptr, *stage_out = nullptr;   // interleaved float staging (device)
-  size_t stage_in_cap = 0, stage_out_cap = 0;
-  T *stage_native = nullptr; size_t stage_native_cap = 0;
+  uint64_t in_rate_ = 0, out_rate_ = 0;
   stream_t s_ = nullptr;             // this handle's own (non-blocking) stream: handles on different host threads overlap
+  // page-locked staging
+  float *pin_in_[2] = {nullptr, nullptr};
+  size_t pin_in_cap_[2] = {0, 0};
+  event_t pin_in_free_[2] = {};      // recorded after the transfer out of the slot
+  bool pin_in_busy_[2] = {false, false};
+  unsigned push_seq_ = 0;
+  float *pin_out_ = nullptr;
+  size_t pin_out_cap_ = 0;
+  event_t user_in_done_ = {};        // transfer out of a caller-owned page-locked buffer
+  bool events_ok_ = false;
+  T *stage_native = nullptr; size_t stage_native_cap = 0;   // device staging of the native tap
 
   ~Stream() override
   {
+    DeviceScope scope(eng.device_id);
     if (s_) be_sync(s_);
-    for (T *p : ring) be_free(p);
-    be_free(stage_in); be_free(stage_out); be_free(stage_native);
+    for (void *p : ring) be_free(p);
+    be_free(stage_native);
+    for (int k = 0; k < 2; ++k) be_host_free(pin_in_[k]);
+    be_host_free(pin_out_);
+    if (events_ok_) { be_event_destroy(pin_in_free_[0]); be_event_destroy(pin_in_free_[1]); be_event_destroy(user_in_done_); }
     be_stream_destroy(s_);
   }
 
   int init(const RR_config &cfg, int nchannels, int device)
   {
-    int rc = eng.init(cfg, device);
+    const int dev = device >= 0 ? device : be_current_device();
+    RR_DEVICE_SCOPE(dev);
+    int rc = eng.init(cfg, dev);
     if (rc) return rc;
     if ((rc = be_stream_create(&s_))) return rc;
+    if ((rc = be_event_create(&pin_in_free_[0])) || (rc = be_event_create(&pin_in_free_[1])) || (rc = be_event_create(&user_in_done_)))
+      return rc;
+    events_ok_ = true;
     nch = nchannels;
     const int ns = eng.ns;
     W.assign(ns + 1, 0); done.assign(ns + 1, 0); produced.assign(ns + 1, 0);
@@ -1744,12 +1907,18 @@ template <class T> class Stream : public IStream {
 
   const Design &design() const override { return eng.design; }
 
+  // ring i holds interleaved float frames (the caller's layout) rather than planar engine-type lanes
+  bool ring_is_frames(int i) const { return i == 0 || (i == eng.ns && !native_tap_); }
+  size_t ring_elem_bytes(int i) const { return ring_is_frames(i) ? sizeof(float) : sizeof(T); }
+
   LaneView ring_view(int i, long long lo, long long hi) const
   {
     LaneView v{};
     v.base = ring[i]; v.origin = 0; v.mask = static_cast<unsigned long long>(ring_cap[i] - 1);
     v.lo = lo; v.hi = hi;
-    v.stream_stride = 0; v.ch_stride = static_cast<int>(ring_cap[i]); v.elem_stride = 1; v.nch = nch;
+    v.stream_stride = 0; v.nch = nch;
+    if (ring_is_frames(i)) { v.ch_stride = 1; v.elem_stride = nch; }
+    else { v.ch_stride = static_cast<int>(ring_cap[i]); v.elem_stride = 1; }
     return v;
   }
 
@@ -1773,28 +1942,24 @@ template <class T> class Stream : public IStream {
     while (cap < need) cap <<= 1;
     if (cap > 0x40000000ll) { set_last_error("FIFO ring would exceed 2^30 samples per channel"); return RR_ENOMEM; }
     void *p = nullptr;
-    int rc = be_malloc(&p, sizeof(T) * static_cast<size_t>(cap) * nch);
+    const size_t bytes = ring_elem_bytes(i) * static_cast<size_t>(cap) * nch;
+    int rc = be_malloc(&p, bytes);
     if (rc) return rc;
+    // a fresh ring is all zeros: the preload region (fifo_write0, rate_base.h:420) and everything not yet written
+    if ((rc = be_memset(p, 0, bytes, s_))) { be_free(p); return rc; }
     if (ring[i]) {                           // carry the live region over (ring -> bigger ring)
+      const bool f32 = ring_is_frames(i);
       LaneView from = ring_view(i, keep, W[i]);
-      T *old = ring[i];
-      const long long old_cap = ring_cap[i];
-      ring[i] = static_cast<T *>(p); ring_cap[i] = cap;
+      void *old = ring[i];
+      ring[i] = p; ring_cap[i] = cap;
       LaneView to = ring_view(i, keep, W[i]);
-      rc = eng.copy(from, false, to, false, keep, W[i] - keep, 0, nch, s_);
+      rc = eng.copy(from, f32, to, f32, keep, W[i] - keep, 0, nch, s_);
       if (!rc) rc = be_sync(s_);
       be_free(old);
-      (void)old_cap;
       return rc;
     }
-    ring[i] = static_cast<T *>(p); ring_cap[i] = cap;
-    // zero the preload region (fifo_write0, rate_base.h:420)
-    LaneView none{}; none.base = ring[i]; none.mask = ~0ull; none.lo = 0; none.hi = 0; none.elem_stride = 1; none.nch = nch;
-    if (W[i] > 0) {
-      LaneView to = ring_view(i, 0, W[i]);
-      rc = eng.copy(none, false, to, false, 0, W[i], 0, nch, s_);
-    }
-    return rc;
+    ring[i] = p; ring_cap[i] = cap;
+    return RR_OK;
   }
 
   void count_input(size_t n)                 // rate_input, rate_base.h:436-441
@@ -1802,7 +1967,6 @@ template <class T> class Stream : public IStream {
     samples_in += n;
     while (samples_in > in_rate_ && samples_out > out_rate_) { samples_in -= in_rate_; samples_out -= out_rate_; }
   }
-  uint64_t in_rate_ = 0, out_rate_ = 0;
 
   // new totals for stage i given W[i]; returns outputs produced in total
   void advance_counts(int i, long long *new_done, long long *new_produced) const
@@ -1827,7 +1991,7 @@ template <class T> class Stream : public IStream {
         if (rc) return rc;
         LaneView in = ring_view(i, 0, W[i]);
         LaneView out = ring_view(i + 1, W[i + 1], newW);
-        rc = eng.run_stage(i, in, false, out, false, out_pre, done[i], nd - done[i], nch, s_);
+        rc = eng.run_stage(i, in, ring_is_frames(i), out, ring_is_frames(i + 1), out_pre, done[i], nd - done[i], nch, s_);
         if (rc) return rc;
         done[i] = nd; produced[i] = np; W[i + 1] = newW;
       }
@@ -1835,52 +1999,131 @@ template <class T> class Stream : public IStream {
     return RR_OK;
   }
 
+  // frames [c0, c0 + n) of a frame ring <-> a host buffer: at most two transfers (ring wrap)
+  int ring_h2d(int i, long long c0, long long n, const float *src)
+  {
+    float *r = static_cast<float *>(ring[i]);
+    const long long cap = ring_cap[i], first = c0 & (cap - 1), n1 = std::min(n, cap - first);
+    int rc = be_h2d(r + first * nch, src, sizeof(float) * static_cast<size_t>(n1) * nch, s_);
+    if (!rc && n1 < n) rc = be_h2d(r, src + n1 * nch, sizeof(float) * static_cast<size_t>(n - n1) * nch, s_);
+    return rc;
+  }
+  int ring_d2h(int i, long long c0, long long n, float *dst)
+  {
+    const float *r = static_cast<const float *>(ring[i]);
+    const long long cap = ring_cap[i], first = c0 & (cap - 1), n1 = std::min(n, cap - first);
+    int rc = be_d2h(dst, r + first * nch, sizeof(float) * static_cast<size_t>(n1) * nch, s_);
+    if (!rc && n1 < n) rc = be_d2h(dst + n1 * nch, r, sizeof(float) * static_cast<size_t>(n - n1) * nch, s_);
+    return rc;
+  }
+  int ring_zero(int i, long long c0, long long n)
+  {
+    float *r = static_cast<float *>(ring[i]);
+    const long long cap = ring_cap[i], first = c0 & (cap - 1), n1 = std::min(n, cap - first);
+    int rc = be_memset(r + first * nch, 0, sizeof(float) * static_cast<size_t>(n1) * nch, s_);
+    if (!rc && n1 < n) rc = be_memset(r, 0, sizeof(float) * static_cast<size_t>(n - n1) * nch, s_);
+    return rc;
+  }
+
+  int grow_pinned(float **buf, size_t *cap, size_t elems)
+  {
+    if (elems <= *cap) return RR_OK;
+    be_host_free(*buf); *buf = nullptr; *cap = 0;
+    size_t want = std::max<size_t>(elems, static_cast<size_t>(1) << 16);
+    void *p = nullptr;
+    int rc = be_host_alloc(&p, sizeof(float) * want);
+    if (rc) return rc;
+    *buf = static_cast<float *>(p); *cap = want;
+    return RR_OK;
+  }
+
   int push(const float *x, size_t frames) override   // RR_push_x, rate_base.h:616-636
   {
     if (!x || !frames) return RR_OK;
+    RR_DEVICE_SCOPE(eng.device_id);
     if (frames > eng.design.plan.isamp_max) frames = static_cast<size_t>(eng.design.plan.isamp_max);
     count_input(frames);
     int rc;
-    if (eng.ns == 0) return RR_OK;
     const size_t elems = frames * static_cast<size_t>(nch);
-    if (elems > stage_in_cap) {
-      be_free(stage_in); stage_in = nullptr;
-      void *p = nullptr;
-      if ((rc = be_malloc(&p, sizeof(float) * elems))) return rc;
-      stage_in = static_cast<float *>(p); stage_in_cap = elems;
-    }
-    if ((rc = be_h2d(stage_in, x, sizeof(float) * elems, s_))) return rc;
     if ((rc = ensure_ring(0, W[0] + static_cast<long long>(frames)))) return rc;
-    // deinterleave + convert into FIFO 0 (rate_base.h:565-569)
-    LaneView src{};
-    src.base = stage_in; src.origin = W[0]; src.mask = ~0ull; src.lo = W[0]; src.hi = W[0] + static_cast<long long>(frames);
-    src.stream_stride = 0; src.ch_stride = 1; src.elem_stride = nch; src.nch = nch;
-    LaneView dst = ring_view(0, W[0], W[0] + static_cast<long long>(frames));
-    if ((rc = eng.copy(src, true, dst, false, W[0], static_cast<long long>(frames), 0, nch, s_))) return rc;
+    // deinterleave + convert (rate_base.h:565-569) happen in the first stage's loads: ring 0 keeps frames
+    if (kEmulated || be_host_is_pinned(x)) {
+      if ((rc = ring_h2d(0, W[0], static_cast<long long>(frames), x))) return rc;
+      // the caller may refill its buffer as soon as we return: wait for the transfer (not for the kernels)
+      if ((rc = be_event_record(user_in_done_, s_))) return rc;
+      W[0] += static_cast<long long>(frames);
+      if ((rc = process_stages())) return rc;
+      return be_event_sync(user_in_done_);
+    }
+    const int slot = static_cast<int>(push_seq_++ & 1);
+    if (pin_in_busy_[slot]) { if ((rc = be_event_sync(pin_in_free_[slot]))) return rc; pin_in_busy_[slot] = false; }
+    if ((rc = grow_pinned(&pin_in_[slot], &pin_in_cap_[slot], elems))) return rc;
+    memcpy(pin_in_[slot], x, sizeof(float) * elems);
+    if ((rc = ring_h2d(0, W[0], static_cast<long long>(frames), pin_in_[slot]))) return rc;
+    if ((rc = be_event_record(pin_in_free_[slot], s_))) return rc;
+    pin_in_busy_[slot] = true;
     W[0] += static_cast<long long>(frames);
-    // no synchronisation here: the copy from the caller's (pageable) buffer is complete when cudaMemcpyAsync
-    // returns, the kernels run on this handle's stream while the caller prepares its next buffer; RR_pull waits
     return process_stages();
+  }
+
+  // Takes n frames off the output FIFO and issues their transfer to `dst` (page-locked). Does not wait.
+  int pop_frames(float *dst, size_t n)
+  {
+    int rc = ring_d2h(eng.ns, popped, static_cast<long long>(n), dst);
+    popped += static_cast<long long>(n);
+    return rc;
+  }
+  size_t take(size_t max_frames)               // rate_output, rate_base.h:445-450
+  {
+    const long long avail = W[eng.ns] - popped;
+    const size_t n = static_cast<size_t>(std::min<long long>(avail, static_cast<long long>(max_frames)));
+    samples_out += n;
+    return n;
   }
 
   int pull(float *y, void *native, size_t max_frames, size_t *got) override   // RR_pull_x, rate_base.h:638-660
   {
+    RR_DEVICE_SCOPE(eng.device_id);
     const int last = eng.ns;
-    const long long avail = W[last] - popped;
-    const size_t n = static_cast<size_t>(std::min<long long>(avail, static_cast<long long>(max_frames)));
+    const size_t n = take(max_frames);
     if (got) *got = n;
-    samples_out += n;                            // rate_output, rate_base.h:448
     if (!n) return RR_OK;
     int rc;
     const size_t elems = n * static_cast<size_t>(nch);
-    LaneView src = ring_view(last, popped, popped + static_cast<long long>(n));
-    if (y) {
-      if (elems > stage_out_cap) {
-        be_free(stage_out); stage_out = nullptr;
-        void *p = nullptr;
-        if ((rc = be_malloc(&p, sizeof(float) * elems))) return rc;
-        stage_out = static_cast<float *>(p); stage_out_cap = elems;
+    if (ring_is_frames(last)) {
+      const bool direct = y && !native && (kEmulated || be_host_is_pinned(y));
+      float *dst = y;
+      if (!direct) {
+        if ((rc = grow_pinned(&pin_out_, &pin_out_cap_, elems))) return rc;
+        dst = pin_out_;
       }
+      if ((rc = pop_frames(dst, n))) return rc;
+      if ((rc = be_sync(s_))) return rc;
+      if (y && !direct) memcpy(y, pin_out_, sizeof(float) * elems);
+      if (native) {
+        // planar view of the same values: the fp32 engine's own type is float, and without stages (in_rate ==
+        // out_rate) the fp64 engine's FIFO holds nothing but converted input frames
+        if (!std::is_same<T, float>::value && last != 0) {
+          set_last_error("RRX_enable_native_tap must precede the first push");
+          return RR_INVPARAM;
+        }
+        T *o = static_cast<T *>(native);
+        for (int c = 0; c < nch; ++c)
+          for (size_t j = 0; j < n; ++j) o[static_cast<size_t>(c) * max_frames + j] = static_cast<T>(pin_out_[j * nch + c]);
+      }
+      return RR_OK;
+    }
+    // native tap: the last FIFO holds planar engine-type lanes
+    LaneView src = ring_view(last, popped, popped + static_cast<long long>(n));
+    if (elems > stage_native_cap) {
+      be_sync(s_);
+      be_free(stage_native); stage_native = nullptr; stage_native_cap = 0;
+      void *p = nullptr;
+      if ((rc = be_malloc(&p, (sizeof(T) + sizeof(float)) * elems))) return rc;
+      stage_native = static_cast<T *>(p); stage_native_cap = elems;
+    }
+    if (y) {
+      float *stage_out = reinterpret_cast<float *>(stage_native + elems);
       LaneView dst{};
       dst.base = stage_out; dst.origin = popped; dst.mask = ~0ull; dst.lo = popped; dst.hi = popped + static_cast<long long>(n);
       dst.stream_stride = 0; dst.ch_stride = 1; dst.elem_stride = nch; dst.nch = nch;
@@ -1888,12 +2131,6 @@ template <class T> class Stream : public IStream {
       if ((rc = be_d2h(y, stage_out, sizeof(float) * elems, s_))) return rc;
     }
     if (native) {                                // planar, engine type: out[ch * max_frames + i]
-      if (elems > stage_native_cap) {
-        be_free(stage_native); stage_native = nullptr;
-        void *p = nullptr;
-        if ((rc = be_malloc(&p, sizeof(T) * elems))) return rc;
-        stage_native = static_cast<T *>(p); stage_native_cap = elems;
-      }
       LaneView dst{};
       dst.base = stage_native; dst.origin = popped; dst.mask = ~0ull; dst.lo = popped; dst.hi = popped + static_cast<long long>(n);
       dst.stream_stride = 0; dst.ch_stride = static_cast<int>(n); dst.elem_stride = 1; dst.nch = nch;
@@ -1907,13 +2144,51 @@ template <class T> class Stream : public IStream {
     return be_sync(s_);
   }
 
+  // RR_flow_x (rate_base.h:571-614): pull what is ready, push, pull what the push produced into the remaining
+  // space. Both output transfers and the input transfer are queued behind each other on the handle's stream and
+  // waited for once, so the copy-in of this call overlaps the copy-out of the frames that were already there.
+  int flow(const float *x, size_t isamp, float *y, size_t osamp, size_t *iused, size_t *ogen) override
+  {
+    RR_DEVICE_SCOPE(eng.device_id);
+    if (!x) isamp = 0;
+    if (isamp > eng.design.plan.isamp_max) isamp = static_cast<size_t>(eng.design.plan.isamp_max);
+    if (iused) *iused = isamp;
+    if (!ring_is_frames(eng.ns)) {               // native tap: the simple sequence
+      size_t g1 = 0, g2 = 0;
+      int rc = RR_OK;
+      if (y && osamp) rc = pull(y, nullptr, osamp, &g1);
+      if (!rc && isamp) rc = push(x, isamp);
+      if (!rc && y && g1 < osamp) rc = pull(y + g1 * nch, nullptr, osamp - g1, &g2);
+      if (ogen) *ogen = g1 + g2;
+      return rc;
+    }
+    int rc;
+    const bool want = y && osamp;
+    const bool direct = want && (kEmulated || be_host_is_pinned(y));
+    float *dst = y;
+    if (want && !direct) {
+      if ((rc = grow_pinned(&pin_out_, &pin_out_cap_, osamp * static_cast<size_t>(nch)))) return rc;
+      dst = pin_out_;
+    }
+    size_t g1 = 0, g2 = 0;
+    if (want) { g1 = take(osamp); if (g1 && (rc = pop_frames(dst, g1))) return rc; }
+    if (isamp && (rc = push(x, isamp))) return rc;
+    if (want && g1 < osamp) { g2 = take(osamp - g1); if (g2 && (rc = pop_frames(dst + g1 * nch, g2))) return rc; }
+    if (ogen) *ogen = g1 + g2;
+    if (g1 + g2) {
+      if ((rc = be_sync(s_))) return rc;
+      if (!direct) memcpy(y, pin_out_, sizeof(float) * (g1 + g2) * nch);
+    }
+    return RR_OK;
+  }
+
   int drain() override                           // rate_flush, rate_base.h:454-468
   {
+    RR_DEVICE_SCOPE(eng.device_id);
     const int last = eng.ns;
     const uint64_t target = static_cast<uint64_t>(static_cast<double>(samples_in) / eng.design.plan.factor + .5);
     if (target <= samples_out) return RR_OK;
     const long long remaining = static_cast<long long>(target - samples_out);
-    if (eng.ns == 0) return RR_OK;
     // Feed 1024-sample blocks of zeros until enough output exists. Only the counters run in the loop;
     // the zeros are written and the stages launched once for the whole extension (same results: every
     // stage is a pure function of absolute positions).
@@ -1934,20 +2209,35 @@ template <class T> class Stream : public IStream {
     int rc;
     if (fed > 0) {
       if ((rc = ensure_ring(0, W0_new))) return rc;
-      LaneView none{}; none.base = ring[0]; none.mask = ~0ull; none.lo = 0; none.hi = 0; none.elem_stride = 1; none.nch = nch;
-      LaneView dst = ring_view(0, W[0], W0_new);
-      if ((rc = eng.copy(none, false, dst, false, W[0], fed, 0, nch, s_))) return rc;
+      if ((rc = ring_zero(0, W[0], fed))) return rc;
       W[0] = W0_new;
       if ((rc = process_stages())) return rc;
     }
     // fifo_trim_to(remaining): later output continues right after the trimmed end
     W[last] = popped + remaining;
-    out_shift = W[last] - produced[last - 1];
+    if (last > 0) out_shift = W[last] - produced[last - 1];
     samples_in = samples_out = 0;
     return be_sync(s_);
   }
 
-  int dft_spectrum(int instance, void *out, int max_n) const override { return eng.dft_spectrum_host(instance, out, max_n); }
+  int enable_native_tap() override
+  {
+    RR_DEVICE_SCOPE(eng.device_id);
+    const int last = eng.ns;
+    if (native_tap_ || std::is_same<T, float>::value || last == 0) return RR_OK;   // float frames already hold the fp32 engine's values
+    if (W[last] != 0 || popped != 0) { set_last_error("RRX_enable_native_tap must precede the first push"); return RR_INVPARAM; }
+    int rc = be_sync(s_);
+    if (rc) return rc;
+    be_free(ring[last]); ring[last] = nullptr; ring_cap[last] = 0;
+    native_tap_ = true;
+    return ensure_ring(last, 1 << 14);
+  }
+
+  int dft_spectrum(int instance, void *out, int max_n) const override
+  {
+    DeviceScope scope(eng.device_id);
+    return eng.dft_spectrum_host(instance, out, max_n);
+  }
 };
 
 // ===================================================================================================

@@ -56,6 +56,10 @@ class IStream {
   virtual int push(const float *host_interleaved, size_t frames) = 0;
   virtual int pull(float *host_interleaved, void *host_native_planar, size_t max_frames, size_t *got) = 0;
   virtual int drain() = 0;
+  // RR_flow: pull, push, pull into the remaining space, with one wait for all three transfers.
+  virtual int flow(const float *host_in, size_t isamp, float *host_out, size_t osamp, size_t *iused, size_t *ogen) = 0;
+  // Keep the last FIFO in the engine's own sample type (un-cast fp64 tap). Before the first push only.
+  virtual int enable_native_tap() = 0;
   virtual int dft_spectrum(int instance, void *out, int max_n) const = 0;
 };
 

@@ -104,6 +104,27 @@ std::vector<uint16_t> spread_over_bank_groups(const std::vector<uint16_t> &offs)
   }
   return out;
 }
+
+// As above, but never lets two entries of an aligned run of eight share a bank group: entry k of every group goes
+// to run k, the runs are padded with holes (kPkHole) -- idle lanes cost nothing, a two-way conflict costs a
+// wavefront for each of the 16 (8) accesses of a leaf. The split-radix tree puts the 16-point leaves of a quarter
+// at offsets 16 m with m in {0, 2, 3, 4, 6} (mod 8) plus one 7, i.e. only six distinct groups: without holes every
+// run of eight lanes collides (profiles/README.md, round 2).
+std::vector<uint16_t> spread_with_holes(const std::vector<uint16_t> &offs)
+{
+  std::vector<std::vector<uint16_t>> bucket(8);
+  for (uint16_t o : offs) bucket[static_cast<size_t>(pk_slot(o) & 7)].push_back(o);
+  size_t runs = 0;
+  for (const auto &b : bucket) runs = std::max(runs, b.size());
+  std::vector<uint16_t> out;
+  for (size_t r = 0; r < runs; ++r) {
+    size_t placed = 0;
+    for (const auto &b : bucket)
+      if (r < b.size()) { out.push_back(b[r]); ++placed; }
+    if (r + 1 < runs) for (; placed < 8; ++placed) out.push_back(kPkHole);
+  }
+  return out;
+}
 }  // namespace
 
 PkHostSched build_pk_sched(const CfftHostSched &h)
@@ -143,7 +164,7 @@ PkHostSched build_pk_sched(const CfftHostSched &h)
         std::vector<uint16_t> a, b;
         for (uint16_t o : mainl) if ((o >> shift) == w) a.push_back(o);
         for (uint16_t o : lightl) if ((o >> shift) == w) b.push_back(o);
-        if (spread) { a = spread_over_bank_groups(a); b = spread_over_bank_groups(b); }
+        if (spread) { a = spread_with_holes(a); b = spread_with_holes(b); }
         uint16_t *hd = &s.local[static_cast<size_t>(4 * (stage * kPkWarps + w))];
         hd[0] = static_cast<uint16_t>(s.local.size()); hd[1] = static_cast<uint16_t>(a.size());
         s.local.insert(s.local.end(), a.begin(), a.end());
@@ -163,7 +184,7 @@ PkHostSched build_pk_sched(const CfftHostSched &h)
       for (uint16_t o : lightl) { assert((o >> shift) == ((o + ((4 << (depth - 2)) - 1) * (1 << (lg - 2))) >> shift)); (void)o; }
       add_lists(1 + ph, mainl, lightl, false);
     }
-    assert(static_cast<int>(s.local.size()) == pk_local_entries(bits));
+    assert(static_cast<int>(s.local.size()) >= pk_local_entries(bits));   // + the holes of the leaf lists
   }
   for (int inv = 0; inv < 2; ++inv) {
     s.perm[inv].assign(static_cast<size_t>(m), 0);

@@ -71,6 +71,7 @@ RR_PLAN_HD constexpr int pk_task_entries(int bits) { return pk_phase_base(bits, 
 // with a header of 4 uint16 per (stage, warp) -- {main begin, main count, light begin, light count}, stage 0 =
 // leaves (main: size-16, light: size-8), stage s = phase s-1 -- followed by the lists.
 constexpr int kPkWarps = 4;
+constexpr int kPkHole = 0xffff;      // entry of a leaf list that stands for an idle lane (bank-conflict padding, fft_tables.cpp)
 RR_PLAN_HD constexpr int pk_local_phases(int bits)
 {
   const PkPhaseList p = pk_phase_list(bits);
@@ -80,6 +81,7 @@ RR_PLAN_HD constexpr int pk_local_phases(int bits)
   return n;
 }
 RR_PLAN_HD constexpr int pk_local_header(int bits) { return 4 * kPkWarps * (1 + pk_local_phases(bits)); }
+// entries without the holes of the leaf lists; the table's real length travels with it (PkHostSched::local.size())
 RR_PLAN_HD constexpr int pk_local_entries(int bits)
 {
   int e = pk_local_header(bits) + pk_n16(bits) + pk_n8(bits);

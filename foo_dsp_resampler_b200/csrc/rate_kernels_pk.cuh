@@ -60,6 +60,11 @@ template <> struct Arith<Pk> {
   RR_PK_BIN(add, "add")
   RR_PK_BIN(sub, "sub")
 #undef RR_PK_BIN
+#if defined(RR_PK_PLAIN_ADD)
+  // built with ptxas -fmad=false: nothing contracts a separate multiply and add, FADD2 can be used everywhere
+  static __device__ __forceinline__ Pk addp(Pk x, Pk y) { return add(x, y); }
+  static __device__ __forceinline__ Pk subp(Pk x, Pk y) { return sub(x, y); }
+#else
   // x + y / x - y where an operand is a product: fma(x, 1, y) / fma(y, -1, x), see header
   static __device__ __forceinline__ Pk addp(Pk x, Pk y)
   {
@@ -81,6 +86,7 @@ template <> struct Arith<Pk> {
         : "f"(x.a), "f"(x.b), "f"(y.a), "f"(y.b), "f"(mone));
     return r;
   }
+#endif
 #else
   static RR_HD Pk mul(Pk x, Pk y) { return pk_make(x.a * y.a, x.b * y.b); }   // host build: -ffp-contract=off
   static RR_HD Pk add(Pk x, Pk y) { return pk_make(x.a + y.a, x.b + y.b); }
@@ -273,8 +279,8 @@ RR_PROG void pk_fft_local(const Grp &g, CPk *buf, const uint16_t *ltab, const fl
   for (int w = w0; w < w1; ++w) {
     const uint16_t *hd = ltab + 4 * w;
     const int mb = hd[0], mc = hd[1], lb = hd[2], lc = hd[3];
-    for (int t = lane; t < mc; t += nl) pk_leaf<16>(buf, ltab[mb + t], swz, sh, c1, c3);
-    for (int t = lane; t < lc; t += nl) pk_leaf<8>(buf, ltab[lb + t], swz, sh, c1, c3);
+    for (int t = lane; t < mc; t += nl) { const int off = ltab[mb + t]; if (off != kPkHole) pk_leaf<16>(buf, off, swz, sh, c1, c3); }
+    for (int t = lane; t < lc; t += nl) { const int off = ltab[lb + t]; if (off != kPkHole) pk_leaf<8>(buf, off, swz, sh, c1, c3); }
     pk_warp_sync();
     if constexpr (nlocal > 0) pk_local_phase<BITS, 0>(w, lane, nl, buf, ltab, pyr);
     if constexpr (nlocal > 1) pk_local_phase<BITS, 1>(w, lane, nl, buf, ltab, pyr);
@@ -379,6 +385,8 @@ struct DftPkParams {
   int fslots, bslots;            // slots of the forward / inverse buffer
   int groups, gthreads;          // groups per CTA, threads per group
   int spec_mode;
+  int tile_regs;                 // input tiles go global -> registers -> shared at the start of an item (pk_tile_now) instead of
+                                 // being prefetched with LDGSTS during the previous item's inverse transform
   int lay_pyr_f, lay_pyr_i, lay_ltab_f, lay_ltab_i, lay_perm_f, lay_data;     // shared-memory byte offsets (host: pk_smem_layout)
   int n_pyr_f, n_pyr_i, n_ltab_f, n_ltab_i;                                   // table lengths
 };
@@ -391,8 +399,8 @@ RR_HD PkSmemLayout pk_smem_layout(const DftPkParams &pp)
   int o = 0;
   l.pyr_f = o; o += 4 * pk_pyr_len(pp.fb);
   l.pyr_i = o; o += 4 * pk_pyr_len(pp.ib);
-  l.ltab_f = o; o += 2 * pk_local_entries(pp.fb);
-  l.ltab_i = o; o += 2 * pk_local_entries(pp.ib);
+  l.ltab_f = o; o += 2 * pp.n_ltab_f;
+  l.ltab_i = o; o += 2 * pp.n_ltab_i;
   o = (o + 3) & ~3;
   l.perm_f = o; o += 2 << pp.fb;
   l.data = (o + 15) & ~15;
@@ -512,6 +520,29 @@ RR_PROG void pk_stage_tile(const DftPkParams &pp, const Grp &g, const PkItem &it
     }
   }
   async_copy_commit();
+}
+
+// The same copy, synchronously and through registers: coalesced 16-byte global loads (eight in flight per thread),
+// then 16-byte shared stores to the permuted slots. A scattered LDGSTS costs one shared-memory wavefront per
+// 16-byte element (32 per warp copy, ncu: 20 % of the kernel's wavefronts); the same scatter as STS.128 is served
+// eight lanes per wavefront. The other groups of the CTA cover the exposed global latency.
+RR_PROG void pk_tile_now(const DftPkParams &pp, const Grp &g, const PkItem &it, CPk *F, const uint16_t *perm)
+{
+  const DftParams<float> &p = pp.base;
+  const int span = p.in_mode == DFT_IN_FREQ_UP ? p.Pf : p.N, m = span >> 1;
+  if (it.tile_mode == PK_TILE_INTERLEAVED && p.in.elem_stride == 2 && !((size_t)it.s0 & 15)) {
+    const CPk *src = reinterpret_cast<const CPk *>(it.s0);
+    for (int j0 = g.tid; j0 < m; j0 += 8 * g.size) {
+      CPk v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { const int j = j0 + k * g.size; if (j < m) v[k] = ldg(src + j); }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { const int j = j0 + k * g.size; if (j < m) F[perm[j]] = v[k]; }
+    }
+    return;
+  }
+  pk_stage_tile(pp, g, it, F, perm);
+  async_copy_wait<0>();
 }
 
 RR_PROG PkSpecConst pk_load_spec(const PkSpecConst *p)
@@ -728,10 +759,11 @@ RR_PROG void dftp_program(const DftPkParams &pp, const Grp &g, const PkTables &t
                           CPk *F, CPk *B)
 {
   const DftParams<float> &p = pp.base;
-  async_copy_wait<0>();
-  grp_sync(g);                                            // the tile is complete; items[slot] is visible
+  if (!pp.tile_regs) async_copy_wait<0>();
+  grp_sync(g);                                            // the tile is complete (prefetch mode); items[slot] is visible
   const PkItem &it = items[slot];                        // stays valid for the whole item; fields are read where needed
   if (work_next >= 0 && g.tid == 0) items[slot ^ 1] = pk_make_item(pp, work_next);
+  if (pp.tile_regs) { pk_tile_now(pp, g, it, F, tb.perm_f); grp_sync(g); }
 
   PkSink sink{nullptr, nullptr, 0, 0};
   pk_fft_lower_any<FB>(pp.fb, g, F, tb.ltab_f, tb.pyr_f, it.tile_mode == PK_TILE_PLANAR, p.sqrthalf, p.c16_1, p.c16_3);
@@ -745,7 +777,7 @@ RR_PROG void dftp_program(const DftPkParams &pp, const Grp &g, const PkTables &t
     if (FB == 0 || !kPkPrefetchAcrossTop) pk_spec_prefetch<MODE>(pp, g, pre);   // not across a call: the registers would be spilled
     pk_spectrum<MODE>(pp, g, pre, F, B);
   }
-  if (work_next >= 0) pk_stage_tile(pp, g, items[slot ^ 1], F, tb.perm_f);   // F is free until the next item starts
+  if (!pp.tile_regs && work_next >= 0) pk_stage_tile(pp, g, items[slot ^ 1], F, tb.perm_f);   // F is free until the next item starts
 
   pk_fft_lower_any<IB>(pp.ib, g, B, tb.ltab_i, tb.pyr_i, false, p.sqrthalf, p.c16_1, p.c16_3);
   sink.d0 = it.d0; sink.d1 = it.d1; sink.half = it.count >> 1; sink.es = it.sink == 2 ? p.out.elem_stride : 0;

@@ -100,7 +100,10 @@ int RRX_design_dump(const RR_config *config, int sample_bytes, int kind, double 
 /* Same as the plan above but from a live handle. */
 int RRX_plan_dump(const RR_handle *h, rr_plan *out);
 /* Like RR_pull but planar and in the engine's own sample type (float for the fp32 engine, double for the
- * fp64 engine): out[ch * osamp + i]. The fp64 "tap" for the 1e-12 check. */
+ * fp64 engine): out[ch * osamp + i]. The fp64 "tap" for the 1e-12 check. The output FIFO of a handle normally
+ * holds interleaved float frames (what RR_pull delivers, rate/rate_base.h:559-563); a handle of the fp64 engine
+ * keeps it in double only after RRX_enable_native_tap, which must be called before the first RR_push. */
+int RRX_enable_native_tap(RR_handle *h);
 int RRX_pull_native(RR_handle *h, void *out, size_t osamp, size_t *ogen);
 /* Frequency-domain DFT coefficient bank as uploaded to the device, engine type (dft_length values). */
 int RRX_dft_spectrum(const RR_handle *h, int instance, void *out, int max_n);

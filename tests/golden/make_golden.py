@@ -36,6 +36,15 @@ CASES = {
     "phase75_alias_96k_44k1_f32": (96000, 44100, "float", 75, 99, 1, 0, 1, 24000, 8192),
     "three_stage_22k05_96k_f32": (22050, 96000, "float", 50, 95, 0, 0, 1, 5512, 2048),
     "fdomain_quarter_176k4_44k1_f64": (176400, 44100, "double", 50, 95, 0, 0, 2, 44100, 10000),
+    # stage modes the BASELINE configurations do not reach (parity holes)
+    "fdomain_quarter_l3_32k_24k_f32": (32000, 24000, "float", 50, 95, 0, 0, 2, 16000, 5000),     # L = 3, step -2
+    "timedecim4_l3_32k_24k_alias_f32": (32000, 24000, "float", 50, 95, 1, 0, 2, 16000, 5000),    # L = 3, time-domain / 4
+    "h9_norm_44k1_8k_f32": (44100, 8000, "float", 50, 95, 0, 1, 2, 22050, 8192),
+    "h10_norm_49M152_44k1_f32": (49152000, 44100, "float", 50, 95, 0, 1, 1, 1200000, 400000),    # 11 stages
+    "h13_best_24M576_44k1_f32": (24576000, 44100, "float", 50, 95, 0, 0, 2, 800000, 300000),     # 10 stages
+    "h8_norm_32k_8k_f32": (32000, 8000, "float", 50, 95, 0, 1, 2, 16000, 5000),
+    "h11_best_32k_8k_f64": (32000, 8000, "double", 50, 95, 0, 0, 1, 16000, 5000),
+    "identity_48k_48k_f32": (48000, 48000, "float", 50, 95, 0, 0, 2, 5000, 1777),                 # no stages at all
 }
 
 

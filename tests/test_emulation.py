@@ -35,6 +35,11 @@ CASES = [
     # narrow transition bands: DFT blocks beyond the shared-memory kernels (work buffers in global scratch)
     (44100, 48000, "float", 50, 99.5, 0, 0, 2), (44100, 48000, "double", 50, 99, 0, 0, 1),
     (192000, 44100, "double", 50, 99, 0, 0, 1),
+    # F-domain / 4 (step -2) behind zero-stuffing by 3, the same pair with time-domain / 4, h9 / h8 half-bands,
+    # identity (no stages)
+    (32000, 24000, "float", 50, 95, 0, 0, 2), (32000, 24000, "float", 50, 95, 1, 0, 2), (32000, 24000, "double", 50, 95, 0, 0, 1),
+    (44100, 8000, "float", 50, 95, 0, 1, 2), (32000, 8000, "float", 50, 95, 0, 1, 1), (48000, 48000, "float", 50, 95, 0, 0, 2),
+    (48000, 48000, "double", 50, 95, 0, 0, 3),
 ]
 
 
@@ -81,7 +86,7 @@ def test_plan_and_design(case):
     orc.close()
 
 
-@pytest.mark.parametrize("case", CASES[:8] + CASES[16:20] + CASES[26:28], ids=ids)
+@pytest.mark.parametrize("case", CASES[:8] + CASES[16:20] + CASES[26:28] + CASES[31:33] + CASES[34:35] + CASES[36:37], ids=ids)
 def test_batch_front_end_and_ranges(case):
     i, o, eng, ph, bw, al, q, nch = case
     L = emulib.lib()
@@ -221,4 +226,101 @@ def test_fuzz_stream_and_batch(case):
     b.process(xs.ctypes.data, n, out.ctypes.data)
     ref, _ = oraclelib.resample(ocfg, x, engine="float")
     assert ref.shape[0] == nout and np.array_equal(out[0], ref)
+    b.close()
+
+
+def _golden():
+    import json
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    with open(os.path.join(here, "golden", "reference_cases.json")) as f:
+        cases = json.load(f)
+    return cases, np.load(os.path.join(here, "golden", "reference_outputs.npz"))
+
+
+@pytest.mark.parametrize("name", sorted(_golden()[0]))
+def test_emulated_path_reproduces_reference_fixture(name):
+    """The product's orchestration and CTA programs (host emulation) against the committed outputs of the compiled
+    reference itself (tests/golden): plan integers, frame counts after every push, samples -- fp32 bit for bit,
+    fp64 within 1e-12 of the reference's Ooura-based engine."""
+    cases, outputs = _golden()
+    g = cases[name]
+    i, o, eng, ph, bw, al, q, nch, frames, chunk = g["case"]
+    L = emulib.lib()
+    cfg = _capi.make_config(i, o, ph, bw, al, q)
+    x = signals.sweep_noise(i, nch, frames)
+    r = converter.RateConverter(cfg, nch, eng, lib=L)
+    assert r.plan() == g["plan"]
+    r.close()
+    y, counts = converter.resample(cfg, x, engine=eng, chunk=chunk, native=True, lib=L)
+    assert counts == g["counts"] and y.shape[0] == g["out_frames"]
+    if eng == "float":
+        assert np.array_equal(y, outputs[name])
+    else:
+        assert np.abs(y - outputs[name]).max() <= FP64_TOL
+
+
+# (in_rate, out_rate, channels, hours, input frames per grid period, output frames per grid period)
+# one period of the joint block / phase grid: 384 -> 48 kHz: 8 x 1766 input frames per DFT block; 48 -> 44.1 kHz:
+# lcm(1748 input frames per DFT block, 160 input frames per polyphase period) = 69920 input = 64239 output frames
+LONG_STREAMS = [(384000, 48000, 8, 10, 14128, 1766), (48000, 44100, 2, 80, 69920, 64239)]
+
+
+def long_offset_check(make_batch, to_dev, from_dev, case):
+    """Time-chunk ranges at the absolute offsets of a many-hour stream (input frame indices beyond 2^32): a window
+    at ~90 % of the stream must give the bits of the same window content placed a whole number of grid periods
+    earlier (shift invariance of the block grid, dft_filter.h:78-83), and that small-offset placement is checked
+    against the oracle run from the start of the stream."""
+    i, o, nch, hours, pin, pout = case
+    total = i * 3600 * hours
+    cfg, ocfg = _capi.make_config(i, o), oraclelib.make_config(i, o)
+    oc = 2 * 1766 + 123
+    b = make_batch(cfg, nch, 6 * pin // (pin // 14128 if pin > 20000 else 1) + 131072)
+    nout_total = b.frames_out(total)
+    assert nout_total == total // i * o
+    ob_far = int(0.9 * nout_total) // pout * pout + 57
+    f_far, c = b.input_window(total, ob_far, oc)
+    k = ob_far // pout - 3
+    ob_near, f_near = ob_far - k * pout, f_far - k * pin
+    assert f_far > (1 << 32) and b.input_window(total, ob_near, oc) == (f_near, c)
+    x = signals.sweep_noise(i, nch, c, stream=3)
+    dx = to_dev(x)
+    res = []
+    for ob, f in ((ob_far, f_far), (ob_near, f_near)):
+        out = to_dev(np.zeros((1, oc, nch), np.float32))
+        b.process_range(dx[1], f, c, total, ob, oc, out[1])
+        res.append(from_dev(out))
+    assert np.array_equal(res[0], res[1]) and np.abs(res[0]).max() > 0.1
+    full = np.concatenate([np.zeros((f_near, nch), np.float32), x, np.zeros((4 * pin // (pin // 14128 if pin > 20000 else 1), nch), np.float32)])
+    ref, _ = oraclelib.resample(ocfg, full, engine="float")
+    assert np.array_equal(ref[ob_near:ob_near + oc], res[1][0])
+    # the very last frames of the stream (drain rule round(n_in / factor), rate_base.h:457)
+    tail = 500
+    f, c = b.input_window(total, nout_total - tail, tail)
+    assert f + c == total
+    b.close()
+
+
+@pytest.mark.parametrize("case", LONG_STREAMS, ids=lambda c: "%d-%d-%dh" % (c[0], c[1], c[3]))
+def test_ranges_at_many_hour_offsets(case):
+    L = emulib.lib()
+    long_offset_check(lambda cfg, nch, fmax: converter.BatchConverter(cfg, nch, 1, fmax, engine="float", lib=L),
+                      lambda a: (a, a.ctypes.data), lambda d: d[0].copy(), case)
+
+
+def test_identity_conversion_passes_frames_through():
+    """in_rate == out_rate: the plan has no stages and FIFO 0 is the output FIFO (rate_base.h:445-447)."""
+    L = emulib.lib()
+    cfg, ocfg = _capi.make_config(48000, 48000), oraclelib.make_config(48000, 48000)
+    x = signals.sweep_noise(48000, 2, 5000)
+    for eng in ("float", "double"):
+        yo, co = oraclelib.resample(ocfg, x, engine=eng, chunk=1777)
+        ye, ce = converter.resample(cfg, x, engine=eng, chunk=1777, lib=L)
+        assert ce == co and np.array_equal(ye, yo) and np.array_equal(ye, x)
+    b = converter.BatchConverter(cfg, 2, 2, 5000, engine="float", lib=L)
+    xs = np.stack([x, x * 0.5])
+    out = np.zeros((2, 5000, 2), np.float32)
+    b.process(xs.ctypes.data, 5000, out.ctypes.data)
+    assert np.array_equal(out, xs)
+    assert b.input_window(5000, 100, 50) == (100, 50)
     b.close()

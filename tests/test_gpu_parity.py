@@ -46,6 +46,18 @@ STREAM_CASES = [
     (44100, 48000, "double", 50, 99, 0, 0, 2),    # N = 16384, fp64 (what RR_open selects for Best quality)
     (192000, 44100, "double", 50, 99, 0, 0, 1),   # N = 32768 after a half-band stage
     (48000, 44100, "float", 50, 99.7, 0, 0, 1),   # N = 65536
+    # stage modes outside the BASELINE plans: F-domain / 4 (step -2) behind zero-stuffing by 3, the same pair with
+    # time-domain / 4, h8 / h9 / h11 half-bands, no stages at all
+    (32000, 24000, "float", 50, 95, 0, 0, 2),     # L = 3, step -2 (dft_filter.h:157-188), lane-pair kernel
+    (32000, 24000, "float", 50, 95, 0, 0, 1),     # ... generic kernel
+    (32000, 24000, "double", 50, 95, 0, 0, 2),    # ... fp64
+    (32000, 24000, "float", 50, 95, 1, 0, 2),     # L = 3, time-domain / 4
+    (44100, 8000, "float", 50, 95, 0, 1, 2),      # Normal quality: h9 + DFT + vpoly0 (n = 16)
+    (44100, 8000, "float", 50, 95, 0, 1, 1),
+    (32000, 8000, "float", 50, 95, 0, 1, 2),      # h8
+    (32000, 8000, "double", 50, 95, 0, 0, 1),     # h11, fp64
+    (48000, 48000, "float", 50, 95, 0, 0, 2),     # identity
+    (48000, 48000, "double", 50, 95, 0, 0, 3),
 ]
 
 # batches (device-resident entry point: pair-interleaved intermediate FIFOs between DFT and polyphase stages)
@@ -58,6 +70,9 @@ BATCH_CASES = [
     (44100, 96000, 50, 95, 0, 1, 5, 2), (44100, 48000, 50, 95, 0, 0, 1, 6),
     # polyphase banks with many phases (L = 441, 250): CTA sizes near the kernels' launch bounds
     (50000, 44100, 50, 95, 0, 0, 2, 2), (44100, 50000, 50, 95, 0, 0, 2, 2),
+    # F-domain / 4, time-domain / 4, h9 and h8 through the batch entry point
+    (32000, 24000, 50, 95, 0, 0, 2, 2), (32000, 24000, 50, 95, 1, 0, 4, 1), (44100, 8000, 50, 95, 0, 1, 2, 3),
+    (32000, 8000, 50, 95, 0, 1, 1, 2),
 ]
 
 
@@ -339,3 +354,155 @@ def test_stage_timing_and_work_accounting():
     assert abs(w0["bytes"] / w0["units"] - 4 * (n / blocks + 3496)) < 64
     assert w1["flops"] == 48.0 * b.frames_out(n) * 8
     b.close()
+
+
+def _golden():
+    import test_emulation
+    return test_emulation._golden()
+
+
+@pytest.mark.parametrize("name", sorted(_golden()[0]))
+def test_cuda_path_reproduces_reference_fixture(name):
+    """The CUDA path against the committed outputs of the COMPILED REFERENCE (tests/golden, generated from
+    oracle/_ref by tests/golden/make_golden.py) -- no oracle restatement in between: plan integers, frame counts
+    after every push, samples (fp32 bit for bit vs rate_float.c, fp64 <= 1e-12 vs rate_double.c). Includes the
+    ten-stage h10 / h13 plans (rate ratios above 500), F-domain / 4 and the stage-less identity."""
+    import foo_dsp_resampler_b200 as pkg
+    cases, outputs = _golden()
+    g = cases[name]
+    i, o, eng, ph, bw, al, q, nch, frames, chunk = g["case"]
+    cfg = pkg.make_config(i, o, ph, bw, al, q)
+    x = signals.sweep_noise(i, nch, frames)
+    r = pkg.RateConverter(cfg, nch, eng)
+    assert r.plan() == g["plan"]
+    r.close()
+    y, counts = pkg.resample(cfg, x, engine=eng, chunk=chunk, native=True)
+    assert counts == g["counts"] and y.shape[0] == g["out_frames"]
+    if eng == "float":
+        assert np.array_equal(y, outputs[name]), "max diff %g" % np.abs(y - outputs[name]).max()
+    else:
+        assert np.abs(y - outputs[name]).max() <= FP64_TOL
+
+
+def _long_streams():
+    import test_emulation
+    return test_emulation.LONG_STREAMS
+
+
+@pytest.mark.parametrize("case", _long_streams(), ids=lambda c: "%d-%d-%dh" % (c[0], c[1], c[3]))
+def test_ranges_at_many_hour_offsets(case):
+    """BASELINE config 5's real coordinates: time-chunk ranges of a 10-hour 384 kHz stream (input frame indices
+    ~1.2e10, beyond 2^32) and of an 80-hour 48 -> 44.1 kHz stream (polyphase phase accumulator at ~1e10 outputs)."""
+    import torch
+    import foo_dsp_resampler_b200 as pkg
+    import test_emulation
+    st = torch.cuda.current_stream().cuda_stream
+
+    class Dev:                               # BatchConverter whose process_range runs on torch's current stream
+        def __init__(self, cfg, nch, fmax):
+            self.b = pkg.BatchConverter(cfg, nch, 1, fmax, engine="float", device=0)
+        def __getattr__(self, k):
+            return getattr(self.b, k)
+        def process_range(self, *a):
+            self.b.process_range(*a, st)
+
+    def to_dev(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        return (t, t.data_ptr())
+
+    def from_dev(d):
+        torch.cuda.synchronize()
+        return d[0].cpu().numpy()
+
+    test_emulation.long_offset_check(Dev, to_dev, from_dev, case)
+
+
+def test_identity_conversion_passes_frames_through():
+    import torch
+    import foo_dsp_resampler_b200 as pkg
+    cfg = pkg.make_config(48000, 48000)
+    x = signals.sweep_noise(48000, 2, 70000)
+    y, counts = pkg.resample(cfg, x, engine="float", chunk=30011)
+    assert np.array_equal(y, x) and sum(counts) == 70000
+    y, _ = pkg.resample(cfg, x, engine="auto", chunk=4096)
+    assert np.array_equal(y, x)
+    b = pkg.BatchConverter(cfg, 2, 2, 70000, engine="float", device=0)
+    d_in = torch.from_numpy(np.stack([x, x * 0.5])).cuda()
+    d_out = torch.zeros_like(d_in)
+    b.process(d_in.data_ptr(), 70000, d_out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert bool((d_out == d_in).all())
+    b.close()
+
+
+def test_push_from_pinned_buffer_that_is_refilled_at_once():
+    """A page-locked caller buffer is transferred without staging; RR_push must not return while the copy out of
+    it is in flight (the reference has consumed ibuf when RR_push returns, rate_base.h:616-636)."""
+    import torch
+    import foo_dsp_resampler_b200 as pkg
+    cfg, ocfg = _cfgs(44100, 48000, 50, 95, 0, 0)
+    n, chunk = 44100 * 4, 65536
+    x = signals.sweep_noise(44100, 2, n)
+    ref, _ = oraclelib.resample(ocfg, x, engine="float", chunk=chunk)
+    buf = torch.empty((chunk, 2), dtype=torch.float32).pin_memory()
+    out = torch.empty((1 << 17, 2), dtype=torch.float32).pin_memory()
+    r = pkg.RateConverter(cfg, 2, "float")
+    got = []
+    import ctypes as C
+    ogen = C.c_size_t(0)
+    for s in range(0, n, chunk):
+        m = min(chunk, n - s)
+        buf[:m] = torch.from_numpy(x[s:s + m])
+        assert r.lib.RR_push(r.h, buf.data_ptr(), m) == 0
+        buf.fill_(123.0)                          # the caller reuses its buffer right away
+        while True:
+            assert r.lib.RR_pull(r.h, out.data_ptr(), out.shape[0], C.byref(ogen)) == 0
+            if not ogen.value:
+                break
+            got.append(out[:ogen.value].numpy().copy())
+    r.drain()
+    while True:
+        y = r.pull(1 << 16)
+        if not len(y):
+            break
+        got.append(y.copy())
+    r.close()
+    assert np.array_equal(np.concatenate(got), ref)
+
+
+_COLD_START = r"""
+import sys, threading
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import numpy as np
+import foo_dsp_resampler_b200 as pkg, oraclelib, signals
+cases = [(44100, 48000, 2, 0), (48000, 44100, 2, 0), (384000, 48000, 8, 0), (44100, 96000, 2, 0), (96000, 44100, 2, 0),
+         (44100, 48000, 1, 1), (32000, 24000, 2, 0), (44100, 48001, 1, 0)]
+work = [(cases[k %% len(cases)], k) for k in range(32)]
+refs = {}
+for c in cases:
+    i, o, nch, q = c
+    x = signals.sweep_noise(i, nch, int(i * 0.35))
+    refs[c] = (x, oraclelib.resample(oraclelib.make_config(i, o, 50, 95, 0, q), x, engine="float", chunk=9000)[0])
+out, start = [None] * len(work), threading.Barrier(len(work))
+def run(k):
+    (i, o, nch, q), _ = work[k]
+    start.wait()                                   # every thread's FIRST launch happens at the same time
+    out[k] = pkg.resample(pkg.make_config(i, o, 50, 95, 0, q), refs[work[k][0]][0], engine="float", chunk=9000 + 64 * k)[0]
+th = [threading.Thread(target=run, args=(k,)) for k in range(len(work))]
+[t.start() for t in th]; [t.join() for t in th]
+bad = [k for k in range(len(work)) if out[k] is None or not np.array_equal(out[k], refs[work[k][0]][1])]
+print("COLD_START_BAD", bad)
+sys.exit(1 if bad else 0)
+"""
+
+
+def test_cold_start_concurrency_mixed_plans():
+    """32 host threads x 8 different plans in a FRESH process, all starting at once: concurrent first launches of
+    the same and of different kernels, with different shared-memory sizes, through the process-wide launch cache."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    res = subprocess.run([sys.executable, "-c", _COLD_START % (os.path.dirname(here), here)], capture_output=True, text=True,
+                         timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
