@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(2 * kDftThreads) dft_big_kernel(const __grid_c
 // a persistent worker with its own forward and inverse buffer behind the shared tables (twiddle pyramids,
 // task tables, forward permutation).
 // FB / IB > 0: specialised on the transform sizes (everything inlined and static); 0: any size.
-template <int MODE, int FB, int IB>
+template <int MODE, int FB, int IB, bool STEREO>
 __global__ void __launch_bounds__(kPkGroupThreads * kPkMaxGroups) dftp_kernel(const __grid_constant__ DftPkParams pp, long long nwork)
 {
   struct { int pyr_f, pyr_i, ltab_f, ltab_i, perm_f, data, group_slots; } lay{pp.lay_pyr_f, pp.lay_pyr_i, pp.lay_ltab_f, pp.lay_ltab_i,
@@ -284,11 +284,10 @@ __global__ void __launch_bounds__(kPkGroupThreads * kPkMaxGroups) dftp_kernel(co
   const int stride = (int)gridDim.x * pp.groups, nw = (int)nwork;
   if (w < nw) {
     if (g.tid == 0) items[gi][0] = pk_make_item(pp, w);
-    if (!pp.tile_regs) { grp_sync(g); pk_stage_tile(pp, g, items[gi][0], F, tb.perm_f); }
   }
   for (int n = 0; w < nw; w += stride, n ^= 1) {
     const int next = w + stride < nw ? w + stride : -1;
-    dftp_program<MODE, FB, IB>(pp, g, tb, items[gi], n, next, F, B);
+    dftp_program<MODE, FB, IB, STEREO>(pp, g, tb, items[gi], n, next, F, B);
   }
 }
 template <class T, class InT, class OutT>
@@ -577,10 +576,12 @@ static int launch_dftp(const DftPkParams &pp, long long nwork, stream_t s)
   for (long long w = 0; w < nwork; ++w) {
     PkItem items[2];
     items[0] = pk_make_item(pp, w);
-    if (!pp.tile_regs) pk_stage_tile(pp, g, items[0], F, tb.perm_f);
-    if (pp.spec_mode == PK_SPEC_UP2) dftp_program<PK_SPEC_UP2, 0, 0>(pp, g, tb, items, 0, -1, F, B);
-    else if (pp.spec_mode == PK_SPEC_SAME) dftp_program<PK_SPEC_SAME, 0, 0>(pp, g, tb, items, 0, -1, F, B);
-    else dftp_program<PK_SPEC_GEN, 0, 0>(pp, g, tb, items, 0, -1, F, B);
+    if (pp.spec_mode == PK_SPEC_UP2 && pp.stereo) dftp_program<PK_SPEC_UP2, 0, 0, true>(pp, g, tb, items, 0, -1, F, B);
+    else if (pp.spec_mode == PK_SPEC_UP2) dftp_program<PK_SPEC_UP2, 0, 0, false>(pp, g, tb, items, 0, -1, F, B);
+    else if (pp.spec_mode == PK_SPEC_SAME && pp.stereo) dftp_program<PK_SPEC_SAME, 0, 0, true>(pp, g, tb, items, 0, -1, F, B);
+    else if (pp.spec_mode == PK_SPEC_SAME) dftp_program<PK_SPEC_SAME, 0, 0, false>(pp, g, tb, items, 0, -1, F, B);
+    else if (pp.stereo) dftp_program<PK_SPEC_GEN, 0, 0, true>(pp, g, tb, items, 0, -1, F, B);
+    else dftp_program<PK_SPEC_GEN, 0, 0, false>(pp, g, tb, items, 0, -1, F, B);
   }
   return RR_OK;
 #else
@@ -595,17 +596,20 @@ static int launch_dftp(const DftPkParams &pp, long long nwork, stream_t s)
     CUDA_TRY(cudaGetLastError());
     return RR_OK;
   };
-  // the common Best-quality sizes get kernels specialised on (forward, inverse) transform size
+  // the common Best-quality sizes get kernels specialised on (forward, inverse) transform size; every kernel exists for
+  // adjacent stereo frames as input (the caller's buffer of a stereo stream, a pair-interleaved FIFO) and for any layout
+#define RR_DFTP(MODE, FBV, IBV) (pp.stereo ? go(dftp_kernel<MODE, FBV, IBV, true>) : go(dftp_kernel<MODE, FBV, IBV, false>))
   if (pp.spec_mode == PK_SPEC_UP2) {
-    if (pp.fb == 10 && pp.ib == 11) return go(dftp_kernel<PK_SPEC_UP2, 10, 11>);      // N = 4096, x2 (44.1 <-> 48 family)
-    return go(dftp_kernel<PK_SPEC_UP2, 0, 0>);
+    if (pp.fb == 10 && pp.ib == 11) return RR_DFTP(PK_SPEC_UP2, 10, 11);      // N = 4096, x2 (44.1 <-> 48 family)
+    return RR_DFTP(PK_SPEC_UP2, 0, 0);
   }
   if (pp.spec_mode == PK_SPEC_SAME) {
-    if (pp.fb == 11 && pp.ib == 11) return go(dftp_kernel<PK_SPEC_SAME, 11, 11>);     // N = 4096, 1:1 pre-filter
-    return go(dftp_kernel<PK_SPEC_SAME, 0, 0>);
+    if (pp.fb == 11 && pp.ib == 11) return RR_DFTP(PK_SPEC_SAME, 11, 11);     // N = 4096, 1:1 pre-filter
+    return RR_DFTP(PK_SPEC_SAME, 0, 0);
   }
-  if (pp.fb == 11 && pp.ib == 10) return go(dftp_kernel<PK_SPEC_GEN, 11, 10>);        // N = 4096, F-domain / 2
-  return go(dftp_kernel<PK_SPEC_GEN, 0, 0>);
+  if (pp.fb == 11 && pp.ib == 10) return RR_DFTP(PK_SPEC_GEN, 11, 10);        // N = 4096, F-domain / 2
+  return RR_DFTP(PK_SPEC_GEN, 0, 0);
+#undef RR_DFTP
 #endif
 }
 
@@ -1267,7 +1271,6 @@ template <class T> class Engine {
   bool use_pair_kernel_ = getenv("B200RATE_NO_PAIR_KERNEL") == nullptr;
   bool use_pair_dft_ = getenv("B200RATE_NO_PAIR_DFT") == nullptr, use_pair_poly_ = getenv("B200RATE_NO_PAIR_POLY") == nullptr;
   bool use_pair_half_ = getenv("B200RATE_NO_PAIR_HALF") == nullptr, use_pair_poly2_ = getenv("B200RATE_NO_PAIR_POLY2") == nullptr;
-  bool tile_regs_ = getenv("B200RATE_TILE_LDGSTS") == nullptr;   // measurement switch: LDGSTS prefetch of the input tiles instead
   int last_dft_kernel_ = 0;
 
   // Parameters of the lane-pair kernel for DFT stage i, or false when it does not apply (transform too
@@ -1286,7 +1289,8 @@ template <class T> class Engine {
     pp.fslots = pk_buf_slots(g.Pf >> 1); pp.bslots = pk_buf_slots(g.Ni >> 1);
     pp.gthreads = kPkGroupThreads;
     pp.spec_mode = pk_spec_mode(g);
-    pp.tile_regs = tile_regs_ ? 1 : 0;
+    pp.stereo = p.in.ch_stride == 1 && p.in.elem_stride == 2 && !(reinterpret_cast<size_t>(p.in.base) & 15) &&
+                !(p.in.stream_stride & 3) && g.in_mode != DFT_IN_ZERO_STUFF;
     pp.spec = pk_spec_dev_[i];
     if (pp.spec_mode != PK_SPEC_GEN && !pp.spec) return false;
     pp.n_pyr_f = pk_pyr_len(fb); pp.n_pyr_i = pk_pyr_len(ib); pp.n_ltab_f = sf->second.pk_ltab_len; pp.n_ltab_i = si->second.pk_ltab_len;

@@ -98,6 +98,16 @@ template <> struct Arith<Pk> {
 
 typedef C2<Pk> CPk;                                        // one 16-byte slot: {re.a, re.b, im.a, im.b}
 
+RR_PROG Pk pk_load8(const Pk *p)                         // one 8-byte shared / global load
+{
+#if defined(__CUDA_ARCH__)
+  const float2 v = *reinterpret_cast<const float2 *>(p);
+  return pk_make(v.x, v.y);
+#else
+  return *p;
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Thread groups
 // ---------------------------------------------------------------------------------------------------
@@ -150,10 +160,9 @@ RR_PROG void pk_sink_store(const PkSink &k, int c, const CPk &v)
 // The FFT of M = 1 << BITS points over FFmpeg's split-radix DAG, everything about its shape a compile-time
 // constant (pk_plan.hpp); `tasks` is the task table of the transform (shared memory), `pyr` its twiddle pyramid.
 // ---------------------------------------------------------------------------------------------------
-// Leaves (fft16 / fft8, fft.c:288-318), in place at position `off`. swz: the slots hold {a.re, a.im, b.re, b.im}
-// (planar input copied 8 bytes per lane) instead of the working layout; the leaf re-pairs them in registers.
+// Leaves (fft16 / fft8, fft.c:288-318), in place at position `off`.
 template <int NV>
-RR_PROG void pk_leaf(CPk *buf, int off, bool swz, Pk sh, Pk c1, Pk c3)
+RR_PROG void pk_leaf(CPk *buf, int off, Pk sh, Pk c1, Pk c3)
 {
   CPk *b = buf + pslot(off);                             // multiple of NV: the NV slots are contiguous
   Pk re[NV], im[NV];
@@ -161,7 +170,6 @@ RR_PROG void pk_leaf(CPk *buf, int off, bool swz, Pk sh, Pk c1, Pk c3)
   for (int e = 0; e < NV; ++e) {
     const CPk v = b[e];
     re[e] = v.x; im[e] = v.y;
-    if (swz) { const float t = re[e].b; re[e].b = im[e].a; im[e].a = t; }
   }
   if constexpr (NV == 16) leaf_fft16<Pk>(re, im, sh, c1, c3);
   else leaf_fft8<Pk>(re, im, sh);
@@ -266,7 +274,7 @@ RR_PROG void pk_local_phase(int w, int lane, int nl, CPk *buf, const uint16_t *l
 }
 
 template <int BITS>
-RR_PROG void pk_fft_local(const Grp &g, CPk *buf, const uint16_t *ltab, const float *pyr, bool swz, float sqrthalf, float c16_1,
+RR_PROG void pk_fft_local(const Grp &g, CPk *buf, const uint16_t *ltab, const float *pyr, float sqrthalf, float c16_1,
                           float c16_3)
 {
   constexpr int nlocal = pk_local_phases(BITS);
@@ -279,8 +287,8 @@ RR_PROG void pk_fft_local(const Grp &g, CPk *buf, const uint16_t *ltab, const fl
   for (int w = w0; w < w1; ++w) {
     const uint16_t *hd = ltab + 4 * w;
     const int mb = hd[0], mc = hd[1], lb = hd[2], lc = hd[3];
-    for (int t = lane; t < mc; t += nl) { const int off = ltab[mb + t]; if (off != kPkHole) pk_leaf<16>(buf, off, swz, sh, c1, c3); }
-    for (int t = lane; t < lc; t += nl) { const int off = ltab[lb + t]; if (off != kPkHole) pk_leaf<8>(buf, off, swz, sh, c1, c3); }
+    for (int t = lane; t < mc; t += nl) { const int off = ltab[mb + t]; if (off != kPkHole) pk_leaf<16>(buf, off, sh, c1, c3); }
+    for (int t = lane; t < lc; t += nl) { const int off = ltab[lb + t]; if (off != kPkHole) pk_leaf<8>(buf, off, sh, c1, c3); }
     pk_warp_sync();
     if constexpr (nlocal > 0) pk_local_phase<BITS, 0>(w, lane, nl, buf, ltab, pyr);
     if constexpr (nlocal > 1) pk_local_phase<BITS, 1>(w, lane, nl, buf, ltab, pyr);
@@ -290,12 +298,12 @@ RR_PROG void pk_fft_local(const Grp &g, CPk *buf, const uint16_t *ltab, const fl
 
 // The warp-local part followed by the group barrier / the top phase, inlined: for kernels specialised on the size.
 template <int BITS>
-RR_PROG void pk_fft_lower_impl(const Grp &g, CPk *buf, const uint16_t *ltab, const float *pyr, bool swz, float sqrthalf, float c16_1,
+RR_PROG void pk_fft_lower_impl(const Grp &g, CPk *buf, const uint16_t *ltab, const float *pyr, float sqrthalf, float c16_1,
                                float c16_3)
 {
   // every supported size (6 <= BITS <= 13) has exactly one phase above the warp-local ones: the top one
   static_assert(BITS < 6 || pk_local_phases(BITS) + 1 == pk_phase_list(BITS).n, "one global phase expected");
-  pk_fft_local<BITS>(g, buf, ltab, pyr, swz, sqrthalf, c16_1, c16_3);
+  pk_fft_local<BITS>(g, buf, ltab, pyr, sqrthalf, c16_1, c16_3);
   grp_sync(g);
 }
 template <int BITS, bool SINK>
@@ -313,9 +321,9 @@ RR_PROG void pk_fft_top_impl(const Grp &g, CPk *buf, const uint16_t *tasks, cons
 // The same as separate, not inlined functions for the size-generic kernels: one copy per size serves the
 // forward and the inverse transform.
 template <int BITS>
-RR_PK_CALL void pk_fft_lower(Grp g, CPk *buf, const uint16_t *ltab, const float *pyr, bool swz, float sqrthalf, float c16_1, float c16_3)
+RR_PK_CALL void pk_fft_lower(Grp g, CPk *buf, const uint16_t *ltab, const float *pyr, float sqrthalf, float c16_1, float c16_3)
 {
-  pk_fft_lower_impl<BITS>(g, buf, ltab, pyr, swz, sqrthalf, c16_1, c16_3);
+  pk_fft_lower_impl<BITS>(g, buf, ltab, pyr, sqrthalf, c16_1, c16_3);
 }
 template <int BITS, bool SINK>
 RR_PK_CALL void pk_fft_top(Grp g, CPk *buf, const uint16_t *tasks, const float *pyr, PkSink sink)
@@ -333,12 +341,12 @@ RR_PK_CALL void pk_fft_top(Grp g, CPk *buf, const uint16_t *tasks, const float *
 
 // BITS > 0: size known at compile time, everything inlined; BITS == 0: dispatch on the run-time size.
 template <int BITS>
-RR_PROG void pk_fft_lower_any(int bits, const Grp &g, CPk *buf, const uint16_t *ltab, const float *pyr, bool swz, float sqrthalf,
+RR_PROG void pk_fft_lower_any(int bits, const Grp &g, CPk *buf, const uint16_t *ltab, const float *pyr, float sqrthalf,
                               float c16_1, float c16_3)
 {
-  if constexpr (BITS > 0) pk_fft_lower_impl<BITS>(g, buf, ltab, pyr, swz, sqrthalf, c16_1, c16_3);
+  if constexpr (BITS > 0) pk_fft_lower_impl<BITS>(g, buf, ltab, pyr, sqrthalf, c16_1, c16_3);
   else {
-#define RR_PK_LOWER(B) pk_fft_lower<B>(g, buf, ltab, pyr, swz, sqrthalf, c16_1, c16_3)
+#define RR_PK_LOWER(B) pk_fft_lower<B>(g, buf, ltab, pyr, sqrthalf, c16_1, c16_3)
     RR_PK_BITS_SWITCH(bits, RR_PK_LOWER)
 #undef RR_PK_LOWER
   }
@@ -385,8 +393,7 @@ struct DftPkParams {
   int fslots, bslots;            // slots of the forward / inverse buffer
   int groups, gthreads;          // groups per CTA, threads per group
   int spec_mode;
-  int tile_regs;                 // input tiles go global -> registers -> shared at the start of an item (pk_tile_now) instead of
-                                 // being prefetched with LDGSTS during the previous item's inverse transform
+  int stereo;                    // every lane pair is the two channels of adjacent stereo frames (16-byte tile loads)
   int lay_pyr_f, lay_pyr_i, lay_ltab_f, lay_ltab_i, lay_perm_f, lay_data;     // shared-memory byte offsets (host: pk_smem_layout)
   int n_pyr_f, n_pyr_i, n_ltab_f, n_ltab_i;                                   // table lengths
 };
@@ -477,72 +484,103 @@ inline void pk_async_copy8(void *dst, const void *src) { memcpy(dst, src, 8); }
 inline void pk_async_copy16(void *dst, const void *src) { memcpy(dst, src, 16); }
 #endif
 
-// Issue the (asynchronous) copy of an item's input tile into `F`, element j at the slot of its permuted
-// position (perm: the forward transform's table, shared memory). Does not wait.
-RR_PROG void pk_stage_tile(const DftPkParams &pp, const Grp &g, const PkItem &it, CPk *F, const uint16_t *perm)
-{
-  const DftParams<float> &p = pp.base;
-  const int span = p.in_mode == DFT_IN_FREQ_UP ? p.Pf : p.N, m = span >> 1;
-  if (it.tile_mode == PK_TILE_INTERLEAVED) {
-    const float *s0 = it.s0;
-    const int es = p.in.elem_stride;
-    if (es == 2 && !((size_t)s0 & 15))
-      for (int j = g.tid; j < m; j += g.size) pk_async_copy16(F + perm[j], s0 + 4 * j);
-    else
-      for (int j = g.tid; j < m; j += g.size) {
-        CPk *d = F + perm[j];
-        const float *f = s0 + (long long)(2 * j) * es;
-        pk_async_copy8(&d->x, f);
-        pk_async_copy8(&d->y, f + es);
-      }
-  } else if (it.tile_mode == PK_TILE_PLANAR) {
-    const float *s0 = it.s0, *s1 = it.s1;
-    for (int j = g.tid; j < m; j += g.size) {
-      CPk *d = F + perm[j];
-      pk_async_copy8(&d->x, s0 + 2 * j);                  // {a.re, a.im}: re-paired by the leaves (swz)
-      pk_async_copy8(&d->y, s1 + 2 * j);                  // {b.re, b.im}
-    }
-  } else {
-    const int L = p.L;
-    for (int w = g.tid; w < 2 * span; w += g.size) {
-      const int l = w & 1, j = w >> 1;
-      long long coord = it.d.Rb + j;
-      bool on_grid = true;
-      if (p.in_mode == DFT_IN_ZERO_STUFF) {
-        const int d = j - it.d.remLb;
-        on_grid = d >= 0 && d % L == 0;
-        coord = it.d.Rb + (on_grid ? d / L : 0);
-      }
-      float *dst = reinterpret_cast<float *>(F + perm[j >> 1]) + 2 * (j & 1) + l;
-      bool valid;
-      const float *src = view_addr<float>(p.in, l ? it.d.in_off1 : it.d.in_off0, coord, &valid);
-      async_copy_elem<float>(dst, src, valid && on_grid);
-    }
-  }
-  async_copy_commit();
-}
-
-// The same copy, synchronously and through registers: coalesced 16-byte global loads (eight in flight per thread),
-// then 16-byte shared stores to the permuted slots. A scattered LDGSTS costs one shared-memory wavefront per
-// 16-byte element (32 per warp copy, ncu: 20 % of the kernel's wavefronts); the same scatter as STS.128 is served
-// eight lanes per wavefront. The other groups of the CTA cover the exposed global latency.
+// Brings an item's input tile into `F`, element j at the slot of its permuted position (perm: the forward
+// transform's table, shared memory): coalesced global loads into registers (eight elements in flight per thread),
+// then 16-byte shared stores. Round 1 prefetched the tile with LDGSTS during the previous item's inverse transform;
+// a scattered LDGSTS, however, costs one shared-memory wavefront per 16-byte element (32 per warp copy: 20 % of the
+// kernel's wavefronts by ncu) where the same scatter as STS.128 is served eight lanes per wavefront. The other
+// groups of the CTA cover the exposed load latency, and the lines are requested into L2 ahead of time
+// (pk_tile_prefetch). Planar lanes are re-paired in registers, so the leaves always see {re.a, re.b, im.a, im.b}.
+// STEREO: the launch reads adjacent stereo frames (two frames = one slot, 16-byte loads); items that are not
+// stored that way (clipped at a stream edge, wrapping in a ring) go element by element. !STEREO: any layout.
+// The two variants are separate kernels: with every path inlined into one, ptxas spills inside the spectrum phase.
+template <int FB, bool STEREO>
 RR_PROG void pk_tile_now(const DftPkParams &pp, const Grp &g, const PkItem &it, CPk *F, const uint16_t *perm)
 {
   const DftParams<float> &p = pp.base;
-  const int span = p.in_mode == DFT_IN_FREQ_UP ? p.Pf : p.N, m = span >> 1;
-  if (it.tile_mode == PK_TILE_INTERLEAVED && p.in.elem_stride == 2 && !((size_t)it.s0 & 15)) {
-    const CPk *src = reinterpret_cast<const CPk *>(it.s0);
-    for (int j0 = g.tid; j0 < m; j0 += 8 * g.size) {
-      CPk v[8];
+  const int span = p.in_mode == DFT_IN_FREQ_UP ? p.Pf : p.N;
+  const int m = FB > 0 ? (1 << FB) : (span >> 1);
+  if (STEREO) {
+    if (it.tile_mode == PK_TILE_INTERLEAVED && p.in.elem_stride == 2 && !((size_t)it.s0 & 15)) {
+      const CPk *src = reinterpret_cast<const CPk *>(it.s0);
+      for (int j0 = g.tid; j0 < m; j0 += 8 * g.size) {
+        CPk v[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { const int j = j0 + k * g.size; if (j < m) v[k] = ldg(src + j); }
+        for (int k = 0; k < 8; ++k) { const int j = j0 + k * g.size; if (j < m) v[k] = ldg(src + j); }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { const int j = j0 + k * g.size; if (j < m) F[perm[j]] = v[k]; }
+        for (int k = 0; k < 8; ++k) { const int j = j0 + k * g.size; if (j < m) F[perm[j]] = v[k]; }
+      }
+      return;
     }
-    return;
+  } else {
+    if (it.tile_mode == PK_TILE_INTERLEAVED) {            // the pair's 8 bytes of every frame, frames es floats apart
+      const int es = p.in.elem_stride;
+      const float *s0 = it.s0;
+      for (int j0 = g.tid; j0 < m; j0 += 4 * g.size) {
+        Pk a[4], b[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int j = j0 + k * g.size;
+          if (j < m) { const float *f = s0 + (long long)(2 * j) * es; a[k] = pk_load8(reinterpret_cast<const Pk *>(f)); b[k] = pk_load8(reinterpret_cast<const Pk *>(f + es)); }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const int j = j0 + k * g.size; if (j < m) F[perm[j]] = CPk{a[k], b[k]}; }
+      }
+      return;
+    }
+    if (it.tile_mode == PK_TILE_PLANAR) {                 // {x[2j], x[2j+1]} of each lane -> {re.a, re.b, im.a, im.b}
+      const Pk *s0 = reinterpret_cast<const Pk *>(it.s0), *s1 = reinterpret_cast<const Pk *>(it.s1);
+      for (int j0 = g.tid; j0 < m; j0 += 4 * g.size) {
+        Pk a[4], b[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const int j = j0 + k * g.size; if (j < m) { a[k] = pk_load8(s0 + j); b[k] = pk_load8(s1 + j); } }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int j = j0 + k * g.size;
+          if (j < m) F[perm[j]] = CPk{pk_make(a[k].a, b[k].a), pk_make(a[k].b, b[k].b)};
+        }
+      }
+      return;
+    }
   }
-  pk_stage_tile(pp, g, it, F, perm);
-  async_copy_wait<0>();
+  // zero-stuffed, clipped or wrapping tiles: element by element through the view
+  const int L = p.L;
+  for (int w = g.tid; w < 2 * span; w += g.size) {
+    const int l = w & 1, j = w >> 1;
+    long long coord = it.d.Rb + j;
+    bool on_grid = true;
+    if (p.in_mode == DFT_IN_ZERO_STUFF) {
+      const int d = j - it.d.remLb;
+      on_grid = d >= 0 && d % L == 0;
+      coord = it.d.Rb + (on_grid ? d / L : 0);
+    }
+    float *dst = reinterpret_cast<float *>(F + perm[j >> 1]) + 2 * (j & 1) + l;
+    *dst = on_grid ? view_read<float, float>(p.in, l ? it.d.in_off1 : it.d.in_off0, coord) : 0.0f;
+  }
+}
+
+// Ask L2 for the next item's tile (one 128-byte line per thread and round) while this item's inverse transform runs.
+RR_PROG void pk_tile_prefetch(const DftPkParams &pp, const Grp &g, const PkItem &it)
+{
+#if defined(__CUDA_ARCH__)
+  const DftParams<float> &p = pp.base;
+  if (it.tile_mode == PK_TILE_SCALAR) return;
+  const int span = p.in_mode == DFT_IN_FREQ_UP ? p.Pf : p.N;
+  if (it.tile_mode == PK_TILE_PLANAR) {
+    const int lines = (span * 4 + 127) >> 7;
+    for (int k = g.tid; k < 2 * lines; k += g.size) {
+      const char *base = reinterpret_cast<const char *>(k & 1 ? it.s1 : it.s0);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)(k >> 1) * 128));
+    }
+  } else {
+    const size_t bytes = (size_t)span * p.in.elem_stride * 4;     // frames of all channels between the pair's samples
+    const int lines = (int)((bytes + 127) >> 7);
+    const char *base = reinterpret_cast<const char *>(it.s0);
+    for (int k = g.tid; k < lines; k += g.size) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)k * 128));
+  }
+#else
+  (void)pp; (void)g; (void)it;
+#endif
 }
 
 RR_PROG PkSpecConst pk_load_spec(const PkSpecConst *p)
@@ -754,19 +792,19 @@ struct PkTables { const float *pyr_f, *pyr_i; const uint16_t *ltab_f, *ltab_i, *
 
 // One work item (block b, lane pair). F holds (or is receiving) the item's input tile; items[slot] describes
 // this item, items[slot ^ 1] is filled for the next one, whose tile is requested as soon as F is free.
-template <int MODE, int FB, int IB>
+template <int MODE, int FB, int IB, bool STEREO>
 RR_PROG void dftp_program(const DftPkParams &pp, const Grp &g, const PkTables &tb, PkItem *items, int slot, long long work_next,
                           CPk *F, CPk *B)
 {
   const DftParams<float> &p = pp.base;
-  if (!pp.tile_regs) async_copy_wait<0>();
-  grp_sync(g);                                            // the tile is complete (prefetch mode); items[slot] is visible
+  grp_sync(g);                                            // items[slot] is visible; F and B are free
   const PkItem &it = items[slot];                        // stays valid for the whole item; fields are read where needed
   if (work_next >= 0 && g.tid == 0) items[slot ^ 1] = pk_make_item(pp, work_next);
-  if (pp.tile_regs) { pk_tile_now(pp, g, it, F, tb.perm_f); grp_sync(g); }
+  pk_tile_now<FB, STEREO>(pp, g, it, F, tb.perm_f);
+  grp_sync(g);
 
   PkSink sink{nullptr, nullptr, 0, 0};
-  pk_fft_lower_any<FB>(pp.fb, g, F, tb.ltab_f, tb.pyr_f, it.tile_mode == PK_TILE_PLANAR, p.sqrthalf, p.c16_1, p.c16_3);
+  pk_fft_lower_any<FB>(pp.fb, g, F, tb.ltab_f, tb.pyr_f, p.sqrthalf, p.c16_1, p.c16_3);
   if (MODE == PK_SPEC_GEN) {
     pk_fft_top_any<FB>(pp.fb, g, F, nullptr, tb.pyr_f, false, sink);
     pk_spectrum_generic(pp, g, F, B);
@@ -777,9 +815,9 @@ RR_PROG void dftp_program(const DftPkParams &pp, const Grp &g, const PkTables &t
     if (FB == 0 || !kPkPrefetchAcrossTop) pk_spec_prefetch<MODE>(pp, g, pre);   // not across a call: the registers would be spilled
     pk_spectrum<MODE>(pp, g, pre, F, B);
   }
-  if (!pp.tile_regs && work_next >= 0) pk_stage_tile(pp, g, items[slot ^ 1], F, tb.perm_f);   // F is free until the next item starts
+  if (work_next >= 0) pk_tile_prefetch(pp, g, items[slot ^ 1]);   // published before the barriers of the forward transform
 
-  pk_fft_lower_any<IB>(pp.ib, g, B, tb.ltab_i, tb.pyr_i, false, p.sqrthalf, p.c16_1, p.c16_3);
+  pk_fft_lower_any<IB>(pp.ib, g, B, tb.ltab_i, tb.pyr_i, p.sqrthalf, p.c16_1, p.c16_3);
   sink.d0 = it.d0; sink.d1 = it.d1; sink.half = it.count >> 1; sink.es = it.sink == 2 ? p.out.elem_stride : 0;
   pk_fft_top_any<IB>(pp.ib, g, B, nullptr, tb.pyr_i, it.sink != 0, sink);
   if (it.sink) return;
@@ -922,15 +960,6 @@ RR_PROG Poly0PairThread<NT> poly0_pair_setup(const Poly0PairParams &pp, const Po
   return st;
 }
 
-RR_PROG Pk pk_load8(const Pk *p)                         // one 8-byte shared / global load
-{
-#if defined(__CUDA_ARCH__)
-  const float2 v = *reinterpret_cast<const float2 *>(p);
-  return pk_make(v.x, v.y);
-#else
-  return *p;
-#endif
-}
 
 // Tile description for the pair kernel: the generic tile plus everything about its output that needs 64-bit
 // arithmetic, computed by one thread per tile.

@@ -24,3 +24,5 @@ probe(192000, 44100, 8, 16, 20, engine="double", phase=25)
 probe(48000, 44100, 2, 256, 10)
 probe(44100, 48000, 2, 256, 10, engine="double")      # what RR_open selects for Best quality (plugin default)
 probe(48000, 44100, 1, 512, 10)                        # mono batch: lanes of different streams paired
+probe(44100, 48000, 2, 256, 10)                        # config 1 conversion as a batch
+probe(44100, 96000, 2, 256, 10)                        # config 2
