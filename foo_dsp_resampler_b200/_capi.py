@@ -110,15 +110,6 @@ def product():
     """The CUDA library. No fallback: a missing or unloadable extension is an error."""
     global _product
     if _product is None:
-        # B200RATE_VARIANT=<name> loads libb200rate_<name>.so, a differently compiled build of the same CUDA sources
-        # (measurement variants, csrc/Makefile); still the product, still no fallback
-        variant = os.environ.get("B200RATE_VARIANT")
-        if variant:
-            path = os.path.join(PKG_DIR, "libb200rate_%s.so" % variant)
-            if not os.path.exists(path):
-                raise RuntimeError("variant library %s is not built" % path)
-            _product = bind(path)
-            return _product
         if not os.path.exists(PRODUCT_SO):
             raise RuntimeError(
                 "libb200rate.so is not built; run `python -c 'import __graft_entry__ as g; g.build()'` "

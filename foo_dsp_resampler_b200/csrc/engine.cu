@@ -26,6 +26,7 @@
 #include "fft_tables.hpp"
 #include "rate_kernels.cuh"
 #include "rate_kernels_pk.cuh"
+#include "rate_kernels_fused.cuh"
 
 #ifndef B200RATE_EMU
 #include <cuda_runtime.h>
@@ -162,7 +163,6 @@ static int be_event_sync(event_t e) { CUDA_TRY(cudaEventSynchronize(e)); return 
 // kernels
 // ===================================================================================================
 constexpr int kDftThreads = 256;
-constexpr int kPkGroupThreads = 128, kPkMaxGroups = 4;   // lane-pair DFT kernel: threads per group, groups per CTA
 constexpr int kTileThreads = 256;
 constexpr int kPolyTile = 2048;      // outputs per CTA tile
 constexpr int kHalfTile = 2048;
@@ -254,29 +254,28 @@ __global__ void __launch_bounds__(2 * kDftThreads) dft_big_kernel(const __grid_c
 // a persistent worker with its own forward and inverse buffer behind the shared tables (twiddle pyramids,
 // task tables, forward permutation).
 // FB / IB > 0: specialised on the transform sizes (everything inlined and static); 0: any size.
+// Tables of the lane-pair DFT kernels, staged once per CTA: twiddle pyramids, task tables, forward permutation.
+__device__ __forceinline__ PkTables pk_stage_tables(const DftPkParams &pp)
+{
+  float *pf = reinterpret_cast<float *>(rr_smem_raw + pp.lay_pyr_f), *pi = reinterpret_cast<float *>(rr_smem_raw + pp.lay_pyr_i);
+  uint16_t *tf = reinterpret_cast<uint16_t *>(rr_smem_raw + pp.lay_ltab_f), *ti = reinterpret_cast<uint16_t *>(rr_smem_raw + pp.lay_ltab_i);
+  uint16_t *pm = reinterpret_cast<uint16_t *>(rr_smem_raw + pp.lay_perm_f);
+  const int nf = pp.n_pyr_f, ni = pp.n_pyr_i, ef = pp.n_ltab_f, ei = pp.n_ltab_i, mf = 1 << pp.fb;
+  for (int i = threadIdx.x; i < nf; i += blockDim.x) pf[i] = pp.base.pyr_f[i];
+  for (int i = threadIdx.x; i < ni; i += blockDim.x) pi[i] = pp.base.pyr_i[i];
+  for (int i = threadIdx.x; i < ef; i += blockDim.x) tf[i] = pp.ltab_f[i];
+  for (int i = threadIdx.x; i < ei; i += blockDim.x) ti[i] = pp.ltab_i[i];
+  for (int i = threadIdx.x; i < mf; i += blockDim.x) pm[i] = pp.perm_f[i];
+  return PkTables{pf, pi, tf, ti, pm};
+}
+
 template <int MODE, int FB, int IB, bool STEREO>
 __global__ void __launch_bounds__(kPkGroupThreads * kPkMaxGroups) dftp_kernel(const __grid_constant__ DftPkParams pp, long long nwork)
 {
-  struct { int pyr_f, pyr_i, ltab_f, ltab_i, perm_f, data, group_slots; } lay{pp.lay_pyr_f, pp.lay_pyr_i, pp.lay_ltab_f, pp.lay_ltab_i,
-                                                                              pp.lay_perm_f, pp.lay_data, pp.fslots + pp.bslots};
-  {
-    float *pf = reinterpret_cast<float *>(rr_smem_raw + lay.pyr_f), *pi = reinterpret_cast<float *>(rr_smem_raw + lay.pyr_i);
-    uint16_t *tf = reinterpret_cast<uint16_t *>(rr_smem_raw + lay.ltab_f), *ti = reinterpret_cast<uint16_t *>(rr_smem_raw + lay.ltab_i);
-    uint16_t *pm = reinterpret_cast<uint16_t *>(rr_smem_raw + lay.perm_f);
-    const int nf = pp.n_pyr_f, ni = pp.n_pyr_i, ef = pp.n_ltab_f, ei = pp.n_ltab_i, mf = 1 << pp.fb;
-    for (int i = threadIdx.x; i < nf; i += blockDim.x) pf[i] = pp.base.pyr_f[i];
-    for (int i = threadIdx.x; i < ni; i += blockDim.x) pi[i] = pp.base.pyr_i[i];
-    for (int i = threadIdx.x; i < ef; i += blockDim.x) tf[i] = pp.ltab_f[i];
-    for (int i = threadIdx.x; i < ei; i += blockDim.x) ti[i] = pp.ltab_i[i];
-    for (int i = threadIdx.x; i < mf; i += blockDim.x) pm[i] = pp.perm_f[i];
-  }
-  const PkTables tb{reinterpret_cast<const float *>(rr_smem_raw + lay.pyr_f), reinterpret_cast<const float *>(rr_smem_raw + lay.pyr_i),
-                    reinterpret_cast<const uint16_t *>(rr_smem_raw + lay.ltab_f),
-                    reinterpret_cast<const uint16_t *>(rr_smem_raw + lay.ltab_i),
-                    reinterpret_cast<const uint16_t *>(rr_smem_raw + lay.perm_f)};
+  const PkTables tb = pk_stage_tables(pp);
   const int gi = threadIdx.x / kPkGroupThreads;          // pp.gthreads == kPkGroupThreads: a literal keeps it out of registers
   const Grp g{(int)threadIdx.x % kPkGroupThreads, kPkGroupThreads, 1 + gi};
-  CPk *F = reinterpret_cast<CPk *>(rr_smem_raw + lay.data) + (size_t)gi * lay.group_slots, *B = F + pp.fslots;
+  CPk *F = reinterpret_cast<CPk *>(rr_smem_raw + pp.lay_data) + (size_t)gi * (pp.fslots + pp.bslots), *B = F + pp.fslots;
   __shared__ PkItem items[kPkMaxGroups][2];
   __syncthreads();
   // 32-bit work counters (the host splits launches of more than 2^30 items)
@@ -288,6 +287,31 @@ __global__ void __launch_bounds__(kPkGroupThreads * kPkMaxGroups) dftp_kernel(co
   for (int n = 0; w < nw; w += stride, n ^= 1) {
     const int next = w + stride < nw ? w + stride : -1;
     dftp_program<MODE, FB, IB, STEREO>(pp, g, tb, items[gi], n, next, F, B);
+  }
+}
+
+// DFT stage + vpoly0 in one kernel (rate_kernels_fused.cuh): a work item is a run of consecutive blocks of a lane pair.
+template <int MODE, int FB, int IB, int NT, int DLO>
+__global__ void __launch_bounds__(kPkGroupThreads * kPkMaxGroups) dft_poly_kernel(const __grid_constant__ DftPolyParams fp, long long nwork)
+{
+  const DftPkParams &pp = fp.dft;
+  const PkTables tb = pk_stage_tables(pp);
+  const int gi = threadIdx.x / kPkGroupThreads;
+  const Grp g{(int)threadIdx.x % kPkGroupThreads, kPkGroupThreads, 1 + gi};
+  CPk *F = reinterpret_cast<CPk *>(rr_smem_raw + pp.lay_data) + (size_t)gi * (pp.fslots + pp.halo_slots + pp.bslots);
+  CPk *B = F + pp.fslots + pp.halo_slots;
+  __shared__ PkFusedBlock blk[kPkMaxGroups][2];
+  __syncthreads();
+  const int stride = (int)gridDim.x * pp.groups, nw = (int)nwork;
+  for (int w = (int)blockIdx.x * pp.groups + gi; w < nw; w += stride) {
+    long long b_first; int count, pair, halo_first;
+    if (!pk_fused_run(fp, w, &b_first, &count, &pair, &halo_first)) continue;
+    grp_sync(g);                                          // the previous run is done with blk[] and with F
+    if (g.tid == 0) blk[gi][0] = pk_fused_block(fp, pair, b_first, halo_first != 0);
+    grp_sync(g);
+    pk_tile_now<FB, true>(pp, g, blk[gi][0].it, F, tb.perm_f);
+    for (int k = 0, slot = 0; k < count; ++k, slot ^= 1)
+      dft_poly_program<MODE, FB, IB, NT, DLO>(fp, g, tb, blk[gi], slot, pair, k + 1 < count ? b_first + k + 1 : -1, k == 0, F, B);
   }
 }
 template <class T, class InT, class OutT>
@@ -610,6 +634,50 @@ static int launch_dftp(const DftPkParams &pp, long long nwork, stream_t s)
   if (pp.fb == 11 && pp.ib == 10) return RR_DFTP(PK_SPEC_GEN, 11, 10);        // N = 4096, F-domain / 2
   return RR_DFTP(PK_SPEC_GEN, 0, 0);
 #undef RR_DFTP
+#endif
+}
+
+// nwork = lane pairs x runs per pair
+static int launch_dft_poly(const DftPolyParams &fp, long long nwork, stream_t s)
+{
+  if (nwork <= 0) return RR_OK;
+  const DftPkParams &pp = fp.dft;
+  const int dlo = static_cast<int>(fp.step / fp.L);
+#ifdef B200RATE_EMU
+  (void)s;
+  std::vector<CPk> mem(static_cast<size_t>(pp.fslots + pp.halo_slots + pp.bslots) + 1);
+  CPk *F = mem.data(), *B = F + pp.fslots + pp.halo_slots;
+  const Grp g{0, 1, 0};
+  const PkTables tb{pp.base.pyr_f, pp.base.pyr_i, pp.ltab_f, pp.ltab_i, pp.perm_f};
+  for (long long w = 0; w < nwork; ++w) {
+    long long b_first; int count, pair, halo_first;
+    if (!pk_fused_run(fp, w, &b_first, &count, &pair, &halo_first)) continue;
+    PkFusedBlock blk[2];
+    blk[0] = pk_fused_block(fp, pair, b_first, halo_first != 0);
+    pk_tile_now<10, true>(pp, g, blk[0].it, F, tb.perm_f);
+    for (int k = 0, slot = 0; k < count; ++k, slot ^= 1) {
+      const long long nb = k + 1 < count ? b_first + k + 1 : -1;
+#define RR_FP(D) dft_poly_program<PK_SPEC_UP2, 10, 11, 24, D>(fp, g, tb, blk, slot, pair, nb, k == 0, F, B)
+      if (dlo == 0) RR_FP(0); else if (dlo == 1) RR_FP(1); else RR_FP(2);
+#undef RR_FP
+    }
+  }
+  return RR_OK;
+#else
+  const size_t smem = pk_smem_layout(pp).total;
+  const int threads = pp.groups * pp.gthreads;
+  auto go = [&](auto kernel) -> int {
+    long long resident = 0;
+    const int rc = launch_geometry(kernel, threads, smem, &resident);
+    if (rc != RR_OK) return rc;
+    const long long ctas = (nwork + pp.groups - 1) / pp.groups;
+    kernel<<<static_cast<unsigned>(std::min(ctas, resident)), threads, smem, s>>>(fp, nwork);
+    CUDA_TRY(cudaGetLastError());
+    return RR_OK;
+  };
+  if (dlo == 0) return go(dft_poly_kernel<PK_SPEC_UP2, 10, 11, 24, 0>);
+  if (dlo == 1) return go(dft_poly_kernel<PK_SPEC_UP2, 10, 11, 24, 1>);
+  return go(dft_poly_kernel<PK_SPEC_UP2, 10, 11, 24, 2>);
 #endif
 }
 
@@ -1197,6 +1265,63 @@ template <class T> class Engine {
     return Launch<T>::polyN(p, in_f32, out_f32, tiles * nlanes, smem, s);
   }
 
+  // ---- DFT stage i and the vpoly0 stage i + 1 as one kernel (rate_kernels_fused.cuh) ----
+  // Static part of the decision: plan shapes the fused kernel is instantiated for (x2 F-domain up-sampling with
+  // N = 4096, i.e. the 44.1 <-> 48 kHz family at Best quality, followed by a 24-tap rational polyphase stage).
+  bool fused_config_ok(int i) const
+  {
+    if (!std::is_same<T, float>::value || !use_pair_kernel_ || !use_pair_dft_ || !use_pair_poly_ || !use_fused_ || i + 1 >= ns) return false;
+    const StageGeom &d = geom[i], &q = geom[i + 1];
+    if (d.kind != RR_STAGE_DFT || q.kind != RR_STAGE_POLY || q.order != 0) return false;
+    if (pk_spec_mode(d) != PK_SPEC_UP2 || ilog2(d.Pf) - 1 != 10 || ilog2(d.Ni) - 1 != 11) return false;
+    if (d.step != 1 || (d.V & 1) || d.V < 8 * kFusedHalo) return false;
+    if (q.n != 24 || design.plan.st[i + 1].pre != 0 || q.at0 < 0 || q.at0 >= q.Lp) return false;
+    // at least sixteen threads of a group must be free of polyphase work: they fetch the next tile meanwhile
+    if (q.pstep / q.Lp > 2 || q.pstep >= (1 << 15) || (q.Lp + 1) / 2 > kFusedPolyThreads - 32) return false;
+    return true;
+  }
+
+  // in: view of the DFT stage's input; out: view the polyphase stage writes (final output or next FIFO); blocks
+  // [b0, b0 + nb) of the DFT stage, outputs [k0, k0 + nk) of the polyphase stage. Returns RR_RATEERROR (nothing
+  // launched) when this call's buffers do not allow the fused kernel (input not adjacent stereo frames).
+  int run_fused(int i, const LaneView &in, const LaneView &out, long long out_preload, long long b0, long long nb, long long k0,
+                long long nk, int nlanes, stream_t s)
+  {
+    if (nb <= 0 || nk <= 0 || nlanes <= 0) return RR_OK;
+    if constexpr (!std::is_same<T, float>::value) return RR_RATEERROR;
+    else {
+      if ((nlanes & 1) || out.mask != ~0ull) return RR_RATEERROR;
+      const StageGeom &d = geom[i], &q = geom[i + 1];
+      int rc;
+      if (!fused_tab_[i].built && (rc = build_fused_tab(i))) return rc;
+      DftPolyParams fp;
+      memset(&fp, 0, sizeof(fp));
+      DftParams<float> p = dft_params_[i];
+      p.in = in; p.out = out; p.out_preload = 0;          // the DFT stage's own output view is not used
+      p.block0 = b0; p.nblocks = static_cast<int>(nb); p.nlanes = nlanes;
+      if (!make_pair_params(i, p, fp.dft, kFusedHalo / 2) || !fp.dft.stereo || fp.dft.groups < 1) return RR_RATEERROR;
+      fp.L = q.Lp; fp.n = q.n; fp.at0 = q.at0; fp.step = q.pstep;
+      fp.poly_preload = q.preload;
+      fp.out0 = k0; fp.nout = nk; fp.out = out; fp.out_preload = out_preload;
+      fp.coef = fused_tab_[i].coef; fp.slot = fused_tab_[i].slot; fp.qs = fused_tab_[i].qs; fp.flags = fused_tab_[i].flags;
+      fp.tile_t0 = fused_tab_[i].tile_t0;
+      fp.block0 = b0; fp.nblocks = static_cast<int>(nb);
+      // runs: whole lanes when there are enough of them, otherwise pieces of at least 16 blocks (each piece but the
+      // first recomputes one block for its history) so that every group of every SM gets a dozen items
+      const long long pairs = nlanes / 2, target = 12ll * num_sms_ * fp.dft.groups;
+      long long runs = std::max(1ll, std::min((target + pairs - 1) / pairs, std::max(1ll, nb / 16)));
+      const long long len = (nb + runs - 1) / runs;
+      runs = (nb + len - 1) / len;
+      fp.run_len = static_cast<int>(len); fp.runs_per_pair = static_cast<int>(runs);
+      if (pairs * runs >= (1ll << 30)) return RR_RATEERROR;
+      (void)d;
+      ++launches;
+      kernel_name[i] = "dft_poly_kernel (DFT stage + vpoly0 fused, lane pairs)";
+      kernel_name[i + 1] = "(fused into the DFT stage's kernel)";
+      return launch_dft_poly(fp, pairs * runs, s);
+    }
+  }
+
   int copy(const LaneView &in, bool in_f32, const LaneView &out, bool out_f32, long long c0, long long n,
            long long in_shift, int nlanes, stream_t s)
   {
@@ -1251,6 +1376,65 @@ template <class T> class Engine {
   size_t big_slice_ = 0;
   static constexpr int kBigCtas = 296;
 
+  struct FusedTab { const float *coef = nullptr; const uint16_t *slot = nullptr, *qs = nullptr; const uint8_t *flags = nullptr; int tile_t0 = 0; bool built = false; };
+  FusedTab fused_tab_[RR_MAX_STAGES];
+  bool use_fused_ = getenv("B200RATE_NO_FUSED") == nullptr;
+
+  // Per-thread tables of the fused kernel's polyphase phase: thread t owns the slot pair (s, s + 1) of every period
+  // (output index mod L); the slot pairs are dealt to the threads so that the sixteen lanes of a half-warp start
+  // their windows in sixteen different 8-byte banks.
+  int build_fused_tab(int i)
+  {
+    const StageGeom &q = geom[i + 1];
+    const int L = q.Lp, n = q.n, nsp = (L + 1) / 2, dlo = static_cast<int>(q.pstep / q.Lp);
+    const int step = static_cast<int>(q.pstep), at0 = static_cast<int>(q.at0);
+    std::vector<uint16_t> slot(kFusedPolyThreads, 0xffff), qs(kFusedPolyThreads, 0);
+    std::vector<uint8_t> flags(kFusedPolyThreads, 0);
+    std::vector<float> coef(static_cast<size_t>(2 * n + 1) * kFusedPolyThreads, 0.f);
+    // deal: bucket the slot pairs by the bank of their first window sample; entry k of every bucket goes to half-warp
+    // k, what does not fit fills the holes
+    std::vector<std::vector<int>> bucket(16);
+    for (int sp = 0; sp < nsp; ++sp) bucket[static_cast<size_t>(((at0 + 2 * sp * step) / L) & 15)].push_back(sp);
+    const int rows = kFusedPolyThreads / 16;
+    std::vector<int> owner(kFusedPolyThreads, -1), rest;
+    for (int b = 0; b < 16; ++b)
+      for (size_t k = 0; k < bucket[static_cast<size_t>(b)].size(); ++k) {
+        if (static_cast<int>(k) < rows) owner[k * 16 + static_cast<size_t>(b)] = bucket[static_cast<size_t>(b)][k];
+        else rest.push_back(bucket[static_cast<size_t>(b)][k]);
+      }
+    // compact: threads beyond the last used half-warp stay idle; leftovers go to the first holes
+    for (int t = 0; t < kFusedPolyThreads && !rest.empty(); ++t)
+      if (owner[static_cast<size_t>(t)] < 0) { owner[static_cast<size_t>(t)] = rest.back(); rest.pop_back(); }
+    if (!rest.empty()) return RR_INTERNAL;
+    int used = 0;
+    for (int t = 0; t < kFusedPolyThreads; ++t) if (owner[static_cast<size_t>(t)] >= 0) used = t + 1;
+    fused_tab_[i].tile_t0 = (used + 15) / 16 * 16;
+    if (fused_tab_[i].tile_t0 > kFusedPolyThreads - 16) return RR_INTERNAL;
+    for (int t = 0; t < kFusedPolyThreads; ++t) {
+      const int sp = owner[static_cast<size_t>(t)];
+      if (sp < 0) continue;
+      const int s0 = 2 * sp, a0 = at0 + s0 * step, q0 = a0 / L, r0 = a0 % L, a1 = a0 + step, q1 = a1 / L, r1 = a1 % L;
+      const bool two = s0 + 1 < L, d_lo = q1 - q0 == dlo;
+      slot[static_cast<size_t>(t)] = static_cast<uint16_t>(s0);
+      qs[static_cast<size_t>(t)] = static_cast<uint16_t>(q0);
+      flags[static_cast<size_t>(t)] = static_cast<uint8_t>((d_lo ? 1 : 0) | (two ? 2 : 0));
+      for (int k = 0; k < n; ++k)
+        coef[static_cast<size_t>(k) * kFusedPolyThreads + t] = static_cast<float>(design.poly_bank[static_cast<size_t>(r0) * n + k]);
+      // window position dlo + j (j = 0 .. n) carries tap j of the second output when d == dlo, tap j - 1 when d == dlo + 1
+      for (int j = 0; j <= n; ++j) {
+        const int k = d_lo ? j : j - 1;
+        if (two && k >= 0 && k < n)
+          coef[static_cast<size_t>(n + j) * kFusedPolyThreads + t] = static_cast<float>(design.poly_bank[static_cast<size_t>(r1) * n + k]);
+      }
+    }
+    FusedTab &ft = fused_tab_[i];
+    int rc;
+    if ((rc = upload(coef, &ft.coef)) || (rc = upload(slot, &ft.slot)) || (rc = upload(qs, &ft.qs)) || (rc = upload(flags, &ft.flags))) return rc;
+    if ((rc = be_sync(0))) return rc;
+    ft.built = true;
+    return RR_OK;
+  }
+
   int ensure_big_scratch(size_t slice_bytes)
   {
     if (big_scratch_ && big_slice_ >= slice_bytes) return RR_OK;
@@ -1275,7 +1459,7 @@ template <class T> class Engine {
 
   // Parameters of the lane-pair kernel for DFT stage i, or false when it does not apply (transform too
   // large for its shared-memory layout).
-  bool make_pair_params(int i, const DftParams<float> &p, DftPkParams &pp)
+  bool make_pair_params(int i, const DftParams<float> &p, DftPkParams &pp, int halo_slots = 0)
   {
     const StageGeom &g = geom[i];
     const int fb = ilog2(g.Pf) - 1, ib = ilog2(g.Ni) - 1;
@@ -1286,11 +1470,11 @@ template <class T> class Engine {
     pp.fb = fb; pp.ib = ib;
     pp.ltab_f = sf->second.pk_ltab; pp.ltab_i = si->second.pk_ltab;
     pp.perm_f = sf->second.pk_perm[0]; pp.perm_i = si->second.pk_perm[1];
-    pp.fslots = pk_buf_slots(g.Pf >> 1); pp.bslots = pk_buf_slots(g.Ni >> 1);
+    pp.fslots = pk_buf_slots(g.Pf >> 1); pp.bslots = pk_buf_slots(g.Ni >> 1); pp.halo_slots = halo_slots;
     pp.gthreads = kPkGroupThreads;
     pp.spec_mode = pk_spec_mode(g);
-    pp.stereo = p.in.ch_stride == 1 && p.in.elem_stride == 2 && !(reinterpret_cast<size_t>(p.in.base) & 15) &&
-                !(p.in.stream_stride & 3) && g.in_mode != DFT_IN_ZERO_STUFF;
+    pp.stereo = p.in.ch_stride == 1 && p.in.elem_stride == 2 && !(reinterpret_cast<size_t>(p.in.base) & 7) &&
+                !(p.in.stream_stride & 1) && g.in_mode != DFT_IN_ZERO_STUFF;
     pp.spec = pk_spec_dev_[i];
     if (pp.spec_mode != PK_SPEC_GEN && !pp.spec) return false;
     pp.n_pyr_f = pk_pyr_len(fb); pp.n_pyr_i = pk_pyr_len(ib); pp.n_ltab_f = sf->second.pk_ltab_len; pp.n_ltab_i = si->second.pk_ltab_len;
@@ -1529,6 +1713,20 @@ template <class T> class Batch : public IBatch {
   cudaEvent_t h2d_done_[2] = {nullptr, nullptr}, comp_done_[2] = {nullptr, nullptr}, d2h_done_[2] = {nullptr, nullptr};
 #endif
   float *slot_in_[2] = {nullptr, nullptr}, *slot_out_[2] = {nullptr, nullptr};
+  std::vector<char> fused_;          // stage i runs fused with stage i + 1
+  // lane pairs a batch needs before its DFT + vpoly0 stages run fused (fewer: not enough runs to fill the device)
+  int kFuseMinPairs = getenv("B200RATE_FUSE_MIN_PAIRS") ? atoi(getenv("B200RATE_FUSE_MIN_PAIRS")) : 64;
+
+  int ensure_fifo(int i)             // intermediate FIFO i (input of stage i), allocated on first use
+  {
+    if (i < 1 || i >= eng.ns || buf[i]) return RR_OK;
+    void *p = nullptr;
+    const size_t bytes = sizeof(T) * static_cast<size_t>(cap[i]) * nch * nstreams;
+    const int rc = be_malloc(&p, bytes);
+    if (rc) return rc;
+    buf[i] = static_cast<T *>(p);
+    return RR_OK;
+  }
 
   ~Batch() override
   {
@@ -1557,15 +1755,21 @@ template <class T> class Batch : public IBatch {
     std::vector<StageRange> r(eng.ns);
     plan_ranges(0, static_cast<long long>(nout), r.data());
     cap.assign(eng.ns + 1, 0); buf.assign(eng.ns + 1, nullptr);
+    fused_.assign(eng.ns + 1, 0);
     for (int i = 1; i < eng.ns; ++i) {
       const StageGeom &up = eng.geom[i - 1];
       long long slack = up.kind == RR_STAGE_DFT ? 2ll * up.N : 64;
       cap[i] = ((r[i - 1].prod_hi - r[i - 1].prod_lo) + slack + 3) & ~3ll;   // lanes stay 16-byte aligned
-      void *p = nullptr;
-      const size_t bytes = sizeof(T) * static_cast<size_t>(cap[i]) * nch * nstreams;
-      if ((rc = be_malloc(&p, bytes))) return rc;
-      buf[i] = static_cast<T *>(p);
     }
+    // A DFT stage and the vpoly0 stage behind it run as one kernel when the batch is large enough to fill the device
+    // with runs of blocks and the DFT stage reads adjacent stereo frames; the FIFO between them is then never
+    // allocated unless a call cannot use the fused kernel (ensure_fifo).
+    for (int i = 0; i + 1 < eng.ns; ++i) {
+      const bool stereo_in = i == 0 ? nch == 2 : pair_fifo(i);
+      if (eng.fused_config_ok(i) && stereo_in && !(nch & 1) && static_cast<long long>(nch) * nstreams / 2 >= kFuseMinPairs) { fused_[i] = 1; ++i; }
+    }
+    for (int i = 1; i < eng.ns; ++i)
+      if (!fused_[i - 1] && (rc = ensure_fifo(i))) return rc;
     return RR_OK;
   }
 
@@ -1661,9 +1865,8 @@ template <class T> class Batch : public IBatch {
       }
     }
 
-    for (int i = 0; i < ns; ++i) {
-      LaneView in{}, out{};
-      bool in_f32, out_f32;
+    // views of the FIFO on either side of stage i for this call
+    auto view_in = [&](int i, LaneView &in, bool &in_f32) -> int {
       if (i == 0) {
         in.base = const_cast<float *>(d_in);
         in.origin = pre0 + static_cast<long long>(win_first); in.mask = ~0ull;
@@ -1671,16 +1874,20 @@ template <class T> class Batch : public IBatch {
         in.hi = pre0 + std::min<long long>(static_cast<long long>(frames_in), static_cast<long long>(win_first + win_frames));
         in.stream_stride = static_cast<long long>(win_frames) * nch; in.ch_stride = 1; in.elem_stride = nch; in.nch = nch;
         in_f32 = true;
-      } else {
-        const long long pre = eng.geom[i].preload;
-        in.base = buf[i];
-        in.origin = pre + r[i - 1].prod_lo; in.mask = ~0ull; in.lo = pre; in.hi = pre + r[i - 1].prod_hi;
-        in.stream_stride = cap[i] * nch; in.ch_stride = static_cast<int>(cap[i]); in.elem_stride = 1; in.nch = nch;
-        if (pair_fifo(i)) { in.stream_stride = 2 * cap[i]; in.ch_stride = 1; in.elem_stride = 2; in.nch = 2; }
-        if (cap[i] > 0x7fffffffll) { set_last_error("intermediate lane too long for one batch"); return RR_INVPARAM; }
-        in_f32 = false;
+        return RR_OK;
       }
-      long long out_preload;
+      int rc = ensure_fifo(i);
+      if (rc) return rc;
+      const long long pre = eng.geom[i].preload;
+      in.base = buf[i];
+      in.origin = pre + r[i - 1].prod_lo; in.mask = ~0ull; in.lo = pre; in.hi = pre + r[i - 1].prod_hi;
+      in.stream_stride = cap[i] * nch; in.ch_stride = static_cast<int>(cap[i]); in.elem_stride = 1; in.nch = nch;
+      if (pair_fifo(i)) { in.stream_stride = 2 * cap[i]; in.ch_stride = 1; in.elem_stride = 2; in.nch = 2; }
+      if (cap[i] > 0x7fffffffll) { set_last_error("intermediate lane too long for one batch"); return RR_INVPARAM; }
+      in_f32 = false;
+      return RR_OK;
+    };
+    auto view_out = [&](int i, LaneView &out, bool &out_f32, long long &out_preload) -> int {
       if (i == ns - 1) {
         out.base = d_out;
         out.origin = klo; out.mask = ~0ull; out.lo = klo; out.hi = khi;
@@ -1689,20 +1896,50 @@ template <class T> class Batch : public IBatch {
         out.nch = nch;
         out_f32 = !native_out;
         out_preload = 0;
-      } else {
-        const long long pre = eng.geom[i + 1].preload;
-        if (r[i].prod_hi - r[i].prod_lo > cap[i + 1]) { set_last_error("range exceeds the batch's frames_in_max"); return RR_INVPARAM; }
-        out.base = buf[i + 1];
-        out.origin = pre + r[i].prod_lo; out.mask = ~0ull; out.lo = out.origin; out.hi = pre + r[i].prod_hi;
-        out.stream_stride = cap[i + 1] * nch; out.ch_stride = static_cast<int>(cap[i + 1]); out.elem_stride = 1; out.nch = nch;
-        if (pair_fifo(i + 1)) { out.stream_stride = 2 * cap[i + 1]; out.ch_stride = 1; out.elem_stride = 2; out.nch = 2; }
-        out_f32 = false;
-        out_preload = pre;
+        return RR_OK;
       }
+      int rc = ensure_fifo(i + 1);
+      if (rc) return rc;
+      const long long pre = eng.geom[i + 1].preload;
+      if (r[i].prod_hi - r[i].prod_lo > cap[i + 1]) { set_last_error("range exceeds the batch's frames_in_max"); return RR_INVPARAM; }
+      out.base = buf[i + 1];
+      out.origin = pre + r[i].prod_lo; out.mask = ~0ull; out.lo = out.origin; out.hi = pre + r[i].prod_hi;
+      out.stream_stride = cap[i + 1] * nch; out.ch_stride = static_cast<int>(cap[i + 1]); out.elem_stride = 1; out.nch = nch;
+      if (pair_fifo(i + 1)) { out.stream_stride = 2 * cap[i + 1]; out.ch_stride = 1; out.elem_stride = 2; out.nch = 2; }
+      out_f32 = false;
+      out_preload = pre;
+      return RR_OK;
+    };
+    for (int i = 0; i < ns; ++i) {
+      LaneView in{}, out{};
+      bool in_f32 = false, out_f32 = false;
+      long long out_preload = 0;
+      int rc = view_in(i, in, in_f32);
+      if (rc) return rc;
 #ifndef B200RATE_EMU
       if (timing_) CUDA_TRY(cudaEventRecord(ev_[2 * i], s));
 #endif
-      int rc = eng.run_stage(i, in, in_f32, out, out_f32, out_preload, r[i].w0, r[i].wn, nlanes, s);
+      if (fused_[i]) {
+        // stage i (DFT) and stage i + 1 (vpoly0) in one kernel: FIFO i + 1 stays on chip
+        if ((rc = view_out(i + 1, out, out_f32, out_preload))) return rc;
+        rc = (native_out && i + 1 == ns - 1) ? RR_RATEERROR
+                                             : eng.run_fused(i, in, out, out_preload, r[i].w0, r[i].wn, r[i + 1].w0, r[i + 1].wn, nlanes, s);
+        if (rc == RR_OK) {
+#ifndef B200RATE_EMU
+          if (timing_) {
+            CUDA_TRY(cudaEventRecord(ev_[2 * i + 1], s));
+            CUDA_TRY(cudaEventRecord(ev_[2 * i + 2], s));
+            CUDA_TRY(cudaEventRecord(ev_[2 * i + 3], s));
+          }
+#endif
+          ++i;
+          continue;
+        }
+        if (rc != RR_RATEERROR) return rc;              // RR_RATEERROR: not applicable to this call's buffers -> two kernels
+        out = LaneView{};
+      }
+      if ((rc = view_out(i, out, out_f32, out_preload))) return rc;
+      rc = eng.run_stage(i, in, in_f32, out, out_f32, out_preload, r[i].w0, r[i].wn, nlanes, s);
       if (rc) return rc;
 #ifndef B200RATE_EMU
       if (timing_) CUDA_TRY(cudaEventRecord(ev_[2 * i + 1], s));

@@ -60,11 +60,6 @@ template <> struct Arith<Pk> {
   RR_PK_BIN(add, "add")
   RR_PK_BIN(sub, "sub")
 #undef RR_PK_BIN
-#if defined(RR_PK_PLAIN_ADD)
-  // built with ptxas -fmad=false: nothing contracts a separate multiply and add, FADD2 can be used everywhere
-  static __device__ __forceinline__ Pk addp(Pk x, Pk y) { return add(x, y); }
-  static __device__ __forceinline__ Pk subp(Pk x, Pk y) { return sub(x, y); }
-#else
   // x + y / x - y where an operand is a product: fma(x, 1, y) / fma(y, -1, x), see header
   static __device__ __forceinline__ Pk addp(Pk x, Pk y)
   {
@@ -86,7 +81,6 @@ template <> struct Arith<Pk> {
         : "f"(x.a), "f"(x.b), "f"(y.a), "f"(y.b), "f"(mone));
     return r;
   }
-#endif
 #else
   static RR_HD Pk mul(Pk x, Pk y) { return pk_make(x.a * y.a, x.b * y.b); }   // host build: -ffp-contract=off
   static RR_HD Pk add(Pk x, Pk y) { return pk_make(x.a + y.a, x.b + y.b); }
@@ -112,6 +106,7 @@ RR_PROG Pk pk_load8(const Pk *p)                         // one 8-byte shared / 
 // Thread groups
 // ---------------------------------------------------------------------------------------------------
 struct Grp { int tid, size, bar; };                        // index inside the group, threads, named barrier id
+constexpr int kPkGroupThreads = 128, kPkMaxGroups = 4;    // threads per group, groups per CTA of the lane-pair DFT kernels
 
 #if defined(__CUDACC__)
 RR_PROG void grp_sync(const Grp &g) { asm volatile("bar.sync %0, %1;" ::"r"(g.bar), "r"(g.size) : "memory"); }
@@ -201,15 +196,15 @@ RR_PROG void pk_bfly(CPk &a0, CPk &a1, CPk &a2, CPk &a3, float wre, float wim, b
 // finished).  DEPTH 3: sizes S, 2S, 4S on a node of size 4S (16 values): the S-pass on the first quarter of the
 // first half and on both quarter children, the 2S-pass on the first half, four butterflies of the 4S-pass.
 // Same butterflies on the same operands as the level-by-level order of fft.c:265-272, hence the same bits.
-template <int LG, int DEPTH, bool SINK>
-RR_PROG void pk_item(int o, CPk *buf, const float *pyr, const PkSink &sink)
+// Loads and butterflies of one task; the results stay in e[] (value j belongs at position o + j * q).
+template <int LG, int DEPTH>
+RR_PROG void pk_item_regs(int o, const CPk *buf, const float *pyr, CPk (&e)[4 << (DEPTH - 1)])
 {
   typedef PkGeo<LG> G;
   constexpr int q = G::q, NV = 4 << (DEPTH - 1);
   const int k = o & (q - 1);
-  CPk *b = buf + pslot(o);
+  const CPk *b = buf + pslot(o);
   const float *twa = pyr + pk_pyr_off(LG);
-  CPk e[NV];
 #pragma unroll
   for (int j = 0; j < NV; ++j) e[j] = b[G::rel(j)];
   {
@@ -231,10 +226,20 @@ RR_PROG void pk_item(int o, CPk *buf, const float *pyr, const PkSink &sink)
     for (int m = 0; m < 4; ++m)
       pk_bfly(e[m], e[m + 4], e[m + 8], e[m + 12], twc[k + m * q], twc[(4 - m) * q - k], m == 0 && k == 0);
   }
+}
+
+template <int LG, int DEPTH, bool SINK>
+RR_PROG void pk_item(int o, CPk *buf, const float *pyr, const PkSink &sink)
+{
+  typedef PkGeo<LG> G;
+  constexpr int q = G::q, NV = 4 << (DEPTH - 1);
+  CPk e[NV];
+  pk_item_regs<LG, DEPTH>(o, buf, pyr, e);
   if (SINK) {
 #pragma unroll
     for (int j = 0; j < NV; ++j) pk_sink_store(sink, o + j * q, e[j]);
   } else {
+    CPk *b = buf + pslot(o);
 #pragma unroll
     for (int j = 0; j < NV; ++j) b[G::rel(j)] = e[j];
   }
@@ -391,6 +396,7 @@ struct DftPkParams {
   const PkSpecConst *spec;       // [M/2] records (modes UP2 / SAME); index 0 holds those of M/2 and of the two real bins
   int fb, ib;                    // log2 of the forward / inverse complex transform sizes
   int fslots, bslots;            // slots of the forward / inverse buffer
+  int halo_slots;                // slots between them (fused DFT + polyphase kernel: history in front of B), else 0
   int groups, gthreads;          // groups per CTA, threads per group
   int spec_mode;
   int stereo;                    // every lane pair is the two channels of adjacent stereo frames (16-byte tile loads)
@@ -411,7 +417,7 @@ RR_HD PkSmemLayout pk_smem_layout(const DftPkParams &pp)
   o = (o + 3) & ~3;
   l.perm_f = o; o += 2 << pp.fb;
   l.data = (o + 15) & ~15;
-  l.group_slots = pp.fslots + pp.bslots;
+  l.group_slots = pp.fslots + pp.halo_slots + pp.bslots;
   l.total = (size_t)l.data + (size_t)pp.groups * l.group_slots * sizeof(CPk);
   return l;
 }
@@ -501,14 +507,25 @@ RR_PROG void pk_tile_now(const DftPkParams &pp, const Grp &g, const PkItem &it, 
   const int span = p.in_mode == DFT_IN_FREQ_UP ? p.Pf : p.N;
   const int m = FB > 0 ? (1 << FB) : (span >> 1);
   if (STEREO) {
-    if (it.tile_mode == PK_TILE_INTERLEAVED && p.in.elem_stride == 2 && !((size_t)it.s0 & 15)) {
-      const CPk *src = reinterpret_cast<const CPk *>(it.s0);
-      for (int j0 = g.tid; j0 < m; j0 += 8 * g.size) {
-        CPk v[8];
+    if (it.tile_mode == PK_TILE_INTERLEAVED && p.in.elem_stride == 2) {
+      if (!((size_t)it.s0 & 15)) {
+        const CPk *src = reinterpret_cast<const CPk *>(it.s0);
+        for (int j0 = g.tid; j0 < m; j0 += 8 * g.size) {
+          CPk v[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { const int j = j0 + k * g.size; if (j < m) v[k] = ldg(src + j); }
+          for (int k = 0; k < 8; ++k) { const int j = j0 + k * g.size; if (j < m) v[k] = ldg(src + j); }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { const int j = j0 + k * g.size; if (j < m) F[perm[j]] = v[k]; }
+          for (int k = 0; k < 8; ++k) { const int j = j0 + k * g.size; if (j < m) F[perm[j]] = v[k]; }
+        }
+      } else {                                            // the stream starts on an odd frame: 8-byte loads
+        const Pk *src = reinterpret_cast<const Pk *>(it.s0);
+        for (int j0 = g.tid; j0 < m; j0 += 4 * g.size) {
+          Pk a[4], b[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { const int j = j0 + k * g.size; if (j < m) { a[k] = pk_load8(src + 2 * j); b[k] = pk_load8(src + 2 * j + 1); } }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { const int j = j0 + k * g.size; if (j < m) F[perm[j]] = CPk{a[k], b[k]}; }
+        }
       }
       return;
     }
@@ -663,7 +680,7 @@ RR_PROG void pk_spec_prefetch(const DftPkParams &pp, const Grp &g, PkSpecRegs &p
   }
 }
 
-template <int MODE>
+template <int MODE, bool PIPE = true>
 RR_PROG void pk_spectrum(const DftPkParams &pp, const Grp &g, const PkSpecRegs &pre, const CPk *F, CPk *B)
 {
   typedef Arith<Pk> A;
@@ -717,6 +734,12 @@ RR_PROG void pk_spectrum(const DftPkParams &pp, const Grp &g, const PkSpecRegs &
   // software pipeline, two records live: the record of the next round is requested before a round is computed
   static_assert(kPkSpecRounds == 1 && kPkSpecLate == 3, "pipeline below is written for 1 + 3 rounds");
   const int i0 = g.tid, i1 = i0 + g.size, i2 = i1 + g.size, i3 = i2 + g.size;
+  if (!PIPE) {                                            // one record live at a time (kernels short of registers)
+    if (i0 < n) body(i0, pre.r[0]);
+    for (int i = i1; i < n; i += g.size) body(i, pk_load_spec(pp.spec + i));
+    grp_sync(g);
+    return;
+  }
   PkSpecConst ra = pre.r[0], rb;
   if (i1 < n) rb = pk_load_spec(pp.spec + i1);
   if (i0 < n) body(i0, ra);

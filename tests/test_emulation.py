@@ -324,3 +324,41 @@ def test_identity_conversion_passes_frames_through():
     assert np.array_equal(out, xs)
     assert b.input_window(5000, 100, 50) == (100, 50)
     b.close()
+
+
+FUSED_CASES = [(48000, 44100, 3, 2.0), (44100, 48000, 2, 1.5), (44100, 96000, 1, 1.2), (48000, 44100, 1, 0.05), (44100, 48000, 1, 0.3)]
+
+
+def fused_check(make_batch, to_dev, from_dev, case):
+    """DFT stage + vpoly0 as one kernel (rate_kernels_fused.cuh): whole streams and time-chunk ranges, bit for bit
+    against the oracle; the runs of blocks a lane pair is cut into must not show (each run but the first recomputes
+    one block for its filter history)."""
+    i, o, ns, secs = case
+    nch = 2
+    cfg, ocfg = _capi.make_config(i, o), oraclelib.make_config(i, o)
+    n = (int(i * secs) + 13) & ~1                      # even: every stream starts on a 16-byte boundary
+    xs = np.stack([signals.sweep_noise(i, nch, n, stream=s) for s in range(ns)])
+    b = make_batch(cfg, nch, ns, n)
+    nout = b.frames_out(n)
+    dx, dy = to_dev(xs), to_dev(np.zeros((ns, nout, nch), np.float32))
+    b.process(dx[1], n, dy[1])
+    out = from_dev(dy)
+    assert b.stage_kernel(0).startswith("dft_poly_kernel") and b.last_launches() == 1
+    for s in range(ns):
+        ref, _ = oraclelib.resample(ocfg, xs[s], engine="float")
+        assert ref.shape[0] == nout and np.array_equal(out[s], ref), "stream %d" % s
+    for ob, oc in ((0, nout // 3), (nout // 3 + 1, nout // 2), (nout - 100, 100)):
+        f, c = b.input_window(n, ob, oc)
+        win = to_dev(np.ascontiguousarray(xs[:, f:f + c, :]))
+        part = to_dev(np.zeros((ns, oc, nch), np.float32))
+        b.process_range(win[1], f, c, n, ob, oc, part[1])
+        assert np.array_equal(from_dev(part), out[:, ob:ob + oc, :])
+    b.close()
+
+
+@pytest.mark.parametrize("case", FUSED_CASES, ids=lambda c: "%d-%d-x%d" % c[:3])
+def test_fused_dft_poly_kernel(case, monkeypatch):
+    monkeypatch.setenv("B200RATE_FUSE_MIN_PAIRS", "1")
+    L = emulib.lib()
+    fused_check(lambda cfg, nch, ns, n: converter.BatchConverter(cfg, nch, ns, n, engine="float", lib=L),
+                lambda a: (a, a.ctypes.data), lambda d: d[0].copy(), case)

@@ -506,3 +506,39 @@ def test_cold_start_concurrency_mixed_plans():
     res = subprocess.run([sys.executable, "-c", _COLD_START % (os.path.dirname(here), here)], capture_output=True, text=True,
                          timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+def _fused_cases():
+    import test_emulation
+    return test_emulation.FUSED_CASES + [(48000, 44100, 80, 3.0), (44100, 48000, 150, 1.0)]
+
+
+@pytest.mark.parametrize("case", _fused_cases(), ids=lambda c: "%d-%d-x%d" % c[:3])
+def test_fused_dft_poly_kernel(case, monkeypatch):
+    """The fused DFT + vpoly0 kernel on small batches (forced), and on batches large enough to be cut into several
+    runs per lane pair: bit-exact vs the oracle, ranges equal the one-shot result."""
+    import torch
+    import foo_dsp_resampler_b200 as pkg
+    import test_emulation
+    monkeypatch.setenv("B200RATE_FUSE_MIN_PAIRS", "1")
+    st = torch.cuda.current_stream().cuda_stream
+
+    class Dev:
+        def __init__(self, cfg, nch, ns, n):
+            self.b = pkg.BatchConverter(cfg, nch, ns, n, engine="float", device=0)
+        def __getattr__(self, k):
+            return getattr(self.b, k)
+        def process(self, a, n, o):
+            self.b.process(a, n, o, st)
+        def process_range(self, *a):
+            self.b.process_range(*a, st)
+
+    def to_dev(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        return (t, t.data_ptr())
+
+    def from_dev(d):
+        torch.cuda.synchronize()
+        return d[0].cpu().numpy()
+
+    test_emulation.fused_check(Dev, to_dev, from_dev, case)
