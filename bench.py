@@ -242,7 +242,39 @@ def cpu_reference_run(wl, budget_s=12.0, steps=1, threads=None):
     return results, nthreads, desc
 
 
-def run_reference_arm(args, rank):
+def workload_config(wl, streams, seconds, world, scaling, stages=None, l2_note=None):
+    """The `config` object of the JSON line: identical for the GPU arm and the reference arm of one workload."""
+    in_rate, out_rate, nch, engine, phase, _, _, text = WORKLOADS[wl]
+    chunked = wl == "cfg5"
+    cfg = {"workload": wl, "description": text, "in_rate": in_rate, "out_rate": out_rate, "channels": nch, "engine": engine,
+           "phase": phase, "quality": "Best", "bandwidth_pc": 95.0,
+           "streams_total": streams * (world if scaling == "weak" and not chunked else 1) if not chunked else 1,
+           "seconds_per_stream": seconds * (world if chunked else 1),
+           "parallelism": ("one stream time-chunked over %d GPU(s) with filter-history halos" % world) if chunked else
+                          ("streams sharded over %d GPU(s), no data-path collective" % world)}
+    return cfg
+
+
+def default_shape(args, wl, world):
+    """(streams per rank, seconds per stream per rank, scaling) of a workload on `world` GPUs. BASELINE config 4 is
+    4096 streams IN TOTAL, sharded by stream (strong scaling); config 5 is one 10-hour stream cut into `world` time
+    chunks (1.25 h per GPU at 8 GPUs; a single GPU holds 20 minutes of it in HBM next to the result)."""
+    in_rate, out_rate, nch, engine, phase, seconds, streams, text = WORKLOADS[wl]
+    scaling = "strong" if wl == "cfg4" else "weak"
+    if args.streams:
+        streams = args.streams
+    elif wl == "cfg4" and world > 1 and not args.weak:
+        streams = streams // world
+    if args.weak:
+        scaling = "weak"
+    if args.seconds:
+        seconds = args.seconds
+    elif wl == "cfg5":
+        seconds = 36000.0 / 8 if world == 8 else 1200.0
+    return streams, seconds, scaling
+
+
+def run_reference_arm(args, rank, world):
     if rank != 0:
         return
     wl = args.workload
@@ -251,13 +283,14 @@ def run_reference_arm(args, rank):
     samples = sum(s for s, _ in timed)
     secs = sum(t for _, t in timed)
     value = samples / secs / 1e6
-    in_rate, out_rate, nch, engine, phase, seconds, streams, text = WORKLOADS[wl]
+    in_rate, out_rate, nch, engine, phase, _, _, text = WORKLOADS[wl]
+    streams, seconds, scaling = default_shape(args, wl, world)
     line = {
         "impl": "reference", "metric": "output Msamples/s", "value": value, "unit": "Msamples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / len(timed),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": "f32" if engine == "float" else "f64", "data": "synthetic",
-        "config": {"workload": wl, "description": text, "in_rate": in_rate, "out_rate": out_rate, "channels": nch},
+        "config": workload_config(wl, streams, seconds, world, scaling),
         "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": nthreads, "kind": "reference", "sample": desc},
         "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -292,6 +325,267 @@ def make_input(torch, nstreams, frames, nch, in_rate, seconds, seed):
     return x
 
 
+PEAKS_NOMINAL = {"f32": 74.4, "f64": 37.2}       # TFLOP/s FMA, 148 SMs x 128 (64) lanes x 2 x 1.965 GHz
+
+
+def load_fp_peaks():
+    p = os.path.join(ROOT, "profiles", "fp_peaks.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return {}
+
+
+class Measurement:
+    """One workload resident on this rank's GPU: step(), device-timed throughput, per-stage times, rooflines."""
+
+    def __init__(self, torch, pkg, wl, streams, seconds, rank, world, local_rank):
+        self.torch, self.pkg, self.wl, self.rank, self.world = torch, pkg, wl, rank, world
+        in_rate, out_rate, nch, engine, phase, _, _, text = WORKLOADS[wl]
+        self.in_rate, self.out_rate, self.nch, self.engine, self.streams, self.seconds = in_rate, out_rate, nch, engine, streams, seconds
+        self.cfg = pkg.make_config(in_rate, out_rate, phase=phase)
+        self.st = torch.cuda.current_stream().cuda_stream
+        self.chunked = wl == "cfg5"
+        if not self.chunked:
+            frames = int(round(in_rate * seconds))
+            frames -= frames & 1                                   # even: every stream starts on a 16-byte boundary
+            self.b = pkg.BatchConverter(self.cfg, nch, streams, frames, engine=engine, device=local_rank)
+            self.nout = self.b.frames_out(frames)
+            self.x = make_input(torch, streams, frames, nch, in_rate, seconds, 1234 + rank)
+            self.y = torch.empty((streams, self.nout, nch), dtype=torch.float32, device="cuda")
+            self.frames = frames
+            self.pieces = None
+            self.out_samples_per_step = self.nout * nch * streams
+        else:
+            # one long stream, this rank's contiguous range of the OUTPUT timeline, processed as consecutive chunks
+            # with halo'd input windows (RRX_batch_input_window / RRX_batch_process_range)
+            frames_total = int(round(in_rate * seconds)) * world
+            chunk_out = out_rate * 60                               # 60 s of output per call
+            self.b = pkg.BatchConverter(self.cfg, nch, 1, int(chunk_out * in_rate / out_rate) + 65536, engine=engine,
+                                        device=local_rank)
+            nout_total = self.b.frames_out(frames_total)
+            import foo_dsp_resampler_b200.sharding as sharding
+            ranges = sharding.time_chunks(nout_total, world, sharding.last_stage_block(self.b.plan()))
+            out_lo, cnt = ranges[rank]
+            out_hi = out_lo + cnt
+            f0, c0 = self.b.input_window(frames_total, out_lo, cnt)
+            self.x = make_input(torch, 1, c0, nch, in_rate, seconds * world, 99 + rank)
+            self.y = torch.empty((1, cnt, nch), dtype=torch.float32, device="cuda")
+            self.pieces = []
+            for ob in range(out_lo, out_hi, chunk_out):
+                oc = min(chunk_out, out_hi - ob)
+                f, c = self.b.input_window(frames_total, ob, oc)
+                self.pieces.append((ob, oc, f, c))
+            self.f0, self.out_lo, self.frames_total, self.frames = f0, out_lo, frames_total, c0
+            self.nout = cnt
+            self.out_samples_per_step = cnt * nch
+        self.in_bytes = self.x.numel() * 4
+        self.out_bytes = self.y.numel() * 4
+        self.l2_note = ("inputs (%.1f GB) larger than L2" % (self.in_bytes / 1e9)) if self.in_bytes > 256e6 else \
+            "L2 flushed between steps (256 MB write)"
+        self.flush = None if self.in_bytes > 256e6 else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def step(self):
+        b, x, y, st, nch = self.b, self.x, self.y, self.st, self.nch
+        if not self.chunked:
+            b.process(x.data_ptr(), self.frames, y.data_ptr(), st)
+        else:
+            for ob, oc, f, c in self.pieces:
+                b.process_range(x.data_ptr() + (f - self.f0) * nch * 4, f, c, self.frames_total, ob, oc,
+                                y.data_ptr() + (ob - self.out_lo) * nch * 4, st)
+
+    def timed(self, steps, W, barrier, dist, sampler=None):
+        torch, b = self.torch, self.b
+        for _ in range(W):
+            self.step()
+        barrier()
+        b.enable_timing(True)
+        if sampler:
+            sampler.start()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        stage_acc, launches = None, 0
+        barrier()
+        for k in range(steps):
+            if self.flush is not None:
+                self.flush.fill_(k)                        # evict L2 between timed iterations
+            ev[k][0].record()
+            self.step()
+            ev[k][1].record()
+            launches += b.last_launches() * (len(self.pieces) if self.chunked else 1)
+            if not self.chunked:
+                tms = b.stage_times()                      # waits for this step's events (recorded on the launching stream)
+                stage_acc = tms if stage_acc is None else [a + c for a, c in zip(stage_acc, tms)]
+        barrier()
+        self.clocks = sampler.stop() if sampler else None
+        b.enable_timing(False)
+        ms_total = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+        tt = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        if dist:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        self.ms_step = float(tt.item()) / steps
+        tot = torch.tensor([float(self.out_samples_per_step)], dtype=torch.float64, device="cuda")
+        if dist:
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        self.total_out_samples = float(tot.item())
+        self.value = self.total_out_samples / self.ms_step / 1e3          # Msamples/s, whole job
+        self.launches = launches
+        self.stage_ms = [m / steps for m in stage_acc] if stage_acc else None
+        return self.value
+
+    def rooflines(self):
+        """SURVEY.md 8(d) accounting. Pipeline: algorithmic flops (split-radix count etc.) and bytes (fp32 in + fp32 out at
+        the API, intermediates on chip) of one step over the CUDA-event time of the step. Dominant kernel: its
+        algorithmic bytes -- the API input if it reads it plus the API output if it writes it -- over its own
+        CUDA-event duration."""
+        if self.chunked or not self.stage_ms:
+            flops = None
+        else:
+            flops = self.b.flops(self.frames)
+        peak_hbm, how = load_peaks()
+        fpp = load_fp_peaks()
+        dt = "f32" if self.engine == "float" else "f64"
+        meas_fma = fpp.get("fp32_ffma_tflops" if dt == "f32" else "fp64_dfma_tflops")
+        per_rank_ms = self.ms_step
+        pipe = {"hbm_GBps": (self.in_bytes + self.out_bytes) / per_rank_ms / 1e6,
+                "hbm_frac": (self.in_bytes + self.out_bytes) / per_rank_ms / 1e6 / peak_hbm,
+                "bytes_per_out_sample": (self.in_bytes + self.out_bytes) / self.out_samples_per_step}
+        if flops:
+            pipe.update({"tflops": flops / per_rank_ms / 1e9, "flop_per_out_sample": flops / self.out_samples_per_step,
+                         "fma_frac_nominal": flops / per_rank_ms / 1e9 / PEAKS_NOMINAL[dt], "fma_peak_nominal_tflops": PEAKS_NOMINAL[dt],
+                         "fma_frac_measured": (flops / per_rank_ms / 1e9 / meas_fma) if meas_fma else None,
+                         "fma_peak_measured_tflops": meas_fma,
+                         "note": "bit-faithful fp32 issues un-fused multiplies and adds (SURVEY.md Appendix A): its attainable "
+                                 "arithmetic peak is half the FMA peak" if dt == "f32" else "DFMA allowed (1e-12 contract)"})
+        roof = None
+        if self.stage_ms:
+            n = len(self.stage_ms)
+            dom = max(range(n), key=lambda i: self.stage_ms[i])
+            dur = self.stage_ms[dom]
+            kname = self.b.stage_kernel(dom) or "?"
+            fused_next = dom + 1 < n and (self.b.stage_kernel(dom + 1) or "").startswith("(fused")
+            last = dom + 1 if fused_next else dom
+            alg = (self.in_bytes if dom == 0 else 0) + (self.out_bytes if last == n - 1 else 0)
+            work = self.b.stage_work(self.frames, dom)
+            kflops = work["flops"] + (self.b.stage_work(self.frames, dom + 1)["flops"] if fused_next else 0.0)
+            kfamily = kname.split(" ")[0]
+            packed = kfamily in ("dftp_kernel", "dft_poly_kernel", "poly0_pair_kernel", "poly0_pair2_kernel", "halfband_pair_kernel")
+            if dt == "f32":
+                alu_peak = fpp.get("fp32_fmul2_fadd2_tflops" if packed else "fp32_fmul_fadd_tflops")
+                alu_how = ("measured, un-fused packed FMUL2+FADD2" if packed else "measured, un-fused FMUL+FADD") + " (profiles/fp_peaks.json)"
+            else:
+                alu_peak, alu_how = fpp.get("fp64_dfma_tflops"), "measured, DFMA (profiles/fp_peaks.json)"
+            traffic = None
+            tp = os.path.join(ROOT, "profiles", "dram_traffic.json")
+            if os.path.exists(tp):
+                with open(tp) as f:
+                    ent = json.load(f).get(kfamily + ":" + self.wl) or (json.load(open(tp)).get(kfamily) if self.wl == "cfg4" else None)
+                if ent:
+                    units = self.out_samples_per_step if ent.get("unit") == "output sample" else work["units"]
+                    traffic = ent["bytes_per_unit"] * units
+            roof = {"bound": "hbm", "kernel": kname, "stage": dom, "achieved": alg / dur / 1e6, "peak": peak_hbm, "unit": "GB/s",
+                    "frac": alg / dur / 1e6 / peak_hbm, "traffic": traffic, "peak_source": how, "ms_per_launch": dur,
+                    "algorithmic_bytes_per_launch": alg, "share_of_step": dur / self.ms_step,
+                    "limiter": "instruction issue / latency: 16 warps per SM (128 registers x 512 threads, 221 KB of shared memory), "
+                               "dependent un-fused FP chains and shared-memory round trips between FFT phases; neither HBM, the "
+                               "shared-memory pipe nor the FP pipe is saturated (profiles/README.md)",
+                    "alu": {"achieved_tflops": kflops / dur / 1e9, "peak_tflops": alu_peak,
+                            "frac": (kflops / dur / 1e9 / alu_peak) if alu_peak else None, "peak_source": alu_how},
+                    "stage_kernels": [self.b.stage_kernel(i) for i in range(n)], "stage_ms": self.stage_ms}
+        return roof, pipe
+
+    def close(self):
+        self.b.close()
+        del self.x, self.y, self.flush
+        self.torch.cuda.empty_cache()
+
+
+def e2e_batch(torch, pkg, m, dist, barrier, local_rank):
+    """End to end through the host-buffer entry point: ALL of this rank's streams from pinned host memory through the
+    device and back (H2D + kernels + D2H inside the timed region, three CUDA streams, sub-batches of 64 streams)."""
+    sub = min(64, m.streams)
+    tot = m.streams
+    bh = pkg.BatchConverter(m.cfg, m.nch, sub, m.frames, engine=m.engine, device=local_rank)
+    h_in = torch.empty((tot, m.frames, m.nch), dtype=torch.float32, pin_memory=True)
+    h_out = torch.empty((tot, m.nout, m.nch), dtype=torch.float32, pin_memory=True)
+    h_in.copy_(m.x)
+    torch.cuda.synchronize()
+    bh.process_host(h_in.data_ptr(), m.frames, h_out.data_ptr(), tot)      # warm-up (allocates the slots)
+    barrier()
+    reps = 3
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        bh.process_host(h_in.data_ptr(), m.frames, h_out.data_ptr(), tot)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / reps
+    tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt.item())
+    h2d, d2h = tot * m.frames * m.nch * 4, tot * m.nout * m.nch * 4
+    e2e = {"value": m.total_out_samples / dt / 1e6, "unit": "Msamples/s",
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "api": "RRX_batch_process_host (pinned host buffers, all %d streams of the rank in sub-batches of %d, "
+                  "H2D / kernels / D2H on three CUDA streams)" % (tot, sub),
+           "streams": tot, "seconds_per_step": dt, "h2d_GBps": h2d / dt / 1e9, "d2h_GBps": d2h / dt / 1e9,
+           "note": "bound by the host link: both directions of PCIe carry %.1f B per output sample" % ((h2d + d2h) / (tot * m.nout * m.nch))}
+    # check: the bits of the device-resident run (slices, to bound the comparison's memory)
+    ok = True
+    for s0 in range(0, tot, 256):
+        ok = ok and bool(torch.equal(h_out[s0:s0 + 256].cuda(), m.y[s0:s0 + 256]))
+    e2e["matches_device_resident_output"] = ok
+    bh.close()
+    del h_in, h_out
+    return e2e
+
+
+def e2e_streaming(torch, pkg, m, nthreads=16, secs=10.0):
+    """The reference's own call shape (the CPU arm's): one handle per host thread, RR_push(64 Ki frames) / RR_pull until
+    empty / RR_drain on page-locked host buffers, all threads at once."""
+    import ctypes as C
+    import threading
+    frames = int(m.in_rate * min(secs, m.seconds))
+    xs = m.x[0, :frames].cpu()
+    bufs = [(xs.clone().pin_memory(), torch.empty((1 << 17, m.nch), dtype=torch.float32).pin_memory()) for _ in range(nthreads)]
+    tot = [0] * nthreads
+
+    def work(k):
+        r = pkg.RateConverter(m.cfg, m.nch, m.engine)
+        L, h = r.lib, r.h
+        x, out = bufs[k]
+        ogen = C.c_size_t(0)
+
+        def pull_all():
+            while True:
+                L.RR_pull(h, out.data_ptr(), out.shape[0], C.byref(ogen))
+                if not ogen.value:
+                    return
+                tot[k] += ogen.value
+        for s in range(0, frames, 65536):
+            n = min(65536, frames - s)
+            L.RR_push(h, x.data_ptr() + s * m.nch * 4, n)
+            pull_all()
+        L.RR_drain(h)
+        pull_all()
+        r.close()
+
+    best = None
+    for _ in range(2):
+        for k in range(nthreads):
+            tot[k] = 0
+        th = [threading.Thread(target=work, args=(k,)) for k in range(nthreads)]
+        t0 = time.perf_counter()
+        [t.start() for t in th]
+        [t.join() for t in th]
+        dt = time.perf_counter() - t0
+        v = sum(tot) * m.nch / dt / 1e6
+        best = v if best is None else max(best, v)
+    return {"value": best, "unit": "Msamples/s", "handles": nthreads, "host_threads": nthreads,
+            "api": "RR_ctor_%s / RR_push(64 Ki frames) / RR_pull / RR_drain, one handle per host thread, page-locked caller buffers"
+                   % ("float" if m.engine == "float" else "double"),
+            "h2d_bytes_per_step": frames * m.nch * 4 * nthreads, "d2h_bytes_per_step": int(sum(tot)) * m.nch * 4,
+            "seconds_of_audio_per_handle": frames / m.in_rate}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -300,9 +594,11 @@ def main():
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=0, help="override streams per GPU")
-    ap.add_argument("--seconds", type=float, default=0.0, help="override seconds per stream")
+    ap.add_argument("--seconds", type=float, default=0.0, help="override seconds per stream (per GPU for cfg5)")
+    ap.add_argument("--weak", action="store_true", help="cfg4 with 4096 streams PER GPU instead of in total")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the secondary BASELINE configurations")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -311,7 +607,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        run_reference_arm(args, rank)
+        run_reference_arm(args, rank, world)
         return
 
     import torch
@@ -335,214 +631,103 @@ def main():
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
     W = max(args.warmup, 3)            # timing rule: at least 3 warm-up steps
 
-    in_rate, out_rate, nch, engine, phase, seconds, streams, text = WORKLOADS[args.workload]
-    if args.streams:
-        streams = args.streams
-    if args.seconds:
-        seconds = args.seconds
-    cfg = pkg.make_config(in_rate, out_rate, phase=phase)
-    st = torch.cuda.current_stream().cuda_stream
-    chunked = args.workload == "cfg5"
-
-    if not chunked:
-        frames = int(round(in_rate * seconds))
-        b = pkg.BatchConverter(cfg, nch, streams, frames, engine=engine, device=local_rank)
-        nout = b.frames_out(frames)
-        x = make_input(torch, streams, frames, nch, in_rate, seconds, 1234 + rank)
-        y = torch.empty((streams, nout, nch), dtype=torch.float32, device="cuda")
-
-        def step():
-            b.process(x.data_ptr(), frames, y.data_ptr(), st)
-        out_samples_per_step = nout * nch * streams
-        in_bytes = x.numel() * 4
-        l2_note = "inputs (%.1f GB) larger than L2" % (in_bytes / 1e9) if in_bytes > 256e6 else "L2 flushed between steps"
-    else:
-        # one long stream per rank-range, processed as consecutive output chunks with halo'd input windows
-        frames_total = int(round(in_rate * seconds)) * world          # the whole stream, all ranks
-        chunk_out = 48000 * 60                                          # 60 s of output per call
-        b = pkg.BatchConverter(cfg, nch, 1, int(chunk_out * in_rate / out_rate) + 65536, engine=engine, device=local_rank)
-        nout_total = b.frames_out(frames_total)
-        per_rank = nout_total // world
-        out_lo = rank * per_rank
-        out_hi = nout_total if rank == world - 1 else out_lo + per_rank
-        f0, c0 = b.input_window(frames_total, out_lo, out_hi - out_lo)
-        x = make_input(torch, 1, c0, nch, in_rate, seconds * world, 99 + rank)   # this rank's halo'd window, resident
-        y = torch.empty((1, out_hi - out_lo, nch), dtype=torch.float32, device="cuda")
-        pieces = []
-        for ob in range(out_lo, out_hi, chunk_out):
-            oc = min(chunk_out, out_hi - ob)
-            f, c = b.input_window(frames_total, ob, oc)
-            pieces.append((ob, oc, f, c))
-
-        def step():
-            for ob, oc, f, c in pieces:
-                b.process_range(x.data_ptr() + (f - f0) * nch * 4, f, c, frames_total, ob, oc,
-                                y.data_ptr() + (ob - out_lo) * nch * 4, st)
-        frames = c0
-        out_samples_per_step = (out_hi - out_lo) * nch
-        in_bytes = x.numel() * 4
-        l2_note = "inputs (%.1f GB) larger than L2" % (in_bytes / 1e9)
-
-    flush = None
-    if in_bytes <= 256e6:
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-
     def barrier():
         torch.cuda.synchronize()
         if dist:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(W):
-        step()
-    barrier()
+    wl = args.workload
+    streams, seconds, scaling = default_shape(args, wl, world)
+    in_rate, out_rate, nch, engine, phase, _, _, text = WORKLOADS[wl]
+    m = Measurement(torch, pkg, wl, streams, seconds, rank, world, local_rank)
+    value = m.timed(args.steps, W, barrier, dist, ClockSampler(local_rank))
+    roofline, pipeline = m.rooflines()
+    plan = m.b.plan()
 
-    b.enable_timing(True)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    stage_ms_acc, launches = None, 0
-    barrier()
-    for k in range(args.steps):
-        if flush is not None:
-            flush.fill_(k)                          # evict L2 between timed iterations
-        ev[k][0].record()
-        step()
-        ev[k][1].record()
-        launches += b.last_launches() * (len(pieces) if chunked else 1)
-        if not chunked:
-            tms = b.stage_times()                   # waits for this step's events (recorded on the launching stream)
-            stage_ms_acc = tms if stage_ms_acc is None else [a + c for a, c in zip(stage_ms_acc, tms)]
-    barrier()
-    clocks = sampler.stop()
-    b.enable_timing(False)
-    ms_total = sum(e0.elapsed_time(e1) for e0, e1 in ev)
-    tt = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    if dist:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms_step = float(tt.item()) / args.steps
-    value = out_samples_per_step * world / ms_step / 1e3            # Msamples/s, whole job
-
-    # ---- roofline of the dominant kernel (measured live, CUDA events on the launching stream) ----
-    roofline = None
-    plan = b.plan()
-    if stage_ms_acc:
-        dom = max(range(len(stage_ms_acc)), key=lambda i: stage_ms_acc[i])
-        dur_ms = stage_ms_acc[dom] / args.steps
-        work = b.stage_work(frames, dom)
-        peak, how = load_peaks()
-        kname = b.stage_kernel(dom) or "?"
-        kfamily = kname.split(" ")[0]
-        # DRAM traffic of this launch from the committed ncu capture (bytes per launch unit x units launched);
-        # captures exist for the cfg4 plan (48 -> 44.1 kHz fp32), other workloads report null
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "dram_traffic.json")
-        if os.path.exists(tp) and engine == "float" and args.workload == "cfg4":
-            with open(tp) as f:
-                ent = json.load(f).get(kfamily)
-            if ent:
-                traffic = ent["bytes_per_unit"] * work["units"]
-        # arithmetic peaks measured on this pool's B200 by tools/peak_fp.cu (profiles/fp_peaks.json): the
-        # bit-faithful fp32 kernels issue un-fused multiplies and adds, packed two lanes per instruction in the
-        # lane-pair kernels (FMUL2 / FADD2), scalar (FMUL / FADD) in the generic ones
-        fpp = {}
-        fp_path = os.path.join(ROOT, "profiles", "fp_peaks.json")
-        if os.path.exists(fp_path):
-            with open(fp_path) as f:
-                fpp = json.load(f)
-        packed = kfamily in ("dftp_kernel", "poly0_pair_kernel", "poly0_pair2_kernel", "halfband_pair_kernel")
-        if engine == "float":
-            alu_peak = fpp.get("fp32_fmul2_fadd2_tflops" if packed else "fp32_fmul_fadd_tflops")
-            alu_how = ("measured, un-fused packed FMUL2+FADD2" if packed else "measured, un-fused FMUL+FADD") + " (profiles/fp_peaks.json)"
-        else:
-            alu_peak = fpp.get("fp64_dfma_tflops")
-            alu_how = "measured, DFMA (profiles/fp_peaks.json)"
-        ach_tflops = work["flops"] / dur_ms / 1e9
-        roofline = {"bound": "hbm", "kernel": kname, "stage": dom,
-                    "achieved": work["bytes"] / dur_ms / 1e6, "peak": peak, "unit": "GB/s",
-                    "frac": work["bytes"] / dur_ms / 1e6 / peak, "traffic": traffic, "peak_source": how,
-                    "ms_per_launch": dur_ms, "algorithmic_bytes_per_launch": work["bytes"],
-                    "share_of_step": dur_ms / ms_step,
-                    "alu": {"achieved_tflops": ach_tflops, "peak_tflops": alu_peak,
-                            "frac": (ach_tflops / alu_peak) if alu_peak else None, "peak_source": alu_how,
-                            "note": "algorithmic flops (SURVEY.md 8d accounting) / kernel time; the kernel is bound by "
-                                    "shared-memory bandwidth and latency, not by HBM (see profiles/README.md)"},
-                    "stage_kernels": [b.stage_kernel(i) for i in range(len(stage_ms_acc))],
-                    "stage_ms": [m / args.steps for m in stage_ms_acc]}
-
-    # ---- end to end through the host-buffer entry point (H2D + kernels + D2H inside the timed region) ----
-    e2e = None
-    if not args.no_e2e and not chunked:
+    e2e, e2e_s = None, None
+    if not args.no_e2e and not m.chunked:
         try:
-            sub = min(64, streams)
-            tot = min(streams, 1024)
-            bh = pkg.BatchConverter(cfg, nch, sub, frames, engine=engine, device=local_rank)
-            h_in = torch.empty((tot, frames, nch), dtype=torch.float32, pin_memory=True)
-            h_out = torch.empty((tot, nout, nch), dtype=torch.float32, pin_memory=True)
-            h_in.copy_(x[:tot])
-            torch.cuda.synchronize()
-            bh.process_host(h_in.data_ptr(), frames, h_out.data_ptr(), tot)      # warm-up (allocates the slots)
-            barrier()
-            reps = 3
-            t0 = time.perf_counter()
-            for _ in range(reps):
-                bh.process_host(h_in.data_ptr(), frames, h_out.data_ptr(), tot)
-            torch.cuda.synchronize()
-            dt = (time.perf_counter() - t0) / reps
-            tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-            if dist:
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt = float(tt.item())
-            e2e = {"value": tot * nout * nch * world / dt / 1e6, "unit": "Msamples/s",
-                   "h2d_bytes_per_step": tot * frames * nch * 4, "d2h_bytes_per_step": tot * nout * nch * 4,
-                   "api": "RRX_batch_process_host (pinned host buffers, sub-batches of %d streams, 3-stream pipeline)" % sub,
-                   "streams": tot, "seconds_per_step": dt}
-            ok = bool(torch.equal(h_out.cuda(), y[:tot]))
-            e2e["matches_device_resident_output"] = ok
-            bh.close()
-            del h_in, h_out
+            e2e = e2e_batch(torch, pkg, m, dist, barrier, local_rank)
         except Exception as exc:  # noqa: BLE001
             e2e = {"value": None, "unit": "Msamples/s", "error": str(exc)}
+        if world == 1:
+            try:
+                e2e_s = e2e_streaming(torch, pkg, m)
+            except Exception as exc:  # noqa: BLE001
+                e2e_s = {"value": None, "unit": "Msamples/s", "error": str(exc)}
 
-    # ---- NCCL result gather (reported separately; the only collective on the path) ----
+    # ---- NCCL gather of the real result shards (reported separately and inclusive; the only collective on the path) ----
     gather = None
-    if dist and not chunked:
-        sl = y[:min(streams, 64)].contiguous()
-        bufs = torch.empty((world,) + tuple(sl.shape), dtype=sl.dtype, device="cuda")
-        dist.all_gather_into_tensor(bufs, sl)
+    if dist:
+        shard = m.y.reshape(-1)
+        n_max = torch.tensor([shard.numel()], dtype=torch.int64, device="cuda")
+        dist.all_reduce(n_max, op=dist.ReduceOp.MAX)
+        n_max = int(n_max.item())
+        send = shard if shard.numel() == n_max else torch.cat([shard, shard.new_zeros(n_max - shard.numel())])
+        bufs = torch.empty((world, n_max), dtype=torch.float32, device="cuda")
+        dist.all_gather_into_tensor(bufs, send)                      # warm-up
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
-        dist.all_gather_into_tensor(bufs, sl)
+        dist.all_gather_into_tensor(bufs, send)
         g1.record()
         torch.cuda.synchronize()
-        gms = g0.elapsed_time(g1)
-        gather = {"collective": "ncclAllGather of output tiles", "bytes_per_rank": sl.numel() * 4, "ms": gms,
-                  "GBps_per_rank": sl.numel() * 4 * (world - 1) / gms / 1e6}
+        gt = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(gt, op=dist.ReduceOp.MAX)
+        gms = float(gt.item())
+        ok = bool(torch.equal(bufs[rank, :shard.numel()], shard))
+        gather = {"collective": "ncclAllGather of every rank's whole result shard", "bytes_per_rank": n_max * 4, "ms": gms,
+                  "GBps_per_rank": n_max * 4 * (world - 1) / gms / 1e6, "own_shard_intact": ok,
+                  "value_including_gather": m.total_out_samples / (m.ms_step + gms) / 1e3}
+        del bufs
+
+    # ---- the other BASELINE configurations, device-timed the same way (N = 1: every one of them fits one GPU) ----
+    configs = None
+    if world == 1 and not args.no_configs and wl == "cfg4" and not args.streams:
+        m.close()
+        configs = []
+        for w2 in ("cfg1", "cfg1x256", "cfg2", "cfg3", "cfg5"):
+            try:
+                s2, sec2, sc2 = default_shape(args, w2, 1)
+                m2 = Measurement(torch, pkg, w2, s2, sec2, 0, 1, local_rank)
+                v2 = m2.timed(max(3, min(args.steps, 5)), 3, barrier, None)
+                r2, p2 = m2.rooflines()
+                configs.append({"workload": w2, "description": WORKLOADS[w2][7], "value": v2, "unit": "Msamples/s",
+                                "ms_per_step": m2.ms_step, "dtype": "f32" if WORKLOADS[w2][3] == "float" else "f64",
+                                "streams": s2, "seconds_per_stream": sec2, "gpu_launches_per_step": m2.launches // max(3, min(args.steps, 5)),
+                                "l2": m2.l2_note, "pipeline": p2,
+                                "stage_kernels": r2["stage_kernels"] if r2 else None, "stage_ms": r2["stage_ms"] if r2 else None})
+                m2.close()
+            except Exception as exc:  # noqa: BLE001
+                configs.append({"workload": w2, "error": str(exc)})
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            res, nthreads, desc = cpu_reference_run(args.workload, budget_s=10.0, steps=1)
+            res, nthreads, desc = cpu_reference_run(wl, budget_s=10.0, steps=1)
             cpu = {"value": res[0][0] / res[0][1] / 1e6, "unit": "Msamples/s", "cores": nthreads, "kind": "reference",
                    "sample": desc}
         except Exception as exc:  # noqa: BLE001
             cpu = {"value": None, "unit": "Msamples/s", "cores": 0, "kind": "reference", "sample": "failed: %s" % exc}
 
     if rank == 0:
+        cfg = workload_config(wl, streams, seconds, world, scaling)
+        cfg.update({"streams_per_gpu": streams, "stages": [{0: "halfband", 1: "dft", 2: "poly"}[s["kind"]] for s in plan["stages"]],
+                    "l2": m.l2_note})
         line = {
             "metric": "output Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if engine == "float" else "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "description": text, "in_rate": in_rate, "out_rate": out_rate,
-                       "channels": nch, "streams_per_gpu": streams, "seconds_per_stream": seconds,
-                       "stages": [{0: "halfband", 1: "dft", 2: "poly"}[s["kind"]] for s in plan["stages"]],
-                       "l2": l2_note, "parallelism": "streams sharded over %d GPU(s), no data-path collective" % world
-                       if not chunked else "one stream time-chunked over %d GPU(s) with halos" % world},
-            "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+            "warmup": W, "ms_per_step": m.ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+            "dtype": "f32" if engine == "float" else "f64", "data": "synthetic", "config": cfg,
+            "clocks": m.clocks, "gpu_launches": m.launches, "roofline": roofline, "pipeline": pipeline, "e2e": e2e,
+            "cpu_baseline": cpu,
         }
+        if e2e_s:
+            line["e2e_streaming"] = e2e_s
         if gather:
             line["gather"] = gather
+        if configs:
+            line["configs"] = configs
         emit_json(line)
     if dist:
         dist.barrier()

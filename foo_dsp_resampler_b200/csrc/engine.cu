@@ -2113,11 +2113,15 @@ template <class T> class Stream : public IStream {
   event_t user_in_done_ = {};        // transfer out of a caller-owned page-locked buffer
   bool events_ok_ = false;
   T *stage_native = nullptr; size_t stage_native_cap = 0;   // device staging of the native tap
+  std::vector<void *> retired_;      // outgrown rings
+
+  void release_retired() { for (void *p : retired_) be_free(p); retired_.clear(); }   // only when the stream is idle
 
   ~Stream() override
   {
     DeviceScope scope(eng.device_id);
     if (s_) be_sync(s_);
+    release_retired();
     for (void *p : ring) be_free(p);
     be_free(stage_native);
     for (int k = 0; k < 2; ++k) be_host_free(pin_in_[k]);
@@ -2141,8 +2145,9 @@ template <class T> class Stream : public IStream {
     W.assign(ns + 1, 0); done.assign(ns + 1, 0); produced.assign(ns + 1, 0);
     ring_cap.assign(ns + 1, 0); ring.assign(ns + 1, nullptr);
     for (int i = 0; i < ns; ++i) W[i] = eng.geom[i].preload;
+    // the caller-facing rings start large enough for the plugin's chunks (65536 + 2 x 8192 frames, foo_dsp_rate.cpp:165-187)
     for (int i = 0; i <= ns; ++i)
-      if ((rc = ensure_ring(i, std::max<long long>(W[i], 1 << 14)))) return rc;
+      if ((rc = ensure_ring(i, std::max<long long>(W[i], (i == 0 || i == ns) ? (1 << 17) : (1 << 14))))) return rc;
     return RR_OK;
   }
 
@@ -2195,8 +2200,7 @@ template <class T> class Stream : public IStream {
       ring[i] = p; ring_cap[i] = cap;
       LaneView to = ring_view(i, keep, W[i]);
       rc = eng.copy(from, f32, to, f32, keep, W[i] - keep, 0, nch, s_);
-      if (!rc) rc = be_sync(s_);
-      be_free(old);
+      retired_.push_back(old);               // still read by the copy just queued: released at the next point the stream is idle
       return rc;
     }
     ring[i] = p; ring_cap[i] = cap;
@@ -2340,6 +2344,7 @@ template <class T> class Stream : public IStream {
       }
       if ((rc = pop_frames(dst, n))) return rc;
       if ((rc = be_sync(s_))) return rc;
+      if (!retired_.empty()) release_retired();
       if (y && !direct) memcpy(y, pin_out_, sizeof(float) * elems);
       if (native) {
         // planar view of the same values: the fp32 engine's own type is float, and without stages (in_rate ==

@@ -190,28 +190,58 @@ RR_PROG void pk_fused_poly(const DftPolyParams &fp, const Grp &g, const PkFusedB
     float *d0 = fb.d_base + (long long)(m_first * L + s0) * es, *d1 = d0 + fb.lane1;
     const int dstep = L * es;
     const bool packed_out = fb.lane1 == 1 && !((size_t)d0 & 7) && !(dstep & 1) && !(es & 1);
-    for (int m = m_first; m <= m_last; ++m, xw += step, d0 += dstep, d1 += dstep) {
-      Pk a0 = pk_bcast(0.0f), a1 = pk_bcast(0.0f);
-#pragma unroll
-      for (int j = 0; j < NT + DLO + 1; ++j) {
-        const Pk xv = pk_load8(xw + j);
-        if (j < NT) a0 = A::addp(a0, A::mul(pk_bcast(c0[j]), xv));
-        if (j >= DLO) {
-          const int jj = j - DLO;                         // 0 .. NT
-          if (jj == 0) { if (dlo) a1 = A::addp(a1, A::mul(pk_bcast(c1[0]), xv)); }
-          else if (jj == NT) { if (!dlo) a1 = A::addp(a1, A::mul(pk_bcast(c1[NT]), xv)); }
-          else a1 = A::addp(a1, A::mul(pk_bcast(c1[jj]), xv));
-        }
+    // one tap of both slots: window sample j carries tap j of the first slot and tap j - DLO (d == DLO) or
+    // j - DLO - 1 (d == DLO + 1) of the second
+    auto tap = [&](int j, Pk xv, Pk &a0, Pk &a1) {
+      if (j < NT) a0 = A::addp(a0, A::mul(pk_bcast(c0[j]), xv));
+      if (j >= DLO) {
+        const int jj = j - DLO;                           // 0 .. NT
+        if (jj == 0) { if (dlo) a1 = A::addp(a1, A::mul(pk_bcast(c1[0]), xv)); }
+        else if (jj == NT) { if (!dlo) a1 = A::addp(a1, A::mul(pk_bcast(c1[NT]), xv)); }
+        else a1 = A::addp(a1, A::mul(pk_bcast(c1[jj]), xv));
       }
+    };
+    auto emit = [&](int m, Pk a0, Pk a1, float *e0, float *e1) {
       const int i = m * L + s0;                           // relative to period m_lo's slot 0
       if (i >= fb.i_lo && i < fb.i_hi) {
-        if (packed_out) *reinterpret_cast<Pk *>(d0) = a0;
-        else { *d0 = a0.a; *d1 = a0.b; }
+        if (packed_out) *reinterpret_cast<Pk *>(e0) = a0;
+        else { *e0 = a0.a; *e1 = a0.b; }
       }
       if (two && i + 1 >= fb.i_lo && i + 1 < fb.i_hi) {
-        if (packed_out) *reinterpret_cast<Pk *>(d0 + es) = a1;
-        else { d0[es] = a1.a; d1[es] = a1.b; }
+        if (packed_out) *reinterpret_cast<Pk *>(e0 + es) = a1;
+        else { e0[es] = a1.a; e1[es] = a1.b; }
       }
+    };
+    constexpr int NW = NT + DLO + 1, KB = 9;              // window samples per period; loads issued KB at a time
+    int m = m_first;
+    // Two periods at a time: four independent accumulation chains and 2 x KB shared-memory loads in flight. Few warps
+    // run this phase (the group's others wait or fetch the next tile), so it must not depend on other warps to hide
+    // the shared-memory latency; its FMUL2 / FFMA2 stream fills issue slots the FFT phases of the other groups leave idle.
+    for (; m + 1 <= m_last; m += 2, xw += 2 * step, d0 += 2 * dstep, d1 += 2 * dstep) {
+      const Pk *xb = xw + step;
+      Pk a0 = pk_bcast(0.0f), a1 = pk_bcast(0.0f), b0 = pk_bcast(0.0f), b1 = pk_bcast(0.0f);
+#pragma unroll
+      for (int j0 = 0; j0 < NW; j0 += KB) {
+        Pk va[KB], vb[KB];
+#pragma unroll
+        for (int j = 0; j < KB; ++j) if (j0 + j < NW) { va[j] = pk_load8(xw + j0 + j); vb[j] = pk_load8(xb + j0 + j); }
+#pragma unroll
+        for (int j = 0; j < KB; ++j) if (j0 + j < NW) { tap(j0 + j, va[j], a0, a1); tap(j0 + j, vb[j], b0, b1); }
+      }
+      emit(m, a0, a1, d0, d1);
+      emit(m + 1, b0, b1, d0 + dstep, d1 + dstep);
+    }
+    if (m <= m_last) {
+      Pk a0 = pk_bcast(0.0f), a1 = pk_bcast(0.0f);
+#pragma unroll
+      for (int j0 = 0; j0 < NW; j0 += KB) {
+        Pk va[KB];
+#pragma unroll
+        for (int j = 0; j < KB; ++j) if (j0 + j < NW) va[j] = pk_load8(xw + j0 + j);
+#pragma unroll
+        for (int j = 0; j < KB; ++j) if (j0 + j < NW) tap(j0 + j, va[j], a0, a1);
+      }
+      emit(m, a0, a1, d0, d1);
     }
   }
 }
