@@ -79,6 +79,17 @@ SYMBOLS = {
                                        C.POINTER(C.c_double)]),
     "RRX_batch_stage_kernel": (C.c_char_p, [C.c_void_p, C.c_int]),
     "RRX_batch_plan": (C.c_int, [C.c_void_p, C.POINTER(Plan)]),
+    "RRX_multi_open": (C.c_int, [C.POINTER(RRConfig), C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.POINTER(C.c_int), C.c_int,
+                                 C.POINTER(C.c_void_p)]),
+    "RRX_multi_devices": (C.c_int, [C.c_void_p]),
+    "RRX_multi_shard": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "RRX_multi_frames_out": (C.c_size_t, [C.c_void_p, C.c_size_t]),
+    "RRX_multi_process_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "RRX_multi_process_stream_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t)]),
+    "RRX_multi_process": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_size_t]),
+    "RRX_multi_result": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "RRX_multi_gather": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "RRX_multi_close": (None, [C.POINTER(C.c_void_p)]),
     "RRX_batch_last_launches": (C.c_int, [C.c_void_p]),
     "RRX_batch_flops": (C.c_double, [C.c_void_p, C.c_size_t]),
     "RRX_batch_close": (None, [C.POINTER(C.c_void_p)]),

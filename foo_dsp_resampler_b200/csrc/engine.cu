@@ -357,109 +357,55 @@ __global__ void __launch_bounds__(512) poly0_fast_kernel(const __grid_constant__
     }
   }
 }
-// vpoly0 for lane pairs (rate_kernels_pk.cuh): persistent CTA, two-deep LDGSTS pipeline over the tiles like
-// poly0_fast_kernel; the slots of a period are dealt to the threads once per CTA.
+// vpoly0 for lane pairs (rate_kernels_pk.cuh): persistent CTA with one window buffer -- with several CTAs per SM the
+// others cover this one's load; the slots of a period are dealt to the threads once per CTA. The window of a tile is
+// staged by one TMA bulk copy per lane pair (completion on an mbarrier) when it is a contiguous 16-byte aligned range
+// of a pair-interleaved FIFO, else with LDGSTS copies by all threads.
+#define RR_POLY0_PAIR_KERNEL_BODY(SETUP, TILE)                                                                        \
+  const Poly0FastParams<float> &p = pp.fast;                                                                          \
+  Pk *smem = reinterpret_cast<Pk *>(rr_smem_raw);                                                                     \
+  const int set = p.win * pp.P;                                                                                       \
+  uint16_t *slot_of = reinterpret_cast<uint16_t *>(smem + set);                                                       \
+  __shared__ Poly0PairTile tiles[2];                                                                                  \
+  __shared__ int cnt[17];                                                                                             \
+  __shared__ uint16_t ovf[kPolyDealOverflow];                                                                         \
+  __shared__ __align__(8) unsigned long long bar;                                                                     \
+  const int tid = threadIdx.x, nt = blockDim.x;                                                                       \
+  long long w = blockIdx.x;                                                                                           \
+  if (w >= nwork) return;                                                                                             \
+  for (int i = tid; i < pp.tslots; i += nt) slot_of[i] = 0xffff;                                                      \
+  if (tid < 17) cnt[tid] = 0;                                                                                         \
+  if (tid == 0) { tma_bar_init(&bar, 1); tiles[0] = poly0_pair_make_tile(pp, w); }                                    \
+  __syncthreads();                                                                                                    \
+  if (pp.spread) poly0_pair_deal(pp, tiles[0].t, slot_of, cnt, ovf, tid, nt); /* one column: holds for every tile */  \
+  poly0_pair_load(pp, tiles[0].t, tiles[0].tma, tiles[0].head, smem, &bar, tid, nt);                                  \
+  __syncthreads();                                                                                                    \
+  if (pp.spread) { poly0_pair_deal_overflow(pp, slot_of, cnt, ovf, tid); __syncthreads(); }                           \
+  const auto st = SETUP;                                                                                              \
+  unsigned phase = 0;                                                                                                 \
+  for (int it = 0; w < nwork; w += gridDim.x, ++it) {                                                                 \
+    const int ts = it & 1;                                                                                            \
+    const long long next = w + gridDim.x;                                                                             \
+    if (tid == 0 && next < nwork) tiles[ts ^ 1] = poly0_pair_make_tile(pp, next);                                     \
+    if (tiles[ts].tma) { tma_bar_wait(&bar, phase); phase ^= 1; } else async_copy_wait<0>();                          \
+    __syncthreads();                                                                                                  \
+    TILE;                                                                                                             \
+    __syncthreads();                                                                                                  \
+    if (next < nwork) poly0_pair_load(pp, tiles[ts ^ 1].t, tiles[ts ^ 1].tma, tiles[ts ^ 1].head, smem, &bar, tid, nt); \
+  }
+
 template <int NT>
 __global__ void __launch_bounds__(512, 2) poly0_pair_kernel(const __grid_constant__ Poly0PairParams pp, long long nwork)
 {
-  const Poly0FastParams<float> &p = pp.fast;
-  Pk *smem = reinterpret_cast<Pk *>(rr_smem_raw);
-  const int set = p.win * pp.P, nbuf = p.double_buffer ? 2 : 1;
-  uint16_t *slot_of = reinterpret_cast<uint16_t *>(smem + nbuf * set);
-  __shared__ Poly0PairTile tiles[3];
-  __shared__ int cnt[17];
-  __shared__ uint16_t ovf[kPolyDealOverflow];
-  const int tid = threadIdx.x, nt = blockDim.x;
-  long long w = blockIdx.x;
-  if (w >= nwork) return;
-  for (int i = tid; i < pp.tslots; i += nt) slot_of[i] = 0xffff;
-  if (tid < 17) cnt[tid] = 0;
-  if (tid == 0) {
-    tiles[0] = poly0_pair_make_tile(pp, w);
-    if (w + gridDim.x < nwork) tiles[1] = poly0_pair_make_tile(pp, w + gridDim.x);
-  }
-  __syncthreads();
-  if (pp.spread) poly0_pair_deal(pp, tiles[0].t, slot_of, cnt, ovf, tid, nt);   // one column: the deal holds for every tile
-  poly0_pair_load(pp, tiles[0].t, smem, tid, nt);
-  __syncthreads();
-  if (pp.spread) { poly0_pair_deal_overflow(pp, slot_of, cnt, ovf, tid); __syncthreads(); }
-  const Poly0PairThread<NT> st = poly0_pair_setup<NT>(pp, tiles[0].t, slot_of, tid);
-  if (p.double_buffer) {
-    for (int it = 0; w < nwork; w += gridDim.x, ++it) {
-      const int cur = it & 1, ts = it % 3, tn = (it + 1) % 3, tnn = (it + 2) % 3;
-      const long long next = w + gridDim.x;
-      if (next < nwork) { poly0_pair_load(pp, tiles[tn].t, smem + (cur ^ 1) * set, tid, nt); async_copy_wait<1>(); }
-      else async_copy_wait<0>();
-      if (tid == 0 && next + gridDim.x < nwork) tiles[tnn] = poly0_pair_make_tile(pp, next + gridDim.x);
-      __syncthreads();
-      poly0_pair_tile<NT>(pp, tiles[ts], smem + cur * set, st);
-      __syncthreads();
-    }
-  } else {
-    // one window buffer: with several CTAs per SM the others cover this one's load
-    for (int it = 0; w < nwork; w += gridDim.x, ++it) {
-      const int ts = it & 1;
-      const long long next = w + gridDim.x;
-      if (tid == 0 && next < nwork) tiles[ts ^ 1] = poly0_pair_make_tile(pp, next);
-      async_copy_wait<0>();
-      __syncthreads();
-      poly0_pair_tile<NT>(pp, tiles[ts], smem, st);
-      __syncthreads();
-      if (next < nwork) poly0_pair_load(pp, tiles[ts ^ 1].t, smem, tid, nt);
-    }
-  }
+  RR_POLY0_PAIR_KERNEL_BODY((poly0_pair_setup<NT>(pp, tiles[0].t, slot_of, tid)), (poly0_pair_tile<NT>(pp, tiles[ts], smem, st)))
 }
 // Two adjacent slots per thread (poly0_pair2_*): same skeleton.
 template <int NT, int DLO>
 __global__ void __launch_bounds__(256, 3) poly0_pair2_kernel(const __grid_constant__ Poly0PairParams pp, long long nwork)
 {
-  const Poly0FastParams<float> &p = pp.fast;
-  Pk *smem = reinterpret_cast<Pk *>(rr_smem_raw);
-  const int set = p.win * pp.P, nbuf = p.double_buffer ? 2 : 1;
-  uint16_t *slot_of = reinterpret_cast<uint16_t *>(smem + nbuf * set);
-  __shared__ Poly0PairTile tiles[3];
-  __shared__ int cnt[17];
-  __shared__ uint16_t ovf[kPolyDealOverflow];
-  const int tid = threadIdx.x, nt = blockDim.x;
-  long long w = blockIdx.x;
-  if (w >= nwork) return;
-  for (int i = tid; i < pp.tslots; i += nt) slot_of[i] = 0xffff;
-  if (tid < 17) cnt[tid] = 0;
-  if (tid == 0) {
-    tiles[0] = poly0_pair_make_tile(pp, w);
-    if (w + gridDim.x < nwork) tiles[1] = poly0_pair_make_tile(pp, w + gridDim.x);
-  }
-  __syncthreads();
-  if (pp.spread) poly0_pair_deal(pp, tiles[0].t, slot_of, cnt, ovf, tid, nt);   // one column: the deal holds for every tile
-  poly0_pair_load(pp, tiles[0].t, smem, tid, nt);
-  __syncthreads();
-  if (pp.spread) { poly0_pair_deal_overflow(pp, slot_of, cnt, ovf, tid); __syncthreads(); }
-  const Poly0Pair2Thread<NT, DLO> st = poly0_pair2_setup<NT, DLO>(pp, tiles[0].t, slot_of, tid);
-  if (p.double_buffer) {
-    for (int it = 0; w < nwork; w += gridDim.x, ++it) {
-      const int cur = it & 1, ts = it % 3, tn = (it + 1) % 3, tnn = (it + 2) % 3;
-      const long long next = w + gridDim.x;
-      if (next < nwork) { poly0_pair_load(pp, tiles[tn].t, smem + (cur ^ 1) * set, tid, nt); async_copy_wait<1>(); }
-      else async_copy_wait<0>();
-      if (tid == 0 && next + gridDim.x < nwork) tiles[tnn] = poly0_pair_make_tile(pp, next + gridDim.x);
-      __syncthreads();
-      poly0_pair2_tile<NT, DLO>(pp, tiles[ts], smem + cur * set, st);
-      __syncthreads();
-    }
-  } else {
-    // one window buffer: with several CTAs per SM the others cover this one's load
-    for (int it = 0; w < nwork; w += gridDim.x, ++it) {
-      const int ts = it & 1;
-      const long long next = w + gridDim.x;
-      if (tid == 0 && next < nwork) tiles[ts ^ 1] = poly0_pair_make_tile(pp, next);
-      async_copy_wait<0>();
-      __syncthreads();
-      poly0_pair2_tile<NT, DLO>(pp, tiles[ts], smem, st);
-      __syncthreads();
-      if (next < nwork) poly0_pair_load(pp, tiles[ts ^ 1].t, smem, tid, nt);
-    }
-  }
+  RR_POLY0_PAIR_KERNEL_BODY((poly0_pair2_setup<NT, DLO>(pp, tiles[0].t, slot_of, tid)), (poly0_pair2_tile<NT, DLO>(pp, tiles[ts], smem, st)))
 }
+#undef RR_POLY0_PAIR_KERNEL_BODY
 template <class T, class InT, class OutT>
 __global__ void __launch_bounds__(kTileThreads) polyN_kernel(const __grid_constant__ PolyParams<T> p, long long nwork)
 {
@@ -708,7 +654,7 @@ static int launch_halfband_pair(const HalfbandPairParams &hp, long long nwork, s
 
 static size_t poly0_pair_smem(const Poly0PairParams &pp)
 {
-  return (pp.fast.double_buffer ? 2 : 1) * sizeof(Pk) * static_cast<size_t>(pp.fast.win) * pp.P + 2 * static_cast<size_t>(pp.tslots) + 16;
+  return sizeof(Pk) * static_cast<size_t>(pp.fast.win) * pp.P + 2 * static_cast<size_t>(pp.tslots) + 16;
 }
 static int launch_poly0_pair(const Poly0PairParams &pp, int threads, long long nwork, stream_t s)
 {
@@ -725,7 +671,7 @@ static int launch_poly0_pair(const Poly0PairParams &pp, int threads, long long n
     uint16_t ovf[kPolyDealOverflow];
     std::fill(slot_of.begin(), slot_of.end(), static_cast<uint16_t>(0xffff));
     if (pp.spread) { poly0_pair_deal(pp, t, slot_of.data(), cnt, ovf, 0, 1); poly0_pair_deal_overflow(pp, slot_of.data(), cnt, ovf, 0); }
-    poly0_pair_load(pp, t, buf.data(), 0, 1);
+    poly0_pair_load(pp, t, pt.tma, pt.head, buf.data(), nullptr, 0, 1);
     if (pp.CL == 2) {
       const int dlo = static_cast<int>(pp.fast.base.step / pp.fast.base.L);
       for (int th = 0; th < pp.tslots * pp.P; ++th) {
@@ -1378,7 +1324,11 @@ template <class T> class Engine {
 
   struct FusedTab { const float *coef = nullptr; const uint16_t *slot = nullptr, *qs = nullptr; const uint8_t *flags = nullptr; int tile_t0 = 0; bool built = false; };
   FusedTab fused_tab_[RR_MAX_STAGES];
-  bool use_fused_ = getenv("B200RATE_NO_FUSED") == nullptr;
+  // The fused DFT + vpoly0 kernel is an option, not the default: it removes the intermediate FIFO (a third of the HBM
+  // traffic and half the device memory of a 48 -> 44.1 kHz batch) but measures 30 % slower than the two kernels on a
+  // B200 -- the stages are issue / latency bound, not HBM bound, and the polyphase phase occupies only the 74 threads
+  // of a group that own a slot pair (profiles/README.md, round 2). B200RATE_FUSED=1 selects it.
+  bool use_fused_ = getenv("B200RATE_FUSED") != nullptr && atoi(getenv("B200RATE_FUSED")) != 0;
 
   // Per-thread tables of the fused kernel's polyphase phase: thread t owns the slot pair (s, s + 1) of every period
   // (output index mod L); the slot pairs are dealt to the threads so that the sixteen lanes of a half-warp start

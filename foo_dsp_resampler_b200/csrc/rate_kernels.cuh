@@ -160,6 +160,41 @@ inline void async_copy_commit() {}
 template <int N> inline void async_copy_wait() {}
 #endif
 
+// TMA bulk copies (cp.async.bulk, SASS UBLKCP): one thread moves a contiguous, 16-byte aligned range global -> shared
+// without touching registers or the LSU issue slots of the other threads; completion is signalled on an mbarrier by
+// transaction bytes. Used where a kernel's input window is contiguous in memory (polyphase windows, tables).
+#if defined(__CUDA_ARCH__)
+RR_PROG void tma_bar_init(unsigned long long *bar, int arrivals)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(arrivals) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+RR_PROG void tma_bar_expect(unsigned long long *bar, unsigned bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+RR_PROG void tma_load_1d(void *smem_dst, const void *gsrc, unsigned bytes, unsigned long long *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+RR_PROG void tma_bar_wait(unsigned long long *bar, unsigned parity)
+{
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned done = 0;
+  while (!done)
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
+}
+#else
+inline void tma_bar_init(unsigned long long *, int) {}
+inline void tma_bar_expect(unsigned long long *, unsigned) {}
+inline void tma_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *) { memcpy(dst, src, bytes); }
+inline void tma_bar_wait(unsigned long long *, unsigned) {}
+#endif
+
 // ---------------------------------------------------------------------------------------------------
 // Complex FFT of size M = 1 << bits over FFmpeg's split-radix DAG (fft.c:186-346)
 // ---------------------------------------------------------------------------------------------------

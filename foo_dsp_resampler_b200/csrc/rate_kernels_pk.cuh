@@ -914,29 +914,33 @@ RR_PROG void poly0_pair_deal_overflow(const Poly0PairParams &pp, uint16_t *slot_
   }
 }
 
-// Stage the pair-interleaved input windows of a tile. Does not wait.
-RR_PROG void poly0_pair_load(const Poly0PairParams &pp, const Poly0Tile &t, Pk *buf, int tid, int nthreads)
+// Stage the pair-interleaved input windows of a tile. Does not wait. tma != 0 (decided per tile by
+// poly0_pair_make_tile): the windows are contiguous 16-byte aligned ranges of a pair-interleaved FIFO and thread 0
+// moves each of them with one bulk copy (TMA) that completes on `bar`; `head` samples in front of the window are
+// copied along so that source and destination share their 16-byte phase.
+RR_PROG void poly0_pair_load(const Poly0PairParams &pp, const Poly0Tile &t, int tma, int head, Pk *buf, unsigned long long *bar, int tid,
+                             int nthreads)
 {
   const Poly0FastParams<float> &fp = pp.fast;
   const PolyParams<float> &p = fp.base;
   const long long c0 = t.q_first + p.pre;
+  if (tma) {
+    if (tid != 0) return;
+    const unsigned bytes = (unsigned)(((t.win + head + 1) & ~1) * (int)sizeof(Pk));
+    tma_bar_expect(bar, bytes * (unsigned)pp.P);
+    for (int pr = 0; pr < pp.P; ++pr) {
+      const float *s0 = view_ptr<const float>(p.in, lane_offset(p.in, t.lane0 + 2 * pr), c0) - 2 * head;
+      tma_load_1d(buf + pr * fp.win, s0, bytes, bar);
+    }
+    return;
+  }
   const bool direct = view_range_direct(p.in, c0, c0 + t.win);
   const int es = p.in.elem_stride;
   for (int pr = 0; pr < pp.P; ++pr) {
     const long long off0 = lane_offset(p.in, t.lane0 + 2 * pr), off1 = lane_offset(p.in, t.lane0 + 2 * pr + 1);
     Pk *dst = buf + pr * fp.win;
     const float *s0 = view_ptr<const float>(p.in, off0, c0), *s1 = view_ptr<const float>(p.in, off1, c0);
-    if (direct && s1 == s0 + 1 && es == 2 && !((size_t)s0 & 7)) {
-      // adjacent stereo frames: 16-byte copies of two frames between an optional odd head and tail
-      // (window rows are 16-byte aligned: win is even and the buffers start aligned)
-      const int head = (int)(((size_t)s0 >> 3) & 1), body = (t.win - head) >> 1;
-      if (tid == 0 && head) pk_async_copy8(dst, s0);
-      if (tid == 0 && ((t.win - head) & 1)) pk_async_copy8(dst + t.win - 1, s0 + 2 * (t.win - 1));
-      if (!head)
-        for (int j = tid; j < body; j += nthreads) pk_async_copy16(dst + 2 * j, s0 + 4 * j);
-      else                                                // source odd: destination pairs are then misaligned for 16 bytes
-        for (int j = tid; j < 2 * body; j += nthreads) pk_async_copy8(dst + head + j, s0 + 2 * (head + j));
-    } else if (direct && s1 == s0 + 1 && !(es & 1) && !((size_t)s0 & 7)) {
+    if (direct && s1 == s0 + 1 && !(es & 1) && !((size_t)s0 & 7)) {
       for (int j = tid; j < t.win; j += nthreads) pk_async_copy8(dst + j, s0 + (long long)j * es);
     } else if (direct) {
       for (int w = tid; w < 2 * t.win; w += nthreads) {
@@ -992,6 +996,7 @@ struct Poly0PairTile {
   long long lane1;               // elements from a pair's first lane to its second (the two need not share a stream)
   long long i_end;               // outputs at or beyond this index do not exist
   int direct;                    // every output of the tile exists and is stored contiguously
+  int tma, head;                 // the windows are staged by bulk copies; window sample j then sits at buffer index head + j
 };
 
 RR_PROG Poly0PairTile poly0_pair_make_tile(const Poly0PairParams &pp, long long work)
@@ -1004,6 +1009,21 @@ RR_PROG Poly0PairTile poly0_pair_make_tile(const Poly0PairParams &pp, long long 
   pt.direct = i_tile_end <= pt.i_end && view_range_direct(p.out, p.out_preload + pt.t.i_first, p.out_preload + i_tile_end);
   pt.d_base = view_ptr<float>(p.out, lane_offset(p.out, pt.t.lane0), p.out_preload + pt.t.i_first);
   pt.lane1 = lane_offset(p.out, pt.t.lane0 + 1) - lane_offset(p.out, pt.t.lane0);
+  // bulk-copy staging: every window of the tile a contiguous range of adjacent stereo frames, one sample of slack
+  // either side inside the view (the copies are rounded out to 16-byte boundaries)
+  const long long c0 = pt.t.q_first + p.pre;
+  pt.tma = 0; pt.head = 0;
+  if (p.in.elem_stride == 2 && view_range_direct(p.in, c0 - 1, c0 + pt.t.win + 1) && pt.t.win + 2 <= pp.fast.win) {
+    const float *s0 = view_ptr<const float>(p.in, lane_offset(p.in, pt.t.lane0), c0);
+    pt.head = (int)(((size_t)s0 >> 3) & 1);
+    pt.tma = 1;
+    for (int pr = 0; pr < pp.P; ++pr) {
+      const long long off0 = lane_offset(p.in, pt.t.lane0 + 2 * pr), off1 = lane_offset(p.in, pt.t.lane0 + 2 * pr + 1);
+      const float *q0 = view_ptr<const float>(p.in, off0, c0) - 2 * pt.head;
+      if (off1 != off0 + 1 || ((size_t)q0 & 15)) pt.tma = 0;
+    }
+    if (!pt.tma) pt.head = 0;
+  }
   return pt;
 }
 
@@ -1023,7 +1043,7 @@ RR_PROG void poly0_pair_tile(const Poly0PairParams &pp, const Poly0PairTile &pt,
   const bool direct = pt.direct != 0;
   const bool packed_out = direct && d1 == d0 + 1 && !((size_t)d0 & 7) && !(dstep & 1);
   const int xstep = PG * (int)p.step;
-  const Pk *x = buf + st.pr * fp.win + st.q + st.g * (int)p.step;
+  const Pk *x = buf + st.pr * fp.win + pt.head + st.q + st.g * (int)p.step;
   int m = st.g;
   auto emit = [&](int mm, Pk s) {
     if (packed_out) *reinterpret_cast<Pk *>(d0) = s;
@@ -1111,7 +1131,7 @@ RR_PROG void poly0_pair2_tile(const Poly0PairParams &pp, const Poly0PairTile &pt
   const bool direct = pt.direct != 0;
   const bool packed_out = direct && d1 == d0 + 1 && !((size_t)d0 & 7) && !(dstep & 1) && !(es & 1);
   const int xstep = (int)p.step;
-  const Pk *x = buf + st.pr * fp.win + st.q;
+  const Pk *x = buf + st.pr * fp.win + pt.head + st.q;
   const bool dlo = st.d_lo, two = st.two;
   auto emit = [&](int mm, int which, Pk s) {             // output of slot fs + which in period mm
     float *e0 = d0 + which * es, *e1 = d1 + which * es;

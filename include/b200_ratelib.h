@@ -159,6 +159,32 @@ int RRX_batch_last_launches(const RRX_batch *b);
 double RRX_batch_flops(const RRX_batch *b, size_t frames_in);
 void RRX_batch_close(RRX_batch **b);
 
+/* ---- several GPUs of one box behind one handle ----
+ * The path shards without a data-path collective: a batch by independent stream (device k of n converts a contiguous
+ * slice of the streams), one long stream by time chunk (device k converts range k of the output timeline from its own
+ * halo'd input window, cut at multiples of the last stage's block, phase and block grid exact). One host thread per
+ * device drives it. NCCL (ncclSend / ncclRecv over NVLink, loaded on first use) appears only in RRX_multi_gather.
+ * `devices` lists CUDA device ordinals; listing one device several times is allowed (the shards then share it). */
+typedef struct RRX_multi_tag RRX_multi;
+int RRX_multi_open(const RR_config *config, int sample_bytes, int nchannels, size_t nstreams, size_t frames_in_max,
+                   const int *devices, int ndevices, RRX_multi **out);
+int RRX_multi_devices(const RRX_multi *m);
+/* Slice of the streams device index k owns. */
+int RRX_multi_shard(const RRX_multi *m, int k, int *device, size_t *first_stream, size_t *stream_count);
+size_t RRX_multi_frames_out(const RRX_multi *m, size_t frames_in);
+/* HOST buffers (ideally page-locked), float32 [nstreams][frames][nchannels]: every device moves its slice through
+ * itself with the three-stream pipeline of RRX_batch_process_host. Blocking. */
+int RRX_multi_process_host(RRX_multi *m, const float *h_in, size_t frames_in, float *h_out);
+/* One long stream (the handle was opened with nstreams == 1; frames_in_max bounds the input window of one call):
+ * h_in holds all frames_in_total frames, h_out receives all output frames, *frames_out their number. */
+int RRX_multi_process_stream_host(RRX_multi *m, const float *h_in, size_t frames_in_total, float *h_out, size_t *frames_out);
+/* Device-resident: d_in[k] is device k's slice on that device; results stay on the devices ... */
+int RRX_multi_process(RRX_multi *m, const float *const *d_in, size_t frames_in);
+int RRX_multi_result(const RRX_multi *m, int k, const float **d_out, size_t *frames_out);
+/* ... until gathered on device index `root`: d_out_root is float32 [nstreams][frames_out][nchannels] on that device. */
+int RRX_multi_gather(RRX_multi *m, int root, float *d_out_root);
+void RRX_multi_close(RRX_multi **m);
+
 /* Last CUDA error string seen by this library on the calling thread ("" if none). */
 const char *RRX_last_error(void);
 /* [host-only] Library version string. */

@@ -359,6 +359,63 @@ def fused_check(make_batch, to_dev, from_dev, case):
 @pytest.mark.parametrize("case", FUSED_CASES, ids=lambda c: "%d-%d-x%d" % c[:3])
 def test_fused_dft_poly_kernel(case, monkeypatch):
     monkeypatch.setenv("B200RATE_FUSE_MIN_PAIRS", "1")
+    monkeypatch.setenv("B200RATE_FUSED", "1")
     L = emulib.lib()
     fused_check(lambda cfg, nch, ns, n: converter.BatchConverter(cfg, nch, ns, n, engine="float", lib=L),
                 lambda a: (a, a.ctypes.data), lambda d: d[0].copy(), case)
+
+
+def multi_check(L, devices, batch_case, stream_case, to_dev=None):
+    """RRX_multi_*: a batch sharded by stream and one long stream cut into time chunks over `devices`, host buffers in and
+    out, against the oracle; device-resident slices gathered on one device."""
+    ndev = len(devices)
+    devs = (C.c_int * ndev)(*devices)
+    i, o, nch, ns, n = batch_case
+    cfg, ocfg = _capi.make_config(i, o), oraclelib.make_config(i, o)
+    xs = np.stack([signals.sweep_noise(i, nch, n, stream=s) for s in range(ns)])
+    m = C.c_void_p()
+    assert L.RRX_multi_open(C.byref(cfg), 4, nch, ns, n, devs, ndev, C.byref(m)) == 0, L.RRX_last_error()
+    assert L.RRX_multi_devices(m) == ndev
+    nout = L.RRX_multi_frames_out(m, n)
+    out = np.zeros((ns, nout, nch), np.float32)
+    assert L.RRX_multi_process_host(m, xs.ctypes.data, n, out.ctypes.data) == 0, L.RRX_last_error()
+    for s in range(ns):
+        ref, _ = oraclelib.resample(ocfg, xs[s], engine="float")
+        assert ref.shape[0] == nout and np.array_equal(out[s], ref), s
+    covered = 0
+    for k in range(ndev):
+        d, f, c = C.c_int(), C.c_size_t(), C.c_size_t()
+        assert L.RRX_multi_shard(m, k, C.byref(d), C.byref(f), C.byref(c)) == 0
+        assert d.value == devices[k] and f.value == covered
+        covered += c.value
+    assert covered == ns
+    if to_dev is not None:                               # device-resident slices, results gathered on the last device
+        keep, ptrs = [], (C.c_void_p * ndev)()
+        for k in range(ndev):
+            d, f, c = C.c_int(), C.c_size_t(), C.c_size_t()
+            L.RRX_multi_shard(m, k, C.byref(d), C.byref(f), C.byref(c))
+            t = to_dev(np.ascontiguousarray(xs[f.value:f.value + c.value]), devices[k])
+            keep.append(t)
+            ptrs[k] = t[1]
+        assert L.RRX_multi_process(m, ptrs, n) == 0, L.RRX_last_error()
+        g = to_dev(np.zeros_like(out), devices[-1])
+        assert L.RRX_multi_gather(m, ndev - 1, g[1]) == 0, L.RRX_last_error()
+        assert np.array_equal(g[2](), out)
+    L.RRX_multi_close(C.byref(m))
+    assert not m.value
+    i, o, nch, n, fmax = stream_case
+    cfg, ocfg = _capi.make_config(i, o), oraclelib.make_config(i, o)
+    x = signals.sweep_noise(i, nch, n)
+    assert L.RRX_multi_open(C.byref(cfg), 4, nch, 1, fmax, devs, ndev, C.byref(m)) == 0, L.RRX_last_error()
+    ref, _ = oraclelib.resample(ocfg, x, engine="float")
+    out = np.zeros((ref.shape[0] + 8, nch), np.float32)
+    fo = C.c_size_t()
+    assert L.RRX_multi_process_stream_host(m, x.ctypes.data, n, out.ctypes.data, C.byref(fo)) == 0, L.RRX_last_error()
+    assert fo.value == ref.shape[0] and np.array_equal(out[:fo.value], ref)      # seams between chunks and devices included
+    L.RRX_multi_close(C.byref(m))
+
+
+@pytest.mark.parametrize("ndev", [1, 3, 4])
+def test_multi_device_layer(ndev):
+    multi_check(emulib.lib(), [0] * ndev, (48000, 44100, 2, 7, 9000), (384000, 48000, 4, 384000 // 2, 60000),
+                to_dev=lambda a, dev: (a, a.ctypes.data, lambda: a))

@@ -521,6 +521,7 @@ def test_fused_dft_poly_kernel(case, monkeypatch):
     import foo_dsp_resampler_b200 as pkg
     import test_emulation
     monkeypatch.setenv("B200RATE_FUSE_MIN_PAIRS", "1")
+    monkeypatch.setenv("B200RATE_FUSED", "1")
     st = torch.cuda.current_stream().cuda_stream
 
     class Dev:
@@ -542,3 +543,25 @@ def test_fused_dft_poly_kernel(case, monkeypatch):
         return d[0].cpu().numpy()
 
     test_emulation.fused_check(Dev, to_dev, from_dev, case)
+
+
+def _multi_devices():
+    import torch
+    n = torch.cuda.device_count()
+    return [[0], [0, 0, 0]] + ([list(range(n))] if n > 1 else [])
+
+
+@pytest.mark.parametrize("devices", _multi_devices() if __import__("torch").cuda.is_available() else [[0]], ids=lambda d: "dev" + "".join(map(str, d)))
+def test_multi_device_layer(devices):
+    """The multi-GPU entry points of the C ABI: stream sharding and time chunking over the listed devices (one device
+    listed several times exercises the sharding on a single-GPU box; with more GPUs the gather runs over NCCL)."""
+    import ctypes as C
+    import torch
+    import foo_dsp_resampler_b200 as pkg
+    import test_emulation
+
+    def to_dev(a, dev):
+        t = torch.from_numpy(a).to("cuda:%d" % dev)
+        return (t, t.data_ptr(), lambda: (torch.cuda.synchronize(dev), t.cpu().numpy())[1])
+
+    test_emulation.multi_check(pkg.product(), devices, (48000, 44100, 2, 11, 30000), (384000, 48000, 8, 384000, 120000), to_dev=to_dev)
