@@ -1578,8 +1578,8 @@ template <class T> class Engine {
         DftParams<T> probe; memset(&probe, 0, sizeof(probe));
         probe.Pf = g.Pf; probe.Ni = g.Ni; probe.fwd.pyr_len = g.Pf / 4 + 16; probe.inv.pyr_len = g.Ni / 4 + 16;
         const size_t need = dft_smem_bytes<T>(g.Pf, g.Ni, 1, false, &xs, &ys, nullptr) + sizeof(T) * dft_table_elems(probe);
-        if (ilog2(g.Pf) - 1 > 15 || ilog2(g.Ni) - 1 > 15) {
-          set_last_error("DFT length " + std::to_string(g.N) + " exceeds the 65536-point limit of the FFT schedule tables");
+        if (ilog2(g.Pf) - 1 > 16 || ilog2(g.Ni) - 1 > 16) {   // the reference's own table limit (rate/rate_uni.c:134-189): N = 2^17
+          set_last_error("DFT length " + std::to_string(g.N) + " exceeds the 131072-point limit of the FFT tables");
           return RR_INTERNAL;
         }
         dft_big_[i] = need > max_smem_;             // work buffers in global scratch instead of shared memory

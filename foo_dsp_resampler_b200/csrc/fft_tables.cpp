@@ -9,8 +9,6 @@
 namespace b200rate {
 
 namespace {
-// Same bank-conflict padding as cslot() in rate_kernels.cuh: one extra complex slot per 16.
-inline int padded_slot(int p) { return p + (p >> 4); }
 constexpr double kPi = 3.14159265358979323846;
 constexpr double kSqrtHalf = 0.70710678118654752440;
 
@@ -46,7 +44,7 @@ int split_radix_index(int i, int n, int inverse)
 
 CfftHostSched build_cfft_sched(int bits)
 {
-  assert(bits >= 5 && bits <= 15);
+  assert(bits >= 5 && bits <= 16);
   CfftHostSched s;
   s.bits = bits;
   const int m = 1 << bits;
@@ -72,10 +70,10 @@ CfftHostSched build_cfft_sched(int bits)
     s.gather8[inv].assign(static_cast<size_t>(8) * n8, 0);
     for (int t = 0; t < n16; ++t)
       for (int e = 0; e < 16; ++e)
-        s.gather16[inv][static_cast<size_t>(e) * n16 + t] = static_cast<uint16_t>(padded_slot(natural[s.leaf16_off[t] + e]));
+        s.gather16[inv][static_cast<size_t>(e) * n16 + t] = static_cast<uint16_t>(natural[s.leaf16_off[t] + e]);
     for (int t = 0; t < n8; ++t)
       for (int e = 0; e < 8; ++e)
-        s.gather8[inv][static_cast<size_t>(e) * n8 + t] = static_cast<uint16_t>(padded_slot(natural[s.leaf8_off[t] + e]));
+        s.gather8[inv][static_cast<size_t>(e) * n8 + t] = static_cast<uint16_t>(natural[s.leaf8_off[t] + e]);
   }
   return s;
 }

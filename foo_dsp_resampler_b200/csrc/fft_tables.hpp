@@ -11,11 +11,11 @@
 
 namespace b200rate {
 
-// Schedule of a complex FFT of M = 1 << bits points (5 <= bits <= 15: padded slots must fit 16 bits).
+// Schedule of a complex FFT of M = 1 << bits points (5 <= bits <= 16: positions are 16-bit; the kernels add the padding).
 struct CfftHostSched {
   int bits = 0;
   std::vector<uint16_t> leaf16_off, leaf8_off;   // permuted offsets of the register-resident leaves
-  std::vector<uint16_t> gather16[2], gather8[2]; // [inverse]: transposed [element][leaf] padded slots of the natural indices
+  std::vector<uint16_t> gather16[2], gather8[2]; // [inverse]: transposed [element][leaf] natural indices feeding the leaf
   std::vector<uint16_t> node_off;                // node offsets of sizes 32..M, concatenated
   int level_begin[17] = {0}, level_cnt[17] = {0};
   // nodes of each size that are QUARTER children of a node four times their size (the others are the first

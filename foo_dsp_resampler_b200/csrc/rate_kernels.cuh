@@ -209,7 +209,7 @@ struct CfftSched {
   int n16, n8;                   // leaves: nodes of size 16, and size-8 quarter-children of size-32 nodes
   const uint16_t *leaf16_off;    // [n16] offset of the leaf in the permuted array
   const uint16_t *leaf8_off;     // [n8]
-  const uint16_t *gather16;      // [16][n16] padded slot (cslot) of the natural index feeding permuted element off+e
+  const uint16_t *gather16;      // [16][n16] natural index feeding permuted element off+e (stored at cslot() of it)
   const uint16_t *gather8;       // [8][n8]
   const uint16_t *node_off;      // concatenated node offsets for sizes 32 .. M
   int level_begin[17], level_cnt[17];
@@ -314,7 +314,7 @@ RR_PROG void cfft_leaf_task(const CfftSched &s, int task, int lanes, const C2<T>
   if (task < s.n16) {
     int g[16];
 #pragma unroll
-    for (int e = 0; e < 16; ++e) g[e] = ldg(s.gather16 + e * s.n16 + task);
+    for (int e = 0; e < 16; ++e) g[e] = cslot(ldg(s.gather16 + e * s.n16 + task));
     const int base = cslot(ldg(s.leaf16_off + task));             // multiples of 16: slots stay contiguous
 #pragma unroll
     for (int l = 0; l < LPC; ++l) {
@@ -331,7 +331,7 @@ RR_PROG void cfft_leaf_task(const CfftSched &s, int task, int lanes, const C2<T>
     const int t8 = task - s.n16;
     int g[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) g[e] = ldg(s.gather8 + e * s.n8 + t8);
+    for (int e = 0; e < 8; ++e) g[e] = cslot(ldg(s.gather8 + e * s.n8 + t8));
     const int base = cslot(ldg(s.leaf8_off + t8));                // multiples of 8: never straddle a pad slot
 #pragma unroll
     for (int l = 0; l < LPC; ++l) {

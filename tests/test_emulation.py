@@ -40,6 +40,8 @@ CASES = [
     (32000, 24000, "float", 50, 95, 0, 0, 2), (32000, 24000, "float", 50, 95, 1, 0, 2), (32000, 24000, "double", 50, 95, 0, 0, 1),
     (44100, 8000, "float", 50, 95, 0, 1, 2), (32000, 8000, "float", 50, 95, 0, 1, 1), (48000, 48000, "float", 50, 95, 0, 0, 2),
     (48000, 48000, "double", 50, 95, 0, 0, 3),
+    # N = 131072, the reference's table limit (rate_uni.c:134-189): bandwidth 99.9 %
+    (44100, 48000, "float", 50, 99.9, 0, 0, 2), (96000, 48000, "double", 50, 99.9, 0, 0, 1),
 ]
 
 
@@ -52,7 +54,7 @@ def test_stream_front_end(case):
     i, o, eng, ph, bw, al, q, nch = case
     L = emulib.lib()
     cfg, ocfg = _capi.make_config(i, o, ph, bw, al, q), oraclelib.make_config(i, o, ph, bw, al, q)
-    x = signals.sweep_noise(i, nch, int(i * 0.3) + 11)
+    x = signals.sweep_noise(i, nch, int(i * (3.3 if bw > 99.8 else 0.3)) + 11)      # N = 131072 blocks consume ~1.2 s each
     yo, co = oraclelib.resample(ocfg, x, engine=eng, chunk=3001, native=True)
     ye, ce = converter.resample(cfg, x, engine=eng, chunk=3001, native=True, lib=L)
     assert ce == co

@@ -58,6 +58,8 @@ STREAM_CASES = [
     (32000, 8000, "double", 50, 95, 0, 0, 1),     # h11, fp64
     (48000, 48000, "float", 50, 95, 0, 0, 2),     # identity
     (48000, 48000, "double", 50, 95, 0, 0, 3),
+    (44100, 48000, "float", 50, 99.9, 0, 0, 2),   # N = 131072: the reference's FFT table limit (rate_uni.c:134-189)
+    (96000, 48000, "double", 50, 99.9, 0, 0, 1),
 ]
 
 # batches (device-resident entry point: pair-interleaved intermediate FIFOs between DFT and polyphase stages)
@@ -86,7 +88,7 @@ def test_stream_matches_oracle(case):
     import foo_dsp_resampler_b200 as pkg
     i, o, eng, ph, bw, al, q, nch = case
     cfg, ocfg = _cfgs(i, o, ph, bw, al, q)
-    x = signals.sweep_noise(i, nch, int(i * 0.6) + 17)
+    x = signals.sweep_noise(i, nch, int(i * (3.3 if bw > 99.8 else 0.6)) + 17)
     y_ref, c_ref = oraclelib.resample(ocfg, x, engine=eng, chunk=7001, native=True)
     y, c = pkg.resample(cfg, x, engine=eng, chunk=7001, native=True)
     assert c == c_ref                                   # frames available after every push / drain
