@@ -528,6 +528,28 @@ def e2e_batch(torch, pkg, m, dist, barrier, local_rank):
                   "H2D / kernels / D2H on three CUDA streams)" % (tot, sub),
            "streams": tot, "seconds_per_step": dt, "h2d_GBps": h2d / dt / 1e9, "d2h_GBps": d2h / dt / 1e9,
            "note": "bound by the host link: both directions of PCIe carry %.1f B per output sample" % ((h2d + d2h) / (tot * m.nout * m.nch))}
+    # the ceiling of this box for the same bytes: H2D and D2H of the whole batch on two streams, no kernels
+    try:
+        d_in, d_out = m.x, m.y
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            with torch.cuda.stream(s_in):
+                d_in.copy_(h_in, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                h_out.copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize()
+        ct = torch.tensor([(time.perf_counter() - t0) / 2], dtype=torch.float64, device="cuda")
+        if dist:
+            dist.all_reduce(ct, op=dist.ReduceOp.MAX)
+        ct = float(ct.item())
+        e2e["copy_only"] = {"seconds_per_step": ct, "value": m.total_out_samples / ct / 1e6, "h2d_GBps_per_gpu": h2d / ct / 1e9,
+                            "d2h_GBps_per_gpu": d2h / ct / 1e9,
+                            "note": "same bytes, both directions at once, no kernels: what the host link of this box allows "
+                                    "(all ranks at once); e2e / copy_only = %.2f" % (ct / dt)}
+    except Exception as exc:  # noqa: BLE001
+        e2e["copy_only"] = {"error": str(exc)}
     # check: the bits of the device-resident run (slices, to bound the comparison's memory)
     ok = True
     for s0 in range(0, tot, 256):

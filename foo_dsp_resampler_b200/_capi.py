@@ -90,6 +90,8 @@ SYMBOLS = {
     "RRX_multi_result": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "RRX_multi_gather": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "RRX_multi_close": (None, [C.POINTER(C.c_void_p)]),
+    "RRX_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "RRX_host_free": (None, [C.c_void_p]),
     "RRX_batch_last_launches": (C.c_int, [C.c_void_p]),
     "RRX_batch_flops": (C.c_double, [C.c_void_p, C.c_size_t]),
     "RRX_batch_close": (None, [C.POINTER(C.c_void_p)]),

@@ -269,14 +269,18 @@ __device__ __forceinline__ PkTables pk_stage_tables(const DftPkParams &pp)
   return PkTables{pf, pi, tf, ti, pm};
 }
 
-template <int MODE, int FB, int IB, bool STEREO>
-__global__ void __launch_bounds__(kPkGroupThreads * kPkMaxGroups) dftp_kernel(const __grid_constant__ DftPkParams pp, long long nwork)
+// GROUPS == kPkMaxGroups: every group has a forward and an inverse buffer. GROUPS == kPkInplaceGroups: one buffer per
+// group (the spectrum phase goes through registers, pk_spectrum_inplace), which lets a fifth group -- four more
+// warps to hide shared-memory latency with -- share the SM at 102 registers per thread.
+template <int MODE, int FB, int IB, bool STEREO, int GROUPS = kPkMaxGroups>
+__global__ void __launch_bounds__(kPkGroupThreads * GROUPS) dftp_kernel(const __grid_constant__ DftPkParams pp, long long nwork)
 {
+  constexpr bool kInplace = GROUPS != kPkMaxGroups;
   const PkTables tb = pk_stage_tables(pp);
   const int gi = threadIdx.x / kPkGroupThreads;          // pp.gthreads == kPkGroupThreads: a literal keeps it out of registers
   const Grp g{(int)threadIdx.x % kPkGroupThreads, kPkGroupThreads, 1 + gi};
-  CPk *F = reinterpret_cast<CPk *>(rr_smem_raw + pp.lay_data) + (size_t)gi * (pp.fslots + pp.bslots), *B = F + pp.fslots;
-  __shared__ PkItem items[kPkMaxGroups][2];
+  CPk *F = reinterpret_cast<CPk *>(rr_smem_raw + pp.lay_data) + (size_t)gi * (pp.fslots + pp.bslots), *B = F + pp.fslots;   // in place: fslots == 0
+  __shared__ PkItem items[GROUPS][2];
   __syncthreads();
   // 32-bit work counters (the host splits launches of more than 2^30 items)
   int w = (int)blockIdx.x * pp.groups + gi;
@@ -286,7 +290,7 @@ __global__ void __launch_bounds__(kPkGroupThreads * kPkMaxGroups) dftp_kernel(co
   }
   for (int n = 0; w < nw; w += stride, n ^= 1) {
     const int next = w + stride < nw ? w + stride : -1;
-    dftp_program<MODE, FB, IB, STEREO>(pp, g, tb, items[gi], n, next, F, B);
+    dftp_program<MODE, FB, IB, STEREO, kInplace>(pp, g, tb, items[gi], n, next, F, B);
   }
 }
 
@@ -546,7 +550,9 @@ static int launch_dftp(const DftPkParams &pp, long long nwork, stream_t s)
   for (long long w = 0; w < nwork; ++w) {
     PkItem items[2];
     items[0] = pk_make_item(pp, w);
-    if (pp.spec_mode == PK_SPEC_UP2 && pp.stereo) dftp_program<PK_SPEC_UP2, 0, 0, true>(pp, g, tb, items, 0, -1, F, B);
+    if (pp.fslots == 0 && pp.stereo) dftp_program<PK_SPEC_UP2, 10, 11, true, true>(pp, g, tb, items, 0, -1, F, B);   // one buffer per group
+    else if (pp.fslots == 0) dftp_program<PK_SPEC_UP2, 10, 11, false, true>(pp, g, tb, items, 0, -1, F, B);
+    else if (pp.spec_mode == PK_SPEC_UP2 && pp.stereo) dftp_program<PK_SPEC_UP2, 0, 0, true>(pp, g, tb, items, 0, -1, F, B);
     else if (pp.spec_mode == PK_SPEC_UP2) dftp_program<PK_SPEC_UP2, 0, 0, false>(pp, g, tb, items, 0, -1, F, B);
     else if (pp.spec_mode == PK_SPEC_SAME && pp.stereo) dftp_program<PK_SPEC_SAME, 0, 0, true>(pp, g, tb, items, 0, -1, F, B);
     else if (pp.spec_mode == PK_SPEC_SAME) dftp_program<PK_SPEC_SAME, 0, 0, false>(pp, g, tb, items, 0, -1, F, B);
@@ -569,7 +575,10 @@ static int launch_dftp(const DftPkParams &pp, long long nwork, stream_t s)
   // the common Best-quality sizes get kernels specialised on (forward, inverse) transform size; every kernel exists for
   // adjacent stereo frames as input (the caller's buffer of a stereo stream, a pair-interleaved FIFO) and for any layout
 #define RR_DFTP(MODE, FBV, IBV) (pp.stereo ? go(dftp_kernel<MODE, FBV, IBV, true>) : go(dftp_kernel<MODE, FBV, IBV, false>))
+#define RR_DFTP_G(MODE, FBV, IBV, G) (pp.stereo ? go(dftp_kernel<MODE, FBV, IBV, true, G>) : go(dftp_kernel<MODE, FBV, IBV, false, G>))
   if (pp.spec_mode == PK_SPEC_UP2) {
+    if (pp.fb == 10 && pp.ib == 11 && pp.fslots == 0 && pp.groups == 5) return RR_DFTP_G(PK_SPEC_UP2, 10, 11, 5);   // one buffer per group
+    if (pp.fb == 10 && pp.ib == 11 && pp.fslots == 0 && pp.groups == 6) return RR_DFTP_G(PK_SPEC_UP2, 10, 11, 6);
     if (pp.fb == 10 && pp.ib == 11) return RR_DFTP(PK_SPEC_UP2, 10, 11);      // N = 4096, x2 (44.1 <-> 48 family)
     return RR_DFTP(PK_SPEC_UP2, 0, 0);
   }
@@ -580,6 +589,7 @@ static int launch_dftp(const DftPkParams &pp, long long nwork, stream_t s)
   if (pp.fb == 11 && pp.ib == 10) return RR_DFTP(PK_SPEC_GEN, 11, 10);        // N = 4096, F-domain / 2
   return RR_DFTP(PK_SPEC_GEN, 0, 0);
 #undef RR_DFTP
+#undef RR_DFTP_G
 #endif
 }
 
@@ -1328,6 +1338,8 @@ template <class T> class Engine {
   // traffic and half the device memory of a 48 -> 44.1 kHz batch) but measures 30 % slower than the two kernels on a
   // B200 -- the stages are issue / latency bound, not HBM bound, and the polyphase phase occupies only the 74 threads
   // of a group that own a slot pair (profiles/README.md, round 2). B200RATE_FUSED=1 selects it.
+  // groups per CTA of the single-buffer DFT kernel: 5 (102 registers per thread) or 6 (85); 4 = the two-buffer kernel
+  int pk_inplace_groups_ = getenv("B200RATE_DFT_GROUPS") ? atoi(getenv("B200RATE_DFT_GROUPS")) : kPkInplaceGroups;
   bool use_fused_ = getenv("B200RATE_FUSED") != nullptr && atoi(getenv("B200RATE_FUSED")) != 0;
 
   // Per-thread tables of the fused kernel's polyphase phase: thread t owns the slot pair (s, s + 1) of every period
@@ -1428,6 +1440,20 @@ template <class T> class Engine {
     pp.spec = pk_spec_dev_[i];
     if (pp.spec_mode != PK_SPEC_GEN && !pp.spec) return false;
     pp.n_pyr_f = pk_pyr_len(fb); pp.n_pyr_i = pk_pyr_len(ib); pp.n_ltab_f = sf->second.pk_ltab_len; pp.n_ltab_i = si->second.pk_ltab_len;
+    // one buffer per group and more groups per SM where the kernel exists (x2 up-sampling with N = 4096, no fused
+    // polyphase stage): the forward transform works in the first slots of the inverse buffer
+    if (halo_slots == 0 && pk_inplace_groups_ > kPkMaxGroups && pp.spec_mode == PK_SPEC_UP2 && fb == 10 && ib == 11) {
+      pp.fslots = 0;
+      pp.bslots = std::max(pk_buf_slots(g.Pf >> 1), pk_buf_slots(g.Ni >> 1));
+      pp.groups = pk_inplace_groups_;
+      if (pk_smem_layout(pp).total + 2048 <= max_smem_) {
+        const PkSmemLayout lay = pk_smem_layout(pp);
+        pp.lay_pyr_f = lay.pyr_f; pp.lay_pyr_i = lay.pyr_i; pp.lay_ltab_f = lay.ltab_f; pp.lay_ltab_i = lay.ltab_i;
+        pp.lay_perm_f = lay.perm_f; pp.lay_data = lay.data;
+        return true;
+      }
+      pp.fslots = pk_buf_slots(g.Pf >> 1); pp.bslots = pk_buf_slots(g.Ni >> 1);
+    }
     for (pp.groups = kPkMaxGroups; pp.groups >= 1; --pp.groups)
       if (pk_smem_layout(pp).total + 1024 <= max_smem_) break;
     if (pp.groups < 1) return false;

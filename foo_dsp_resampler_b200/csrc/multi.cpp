@@ -353,6 +353,27 @@ int RRX_multi_gather(RRX_multi *m, int root, float *d_out_root)
 #endif
 }
 
+// Page-locked host memory for callers that do not link CUDA themselves (a C host program): buffers from here make
+// the host-buffer entry points run at the speed of the host link instead of that of a pageable staging copy.
+void *RRX_host_alloc(size_t bytes)
+{
+#ifdef B200RATE_EMU
+  return malloc(bytes ? bytes : 1);
+#else
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+#endif
+}
+void RRX_host_free(void *p)
+{
+#ifdef B200RATE_EMU
+  free(p);
+#else
+  if (p) cudaFreeHost(p);
+#endif
+}
+
 void RRX_multi_close(RRX_multi **pm)
 {
   if (!pm || !*pm) return;

@@ -107,6 +107,7 @@ RR_PROG Pk pk_load8(const Pk *p)                         // one 8-byte shared / 
 // ---------------------------------------------------------------------------------------------------
 struct Grp { int tid, size, bar; };                        // index inside the group, threads, named barrier id
 constexpr int kPkGroupThreads = 128, kPkMaxGroups = 4;    // threads per group, groups per CTA of the lane-pair DFT kernels
+constexpr int kPkInplaceGroups = 5;                        // ... of the single-buffer variant (pk_spectrum_inplace)
 
 #if defined(__CUDACC__)
 RR_PROG void grp_sync(const Grp &g) { asm volatile("bar.sync %0, %1;" ::"r"(g.bar), "r"(g.size) : "memory"); }
@@ -680,56 +681,63 @@ RR_PROG void pk_spec_prefetch(const DftPkParams &pp, const Grp &g, PkSpecRegs &p
   }
 }
 
+// One index of the spectrum phase: (za, zb) = (F[i], F[M - i]) -- for i == 0: (F[0], F[M/2]) -- and its constants k;
+// writes the two or four bins of the inverse transform's input they determine.
+template <int MODE>
+RR_PROG void pk_spec_index(int i, const PkSpecConst &k, const CPk &za, const CPk &zb, CPk *B)
+{
+  typedef Arith<Pk> A;
+  const int sl0 = k.s01 & 0xffff, sl1 = k.s01 >> 16, sl2 = k.s23 & 0xffff, sl3 = k.s23 >> 16;
+  if (i == 0) {
+    // bins 0 and Pf/2 (packed in F[0]) and the self-paired bin M/2
+    // record 0 carries the constants of M/2 in c0, c1, tic, tis, s01 and those of the real bins in the
+    // fields index 0 has no use for: c2 = coef[0], c3 = coef[M], s23 = slots of d[0] and d[M]
+    const CPk x0 = CPk{A::add(za.x, za.y), A::sub(za.x, za.y)};                // rdft.c:46-48
+    CPk zm = zb;
+    zm.y = pk_neg(zm.y);                                                       // rdft.c:77 (forward)
+    if (MODE == PK_SPEC_UP2) {
+      // spectrum[0] = (X0.re, X0.re); d[0] = (.5 (d0 + d1), .5 (d0 - d1)), dft_filter.h:96-98,118-119, rdft.c:44-46,79-80
+      const Pk d0 = A::mul(x0.x, pk_bcast(k.c2.x)), d1 = A::mul(x0.x, pk_bcast(k.c2.y));
+      B[sl2] = CPk{A::mul(A::addp(d0, d1), pk_bcast(0.5f)), A::mul(A::subp(d0, d1), pk_bcast(0.5f))};
+      // bin Ni/4 = M: spectrum = (X0.im, 0); d[M] = conj(coef[M] * spectrum)
+      B[sl3] = pk_conj(pk_cmul(k.c3, CPk{x0.y, pk_bcast(0.0f)}));
+      // bins M/2 and Ni/2 - M/2: spectrum[M/2] = X[M/2], spectrum[Ni/2 - M/2] = conj(X[M/2])
+      CPk da, db;
+      pk_mul_pre_pair(zm, pk_conj(zm), k.c0, k.c1, k.tic, k.tis, da, db);
+      B[sl0] = da; B[sl1] = db;
+    } else {
+      const Pk d0 = A::mul(x0.x, pk_bcast(k.c2.x)), d1 = A::mul(x0.y, pk_bcast(k.c2.y));
+      B[sl2] = CPk{A::mul(A::addp(d0, d1), pk_bcast(0.5f)), A::mul(A::subp(d0, d1), pk_bcast(0.5f))};
+      // bin Ni/4 = M/2: d = conj(coef * X[M/2])
+      B[sl0] = pk_conj(pk_cmul(k.c0, zm));
+    }
+    return;
+  }
+  CPk xa, xb;
+  pk_post_pair(za, zb, k.tfc, k.tfs, xa, xb);
+  if (MODE == PK_SPEC_UP2) {
+    // bins i / Ni/2 - i see X[i] / conj(X[i]); bins M - i / M + i see X[M-i] / conj(X[M-i])
+    CPk da, db;
+    pk_mul_pre_pair(xa, pk_conj(xa), k.c0, k.c1, k.tic, k.tis, da, db);
+    B[sl0] = da; B[sl1] = db;
+    pk_mul_pre_pair(xb, pk_conj(xb), k.c2, k.c3, k.tis, k.tic, da, db);
+    B[sl2] = da; B[sl3] = db;
+  } else {
+    CPk da, db;
+    pk_mul_pre_pair(xa, xb, k.c0, k.c1, k.tic, k.tis, da, db);
+    B[sl0] = da; B[sl1] = db;
+  }
+}
+
 template <int MODE, bool PIPE = true>
 RR_PROG void pk_spectrum(const DftPkParams &pp, const Grp &g, const PkSpecRegs &pre, const CPk *F, CPk *B)
 {
-  typedef Arith<Pk> A;
   const DftParams<float> &p = pp.base;
   const int M = p.Pf >> 1;                               // forward transform: M complex points
   const int n = M >> 1;
   auto body = [&](int i, const PkSpecConst &k) {
-    const int sl0 = k.s01 & 0xffff, sl1 = k.s01 >> 16, sl2 = k.s23 & 0xffff, sl3 = k.s23 >> 16;
-    if (i == 0) {
-      // bins 0 and Pf/2 (packed in F[0]) and the self-paired bin M/2
-      // record 0 carries the constants of M/2 in c0, c1, tic, tis, s01 and those of the real bins in the
-      // fields index 0 has no use for: c2 = coef[0], c3 = coef[M], s23 = slots of d[0] and d[M]
-      const CPk z = F[0];
-      const CPk x0 = CPk{A::add(z.x, z.y), A::sub(z.x, z.y)};                  // rdft.c:46-48
-      CPk zm = F[pslot(n)];
-      zm.y = pk_neg(zm.y);                                                       // rdft.c:77 (forward)
-      if (MODE == PK_SPEC_UP2) {
-        // spectrum[0] = (X0.re, X0.re); d[0] = (.5 (d0 + d1), .5 (d0 - d1)), dft_filter.h:96-98,118-119, rdft.c:44-46,79-80
-        const Pk d0 = A::mul(x0.x, pk_bcast(k.c2.x)), d1 = A::mul(x0.x, pk_bcast(k.c2.y));
-        B[sl2] = CPk{A::mul(A::addp(d0, d1), pk_bcast(0.5f)), A::mul(A::subp(d0, d1), pk_bcast(0.5f))};
-        // bin Ni/4 = M: spectrum = (X0.im, 0); d[M] = conj(coef[M] * spectrum)
-        B[sl3] = pk_conj(pk_cmul(k.c3, CPk{x0.y, pk_bcast(0.0f)}));
-        // bins M/2 and Ni/2 - M/2: spectrum[M/2] = X[M/2], spectrum[Ni/2 - M/2] = conj(X[M/2])
-        CPk da, db;
-        pk_mul_pre_pair(zm, pk_conj(zm), k.c0, k.c1, k.tic, k.tis, da, db);
-        B[sl0] = da; B[sl1] = db;
-      } else {
-        const Pk d0 = A::mul(x0.x, pk_bcast(k.c2.x)), d1 = A::mul(x0.y, pk_bcast(k.c2.y));
-        B[sl2] = CPk{A::mul(A::addp(d0, d1), pk_bcast(0.5f)), A::mul(A::subp(d0, d1), pk_bcast(0.5f))};
-        // bin Ni/4 = M/2: d = conj(coef * X[M/2])
-        B[sl0] = pk_conj(pk_cmul(k.c0, zm));
-      }
-      return;
-    }
-    const CPk za = F[pslot(i)], zb = F[pslot(M - i)];
-    CPk xa, xb;
-    pk_post_pair(za, zb, k.tfc, k.tfs, xa, xb);
-    if (MODE == PK_SPEC_UP2) {
-      // bins i / Ni/2 - i see X[i] / conj(X[i]); bins M - i / M + i see X[M-i] / conj(X[M-i])
-      CPk da, db;
-      pk_mul_pre_pair(xa, pk_conj(xa), k.c0, k.c1, k.tic, k.tis, da, db);
-      B[sl0] = da; B[sl1] = db;
-      pk_mul_pre_pair(xb, pk_conj(xb), k.c2, k.c3, k.tis, k.tic, da, db);
-      B[sl2] = da; B[sl3] = db;
-    } else {
-      CPk da, db;
-      pk_mul_pre_pair(xa, xb, k.c0, k.c1, k.tic, k.tis, da, db);
-      B[sl0] = da; B[sl1] = db;
-    }
+    if (i == 0) pk_spec_index<MODE>(0, k, F[0], F[pslot(n)], B);
+    else pk_spec_index<MODE>(i, k, F[pslot(i)], F[pslot(M - i)], B);
   };
   // software pipeline, two records live: the record of the next round is requested before a round is computed
   static_assert(kPkSpecRounds == 1 && kPkSpecLate == 3, "pipeline below is written for 1 + 3 rounds");
@@ -750,6 +758,38 @@ RR_PROG void pk_spectrum(const DftPkParams &pp, const Grp &g, const PkSpecRegs &
   if (i3 < n) body(i3, rb);
   for (int i = g.tid + (kPkSpecRounds + kPkSpecLate) * g.size; i < n; i += g.size) body(i, pk_load_spec(pp.spec + i));
   grp_sync(g);
+}
+
+// The same phase IN PLACE: the forward transform's result and the inverse transform's input share one buffer W (the
+// forward result occupies its first slots). Every thread first takes its pairs (F[i], F[M - i]) into registers, the
+// group synchronises, then the bins are written -- so a group needs one buffer instead of two and five groups fit an
+// SM where four did. Compile-time size only (the register arrays must be static).
+template <int MODE, int FB>
+RR_PROG void pk_spectrum_inplace(const DftPkParams &pp, const Grp &g, CPk *W)
+{
+  constexpr int M = 1 << FB, n = M >> 1;
+#if defined(__CUDA_ARCH__)
+  constexpr int R = (n + kPkGroupThreads - 1) / kPkGroupThreads;
+  CPk za[R], zb[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int i = g.tid + r * kPkGroupThreads;
+    if (i < n) { za[r] = W[i ? pslot(i) : 0]; zb[r] = W[i ? pslot(M - i) : pslot(n)]; }
+  }
+  grp_sync(g);
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int i = g.tid + r * kPkGroupThreads;
+    if (i < n) pk_spec_index<MODE>(i, pk_load_spec(pp.spec + i), za[r], zb[r], W);
+  }
+  grp_sync(g);
+#else
+  (void)g;
+  CPk *za = new CPk[n], *zb = new CPk[n];
+  for (int i = 0; i < n; ++i) { za[i] = W[i ? pslot(i) : 0]; zb[i] = W[i ? pslot(M - i) : pslot(n)]; }
+  for (int i = 0; i < n; ++i) pk_spec_index<MODE>(i, pk_load_spec(pp.spec + i), za[i], zb[i], W);
+  delete[] za; delete[] zb;
+#endif
 }
 
 // Generic spectrum path (any L, F-domain decimation): forward post-processing in place, then the bins of
@@ -815,7 +855,7 @@ struct PkTables { const float *pyr_f, *pyr_i; const uint16_t *ltab_f, *ltab_i, *
 
 // One work item (block b, lane pair). F holds (or is receiving) the item's input tile; items[slot] describes
 // this item, items[slot ^ 1] is filled for the next one, whose tile is requested as soon as F is free.
-template <int MODE, int FB, int IB, bool STEREO>
+template <int MODE, int FB, int IB, bool STEREO, bool INPLACE = false>
 RR_PROG void dftp_program(const DftPkParams &pp, const Grp &g, const PkTables &tb, PkItem *items, int slot, long long work_next,
                           CPk *F, CPk *B)
 {
@@ -832,11 +872,17 @@ RR_PROG void dftp_program(const DftPkParams &pp, const Grp &g, const PkTables &t
     pk_fft_top_any<FB>(pp.fb, g, F, nullptr, tb.pyr_f, false, sink);
     pk_spectrum_generic(pp, g, F, B);
   } else {
-    PkSpecRegs pre;
-    if (FB > 0 && kPkPrefetchAcrossTop) pk_spec_prefetch<MODE>(pp, g, pre);   // in flight while the (inlined) top forward phase runs
-    pk_fft_top_any<FB>(pp.fb, g, F, nullptr, tb.pyr_f, false, sink);
-    if (FB == 0 || !kPkPrefetchAcrossTop) pk_spec_prefetch<MODE>(pp, g, pre);   // not across a call: the registers would be spilled
-    pk_spectrum<MODE>(pp, g, pre, F, B);
+    if constexpr (INPLACE) {
+      static_assert(FB > 0, "in-place spectrum phase needs a compile-time size");
+      pk_fft_top_any<FB>(pp.fb, g, F, nullptr, tb.pyr_f, false, sink);
+      pk_spectrum_inplace<MODE, FB>(pp, g, B);                                  // F == B
+    } else {
+      PkSpecRegs pre;
+      if (FB > 0 && kPkPrefetchAcrossTop) pk_spec_prefetch<MODE>(pp, g, pre);   // in flight while the (inlined) top forward phase runs
+      pk_fft_top_any<FB>(pp.fb, g, F, nullptr, tb.pyr_f, false, sink);
+      if (FB == 0 || !kPkPrefetchAcrossTop) pk_spec_prefetch<MODE>(pp, g, pre);   // not across a call: the registers would be spilled
+      pk_spectrum<MODE>(pp, g, pre, F, B);
+    }
   }
   if (work_next >= 0) pk_tile_prefetch(pp, g, items[slot ^ 1]);   // published before the barriers of the forward transform
 

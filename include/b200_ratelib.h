@@ -66,7 +66,10 @@ int RR_open(const RR_config *config, int nchannels, RR_handle **const handle);
 /* rate/rate_base.h:571-614: pull, then push, then pull again into the remaining space. */
 int RR_flow(RR_handle *h, const fb_sample_t *ibuf, fb_sample_t *obuf, size_t isamp, size_t osamp,
             size_t *iused, size_t *ogen);
-/* rate/rate_base.h:616-636: consumes min(isamp, isamp_max) frames (silently, like the reference). */
+/* rate/rate_base.h:616-636: consumes min(isamp, isamp_max) frames (silently, like the reference). Returns when
+ * ibuf has been consumed (copied into the handle's page-locked staging, or -- for a page-locked ibuf -- transferred),
+ * NOT when the stage kernels have run: they execute asynchronously on the handle's CUDA stream, and a device failure
+ * in one of them is reported by the next RR_pull / RR_drain / RR_flow of the handle. */
 int RR_push(RR_handle *h, const fb_sample_t *ibuf, size_t isamp);
 /* rate/rate_base.h:638-660: writes at most osamp frames; *ogen = frames written (0: nothing ready). */
 int RR_pull(RR_handle *h, fb_sample_t *obuf, size_t osamp, size_t *ogen);
@@ -184,6 +187,11 @@ int RRX_multi_result(const RRX_multi *m, int k, const float **d_out, size_t *fra
 /* ... until gathered on device index `root`: d_out_root is float32 [nstreams][frames_out][nchannels] on that device. */
 int RRX_multi_gather(RRX_multi *m, int root, float *d_out_root);
 void RRX_multi_close(RRX_multi **m);
+/* Page-locked ("pinned") host memory for callers that do not link CUDA themselves: buffers from here let the
+ * host-buffer entry points (RR_push / RR_pull, RRX_batch_process_host, RRX_multi_process_*_host) transfer at the
+ * speed of the host link, without a staging copy. NULL on failure. */
+void *RRX_host_alloc(size_t bytes);
+void RRX_host_free(void *p);
 
 /* Last CUDA error string seen by this library on the calling thread ("" if none). */
 const char *RRX_last_error(void);
