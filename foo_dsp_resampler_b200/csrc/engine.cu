@@ -416,6 +416,33 @@ __global__ void __launch_bounds__(kTileThreads) polyN_kernel(const __grid_consta
   T *smem = reinterpret_cast<T *>(rr_smem_raw);
   for (long long w = blockIdx.x; w < nwork; w += gridDim.x) polyN_program<T, InT, OutT>(p, w, smem);
 }
+// vpoly0 with two slots per thread for scalar (fp64) lanes: persistent CTA, one window buffer staged by TMA bulk copies
+// (the other CTAs of the SM cover the load), coefficient rows in registers for the whole launch.
+template <class T, class OutT, int NT, int DLO>
+__global__ void __launch_bounds__(256, 2) poly0_dual_kernel(const __grid_constant__ Poly0DualParams<T> dp, long long nwork)
+{
+  T *smem = reinterpret_cast<T *>(rr_smem_raw);
+  __shared__ Poly0DualTile tiles[2];
+  __shared__ __align__(8) unsigned long long bar;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  long long w = blockIdx.x;
+  if (w >= nwork) return;
+  if (tid == 0) { tma_bar_init(&bar, 1); tiles[0] = poly0_dual_tile(dp, w); }
+  __syncthreads();
+  poly0_dual_load(dp, tiles[0], smem, &bar, tid, nt);
+  const Poly0DualThread<T, OutT, NT, DLO> st = poly0_dual_setup<T, OutT, NT, DLO>(dp, tid);
+  unsigned phase = 0;
+  for (int it = 0; w < nwork; w += gridDim.x, ++it) {
+    const int ts = it & 1;
+    const long long next = w + gridDim.x;
+    if (tid == 0 && next < nwork) tiles[ts ^ 1] = poly0_dual_tile(dp, next);
+    if (tiles[ts].tma) { tma_bar_wait(&bar, phase); phase ^= 1; }
+    __syncthreads();
+    poly0_dual_compute<T, OutT, NT, DLO>(dp, tiles[ts], smem, st);
+    __syncthreads();
+    if (next < nwork) poly0_dual_load(dp, tiles[ts ^ 1], smem, &bar, tid, nt);
+  }
+}
 template <class T, class InT, class OutT, int NC>
 __global__ void __launch_bounds__(kTileThreads) halfband_kernel(const __grid_constant__ HalfbandParams<T> p, long long nwork)
 {
@@ -818,6 +845,33 @@ template <class T> struct Launch {
 #undef RR_CALL32
 #undef RR_CALLN
   }
+  static int poly0_dual(const Poly0DualParams<T> &dp, bool out_f32, long long nwork, size_t smem, stream_t s)
+  {
+    (void)s;
+    const int dlo = static_cast<int>(dp.base.step / dp.base.L), threads = dp.TS * dp.NL;
+#ifdef B200RATE_EMU
+#define RR_CALLD(O, NT, D)                                                                        \
+  serial(nwork, smem, [&](long long w, T *sm) {                                                   \
+    const Poly0DualTile t = poly0_dual_tile(dp, w);                                               \
+    poly0_dual_load(dp, t, sm, nullptr, 0, 1);                                                    \
+    for (int th = 0; th < threads; ++th)                                                          \
+      poly0_dual_compute<T, O, NT, D>(dp, t, sm, poly0_dual_setup<T, O, NT, D>(dp, th));          \
+  })
+#else
+#define RR_CALLD(O, NT, D) launch_persistent(poly0_dual_kernel<T, O, NT, D>, dp, nwork, threads, smem, s)
+#endif
+#define RR_CALLDN(O)                                                                              \
+  do {                                                                                            \
+    if (dp.base.n == 16) { if (dlo == 0) return RR_CALLD(O, 16, 0); if (dlo == 1) return RR_CALLD(O, 16, 1); return RR_CALLD(O, 16, 2); } \
+    if (dlo == 0) return RR_CALLD(O, 24, 0);                                                      \
+    if (dlo == 1) return RR_CALLD(O, 24, 1);                                                      \
+    return RR_CALLD(O, 24, 2);                                                                    \
+  } while (0)
+    if (out_f32 && !kIsF32) RR_CALLDN(float);
+    RR_CALLDN(T);
+#undef RR_CALLDN
+#undef RR_CALLD
+  }
   static int polyN(const PolyParams<T> &p, bool in_f32, bool out_f32, long long nwork, size_t smem, stream_t s)
   {
 #ifdef B200RATE_EMU
@@ -1171,6 +1225,31 @@ template <class T> class Engine {
         }
       }
     }
+    if constexpr (sizeof(T) == 8) {
+      // fp64 engine: two slots per thread, host-dealt slot pairs, TMA-staged windows (poly0_dual_kernel)
+      if (use_dual_poly_ && g.order == 0 && (g.n == 16 || g.n == 24) && !in_f32 && in.elem_stride == 1 && g.Lp >= 32 &&
+          (g.Lp + 1) / 2 <= 128 && g.pstep / g.Lp <= 2 && g.pstep < (1 << 15) && g.at0 >= 0 && g.at0 < g.Lp && p.pre == 0) {
+        int rc;
+        if (!dual_tab_[i].built && (rc = build_dual_tab(i))) return rc;
+        const DualTab &dt = dual_tab_[i];
+        Poly0DualParams<T> dp;
+        dp.base = p;
+        dp.coef = dt.coef; dp.slot = dt.slot; dp.qs = dt.qs; dp.flags = dt.flags; dp.TS = dt.TS;
+        dp.NL = std::max(1, std::min(nlanes, 256 / dt.TS));
+        const int budget = 1536;                                   // doubles per lane window: 12 KB
+        dp.MM = std::max(2, static_cast<int>((budget - g.n - 8) / g.pstep));
+        dp.win = static_cast<int>(((static_cast<long long>(dp.MM) * g.pstep + g.n + 8 + 1) & ~1ll) + 2);
+        dp.m_begin = w0 / g.Lp;
+        const long long m_end = (w0 + wn + g.Lp - 1) / g.Lp;
+        dp.mtiles = (m_end - dp.m_begin + dp.MM - 1) / dp.MM;
+        const long long groups = (nlanes + dp.NL - 1) / dp.NL;
+        const size_t smem = sizeof(T) * static_cast<size_t>(dp.win) * dp.NL;
+        if (dp.mtiles < 0x7fffffffll && smem <= 100 * 1024) {
+          kernel_name[i] = "poly0_dual_kernel (two slots per thread, TMA windows)";
+          return Launch<T>::poly0_dual(dp, out_f32, groups * dp.mtiles, smem, s);
+        }
+      }
+    }
     if (g.order == 0 && (g.n == 16 || g.n == 24 || g.n == 32)) {
       // phase-stationary kernel: needs enough phases to fill a CTA and a window that fits shared memory
       const int nch = in.nch;
@@ -1331,6 +1410,58 @@ template <class T> class Engine {
   void *big_scratch_ = nullptr;              // global work buffers of dft_big_kernel, kBigCtas slices of big_slice_ bytes
   size_t big_slice_ = 0;
   static constexpr int kBigCtas = 296;
+
+  // ---- per-thread tables of poly0_dual_kernel (fp64 vpoly0, two slots per thread): see build_fused_tab ----
+  struct DualTab { const T *coef = nullptr; const uint16_t *slot = nullptr, *qs = nullptr; const uint8_t *flags = nullptr; int TS = 0; bool built = false; };
+  DualTab dual_tab_[RR_MAX_STAGES];
+  bool use_dual_poly_ = getenv("B200RATE_NO_DUAL_POLY") == nullptr;
+
+  int build_dual_tab(int i)
+  {
+    const StageGeom &q = geom[i];
+    const int L = q.Lp, n = q.n, nsp = (L + 1) / 2, dlo = static_cast<int>(q.pstep / q.Lp);
+    const int step = static_cast<int>(q.pstep), at0 = static_cast<int>(q.at0);
+    // deal the slot pairs to half-warps by the 8-byte bank of their first window sample; what does not fit a bank's rows
+    // fills the holes (a two-way conflict each)
+    std::vector<std::vector<int>> bucket(16);
+    for (int sp = 0; sp < nsp; ++sp) bucket[static_cast<size_t>(((at0 + 2 * sp * step) / L) & 15)].push_back(sp);
+    int rows = (nsp + 15) / 16;
+    auto spill_of = [&](int r) { int sp = 0; for (const auto &b : bucket) sp += std::max(0, static_cast<int>(b.size()) - r); return sp; };
+    while (rows < 8 && spill_of(rows) > nsp / 8) ++rows;
+    const int TS = 16 * rows;
+    std::vector<int> owner(static_cast<size_t>(TS), -1), rest;
+    for (int b = 0; b < 16; ++b)
+      for (size_t k = 0; k < bucket[static_cast<size_t>(b)].size(); ++k) {
+        if (static_cast<int>(k) < rows) owner[k * 16 + static_cast<size_t>(b)] = bucket[static_cast<size_t>(b)][k];
+        else rest.push_back(bucket[static_cast<size_t>(b)][k]);
+      }
+    for (int t = 0; t < TS && !rest.empty(); ++t)
+      if (owner[static_cast<size_t>(t)] < 0) { owner[static_cast<size_t>(t)] = rest.back(); rest.pop_back(); }
+    if (!rest.empty()) return RR_INTERNAL;
+    std::vector<uint16_t> slot(static_cast<size_t>(TS), 0xffff), qs(static_cast<size_t>(TS), 0);
+    std::vector<uint8_t> flags(static_cast<size_t>(TS), 0);
+    std::vector<T> coef(static_cast<size_t>(2 * n + 1) * TS, static_cast<T>(0));
+    for (int t = 0; t < TS; ++t) {
+      const int sp = owner[static_cast<size_t>(t)];
+      if (sp < 0) continue;
+      const int s0 = 2 * sp, a0 = at0 + s0 * step, q0 = a0 / L, r0 = a0 % L, a1 = a0 + step, q1 = a1 / L, r1 = a1 % L;
+      const bool two = s0 + 1 < L, d_lo = q1 - q0 == dlo;
+      slot[static_cast<size_t>(t)] = static_cast<uint16_t>(s0);
+      qs[static_cast<size_t>(t)] = static_cast<uint16_t>(q0);
+      flags[static_cast<size_t>(t)] = static_cast<uint8_t>((d_lo ? 1 : 0) | (two ? 2 : 0));
+      for (int k = 0; k < n; ++k) coef[static_cast<size_t>(k) * TS + t] = static_cast<T>(design.poly_bank[static_cast<size_t>(r0) * n + k]);
+      for (int j = 0; j <= n; ++j) {
+        const int k = d_lo ? j : j - 1;
+        if (two && k >= 0 && k < n) coef[static_cast<size_t>(n + j) * TS + t] = static_cast<T>(design.poly_bank[static_cast<size_t>(r1) * n + k]);
+      }
+    }
+    DualTab &dt = dual_tab_[i];
+    int rc;
+    if ((rc = upload(coef, &dt.coef)) || (rc = upload(slot, &dt.slot)) || (rc = upload(qs, &dt.qs)) || (rc = upload(flags, &dt.flags))) return rc;
+    if ((rc = be_sync(0))) return rc;
+    dt.TS = TS; dt.built = true;
+    return RR_OK;
+  }
 
   struct FusedTab { const float *coef = nullptr; const uint16_t *slot = nullptr, *qs = nullptr; const uint8_t *flags = nullptr; int tile_t0 = 0; bool built = false; };
   FusedTab fused_tab_[RR_MAX_STAGES];
@@ -1506,6 +1637,48 @@ template <class T> class Engine {
     sp.s23 = perm[0];
     sp.c3 = C2<float>{0.f, 0.f};
     if (mode == PK_SPEC_UP2) { sp.c3 = coef[M]; sp.s23 |= static_cast<unsigned>(perm[static_cast<size_t>(M)]) << 16; }
+    // where the record's two inputs live in the forward buffer, and whether it is the special index 0
+    for (int k = 0; k < n; ++k) {
+      PkSpecConst &r = rec[static_cast<size_t>(k)];
+      r.fab = k ? static_cast<unsigned>(pk_slot(k)) | (static_cast<unsigned>(pk_slot(M - k)) << 16)
+                : static_cast<unsigned>(pk_slot(0)) | (static_cast<unsigned>(pk_slot(n)) << 16);
+      r.first = k == 0 ? 1u : 0u;
+    }
+    rec.resize(static_cast<size_t>(n));
+    // Record e is handled by lane e % 32 of a warp: order the records so that the eight lanes of every quarter-warp
+    // read and write eight different 16-byte bank groups (slot mod 8) in each of their two loads and two / four stores
+    // -- as far as a greedy choice gets. In natural order the scattered stores cost 1.75 wavefronts where 1 would do.
+    {
+      auto slots_of = [&](const PkSpecConst &r, int *out) {
+        int c = 0;
+        out[c++] = r.fab & 0xffff; out[c++] = r.fab >> 16; out[c++] = r.s01 & 0xffff; out[c++] = r.s01 >> 16;
+        if (mode == PK_SPEC_UP2) { out[c++] = r.s23 & 0xffff; out[c++] = r.s23 >> 16; }
+        return c;
+      };
+      std::vector<PkSpecConst> pool(rec), ordered;
+      std::vector<char> used(pool.size(), 0);
+      for (size_t base = 0; base < pool.size(); base += 8) {
+        int cnt[6][8];
+        memset(cnt, 0, sizeof(cnt));
+        for (size_t l = 0; l < 8 && base + l < pool.size(); ++l) {
+          int best = -1, best_cost = 1 << 30;
+          for (size_t c = 0; c < pool.size(); ++c) {
+            if (used[c]) continue;
+            int sl[6];
+            const int ns = slots_of(pool[c], sl);
+            int cost = 0;
+            for (int a = 0; a < ns; ++a) cost += cnt[a][sl[a] & 7];
+            if (cost < best_cost) { best_cost = cost; best = static_cast<int>(c); if (!cost) break; }
+          }
+          int sl[6];
+          const int ns = slots_of(pool[static_cast<size_t>(best)], sl);
+          for (int a = 0; a < ns; ++a) ++cnt[a][sl[a] & 7];
+          used[static_cast<size_t>(best)] = 1;
+          ordered.push_back(pool[static_cast<size_t>(best)]);
+        }
+      }
+      rec.swap(ordered);
+    }
     return upload(rec, &pk_spec_dev_[i]);
   }
 

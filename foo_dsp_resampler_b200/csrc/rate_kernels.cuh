@@ -1064,6 +1064,158 @@ RR_PROG void poly0_fast_compute(const Poly0FastParams<T> &fp, const Poly0Tile &t
   });
 }
 
+// ---------------------------------------------------------------------------------------------------
+// vpoly0, two adjacent slots per thread, for the fp64 engine (what RR_open selects for Best quality).
+// The scheme of the lane-pair kernel poly0_pair2 (rate_kernels_pk.cuh) for scalar lanes: a thread owns the slot pair
+// (s, s + 1) of every period (output index mod L) of one lane, its two coefficient rows stay in registers for the
+// whole launch, the windows of its two outputs overlap almost entirely (they start DLO or DLO + 1 samples apart,
+// DLO = floor(step / L)), so one pass over NT + DLO + 1 window samples feeds both: 1.8x fewer shared-memory loads per
+// output than the one-slot kernel, which is bound by exactly those loads. The slot pairs are dealt to the threads on
+// the host so that the sixteen lanes of a half-warp start in sixteen different 8-byte banks; the lane's window of a
+// tile of periods is staged with one TMA bulk copy. DFMA in tap order (the fp64 contract is 1e-12, not bit equality).
+// ---------------------------------------------------------------------------------------------------
+template <class T> struct Poly0DualParams {
+  PolyParams<T> base;
+  const T *coef;                 // [2 n + 1][TS] transposed per-thread rows (first slot, then the shifted row of the second)
+  const uint16_t *slot, *qs;     // [TS] first slot of the thread's pair (0xffff: idle), its first window sample within the period
+  const uint8_t *flags;          // [TS] bit 0: the second slot's window starts DLO samples later (else DLO + 1); bit 1: it exists
+  int TS, NL;                    // threads per lane, lanes per CTA
+  int MM, win;                   // periods per tile, window capacity per lane (samples, even)
+  long long m_begin, mtiles;     // first period of the launch (output index / L), tiles along the periods
+};
+
+struct Poly0DualTile {
+  long long c0;                  // first window coordinate (input FIFO) of the tile
+  int lane0, nl, mcount, len;    // lanes [lane0, lane0 + nl), periods, window samples needed
+  int tma, head;                 // window staged by bulk copies; window sample j then sits at row index head + j
+  int i_lo, i_hi;                // outputs of the tile, relative to its first period's slot 0
+  long long i_base;              // output index of the first period's slot 0
+};
+
+template <class T> RR_PROG Poly0DualTile poly0_dual_tile(const Poly0DualParams<T> &dp, long long work)
+{
+  const PolyParams<T> &p = dp.base;
+  Poly0DualTile t;
+  long long grp; int mt;
+  divmod_ll(work, (int)dp.mtiles, grp, mt);
+  t.lane0 = (int)grp * dp.NL;
+  t.nl = p.nlanes - t.lane0 < dp.NL ? p.nlanes - t.lane0 : dp.NL;
+  const long long m0 = dp.m_begin + (long long)mt * dp.MM, m_end = (p.out0 + p.nout + p.L - 1) / p.L;
+  t.mcount = m_end - m0 < dp.MM ? (int)(m_end - m0) : dp.MM;
+  t.i_base = m0 * p.L;
+  const long long lo = p.out0 > t.i_base ? p.out0 : t.i_base, hi_all = p.out0 + p.nout, hi_t = t.i_base + (long long)t.mcount * p.L;
+  t.i_lo = (int)(lo - t.i_base);
+  t.i_hi = (int)((hi_all < hi_t ? hi_all : hi_t) - t.i_base);
+  // window: from the first sample of (period m0, slot 0) to the last sample of the tile's last slot
+  const long long at_first = p.at0 + t.i_base * p.step;
+  const long long q_first = at_first / p.L;
+  const long long q_last = (p.at0 + (hi_t - 1) * p.step) / p.L;
+  t.c0 = q_first + p.pre;
+  t.len = (int)(q_last - q_first) + p.n + 2;
+  t.tma = 0; t.head = 0;
+  if (p.in.elem_stride == 1 && t.len + 2 <= dp.win && view_range_direct(p.in, t.c0 - 1, t.c0 + t.len + 1)) {
+    const T *s0 = view_ptr<const T>(p.in, lane_offset(p.in, t.lane0), t.c0);
+    t.head = sizeof(T) == 8 ? (int)(((size_t)s0 >> 3) & 1) : 0;
+    t.tma = sizeof(T) == 8;
+    for (int l = 0; l < t.nl; ++l) {
+      const T *q0 = view_ptr<const T>(p.in, lane_offset(p.in, t.lane0 + l), t.c0) - t.head;
+      if ((size_t)q0 & 15) t.tma = 0;
+    }
+    if (!t.tma) t.head = 0;
+  }
+  return t;
+}
+
+template <class T> RR_PROG void poly0_dual_load(const Poly0DualParams<T> &dp, const Poly0DualTile &t, T *buf, unsigned long long *bar,
+                                               int tid, int nthreads)
+{
+  const PolyParams<T> &p = dp.base;
+  if (t.tma) {
+    if (tid != 0) return;
+    const unsigned bytes = (unsigned)(((t.len + t.head + 1) & ~1) * (int)sizeof(T));
+    tma_bar_expect(bar, bytes * (unsigned)t.nl);
+    for (int l = 0; l < t.nl; ++l)
+      tma_load_1d(buf + l * dp.win, view_ptr<const T>(p.in, lane_offset(p.in, t.lane0 + l), t.c0) - t.head, bytes, bar);
+    return;
+  }
+  for (int l = 0; l < t.nl; ++l) {
+    const long long off = lane_offset(p.in, t.lane0 + l);
+    for (int j = tid; j < t.len; j += nthreads) buf[l * dp.win + j] = view_read<T, T>(p.in, off, t.c0 + j);
+  }
+}
+
+template <class T, class OutT, int NT, int DLO> struct Poly0DualThread {
+  int lane, s0, q;               // lane within the CTA, first slot (< 0: idle), window start within the period
+  bool dlo, two;
+  T c0[NT], c1[NT + 1];
+};
+
+template <class T, class OutT, int NT, int DLO>
+RR_PROG Poly0DualThread<T, OutT, NT, DLO> poly0_dual_setup(const Poly0DualParams<T> &dp, int tid)
+{
+  Poly0DualThread<T, OutT, NT, DLO> st;
+  st.lane = tid / dp.TS;
+  const int ts = tid - st.lane * dp.TS;
+  const int s = st.lane < dp.NL ? (int)ldg(dp.slot + ts) : 0xffff;
+  st.s0 = s == 0xffff ? -1 : s;
+  st.q = ldg(dp.qs + ts);
+  const unsigned fl = ldg(dp.flags + ts);
+  st.dlo = fl & 1; st.two = (fl & 2) != 0;
+#pragma unroll
+  for (int k = 0; k < NT; ++k) st.c0[k] = ldg(dp.coef + k * dp.TS + ts);
+#pragma unroll
+  for (int k = 0; k <= NT; ++k) st.c1[k] = ldg(dp.coef + (NT + k) * dp.TS + ts);
+  return st;
+}
+
+template <class T, class OutT, int NT, int DLO>
+RR_PROG void poly0_dual_compute(const Poly0DualParams<T> &dp, const Poly0DualTile &t, const T *buf,
+                                const Poly0DualThread<T, OutT, NT, DLO> &st)
+{
+  const PolyParams<T> &p = dp.base;
+  if (st.s0 < 0 || st.lane >= t.nl) return;
+  const int L = p.L, step = (int)p.step, es = p.out.elem_stride;
+  const long long out_off = lane_offset(p.out, t.lane0 + st.lane);
+  const bool direct = view_range_direct(p.out, p.out_preload + t.i_base + t.i_lo, p.out_preload + t.i_base + t.i_hi);
+  OutT *d = view_ptr<OutT>(p.out, out_off, p.out_preload + t.i_base + st.s0);
+  const T *xw = buf + st.lane * dp.win + t.head + st.q;
+  auto tap = [&](int j, T xv, T &a0, T &a1) {
+    if (j < NT) a0 += st.c0[j] * xv;
+    if (j >= DLO) {
+      const int jj = j - DLO;
+      if (jj == 0) { if (st.dlo) a1 += st.c1[0] * xv; }
+      else if (jj == NT) { if (!st.dlo) a1 += st.c1[NT] * xv; }
+      else a1 += st.c1[jj] * xv;
+    }
+  };
+  auto emit = [&](int m, T a0, T a1) {
+    const int i = m * L + st.s0;
+    if (i >= t.i_lo && i < t.i_hi) {
+      if (direct) d[(long long)m * L * es] = (OutT)a0;
+      else view_write<OutT, T>(p.out, out_off, p.out_preload + t.i_base + i, a0);
+    }
+    if (st.two && i + 1 >= t.i_lo && i + 1 < t.i_hi) {
+      if (direct) d[((long long)m * L + 1) * es] = (OutT)a1;
+      else view_write<OutT, T>(p.out, out_off, p.out_preload + t.i_base + i + 1, a1);
+    }
+  };
+  constexpr int NW = NT + DLO + 1;
+  int m = 0;
+  for (; m + 1 < t.mcount; m += 2, xw += 2 * step) {        // two periods at a time: four independent DFMA chains
+    const T *xb = xw + step;
+    T a0 = (T)0, a1 = (T)0, b0 = (T)0, b1 = (T)0;
+#pragma unroll
+    for (int j = 0; j < NW; ++j) { tap(j, xw[j], a0, a1); tap(j, xb[j], b0, b1); }
+    emit(m, a0, a1); emit(m + 1, b0, b1);
+  }
+  if (m < t.mcount) {
+    T a0 = (T)0, a1 = (T)0;
+#pragma unroll
+    for (int j = 0; j < NW; ++j) tap(j, xw[j], a0, a1);
+    emit(m, a0, a1);
+  }
+}
+
 // vpoly1..3: 32.32 fixed-point position, Horner-interpolated coefficients.
 template <class T, class InT, class OutT>
 RR_PROG void polyN_program(const PolyParams<T> &p, long long work, T *smem)

@@ -387,8 +387,9 @@ enum PkSpecMode {
 struct alignas(16) PkSpecConst {
   C2<float> c0, c1, c2, c3;
   float tfc, tfs, tic, tis;
-  unsigned s01, s23;             // two 16-bit slots each
-  unsigned pad[2];
+  unsigned s01, s23;             // two 16-bit slots each: where the results go in the inverse buffer
+  unsigned fab;                  // two 16-bit slots: the record's inputs F[i], F[M - i] in the forward buffer
+  unsigned first;                // 1: the record of index 0 (the two real bins and the self-paired bin M/2)
 };
 
 struct DftPkParams {
@@ -607,13 +608,12 @@ RR_PROG PkSpecConst pk_load_spec(const PkSpecConst *p)
   // field-by-field from three 16-byte and one 8-byte load (no memcpy: the record must stay in registers)
   const float4 *q = reinterpret_cast<const float4 *>(p);
   const float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
-  const uint2 d = __ldg(reinterpret_cast<const uint2 *>(p) + 6);
+  const uint4 d = __ldg(reinterpret_cast<const uint4 *>(p) + 3);
   PkSpecConst r;
   r.c0 = C2<float>{a.x, a.y}; r.c1 = C2<float>{a.z, a.w};
   r.c2 = C2<float>{b.x, b.y}; r.c3 = C2<float>{b.z, b.w};
   r.tfc = c.x; r.tfs = c.y; r.tic = c.z; r.tis = c.w;
-  r.s01 = d.x; r.s23 = d.y;
-  r.pad[0] = 0; r.pad[1] = 0;
+  r.s01 = d.x; r.s23 = d.y; r.fab = d.z; r.first = d.w;
   return r;
 #else
   return *p;
@@ -681,14 +681,15 @@ RR_PROG void pk_spec_prefetch(const DftPkParams &pp, const Grp &g, PkSpecRegs &p
   }
 }
 
-// One index of the spectrum phase: (za, zb) = (F[i], F[M - i]) -- for i == 0: (F[0], F[M/2]) -- and its constants k;
-// writes the two or four bins of the inverse transform's input they determine.
+// One record of the spectrum phase: (za, zb) = (F[i], F[M - i]) -- for i == 0: (F[0], F[M/2]) -- and its constants k;
+// writes the two or four bins of the inverse transform's input they determine. The records are stored in an order
+// chosen for bank-conflict-free accesses (build_pk_spec), so a record carries the slots of its own inputs.
 template <int MODE>
-RR_PROG void pk_spec_index(int i, const PkSpecConst &k, const CPk &za, const CPk &zb, CPk *B)
+RR_PROG void pk_spec_index(const PkSpecConst &k, const CPk &za, const CPk &zb, CPk *B)
 {
   typedef Arith<Pk> A;
   const int sl0 = k.s01 & 0xffff, sl1 = k.s01 >> 16, sl2 = k.s23 & 0xffff, sl3 = k.s23 >> 16;
-  if (i == 0) {
+  if (k.first) {
     // bins 0 and Pf/2 (packed in F[0]) and the self-paired bin M/2
     // record 0 carries the constants of M/2 in c0, c1, tic, tis, s01 and those of the real bins in the
     // fields index 0 has no use for: c2 = coef[0], c3 = coef[M], s23 = slots of d[0] and d[M]
@@ -735,10 +736,8 @@ RR_PROG void pk_spectrum(const DftPkParams &pp, const Grp &g, const PkSpecRegs &
   const DftParams<float> &p = pp.base;
   const int M = p.Pf >> 1;                               // forward transform: M complex points
   const int n = M >> 1;
-  auto body = [&](int i, const PkSpecConst &k) {
-    if (i == 0) pk_spec_index<MODE>(0, k, F[0], F[pslot(n)], B);
-    else pk_spec_index<MODE>(i, k, F[pslot(i)], F[pslot(M - i)], B);
-  };
+  auto body = [&](int, const PkSpecConst &k) { pk_spec_index<MODE>(k, F[k.fab & 0xffff], F[k.fab >> 16], B); };
+  (void)M;
   // software pipeline, two records live: the record of the next round is requested before a round is computed
   static_assert(kPkSpecRounds == 1 && kPkSpecLate == 3, "pipeline below is written for 1 + 3 rounds");
   const int i0 = g.tid, i1 = i0 + g.size, i2 = i1 + g.size, i3 = i2 + g.size;
@@ -767,27 +766,27 @@ RR_PROG void pk_spectrum(const DftPkParams &pp, const Grp &g, const PkSpecRegs &
 template <int MODE, int FB>
 RR_PROG void pk_spectrum_inplace(const DftPkParams &pp, const Grp &g, CPk *W)
 {
-  constexpr int M = 1 << FB, n = M >> 1;
+  constexpr int n = 1 << (FB - 1);
 #if defined(__CUDA_ARCH__)
   constexpr int R = (n + kPkGroupThreads - 1) / kPkGroupThreads;
   CPk za[R], zb[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    const int i = g.tid + r * kPkGroupThreads;
-    if (i < n) { za[r] = W[i ? pslot(i) : 0]; zb[r] = W[i ? pslot(M - i) : pslot(n)]; }
+    const int e = g.tid + r * kPkGroupThreads;
+    if (e < n) { const unsigned fab = ldg(&pp.spec[e].fab); za[r] = W[fab & 0xffff]; zb[r] = W[fab >> 16]; }
   }
   grp_sync(g);
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    const int i = g.tid + r * kPkGroupThreads;
-    if (i < n) pk_spec_index<MODE>(i, pk_load_spec(pp.spec + i), za[r], zb[r], W);
+    const int e = g.tid + r * kPkGroupThreads;
+    if (e < n) pk_spec_index<MODE>(pk_load_spec(pp.spec + e), za[r], zb[r], W);
   }
   grp_sync(g);
 #else
   (void)g;
   CPk *za = new CPk[n], *zb = new CPk[n];
-  for (int i = 0; i < n; ++i) { za[i] = W[i ? pslot(i) : 0]; zb[i] = W[i ? pslot(M - i) : pslot(n)]; }
-  for (int i = 0; i < n; ++i) pk_spec_index<MODE>(i, pk_load_spec(pp.spec + i), za[i], zb[i], W);
+  for (int e = 0; e < n; ++e) { const unsigned fab = pp.spec[e].fab; za[e] = W[fab & 0xffff]; zb[e] = W[fab >> 16]; }
+  for (int e = 0; e < n; ++e) pk_spec_index<MODE>(pk_load_spec(pp.spec + e), za[e], zb[e], W);
   delete[] za; delete[] zb;
 #endif
 }
