@@ -26,6 +26,7 @@
 #include "fft_tables.hpp"
 #include "rate_kernels.cuh"
 #include "rate_kernels_pk.cuh"
+#include "rate_kernels_f64.cuh"
 #include "rate_kernels_fused.cuh"
 
 #ifndef B200RATE_EMU
@@ -620,6 +621,9 @@ static int launch_dftp(const DftPkParams &pp, long long nwork, stream_t s)
 #endif
 }
 
+// fp64 DFT stage: kernel and launcher live in dft64.cu (rate_kernels_f64.cuh)
+int launch_dft64(const Dft64Params &dp, long long nwork, void *stream);
+
 // nwork = lane pairs x runs per pair
 static int launch_dft_poly(const DftPolyParams &fp, long long nwork, stream_t s)
 {
@@ -1105,6 +1109,22 @@ template <class T> class Engine {
           }
         }
       }
+      if constexpr (sizeof(T) == 8) {
+        // fp64 engine: in-place radix-16 kernel (rate_kernels_f64.cuh) for the block sizes that fit shared memory
+        if (use_dft64_ && wn * nlanes < (1ll << 30)) {
+          int rc;
+          if (!d64_tab_[i].built && (rc = build_d64_tab(i))) return rc;
+          const D64Tab &dt = d64_tab_[i];
+          if (dt.ok) {
+            Dft64Params dp = dt.params;
+            dp.base = p;
+            dp.in_f32 = in_f32 ? 1 : 0; dp.out_f32 = out_f32 ? 1 : 0;
+            last_dft_kernel_ = 2;
+            kernel_name[i] = "dft64_kernel (fp64, in-place radix-16)";
+            return launch_dft64(dp, wn * nlanes, reinterpret_cast<void *>(s));
+          }
+        }
+      }
       last_dft_kernel_ = 0;
       kernel_name[i] = "dft_kernel";
       const int lpc = dft_lanes_per_cta(g, nlanes);
@@ -1415,6 +1435,75 @@ template <class T> class Engine {
   struct DualTab { const T *coef = nullptr; const uint16_t *slot = nullptr, *qs = nullptr; const uint8_t *flags = nullptr; int TS = 0; bool built = false; };
   DualTab dual_tab_[RR_MAX_STAGES];
   bool use_dual_poly_ = getenv("B200RATE_NO_DUAL_POLY") == nullptr;
+
+  // ---- tables of dft64_kernel (fp64 DFT stage, rate_kernels_f64.cuh) ----
+  struct D64Tab { bool built = false, ok = false; Dft64Params params; };
+  D64Tab d64_tab_[RR_MAX_STAGES];
+  bool use_dft64_ = getenv("B200RATE_NO_DFT64") == nullptr;
+
+  int build_d64_tab(int i)
+  {
+    D64Tab &dt = d64_tab_[i];
+    dt.built = true;
+    dt.ok = false;
+    if constexpr (sizeof(T) == 8) {
+      const StageGeom &g = geom[i];
+      Dft64Params &dp = dt.params;
+      memset(&dp, 0, sizeof(dp));
+      if (g.in_mode == DFT_IN_FREQ_UP && g.L == 2 && g.step >= 1) dp.mode = D64_UP2;
+      else if (g.Ni == g.Pf && g.step >= 1 && g.in_mode != DFT_IN_FREQ_UP) dp.mode = D64_SAME;
+      else if (g.step < 0 && g.in_mode != DFT_IN_FREQ_UP && g.Pf == g.N) dp.mode = D64_DECIM;
+      else return RR_OK;                                   // other shapes stay on the generic kernel
+      dp.fb = ilog2(g.Pf) - 1;
+      dp.ib = dp.mode == D64_DECIM ? ilog2(g.Ni) - 1 : dp.fb;
+      if (dp.fb < 5 || dp.fb > 13 || dp.ib < 5 || dp.ib > 13) return RR_OK;
+      const D64Plan pf = d64_plan(dp.fb), pi = d64_plan(dp.ib);
+      dp.npf = pf.n; dp.npi = pi.n;
+      // pass twiddle rows: forward pass ps works on sub-blocks of 2^lgS points with stride 2^(lgS - lr)
+      std::vector<double> tw;
+      auto add_row = [&](int lgS, int lr, int sign) -> int {
+        const int s = 1 << (lgS - lr);
+        if (s == 1) return -1;                             // the stride-1 pass has no twiddles
+        const int off = static_cast<int>(tw.size() / 2);
+        const std::vector<double> row = unit_circle(1 << lgS, s, sign);
+        tw.insert(tw.end(), row.begin(), row.end());
+        return off;
+      };
+      int lgS = dp.fb;
+      for (int ps = 0; ps < pf.n; ++ps) { dp.lr_f[ps] = pf.lr[ps]; dp.tw_f[ps] = add_row(lgS, pf.lr[ps], -1); lgS -= pf.lr[ps]; }
+      lgS = 0;
+      for (int ps = 0; ps < pi.n; ++ps) {                  // the transposed network runs the plan backwards
+        const int lr = pi.lr[pi.n - 1 - ps];
+        lgS += lr;
+        dp.lr_i[ps] = lr; dp.tw_i[ps] = add_row(lgS, lr, +1);
+      }
+      dp.ntw = static_cast<int>(tw.size() / 2);
+      dp.fslots = d64_buf_slots(dp.fb); dp.bslots = d64_buf_slots(dp.ib);
+      dp.hstride = dp.bslots + 4;                          // 4 mod 8: the two halves of a position sit in different bank groups
+      dp.group_slots = dp.mode == D64_UP2 ? 2 * dp.hstride : dp.mode == D64_SAME ? dp.fslots : dp.fslots + dp.bslots;
+      // groups: 64 threads for blocks up to 1024 complex points, else 128; as many as shared memory and the launch bound allow
+      dp.gthreads = dp.fb <= 10 ? 64 : 128;
+      if (const char *e = getenv("B200RATE_D64_GT")) dp.gthreads = atoi(e) == 64 ? 64 : atoi(e) == 256 ? 256 : 128;
+      const size_t per_group = sizeof(CD) * static_cast<size_t>(dp.group_slots), fixed = sizeof(CD) * static_cast<size_t>(dp.ntw) + 2048;
+      if (fixed + per_group > max_smem_) return RR_OK;
+      dp.groups = static_cast<int>(std::min<size_t>((max_smem_ - fixed) / per_group, static_cast<size_t>(kD64MaxThreads / dp.gthreads)));
+      dp.groups = std::min(dp.groups, kD64MaxGroups);
+      dp.lane_major = getenv("B200RATE_D64_LANE_MAJOR") ? 1 : 0;
+      if (const char *e = getenv("B200RATE_D64_GROUPS")) dp.groups = std::max(1, std::min(dp.groups, atoi(e)));
+      const DftFilterDesign &f = design.dft[g.filter];
+      const std::vector<double> H = real_spectrum(f.coefs_time, 0.25);
+      const std::vector<double> ta = unit_circle(g.Pf, g.Pf / 4 + 1, -1), tb = unit_circle(g.Ni, g.Ni / 4 + 1, +1);
+      const double *dH = nullptr, *dta = nullptr, *dtb = nullptr, *dtw = nullptr;
+      int rc;
+      if ((rc = upload(H, &dH)) || (rc = upload(ta, &dta)) || (rc = upload(tb, &dtb)) || (rc = upload(tw, &dtw))) return rc;
+      if ((rc = be_sync(0))) return rc;
+      dp.H = reinterpret_cast<const CD *>(dH); dp.ta = reinterpret_cast<const CD *>(dta);
+      dp.tb = reinterpret_cast<const CD *>(dtb); dp.tw = reinterpret_cast<const CD *>(dtw);
+      dt.ok = true;
+    }
+    (void)i;
+    return RR_OK;
+  }
 
   int build_dual_tab(int i)
   {

@@ -228,4 +228,67 @@ template std::vector<double> twiddle_pyramid<double>(const CfftHostSched &);
 template void leaf_constants<float>(float &, float &, float &);
 template void leaf_constants<double>(double &, double &, double &);
 
+// ---------------------------------------------------------------------------------------------------
+// fp64 DFT-stage kernel tables
+// ---------------------------------------------------------------------------------------------------
+std::vector<double> unit_circle(int n, int count, int sign)
+{
+  std::vector<double> t(2 * static_cast<size_t>(count));
+  const double step = 2.0 * M_PI / n;
+  for (int k = 0; k < count; ++k) {
+    // reduce k to the first octant of the n-point circle
+    int r = k % n, oct = 0;
+    double c, s;
+    if (n % 8 == 0) {
+      const int e = n / 8;
+      oct = r / e;
+      const int rr = r - oct * e;
+      const int m = (oct & 1) ? e - rr : rr;               // mirrored in odd octants
+      const double cc = std::cos(step * m), ss = std::sin(step * m);
+      switch (oct) {
+        case 0: c = cc; s = ss; break;
+        case 1: c = ss; s = cc; break;
+        case 2: c = -ss; s = cc; break;
+        case 3: c = -cc; s = ss; break;
+        case 4: c = -cc; s = -ss; break;
+        case 5: c = -ss; s = -cc; break;
+        case 6: c = ss; s = -cc; break;
+        default: c = cc; s = -ss; break;
+      }
+    } else { c = std::cos(step * r); s = std::sin(step * r); }
+    t[2 * static_cast<size_t>(k)] = c;
+    t[2 * static_cast<size_t>(k) + 1] = sign < 0 ? -s : s;
+  }
+  return t;
+}
+
+std::vector<double> real_spectrum(const std::vector<double> &taps, double scale)
+{
+  const int n = static_cast<int>(taps.size());
+  int bits = 0;
+  while ((1 << bits) < n) ++bits;
+  // plain iterative radix-2 decimation-in-time transform of the real sequence taken as complex
+  std::vector<double> re(static_cast<size_t>(n)), im(static_cast<size_t>(n), 0.0);
+  for (int i = 0; i < n; ++i) {
+    int r = 0;
+    for (int b = 0; b < bits; ++b) r |= ((i >> b) & 1) << (bits - 1 - b);
+    re[static_cast<size_t>(r)] = taps[static_cast<size_t>(i)];
+  }
+  const std::vector<double> w = unit_circle(n, n / 2 > 0 ? n / 2 : 1, -1);
+  for (int len = 2; len <= n; len <<= 1) {
+    const int half = len >> 1, stride = n / len;
+    for (int base = 0; base < n; base += len)
+      for (int j = 0; j < half; ++j) {
+        const double wr = w[2 * static_cast<size_t>(j * stride)], wi = w[2 * static_cast<size_t>(j * stride) + 1];
+        const size_t a = static_cast<size_t>(base + j), b = a + static_cast<size_t>(half);
+        const double tr = re[b] * wr - im[b] * wi, ti = re[b] * wi + im[b] * wr;
+        re[b] = re[a] - tr; im[b] = im[a] - ti;
+        re[a] += tr; im[a] += ti;
+      }
+  }
+  std::vector<double> out(2 * (static_cast<size_t>(n) / 2 + 1));
+  for (int k = 0; k <= n / 2; ++k) { out[2 * static_cast<size_t>(k)] = scale * re[static_cast<size_t>(k)]; out[2 * static_cast<size_t>(k) + 1] = scale * im[static_cast<size_t>(k)]; }
+  return out;
+}
+
 }  // namespace b200rate

@@ -50,4 +50,12 @@ template <class T> std::vector<T> twiddle_pyramid(const CfftHostSched &sched);
 // Constants of the size-8/16 leaves: sqrt(1/2), cos(2 pi/16), cos(6 pi/16) (fft.c:300,304-318).
 template <class T> void leaf_constants(T &sqrthalf, T &c16_1, T &c16_3);
 
+// ---- tables of the fp64 DFT-stage kernel (rate_kernels_f64.cuh), all in double precision ----
+// exp(sign * 2 pi i k / n), k = 0 .. count-1, as (re, im) pairs; the angle is reduced to an octant first so that
+// the values carry the symmetries of the circle exactly.
+std::vector<double> unit_circle(int n, int count, int sign);
+// The filter spectrum the kernel multiplies with: scale * sum_j taps[j] exp(-2 pi i j k / n), k = 0 .. n/2,
+// as (re, im) pairs. n is a power of two.
+std::vector<double> real_spectrum(const std::vector<double> &taps, double scale);
+
 }  // namespace b200rate

@@ -37,9 +37,12 @@ def main():
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     want = sys.argv[5] if len(sys.argv) > 5 else None      # substring of the demangled kernel name
-    hdr_i = None
+    hdr_i, skip = None, int(os.environ.get("KERNEL_INDEX", "0"))      # KERNEL_INDEX=n: the n-th matching launch
     for i, r in enumerate(rows):
         if r and r[0] == "Kernel Name" and (want is None or want in r[1]):
+            if skip > 0:
+                skip -= 1
+                continue
             hdr_i = next(j for j in range(i, len(rows)) if rows[j] and rows[j][0] == "Address")
             break
     hdr = rows[hdr_i]
