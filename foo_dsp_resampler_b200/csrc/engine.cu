@@ -444,11 +444,34 @@ __global__ void __launch_bounds__(256, 2) poly0_dual_kernel(const __grid_constan
     if (next < nwork) poly0_dual_load(dp, tiles[ts ^ 1], smem, &bar, tid, nt);
   }
 }
+// fp64 engine: eight outputs per thread from padded rows (kHalfOpt, rate_kernels.cuh)
+template <class T> struct HalfOpt { static constexpr int value = sizeof(T) == 8 ? 8 : 4; };
 template <class T, class InT, class OutT, int NC>
-__global__ void __launch_bounds__(kTileThreads) halfband_kernel(const __grid_constant__ HalfbandParams<T> p, long long nwork)
+__global__ void __launch_bounds__(kTileThreads, 2) halfband_kernel(const __grid_constant__ HalfbandParams<T> p, long long nwork)
 {
   T *smem = reinterpret_cast<T *>(rr_smem_raw);
-  for (long long w = blockIdx.x; w < nwork; w += gridDim.x) halfband_program<T, InT, OutT, NC>(p, w, smem);
+  if constexpr (sizeof(T) == 8) {
+    // fp64 engine: the global loads of the CTA's next tile are in flight (in registers) while the current one is computed
+    constexpr int OPT = HalfOpt<T>::value;
+    __shared__ HbTile<InT, OutT> tiles[2];
+    const int tid = threadIdx.x, nthreads = blockDim.x, items = (p.CH * p.tile) / OPT;
+    long long w = blockIdx.x;
+    if (tid == 0 && w < nwork) tiles[0] = hb_make_tile<T, InT, OutT, NC>(p, w);
+    __syncthreads();
+    HbRegs<InT> r;
+    if (w < nwork) hb_fetch(p, tiles[0], r, tid, nthreads);
+    for (int it = 0; w < nwork; w += gridDim.x, it ^= 1) {
+      const long long next = w + gridDim.x;
+      if (tid == 0 && next < nwork) tiles[it ^ 1] = hb_make_tile<T, InT, OutT, NC>(p, next);
+      hb_put<T, InT, OutT, NC, OPT>(p, tiles[it], r, smem, tid, nthreads);
+      __syncthreads();
+      if (next < nwork) hb_fetch(p, tiles[it ^ 1], r, tid, nthreads);
+      for (int i = tid; i < items; i += nthreads) hb_compute_item<T, InT, OutT, NC, OPT>(p, tiles[it], smem, i);
+      __syncthreads();
+    }
+  } else {
+    for (long long w = blockIdx.x; w < nwork; w += gridDim.x) halfband_program<T, InT, OutT, NC, HalfOpt<T>::value>(p, w, smem);
+  }
 }
 template <int NC>
 __global__ void __launch_bounds__(kTileThreads) halfband_pair_kernel(const __grid_constant__ HalfbandPairParams p, long long nwork)
@@ -891,7 +914,7 @@ template <class T> struct Launch {
   {
     (void)s;
 #ifdef B200RATE_EMU
-#define RR_CALLN(I, O, NC) serial(nwork, smem, [&](long long w, T *sm) { halfband_program<T, I, O, NC>(p, w, sm); })
+#define RR_CALLN(I, O, NC) serial(nwork, smem, [&](long long w, T *sm) { halfband_program<T, I, O, NC, sizeof(T) == 8 ? 8 : 4>(p, w, sm); })
 #else
 #define RR_CALLN(I, O, NC) launch_persistent(halfband_kernel<T, I, O, NC>, p, nwork, kTileThreads, smem, s)
 #endif
@@ -1189,6 +1212,8 @@ template <class T> class Engine {
       p.qbits = 0;
       while ((4 << p.qbits) < p.tile) ++p.qbits;
       p.half = ((p.tile + 2 * p.ncoef + 8 + 31) / 32) * 32 + 4;
+      // padded rows (hb_pad); 2 mod 4 doubles: rows four lanes apart (one staging store instruction) sit 64 bytes apart
+      if (sizeof(T) == 8) p.half = ((hb_pad<8>(p.tile + 2 * p.ncoef + 8) + 2 + 31) / 32) * 32 + 6;
       const long long tiles = (wn + p.tile - 1) / p.tile;
       const size_t smem = sizeof(T) * 2 * static_cast<size_t>(p.half) * p.CH;
       kernel_name[i] = "halfband_kernel";

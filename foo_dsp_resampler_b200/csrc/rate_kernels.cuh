@@ -1280,137 +1280,208 @@ template <class T> struct HalfbandParams {
 // The window is split by sample parity in shared memory (the centre tap reads one parity, all other taps the
 // other one), so consecutive outputs read consecutive words; each thread produces four consecutive outputs
 // from 16-byte shared loads (6.75 loaded values per output instead of 25).
+// OPT = 8 (fp64 engine): eight consecutive outputs per thread, 5 loaded values per output, and rows padded by 16 bytes
+// after every 64 so that the eight threads of a quarter-warp (80 bytes apart) hit eight different 16-byte bank groups.
+template <int OPT> RR_HD int hb_pad(int j) { return OPT == 8 ? j + 2 * (j >> 3) : j; }
+
+// Geometry of one tile (divisions, 64-bit coordinates), computed once per tile by the CTA leader.
+template <class InT, class OutT> struct HbTile {
+  long long k0, x0, in_off0, out_off0;
+  const InT *src0; OutT *dst0;
+  int cnt, win, in_direct, out_direct;
+};
 template <class T, class InT, class OutT, int NC>
-RR_PROG void halfband_program(const HalfbandParams<T> &p, long long work, T *smem)
+RR_PROG HbTile<InT, OutT> hb_make_tile(const HalfbandParams<T> &p, long long work)
+{
+  constexpr int c = NC;
+  const int CH = p.CH;                                   // 1, 2, 4 or 8; > 1 only for interleaved input
+  HbTile<InT, OutT> t;
+  const long long tiles = (p.nout + p.tile - 1) / p.tile;
+  long long group; int tix_i;
+  divmod_ll(work, (int)tiles, group, tix_i);
+  const int lane0 = (int)group * CH;
+  t.k0 = p.out0 + (long long)tix_i * p.tile;
+  const long long rest = p.out0 + p.nout - t.k0;
+  t.cnt = rest < p.tile ? (int)rest : p.tile;
+  t.x0 = 2 * t.k0 + p.pre - (2 * c - 1);                 // first coordinate needed (window index u = coord - x0)
+  t.win = 2 * (t.cnt - 1) + 2 * (2 * c - 1) + 1;
+  t.in_off0 = lane_offset(p.in, lane0); t.out_off0 = lane_offset(p.out, lane0);
+  t.in_direct = view_range_direct(p.in, t.x0, t.x0 + t.win);
+  t.out_direct = view_range_direct(p.out, p.out_preload + t.k0, p.out_preload + t.k0 + t.cnt);
+  t.src0 = view_ptr<const InT>(p.in, t.in_off0, t.x0);
+  t.dst0 = view_ptr<OutT>(p.out, t.out_off0, p.out_preload + t.k0);
+  return t;
+}
+
+// The window of a tile travels global -> registers -> shared memory in two steps, so that a persistent CTA can have
+// the loads of its next tile in flight while it computes the current one. Thread `tid` of `nthreads` takes elements
+// w = tid + k * nthreads, k < kHbRaw (vector path: 16-byte groups of four channels, k < kHbRaw / 4).
+constexpr int kHbRaw = 20;
+template <class InT> struct HbRegs { InT v[kHbRaw]; };
+template <class T, class InT, class OutT> RR_HD bool hb_vec_path(const HalfbandParams<T> &p, const HbTile<InT, OutT> &tl)
+{
+  // interleaved frames of 4 or 8 channels of floats: one 16-byte load brings four channels of a frame
+  return tl.in_direct && p.CH >= 4 && sizeof(InT) == 4 && p.in.ch_stride == 1 && p.in.elem_stride == p.CH && !((size_t)tl.src0 & 15);
+}
+template <class T, class InT, class OutT>
+RR_PROG void hb_fetch(const HalfbandParams<T> &p, const HbTile<InT, OutT> &tl, HbRegs<InT> &r, int tid, int nthreads)
+{
+  const int CH = p.CH, chbits = CH == 8 ? 3 : CH == 4 ? 2 : CH == 2 ? 1 : 0;
+  if (hb_vec_path(p, tl)) {
+    struct alignas(16) V4 { InT a, b, c, d; };
+    const int nvec = tl.win << (chbits - 2);
+#pragma unroll
+    for (int k = 0; k < kHbRaw / 4; ++k) {
+      const int w = tid + k * nthreads;
+      if (w < nvec) {
+        const V4 v = ldg(reinterpret_cast<const V4 *>(tl.src0) + w);
+        r.v[4 * k] = v.a; r.v[4 * k + 1] = v.b; r.v[4 * k + 2] = v.c; r.v[4 * k + 3] = v.d;
+      } else { r.v[4 * k] = r.v[4 * k + 1] = r.v[4 * k + 2] = r.v[4 * k + 3] = (InT)0; }
+    }
+    return;
+  }
+  const int total = tl.win << chbits;
+#pragma unroll
+  for (int k = 0; k < kHbRaw; ++k) {
+    const int w = tid + k * nthreads;
+    InT v = (InT)0;
+    if (w < total) {
+      const int l = w & (CH - 1), u = w >> chbits;        // channel fastest: coalesced for interleaved input
+      if (tl.in_direct) v = ldg(tl.src0 + (long long)l * p.in.ch_stride + (long long)u * p.in.elem_stride);
+      else v = view_read<InT, InT>(p.in, tl.in_off0 + (long long)l * p.in.ch_stride, tl.x0 + u);
+    }
+    r.v[k] = v;
+  }
+}
+// window index u: even u -> P0[u/2], odd u -> P1[(u+1)/2 + shift] with shift chosen so that the centre tap of
+// output j (u = 2j + reach, odd) sits at P1[j + 4]: rows stay 16-byte aligned for the vector loads of the compute phase
+template <class T, class InT, class OutT, int NC, int OPT>
+RR_PROG void hb_put(const HalfbandParams<T> &p, const HbTile<InT, OutT> &tl, const HbRegs<InT> &r, T *smem, int tid, int nthreads)
+{
+  const int CH = p.CH, chbits = CH == 8 ? 3 : CH == 4 ? 2 : CH == 2 ? 1 : 0;
+  T *P0 = smem, *P1 = smem + (long long)CH * p.half;     // even-u / odd-u samples, [lane][half]
+  const int shift = 4 - NC;
+  const bool vec = hb_vec_path(p, tl);
+  // A thread's elements are nthreads apart: the same lane(s), frames u0 + k * du with du even (nthreads is a multiple
+  // of 16 frames), so the parity array, the row and the index step are per-thread constants; the index step is a
+  // multiple of 8, which the row padding maps to a constant step as well.
+  const int ebits = vec ? chbits - 2 : chbits;           // log2 (elements or 16-byte vectors per frame)
+  const int l0 = vec ? 4 * (tid & ((1 << ebits) - 1)) : (tid & (CH - 1));
+  const int u0 = tid >> ebits, didx = (nthreads >> ebits) >> 1;
+  const bool odd = u0 & 1;
+  const int idx0 = odd ? ((u0 + 1) >> 1) + shift : (u0 >> 1);
+  T *row = (odd ? P1 : P0) + l0 * p.half + hb_pad<OPT>(idx0);
+  const int dph = hb_pad<OPT>(didx), n = (tl.win << chbits) >> (vec ? 2 : 0), half = p.half;
+#pragma unroll
+  for (int k = 0; k < (kHbRaw / 4); ++k) {
+    if (!vec) break;
+    const int w = tid + k * nthreads;
+    if (w < n && (!odd || idx0 + k * didx >= 4)) {       // odd samples below the first centre tap are never read
+      T *d = row + k * dph;
+      d[0] = (T)r.v[4 * k]; d[half] = (T)r.v[4 * k + 1]; d[2 * half] = (T)r.v[4 * k + 2]; d[3 * half] = (T)r.v[4 * k + 3];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kHbRaw; ++k) {
+    if (vec) break;
+    const int w = tid + k * nthreads;
+    if (w < n && (!odd || idx0 + k * didx >= 4)) row[k * dph] = (T)r.v[k];
+  }
+}
+
+// Outputs of work item `w` (< CH * tile / OPT) of the tile: OPT consecutive outputs of one lane.
+template <class T, class InT, class OutT, int NC, int OPT>
+RR_PROG void hb_compute_item(const HalfbandParams<T> &p, const HbTile<InT, OutT> &tl, const T *smem, int w)
 {
   typedef Arith<T> A;
-  const int CH = p.CH;                                   // 1, 2, 4 or 8; > 1 only for interleaved input
-  constexpr int c = NC;                                  // compile-time tap count keeps the window in registers
-  // tile geometry (divisions, 64-bit coordinates) once per tile, by the CTA leader
-  struct Tile {
-    long long k0, x0, in_off0, out_off0;
-    const InT *src0; OutT *dst0;
-    int cnt, win, in_direct, out_direct;
-  };
-  auto make_tile = [&]() {
-    Tile t;
-    const long long tiles = (p.nout + p.tile - 1) / p.tile;
-    long long group; int tix_i;
-    divmod_ll(work, (int)tiles, group, tix_i);
-    const int lane0 = (int)group * CH;
-    t.k0 = p.out0 + (long long)tix_i * p.tile;
-    const long long rest = p.out0 + p.nout - t.k0;
-    t.cnt = rest < p.tile ? (int)rest : p.tile;
-    t.x0 = 2 * t.k0 + p.pre - (2 * c - 1);               // first coordinate needed (window index u = coord - x0)
-    t.win = 2 * (t.cnt - 1) + 2 * (2 * c - 1) + 1;
-    t.in_off0 = lane_offset(p.in, lane0); t.out_off0 = lane_offset(p.out, lane0);
-    t.in_direct = view_range_direct(p.in, t.x0, t.x0 + t.win);
-    t.out_direct = view_range_direct(p.out, p.out_preload + t.k0, p.out_preload + t.k0 + t.cnt);
-    t.src0 = view_ptr<const InT>(p.in, t.in_off0, t.x0);
-    t.dst0 = view_ptr<OutT>(p.out, t.out_off0, p.out_preload + t.k0);
-    return t;
-  };
-#if defined(__CUDA_ARCH__)
-  __shared__ Tile tile_s;
-  if (threadIdx.x == 0) tile_s = make_tile();
-  __syncthreads();
-  const Tile tl = tile_s;                                // the program's last phase ends with a barrier: safe to reuse
-#else
-  const Tile tl = make_tile();
-#endif
-  const long long k0 = tl.k0, x0 = tl.x0;
-  const int cnt = tl.cnt, win = tl.win;
-  T *P0 = smem, *P1 = smem + (long long)CH * p.half;     // even-u / odd-u samples, [lane][half]
-  // window index u: even u -> P0[u/2], odd u -> P1[(u+1)/2 + shift] with shift chosen so that the centre tap of
-  // output j (u = 2j + reach, odd) sits at P1[j + 4]: rows stay 16-byte aligned for the vector loads below
-  const int shift = 4 - c;
-  const int chbits = CH == 8 ? 3 : CH == 4 ? 2 : CH == 2 ? 1 : 0;
-  const long long in_off0 = tl.in_off0, out_off0 = tl.out_off0;
-
-  const bool direct = tl.in_direct != 0;
-  const InT *src0 = tl.src0;
-  auto put = [&](int l, int u, T v) {
-    if (u & 1) {                                         // odd samples below the first centre tap are never read
-      const int idx = ((u + 1) >> 1) + shift;
-      if (idx >= 4) P1[l * p.half + idx] = v;
-    } else P0[l * p.half + (u >> 1)] = v;
-  };
-  // interleaved frames of 4 or 8 channels: one 16-byte load brings four channels of a frame
-  const bool vec = direct && CH >= 4 && sizeof(InT) == 4 && p.in.ch_stride == 1 && p.in.elem_stride == CH &&
-                   !((size_t)src0 & 15);
-  if (vec) {
-    struct alignas(16) V4 { InT a, b, c, d; };
-    const int vbits = chbits - 2;                        // vectors per frame = CH / 4
-    const int nvec = win << vbits, nhalf = (nvec + 1) >> 1;
-    cta_for(nhalf, [&](int w) {                          // two independent 16-byte loads in flight per thread
-      const int w2 = w + nhalf;
-      const V4 va = ldg(reinterpret_cast<const V4 *>(src0) + w);
-      const V4 vb = w2 < nvec ? ldg(reinterpret_cast<const V4 *>(src0) + w2) : va;
-      {
-        const int l = 4 * (w & ((1 << vbits) - 1)), u = w >> vbits;
-        put(l, u, (T)va.a); put(l + 1, u, (T)va.b); put(l + 2, u, (T)va.c); put(l + 3, u, (T)va.d);
-      }
-      if (w2 < nvec) {
-        const int l = 4 * (w2 & ((1 << vbits) - 1)), u = w2 >> vbits;
-        put(l, u, (T)vb.a); put(l + 1, u, (T)vb.b); put(l + 2, u, (T)vb.c); put(l + 3, u, (T)vb.d);
-      }
-    });
-  } else
-  cta_for(win << chbits, [&](int w) {                    // channel fastest: coalesced for interleaved input
-    const int l = w & (CH - 1), u = w >> chbits;
-    const long long off = in_off0 + (long long)l * p.in.ch_stride;
-    const T v = direct ? (T)src0[(long long)l * p.in.ch_stride + (long long)u * p.in.elem_stride]
-                       : view_read<InT, T>(p.in, off, x0 + u);
-    put(l, u, v);
-  });
-  const int qbits = p.qbits;                             // log2(tile / 4)
-  cta_for(CH << qbits, [&](int w) {
-    const int l = w >> qbits, j = 4 * (w & ((1 << qbits) - 1));
-    if (j >= cnt) return;
-    const T *e = P0 + l * p.half + j, *o = P1 + l * p.half + j + 4;
-    // outputs j..j+3 use P0[j .. j+2c+2] and the centres P1[j+4 .. j+7]
-    constexpr int kPer = 16 / (int)sizeof(T);            // samples per 16-byte shared load
-    constexpr int kVecs = (2 * c + 3 + kPer - 1) / kPer;
-    struct alignas(16) Q { T v[kPer]; };
-    T x[kVecs * kPer], ctr[4];
+  constexpr int c = NC;
+  const int CH = p.CH, cnt = tl.cnt;
+  const T *P0 = smem, *P1 = smem + (long long)CH * p.half;
+  const int qbits = p.qbits - (OPT == 8 ? 1 : 0);        // log2(tile / OPT); p.qbits = log2(tile / 4)
+  const int l = w >> qbits, j = OPT * (w & ((1 << qbits) - 1));
+  if (j >= cnt) return;
+  const T *e = P0 + l * p.half + hb_pad<OPT>(j), *o = P1 + l * p.half + hb_pad<OPT>(j);
+  // outputs j..j+OPT-1 use P0[j .. j+2c+OPT-2] and the centres P1[j+4 .. j+OPT+3]; j is a multiple of OPT, so the
+  // padding of a logical offset from j is a compile-time constant
+  constexpr int kPer = 16 / (int)sizeof(T);              // samples per 16-byte shared load
+  constexpr int kVecs = (2 * c + OPT - 1 + kPer - 1) / kPer;
+  struct alignas(16) Q { T v[kPer]; };
+  T x[kVecs * kPer], ctr[OPT];
 #pragma unroll
-    for (int i = 0; i < kVecs; ++i) {
-      const Q qv = reinterpret_cast<const Q *>(e)[i];
+  for (int i = 0; i < kVecs; ++i) {
+    const Q qv = *reinterpret_cast<const Q *>(e + hb_pad<OPT>(i * kPer));
 #pragma unroll
-      for (int k = 0; k < kPer; ++k) x[i * kPer + k] = qv.v[k];
-    }
+    for (int k = 0; k < kPer; ++k) x[i * kPer + k] = qv.v[k];
+  }
 #pragma unroll
-    for (int i = 0; i < 4 / kPer; ++i) {
-      const Q qv = reinterpret_cast<const Q *>(o)[i];
+  for (int i = 0; i < OPT / kPer; ++i) {
+    const Q qv = *reinterpret_cast<const Q *>(o + hb_pad<OPT>(4 + i * kPer));
 #pragma unroll
-      for (int k = 0; k < kPer; ++k) ctr[i * kPer + k] = qv.v[k];
-    }
-    T y[4];
+    for (int k = 0; k < kPer; ++k) ctr[i * kPer + k] = qv.v[k];
+  }
+  T y[OPT];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      T sum = A::mul(ctr[r], (T)0.5);
+  for (int r = 0; r < OPT; ++r) {
+    T sum = A::mul(ctr[r], (T)0.5);
 #pragma unroll
-      for (int t = 0; t < c; ++t) sum = A::add(sum, A::mul(A::add(x[r + c - 1 - t], x[r + c + t]), p.coef[t]));
-      y[r] = sum;
-    }
-    const long long off = out_off0 + (long long)l * p.out.ch_stride;
-    const long long cbase = p.out_preload + k0 + j;
-    if (j + 4 <= cnt && tl.out_direct) {
-      const int es = p.out.elem_stride;
-      OutT *d = tl.dst0 + (long long)l * p.out.ch_stride + j * es;
-      if (es == 1 && !((size_t)d & (4 * sizeof(OutT) - 1))) {          // planar, aligned: one vector store
-        struct alignas(4 * sizeof(OutT)) O4 { OutT a, b, c, d; };
-        *reinterpret_cast<O4 *>(d) = O4{(OutT)y[0], (OutT)y[1], (OutT)y[2], (OutT)y[3]};
-      } else {
+    for (int t = 0; t < c; ++t) sum = A::add(sum, A::mul(A::add(x[r + c - 1 - t], x[r + c + t]), p.coef[t]));
+    y[r] = sum;
+  }
+  const long long off = tl.out_off0 + (long long)l * p.out.ch_stride;
+  const long long cbase = p.out_preload + tl.k0 + j;
+  if (j + OPT <= cnt && tl.out_direct) {
+    const int es = p.out.elem_stride;
+    OutT *d = tl.dst0 + (long long)l * p.out.ch_stride + j * es;
+    if (es == 1 && !((size_t)d & (4 * sizeof(OutT) - 1))) {            // planar, aligned: vector stores
+      struct alignas(4 * sizeof(OutT)) O4 { OutT a, b, c, d; };
 #pragma unroll
-        for (int r = 0; r < 4; ++r) d[r * es] = (OutT)y[r];
-      }
+      for (int r = 0; r < OPT; r += 4)
+        reinterpret_cast<O4 *>(d)[r >> 2] = O4{(OutT)y[r], (OutT)y[r + 1], (OutT)y[r + 2], (OutT)y[r + 3]};
     } else {
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
-        if (j + r < cnt) view_write<OutT, T>(p.out, off, cbase + r, y[r]);
+      for (int r = 0; r < OPT; ++r) d[r * es] = (OutT)y[r];
     }
-  });
+  } else {
+#pragma unroll
+    for (int r = 0; r < OPT; ++r)
+      if (j + r < cnt) view_write<OutT, T>(p.out, off, cbase + r, y[r]);
+  }
+}
+
+// One tile, start to end (the generic kernel; the emulation): y[k] = 0.5 x[2k+pre] + sum_t c[t] (x[2k+pre-(2t+1)] +
+// x[2k+pre+(2t+1)]), summed in that order. The window is split by sample parity in shared memory (the centre tap
+// reads one parity, all other taps the other one), so consecutive outputs read consecutive words; each thread
+// produces OPT consecutive outputs from 16-byte shared loads.
+template <class T, class InT, class OutT, int NC, int OPT = 4>
+RR_PROG void halfband_program(const HalfbandParams<T> &p, long long work, T *smem)
+{
+#if defined(__CUDA_ARCH__)
+  __shared__ HbTile<InT, OutT> tile_s;
+  if (threadIdx.x == 0) tile_s = hb_make_tile<T, InT, OutT, NC>(p, work);
+  __syncthreads();
+  const HbTile<InT, OutT> tl = tile_s;                   // the program's last phase ends with a barrier: safe to reuse
+  const int nthreads = blockDim.x;
+  // the window in rounds of kHbRaw elements per thread
+  const int total = hb_vec_path(p, tl) ? (tl.win * p.CH) >> 2 : tl.win * p.CH;
+  (void)total;
+  HbRegs<InT> r;
+  hb_fetch(p, tl, r, (int)threadIdx.x, nthreads);
+  hb_put<T, InT, OutT, NC, OPT>(p, tl, r, smem, (int)threadIdx.x, nthreads);
+  __syncthreads();
+  const int items = (p.CH * p.tile) / OPT;
+  for (int w = threadIdx.x; w < items; w += nthreads) hb_compute_item<T, InT, OutT, NC, OPT>(p, tl, smem, w);
+  __syncthreads();
+#else
+  const HbTile<InT, OutT> tl = hb_make_tile<T, InT, OutT, NC>(p, work);
+  const int nthreads = 256;
+  for (int tid = 0; tid < nthreads; ++tid) {
+    HbRegs<InT> r;
+    hb_fetch(p, tl, r, tid, nthreads);
+    hb_put<T, InT, OutT, NC, OPT>(p, tl, r, smem, tid, nthreads);
+  }
+  const int items = (p.CH * p.tile) / OPT;
+  for (int w = 0; w < items; ++w) hb_compute_item<T, InT, OutT, NC, OPT>(p, tl, smem, w);
+#endif
 }
 
 }  // namespace b200rate
