@@ -46,29 +46,7 @@ const char *last_error() { return g_last_error.c_str(); }
 // backend: CUDA, or host emulation for tests
 // ===================================================================================================
 #ifdef B200RATE_EMU
-constexpr int kEmulated = 1;
-typedef void *stream_t;
-static int be_set_device(int) { return RR_OK; }
-static int be_malloc(void **p, size_t n) { *p = calloc(1, n ? n : 1); return *p ? RR_OK : RR_ENOMEM; }
-static void be_free(void *p) { free(p); }
-static int be_h2d(void *d, const void *h, size_t n, stream_t) { memcpy(d, h, n); return RR_OK; }
-static int be_d2h(void *h, const void *d, size_t n, stream_t) { memcpy(h, d, n); return RR_OK; }
-static int be_sync(stream_t) { return RR_OK; }
-static int be_stream_create(stream_t *s) { *s = nullptr; return RR_OK; }
-static void be_stream_destroy(stream_t) {}
-static int be_num_sms() { return 1; }
-static size_t be_max_smem() { return 227 * 1024; }
-static int be_current_device() { return 0; }
-struct DeviceScope { explicit DeviceScope(int) {} bool ok() const { return true; } };
-typedef int event_t;
-static int be_host_alloc(void **p, size_t n) { *p = malloc(n ? n : 1); return *p ? RR_OK : RR_ENOMEM; }
-static void be_host_free(void *p) { free(p); }
-static bool be_host_is_pinned(const void *) { return false; }
-static int be_memset(void *d, int v, size_t n, stream_t) { memset(d, v, n); return RR_OK; }
-static int be_event_create(event_t *e) { *e = 1; return RR_OK; }
-static void be_event_destroy(event_t) {}
-static int be_event_record(event_t, stream_t) { return RR_OK; }
-static int be_event_sync(event_t) { return RR_OK; }
+#include "emu_backend.inc"   // tests/emu: host memory as the "device" (test infrastructure, not in this tree)
 #else
 constexpr int kEmulated = 0;
 typedef cudaStream_t stream_t;

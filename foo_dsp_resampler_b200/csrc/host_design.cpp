@@ -318,82 +318,133 @@ std::vector<double> design_lpf(double Fp, double Fs, double Fn, double att, int 
   return windowed_sinc(num_taps, Fc, beta, rho, static_cast<double>(phases));
 }
 
-int fir_to_phase(std::vector<double> &h, double phase)   // effects_i_dsp.c:181-278
+// ---------------------------------------------------------------------------------------------------
+// Phase response transform of a linear-phase prototype (lsx_fir_to_phase, effects_i_dsp.c:181-278): the filter
+// keeps its magnitude response and gets a phase response between minimum phase (phase 0), linear phase (50) and
+// maximum phase (100). Homomorphic method: log-magnitude spectrum -> real cepstrum -> fold onto the causal side ->
+// back to a (log-magnitude, phase) spectrum of the minimum-phase filter -> blend that phase with the linear one ->
+// impulse response, cropped around its peak. Every expression keeps the reference's operand order (the taps are
+// part of the parity contract); the transforms are the Ooura-ordered host FFT above.
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+struct PhaseWork {
+  int n;                           // transform length (power of two, >= 32 and > 2 * taps)
+  std::vector<double> v;           // packed spectrum / sequence, n + 2 values (explicit Nyquist pair at [n], [n + 1])
+  std::vector<double> half_turns;  // per bin: accumulated phase discontinuities of the prototype, in units of pi
+};
+
+void scaled_inverse(PhaseWork &w)
 {
-  const double phase1 = (phase > 50 ? 100 - phase : phase) / 50;
-  int len = static_cast<int>(h.size());
-  int work_len = 2 * 2 * 8;
-  for (int i = len; i > 1; work_len <<= 1, i >>= 1) {}
-  std::vector<double> work(static_cast<size_t>(work_len) + 2, 0.0), pi_wraps((static_cast<size_t>(work_len) + 2) / 2);
+  rdft_f64_host(w.n, true, w.v.data());
+  for (int i = 0; i < w.n; ++i) w.v[i] *= 2. / w.n;
+}
 
-  std::copy(h.begin(), h.end(), work.begin());
-  rdft_f64_host(work_len, false, work.data());
-  work[work_len] = work[1]; work[work_len + 1] = work[1] = 0;        // unpack Nyquist
-
-  double prev_angle2 = 0, cum_2pi = 0, prev_angle1 = 0, cum_1pi = 0;
-  for (int i = 0; i <= work_len; i += 2) {
-    double angle = std::atan2(work[i + 1], work[i]);
-    double detect = 2 * kPi;
-    double delta = angle - prev_angle2;
-    double adjust = detect * ((delta < -detect * .7) - (delta > detect * .7));
-    prev_angle2 = angle;
-    cum_2pi += adjust;
-    angle += cum_2pi;
-    detect = kPi;
-    delta = angle - prev_angle1;
-    adjust = detect * ((delta < -detect * .7) - (delta > detect * .7));
-    prev_angle1 = angle;
-    cum_1pi += std::fabs(adjust);
-    pi_wraps[i >> 1] = cum_1pi;
-    const double mag = std::sqrt(work[i] * work[i] + work[i + 1] * work[i + 1]);
-    work[i] = mag ? std::log(mag) : -26;
-    work[i + 1] = 0;
+// Spectrum of the prototype -> log magnitudes (imaginary parts cleared), counting on the way how often its phase
+// jumps by a whole and by half a turn: the half-turn count at Nyquist is the prototype's group delay in samples.
+void log_magnitude(PhaseWork &w)
+{
+  rdft_f64_host(w.n, false, w.v.data());
+  w.v[w.n] = w.v[1]; w.v[w.n + 1] = w.v[1] = 0;                        // unpack Nyquist
+  double last_raw = 0, turns = 0, last_unwrapped = 0, half_turns = 0;
+  for (int i = 0; i <= w.n; i += 2) {
+    double angle = std::atan2(w.v[i + 1], w.v[i]);
+    double unit = 2 * kPi;
+    double jump = angle - last_raw;
+    double fix = unit * ((jump < -unit * .7) - (jump > unit * .7));
+    last_raw = angle;
+    turns += fix;
+    angle += turns;
+    unit = kPi;
+    jump = angle - last_unwrapped;
+    fix = unit * ((jump < -unit * .7) - (jump > unit * .7));
+    last_unwrapped = angle;
+    half_turns += std::fabs(fix);
+    w.half_turns[i >> 1] = half_turns;
+    const double mag = std::sqrt(w.v[i] * w.v[i] + w.v[i + 1] * w.v[i + 1]);
+    w.v[i] = mag ? std::log(mag) : -26;
+    w.v[i + 1] = 0;
   }
-  work[1] = work[work_len];                                           // pack Nyquist
-  rdft_f64_host(work_len, true, work.data());
-  for (int i = 0; i < work_len; ++i) work[i] *= 2. / work_len;
+  w.v[1] = w.v[w.n];                                                   // pack Nyquist
+}
 
-  for (int i = 1; i < work_len / 2; ++i) {   // keep the causal part of the cepstrum
-    work[i] *= 2;
-    work[i + work_len / 2] = 0;
+// Real cepstrum folded onto the causal side, transformed back: v = (log magnitude, minimum phase) per bin.
+void minimum_phase_spectrum(PhaseWork &w)
+{
+  scaled_inverse(w);
+  for (int i = 1; i < w.n / 2; ++i) {
+    w.v[i] *= 2;
+    w.v[i + w.n / 2] = 0;
   }
-  rdft_f64_host(work_len, false, work.data());
+  rdft_f64_host(w.n, false, w.v.data());
+}
 
-  for (int i = 2; i < work_len; i += 2)
-    work[i + 1] = phase1 * i / work_len * pi_wraps[work_len >> 1] +
-                  (1 - phase1) * (work[i + 1] + pi_wraps[i >> 1]) - pi_wraps[i >> 1];
-
-  work[0] = std::exp(work[0]); work[1] = std::exp(work[1]);
-  for (int i = 2; i < work_len; i += 2) {
-    const double x = std::exp(work[i]);
-    work[i] = x * std::cos(work[i + 1]);
-    work[i + 1] = x * std::sin(work[i + 1]);
+// Blend the minimum phase with the prototype's linear phase (mix = 0: minimum, 1: linear) and leave the impulse
+// response of the result in v.
+void blended_impulse(PhaseWork &w, double mix)
+{
+  const double total = w.half_turns[w.n >> 1];
+  for (int i = 2; i < w.n; i += 2)
+    w.v[i + 1] = mix * i / w.n * total + (1 - mix) * (w.v[i + 1] + w.half_turns[i >> 1]) - w.half_turns[i >> 1];
+  w.v[0] = std::exp(w.v[0]); w.v[1] = std::exp(w.v[1]);
+  for (int i = 2; i < w.n; i += 2) {
+    const double mag = std::exp(w.v[i]);
+    w.v[i] = mag * std::cos(w.v[i + 1]);
+    w.v[i + 1] = mag * std::sin(w.v[i + 1]);
   }
-  rdft_f64_host(work_len, true, work.data());
-  for (int i = 0; i < work_len; ++i) work[i] *= 2. / work_len;
+  scaled_inverse(w);
+}
 
+// Index of the main lobe: where the running sum of the response peaks within the prototype's group delay, walked
+// back to the local extremum.
+int impulse_peak(const PhaseWork &w)
+{
   int peak = 0;
-  double imp_sum = 0, peak_imp_sum = 0;
-  for (int i = 0; i <= static_cast<int>(pi_wraps[work_len >> 1] / kPi + .5); ++i) {
-    imp_sum += work[i];
-    if (std::fabs(imp_sum) > std::fabs(peak_imp_sum)) { peak_imp_sum = imp_sum; peak = i; }
+  double running = 0, best = 0;
+  const int last = static_cast<int>(w.half_turns[w.n >> 1] / kPi + .5);
+  for (int i = 0; i <= last; ++i) {
+    running += w.v[i];
+    if (std::fabs(running) > std::fabs(best)) { best = running; peak = i; }
   }
-  while (peak && std::fabs(work[peak - 1]) > std::fabs(work[peak]) && work[peak - 1] * work[peak] > 0) --peak;
+  while (peak && std::fabs(w.v[peak - 1]) > std::fabs(w.v[peak]) && w.v[peak - 1] * w.v[peak] > 0) --peak;
+  return peak;
+}
 
+}  // namespace
+
+// Replaces h by the transformed filter (its length may change) and returns the number of taps behind the peak.
+int fir_to_phase(std::vector<double> &h, double phase)
+{
+  const bool mirrored = phase > 50;                      // maximum-phase side: the minimum-phase side reversed in time
+  const double mix = (mirrored ? 100 - phase : phase) / 50;
+  int len = static_cast<int>(h.size());
+  PhaseWork w;
+  w.n = 2 * 2 * 8;
+  for (int i = len; i > 1; w.n <<= 1, i >>= 1) {}
+  w.v.assign(static_cast<size_t>(w.n) + 2, 0.0);
+  w.half_turns.assign((static_cast<size_t>(w.n) + 2) / 2, 0.0);
+  std::copy(h.begin(), h.end(), w.v.begin());
+
+  log_magnitude(w);
+  minimum_phase_spectrum(w);
+  blended_impulse(w, mix);
+  const int peak = impulse_peak(w);
+
+  // crop: everything from the start (minimum phase), centred on the peak (linear), or a window around the peak whose
+  // two sides grow with their share of the phase
   int begin;
-  if (!phase1) begin = 0;
-  else if (phase1 == 1) begin = peak - len / 2;
+  if (!mix) begin = 0;
+  else if (mix == 1) begin = peak - len / 2;
   else {
-    begin = static_cast<int>((.997 - (2 - phase1) * .22) * len + .5);
-    int end = static_cast<int>((.997 + (0 - phase1) * .22) * len + .5);
+    begin = static_cast<int>((.997 - (2 - mix) * .22) * len + .5);
+    int end = static_cast<int>((.997 + (0 - mix) * .22) * len + .5);
     begin = peak - (begin & ~3);
     end = peak + 1 + ((end + 3) & ~3);
     len = end - begin;
     h.resize(static_cast<size_t>(len));
   }
-  for (int i = 0; i < len; ++i)
-    h[i] = work[(begin + (phase > 50 ? len - 1 - i : i) + work_len) & (work_len - 1)];
-  return phase > 50 ? peak - begin : begin + len - (peak + 1);
+  for (int i = 0; i < len; ++i) h[i] = w.v[(begin + (mirrored ? len - 1 - i : i) + w.n) & (w.n - 1)];
+  return mirrored ? peak - begin : begin + len - (peak + 1);
 }
 
 const double *half_band_coefs(int num_coefs)
@@ -500,27 +551,116 @@ std::vector<double> poly_bank_layout(const std::vector<double> &h, int taps, int
   return bank;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Planner (rate_base.h:247-423,674-704), in four steps: what the configuration asks for (QualitySpec), how the
+// rate ratio is split over stage kinds (RatioSplit), how much stop-band attenuation each stage must deliver
+// (attenuation budget), and the stages themselves. The floating-point expressions keep the reference's operand
+// order: the plan integers and the filter taps are part of the parity contract.
+// ---------------------------------------------------------------------------------------------------
+
+// Step 1: the switches of RR_config in numbers (convert_settings, rate_base.h:674-704).
+struct QualitySpec {
+  int rolloff;                 // 0: none (Best), 1: small (Normal)
+  double precision_bits;       // 28 (Best) / 20 (Normal)
+  double passband_pc;          // 0 dB point of the pass band, % of Nyquist
+  double antialias_pc;         // 100 unless aliasing above the pass band is allowed
+  double phase_pc;             // 50 = linear
+};
+bool quality_spec(const RR_config &cfg, QualitySpec &q)
+{
+  const bool best = cfg.quality == RR_best;
+  q.rolloff = best ? 0 : 1;
+  q.precision_bits = 16 + 4 * std::max((best ? 6 : 4) - 3, 0);
+  const double rejection = q.precision_bits * to_dB(2.);
+  q.passband_pc = 100 - (100 - cfg.bandwidth) / to_3dB(rejection);
+  q.antialias_pc = cfg.allow_aliasing ? cfg.bandwidth : 100;
+  q.phase_pc = cfg.phase;
+  // the reference asserts these ranges (rate_base.h:276-280)
+  return q.phase_pc >= 0 && q.phase_pc <= 100 && q.passband_pc >= 53 && q.passband_pc <= 100 && q.antialias_pc >= 85 &&
+         q.antialias_pc <= 100;
+}
+
+// Step 2: in_rate / out_rate = 2^halvings * (pre_down / pre_up) * (poly_ratio / poly_up) * (post_down / post_up)
+// (rate_base.h:283-310). `mode` picks the polyphase filter family; a ratio that is not rational within 2^-32 leaves
+// poly_up == 1 and a fractional poly_ratio for the interpolated polyphase stages.
+struct RatioSplit {
+  int halvings = 0, pre_up = 1, pre_down = 1, poly_up = 1, post_up = 1, post_down = 1, mode = 0;
+  double poly_ratio = 1;
+  bool upsampling = false, rational = false;
+};
+RatioSplit split_ratio(double factor, const QualitySpec &q, int sample_bytes)
+{
+  constexpr double kTwo32 = 65536. * 65536.;
+  constexpr int kMaxBankKB = 400;                        // max_coefs_size
+  const bool allow_post_stage = true;                    // iOpt
+  RatioSplit r;
+  r.poly_ratio = factor;
+  r.mode = q.rolloff > 1 ? (factor > 1 || q.passband_pc > (67 + 5 / 8.)) : static_cast<int>(std::ceil(2 + (q.precision_bits - 17) / 4));
+  for (bool again = true; again;) {
+    again = false;
+    const int max_phases = r.mode ? 2048 : static_cast<int>(std::ceil(kMaxBankKB * 1000. / (44 * sample_bytes)));
+    r.upsampling = r.poly_ratio < 1;
+    // whole octaves of decimation become half-band stages
+    r.halvings = 0;
+    for (int i = static_cast<int>(r.poly_ratio * .5); i >>= 1; r.poly_ratio *= .5, ++r.halvings) {}
+    r.pre_down = r.upsampling || (r.poly_ratio > 1.5 && r.poly_ratio < 2);
+    r.post_down = 1 + (r.poly_ratio > 1 && r.pre_down);
+    r.poly_ratio /= r.post_down;
+    r.pre_up = 1 + (!r.pre_down && r.poly_ratio < 2) + (r.upsampling && r.mode);
+    r.poly_ratio *= r.pre_up;
+    // is what is left a ratio of small integers (to the precision of the 32.32 phase accumulator)?
+    const double frac = r.poly_ratio - static_cast<int>(r.poly_ratio);
+    double epsilon = 0;
+    if (frac != 0) epsilon = std::fabs(std::floor(frac * kTwo32 + .5) / (frac * kTwo32) - 1);
+    r.rational = !frac;
+    for (int i = 1; i <= max_phases && !r.rational; ++i) {
+      const double d = frac * i;
+      const int nearest = static_cast<int>(d + .5);
+      if ((r.rational = std::fabs(nearest / d - 1) <= epsilon)) {
+        if (nearest == i) {
+          r.poly_ratio = std::ceil(r.poly_ratio);
+          const int extra = r.poly_ratio > 3;
+          r.halvings += extra;
+          r.poly_ratio /= 1 + extra;
+        } else {
+          r.poly_ratio = i * static_cast<int>(r.poly_ratio) + nearest;
+          r.poly_up = i;
+        }
+      }
+    }
+    int up = r.pre_up * r.poly_up, down = static_cast<int>(r.poly_ratio * r.post_down);
+    const int odd = (up | down) & 1;
+    up >>= !odd; down >>= !odd;
+    const double gain = r.pre_up * r.poly_up / r.poly_ratio;
+    bool restarted = false;
+    if (allow_post_stage && r.post_up == 1 && gain > 4 && gain != 5) {
+      // steep up-sampling: move a power of two >= 4 into a post stage and split what is left again
+      r.post_up = 4;
+      for (int i = static_cast<int>(gain / 16); i >>= 1; r.post_up <<= 1) {}
+      r.poly_ratio = r.poly_ratio * r.post_up / r.poly_up / r.pre_up;
+      r.poly_up = 1;
+      again = restarted = true;
+    } else if (r.rational && (std::max(up, down) < 3 + 2 * allow_post_stage || up * down < 6 * allow_post_stage)) {
+      // tiny integer ratios: one DFT stage does it all
+      r.pre_up = up; r.pre_down = down;
+      r.poly_ratio = 1; r.poly_up = 1; r.post_down = 1;
+    }
+    if (!r.mode && (!r.rational || restarted)) { ++r.mode; again = true; }
+  }
+  return r;
+}
+
 }  // namespace
 
 int build_design(const RR_config &cfg, int sample_bytes, Design &D)
 {
-  // ---- convert_settings ----
-  const bool best = cfg.quality == RR_best;
-  const int rolloff = best ? 0 : 1;                                   // none / small
-  const double bits = 16 + 4 * std::max((best ? 6 : 4) - 3, 0);
-  const double rej = bits * to_dB(2.);
-  const double bw_pc = 100 - (100 - cfg.bandwidth) / to_3dB(rej);
-  const double anti_aliasing_pc = cfg.allow_aliasing ? cfg.bandwidth : 100;
-  const double phase = cfg.phase;
-  const int interpolator = -1, max_coefs_size = 400;
-  const bool iOpt = true;
-
+  constexpr double kTwo32 = 65536. * 65536.;
+  constexpr int kMaxBankKB = 400;
   if (!cfg.in_rate || !cfg.out_rate) return RR_INVPARAM;
   const double factor = static_cast<double>(cfg.in_rate) / static_cast<double>(cfg.out_rate);
   if (factor > 5644.8 || factor < 1.0 / 5644.8) return RR_INVPARAM;
-  if (!(phase >= 0 && phase <= 100) || !(bw_pc >= 53 && bw_pc <= 100) ||
-      !(anti_aliasing_pc >= 85 && anti_aliasing_pc <= 100))
-    return RR_INVPARAM;                                              // the reference asserts (rate_base.h:276-280)
+  QualitySpec q;
+  if (!quality_spec(cfg, q)) return RR_INVPARAM;
 
   D = Design{};
   rr_plan &P = D.plan;
@@ -529,56 +669,29 @@ int build_design(const RR_config &cfg, int sample_bytes, Design &D)
   P.isamp_max = 1048576;
   if (factor < 1) P.isamp_max = static_cast<uint64_t>(P.isamp_max * factor);
 
-  const double MULT32 = 65536. * 65536.;
-  double att = (bits + 1) * to_dB(2.), attArb = att;
-  const double tbw0 = 1 - bw_pc / 100, Fs_a = 2 - anti_aliasing_pc / 100;
-  double arbM = factor, tbw_tighten = 1;
-  int n = 0, i, preL = 1, preM = 1, shift = 0, arbL = 1, postL = 1, postM = 1;
-  bool upsample = false, rational = false;
-  int mode = rolloff > 1 ? (factor > 1 || bw_pc > (67 + 5 / 8.)) : static_cast<int>(std::ceil(2 + (bits - 17) / 4));
-
-  while (!n++) {                                                      // rate_base.h:283-310
-    const int maxL = interpolator > 0 ? 1 : mode ? 2048
-                     : static_cast<int>(std::ceil(max_coefs_size * 1000. / (44 * sample_bytes)));
-    double d, epsilon = 0, frac;
-    int try_i, L, M, x;
-    upsample = arbM < 1;
-    for (i = static_cast<int>(arbM * .5), shift = 0; i >>= 1; arbM *= .5, ++shift) {}
-    preM = upsample || (arbM > 1.5 && arbM < 2);
-    postM = 1 + (arbM > 1 && preM); arbM /= postM;
-    preL = 1 + (!preM && arbM < 2) + (upsample && mode); arbM *= preL;
-    if ((frac = arbM - static_cast<int>(arbM)) != 0)
-      epsilon = std::fabs(std::floor(frac * MULT32 + .5) / (frac * MULT32) - 1);
-    for (i = 1, rational = !frac; i <= maxL && !rational; ++i) {
-      d = frac * i; try_i = static_cast<int>(d + .5);
-      if ((rational = std::fabs(try_i / d - 1) <= epsilon)) {
-        if (try_i == i) { arbM = std::ceil(arbM); x = arbM > 3; shift += x; arbM /= 1 + x; }
-        else { arbM = i * static_cast<int>(arbM) + try_i; arbL = i; }
-      }
-    }
-    L = preL * arbL; M = static_cast<int>(arbM * postM); x = (L | M) & 1; L >>= !x; M >>= !x;
-    if (iOpt && postL == 1 && (d = preL * arbL / arbM) > 4 && d != 5) {
-      for (postL = 4, i = static_cast<int>(d / 16); i >>= 1; postL <<= 1) {}
-      arbM = arbM * postL / arbL / preL; arbL = 1; n = 0;
-    } else if (rational && (std::max(L, M) < 3 + 2 * iOpt || L * M < 6 * iOpt)) {
-      preL = L; preM = M; arbM = arbL = postM = 1;
-    }
-    if (!mode && (!rational || !n)) { ++mode; n = 0; }
-  }
-
-  const bool have_pre = preM * preL != 1, have_arb = arbM * arbL != 1, have_post = postM * postL != 1;
-  const int num_stages = shift + have_pre + have_arb + have_post;
+  RatioSplit r = split_ratio(factor, q, sample_bytes);
+  const bool have_pre = r.pre_down * r.pre_up != 1, have_poly = r.poly_ratio * r.poly_up != 1,
+             have_post = r.post_down * r.post_up != 1;
+  const int num_stages = r.halvings + have_pre + have_poly + have_post;
   if (num_stages > RR_MAX_STAGES) return RR_INVPARAM;
   P.num_stages = num_stages;
 
-  if ((n = num_stages) > 1) {
-    if (have_arb) { att += to_dB(2.); attArb = att; --n; }
-    att += to_dB(static_cast<double>(n));
+  // Step 3: attenuation budget. Every stage adds its stop-band leakage, so each must reject a little more than the
+  // target; the polyphase stage is budgeted separately (rate_base.h:321-327).
+  double atten = (q.precision_bits + 1) * to_dB(2.), atten_poly = atten;
+  if (num_stages > 1) {
+    int others = num_stages;
+    if (have_poly) { atten += to_dB(2.); atten_poly = atten; --others; }
+    atten += to_dB(static_cast<double>(others));
   }
+  const double trans0 = 1 - q.passband_pc / 100;         // transition band of the whole conversion, fraction of Nyquist
+  const double stop_alias = 2 - q.antialias_pc / 100;
+  double tighten = 1;
 
+  // Step 4a: the half-band stages, the shortest table entry that meets the budget (rate_base.h:329-341)
   int hb = 0;
-  while (hb + 1 < 6 && att > kHalfBands[hb].att) ++hb;
-  for (i = 0; i < shift; ++i) {
+  while (hb + 1 < 6 && atten > kHalfBands[hb].att) ++hb;
+  for (int i = 0; i < r.halvings; ++i) {
     rr_stage_plan &s = P.st[i];
     s.kind = RR_STAGE_HALFBAND;
     s.hb_coefs = kHalfBands[hb].num_coefs;
@@ -587,70 +700,76 @@ int build_design(const RR_config &cfg, int sample_bytes, Design &D)
     s.interp_order = -1;
   }
 
+  // Step 4b: the DFT stage in front of the polyphase stage (rate_base.h:343-358). When a post stage follows, its
+  // transition band is tightened so that the cascade keeps the 3 dB point.
   if (have_pre) {
-    if (have_post) {                                                  // maintain_3dB_pt is always true here
-      const double tbw3 = tbw0 * to_3dB(att);
-      double x = ((2.1429e-4 - 5.2083e-7 * att) * att - .015863) * att + 3.95;
-      x = att * std::pow((tbw0 - tbw3) / (postM / (factor * postL) - 1 + tbw0), x);
-      if (x > .035) tbw_tighten = ((4.3074e-3 - 3.9121e-4 * x) * x - .040009) * x + 1.0014;
+    if (have_post) {
+      const double trans3 = trans0 * to_3dB(atten);
+      double x = ((2.1429e-4 - 5.2083e-7 * atten) * atten - .015863) * atten + 3.95;
+      x = atten * std::pow((trans0 - trans3) / (r.post_down / (factor * r.post_up) - 1 + trans0), x);
+      if (x > .035) tighten = ((4.3074e-3 - 3.9121e-4 * x) * x - .040009) * x + 1.0014;
     }
-    plan_dft_stage(D, 0, 1 - tbw0 * tbw_tighten, Fs_a, preM ? std::max(preL, preM) : arbM / arbL, att, phase,
-                   P.st[shift], preL, std::max(preM, 1));
+    plan_dft_stage(D, 0, 1 - trans0 * tighten, stop_alias, r.pre_down ? std::max(r.pre_up, r.pre_down) : r.poly_ratio / r.poly_up,
+                   atten, q.phase_pc, P.st[r.halvings], r.pre_up, std::max(r.pre_down, 1));
   }
 
-  if (have_arb) {
-    const PolyFamily &f = kPolyFamilies[6 * (upsample + !!preM) + mode - !upsample];
-    int order, num_coefs = static_cast<int>(f.cand[0].scalar), phase_bits, phases, coefs_size;
-    double x = .5, at, Fp, Fs, Fn;
-    const double mult = upsample ? 1 : arbL / arbM;
-    rr_stage_plan &a = P.st[shift + have_pre];
+  // Step 4c: the polyphase stage (rate_base.h:360-411): filter family by direction and mode, band edges, then the
+  // cheapest interpolation order whose coefficient bank stays under the size cap.
+  if (have_poly) {
+    const PolyFamily &fam = kPolyFamilies[6 * (r.upsampling + !!r.pre_down) + r.mode - !r.upsampling];
+    rr_stage_plan &a = P.st[r.halvings + have_pre];
+    const double mult = r.upsampling ? 1 : r.poly_up / r.poly_ratio;
+    double x = .5;
+    const double Fn = !r.upsampling && r.pre_down ? x = r.poly_ratio / r.poly_up : 1;
+    double Fp = !r.pre_down ? mult : r.mode ? .5 : 1;
+    const double Fs = 2 - Fp;
+    Fp *= 1 - trans0;
+    if (q.rolloff > 1 && r.mode) Fp = !r.pre_down ? mult * .5 - .125 : mult * .05 + .1;
+    else if (q.rolloff == 1) Fp = Fs - (Fs - .148 * x - Fp * .852) * (.00813 * q.precision_bits + .973);
 
-    Fn = !upsample && preM ? x = arbM / arbL : 1;
-    Fp = !preM ? mult : mode ? .5 : 1;
-    Fs = 2 - Fp;
-    Fp *= 1 - tbw0;
-    if (rolloff > 1 && mode) Fp = !preM ? mult * .5 - .125 : mult * .05 + .1;
-    else if (rolloff == 1) Fp = Fs - (Fs - .148 * x - Fp * .852) * (.00813 * bits + .973);
-
-    i = (interpolator < 0 ? !rational : std::max(interpolator, static_cast<int>(!rational))) - 1;
-    do {
-      ++i;
-      if (f.cand[i].order < 0) return RR_INTERNAL;
-      if (i) { arbM /= arbL; arbL = 1; rational = false; }
-      phase_bits = static_cast<int>(std::ceil(f.cand[i].scalar + std::log(mult) / std::log(2.)));
-      phases = !rational ? (1 << phase_bits) : arbL;
-      if (!f.cand[0].scalar) {
+    int order = 0, taps_per_phase = static_cast<int>(fam.cand[0].scalar), phase_bits = 0, phases = 0;
+    double start_phase = 0;
+    int cand = (r.rational ? 0 : 1) - 1;                 // rational ratios start with the un-interpolated bank
+    for (;;) {
+      ++cand;
+      if (fam.cand[cand].order < 0) return RR_INTERNAL;
+      if (cand) { r.poly_ratio /= r.poly_up; r.poly_up = 1; r.rational = false; }
+      phase_bits = static_cast<int>(std::ceil(fam.cand[cand].scalar + std::log(mult) / std::log(2.)));
+      phases = !r.rational ? (1 << phase_bits) : r.poly_up;
+      if (!fam.cand[0].scalar) {                           // tap count by design rather than from the table
         const int phases0 = std::max(phases, 19);
         int n0 = 0;
-        design_lpf(Fp, Fs, -Fn, attArb, n0, phases0, f.beta);
-        num_coefs = n0 / phases0 + 1; num_coefs += num_coefs & !preM;
+        design_lpf(Fp, Fs, -Fn, atten_poly, n0, phases0, fam.beta);
+        taps_per_phase = n0 / phases0 + 1;
+        taps_per_phase += taps_per_phase & !r.pre_down;
       }
-      if ((num_coefs & 1) && rational && (arbL & 1)) { phases <<= 1; arbL <<= 1; arbM *= 2; }
-      at = arbL * .5 * (num_coefs & 1);
-      order = i + (i && mode > 4);
-      coefs_size = num_coefs * phases * (order + 1) * sample_bytes;
-    } while (interpolator < 0 && i < 2 && f.cand[i + 1].order >= 0 && coefs_size / 1000 > max_coefs_size);
-
-    int num_taps = num_coefs * phases - 1;
-    const std::vector<double> h = design_lpf(Fp, Fs, Fn, attArb, num_taps, phases, f.beta);
-    D.poly_bank = poly_bank_layout(h, num_coefs, phases, order);
+      if ((taps_per_phase & 1) && r.rational && (r.poly_up & 1)) { phases <<= 1; r.poly_up <<= 1; r.poly_ratio *= 2; }
+      start_phase = r.poly_up * .5 * (taps_per_phase & 1);
+      order = cand + (cand && r.mode > 4);
+      const int bank_bytes = taps_per_phase * phases * (order + 1) * sample_bytes;
+      if (!(cand < 2 && fam.cand[cand + 1].order >= 0 && bank_bytes / 1000 > kMaxBankKB)) break;
+    }
+    int num_taps = taps_per_phase * phases - 1;
+    const std::vector<double> h = design_lpf(Fp, Fs, Fn, atten_poly, num_taps, phases, fam.beta);
+    D.poly_bank = poly_bank_layout(h, taps_per_phase, phases, order);
     D.poly_phases = phases; D.poly_order = order;
 
     a.kind = RR_STAGE_POLY;
     a.interp_order = order;
-    a.pre_post = num_coefs - 1;
-    a.preload = (num_coefs - 1) >> 1;
-    a.n = num_coefs;
+    a.pre_post = taps_per_phase - 1;
+    a.preload = (taps_per_phase - 1) >> 1;
+    a.n = taps_per_phase;
     a.phase_bits = phase_bits;
-    a.L = arbL;
-    a.at = static_cast<int64_t>(at * MULT32 + .5);
-    a.step = static_cast<int64_t>(arbM * MULT32 + .5);
+    a.L = r.poly_up;
+    a.at = static_cast<int64_t>(start_phase * kTwo32 + .5);
+    a.step = static_cast<int64_t>(r.poly_ratio * kTwo32 + .5);
   }
 
+  // Step 4d: the DFT stage behind it (rate_base.h:412-415)
   if (have_post)
-    plan_dft_stage(D, 1, 1 - (1 - (1 - tbw0) * (upsample ? factor * postL / postM : 1)) * tbw_tighten, Fs_a,
-                   static_cast<double>(std::max(postL, postM)), att, phase, P.st[shift + have_pre + have_arb],
-                   postL, postM);
+    plan_dft_stage(D, 1, 1 - (1 - (1 - trans0) * (r.upsampling ? factor * r.post_up / r.post_down : 1)) * tighten, stop_alias,
+                   static_cast<double>(std::max(r.post_up, r.post_down)), atten, q.phase_pc,
+                   P.st[r.halvings + have_pre + have_poly], r.post_up, r.post_down);
   return RR_OK;
 }
 
