@@ -218,6 +218,52 @@ def test_batch_cases_match_oracle(case):
     b.close()
 
 
+# fp64 engine through the batch entry point: every block shape of dft64_kernel (x2 F-domain up-sampling, 1:1 with plain /
+# zero-stuffed input and time-domain decimation, F-domain /2 and /4), the eight-output half-band and the two-slot
+# polyphase kernel. (in, out, phase, bw, aliasing, quality, channels, streams, DFT kernel expected)
+FP64_BATCH_CASES = [
+    (44100, 48000, 50, 95, 0, 0, 2, 5, "dft64"), (48000, 44100, 25, 95, 0, 0, 2, 3, "dft64"), (44100, 96000, 50, 95, 0, 1, 1, 7, "dft64"),
+    (192000, 44100, 25, 95, 0, 0, 8, 2, "dft64"), (384000, 48000, 50, 95, 0, 0, 8, 1, "dft64"), (44100, 11025, 50, 95, 0, 0, 2, 3, "dft64"),
+    (32000, 24000, 50, 95, 0, 0, 2, 2, "dft64"), (32000, 24000, 50, 95, 1, 0, 3, 1, "dft64"), (48000, 32000, 50, 95, 0, 0, 2, 2, "dft64"),
+    (96000, 48000, 75, 95, 0, 0, 1, 4, "dft64"), (50000, 40000, 50, 95, 0, 0, 2, 2, "dft64"), (8000, 48000, 50, 95, 0, 0, 1, 3, "dft"),      # zero-stuffed x3 (dft64) + x4 post stage (generic)
+    (44100, 176400, 50, 95, 0, 0, 2, 2, "dft_kernel"),          # x4 F-domain up-sampling stays on the generic kernel
+]
+
+
+@pytest.mark.parametrize("case", FP64_BATCH_CASES, ids=lambda c: "%d-%d-p%d-q%d-%dch-x%d" % (c[0], c[1], c[2], c[5], c[6], c[7]))
+def test_fp64_batch_kernels_match_oracle(case):
+    import torch
+    import foo_dsp_resampler_b200 as pkg
+    i, o, ph, bw, al, q, nch, nstreams, dft_kernel = case
+    cfg, ocfg = _cfgs(i, o, ph, bw, al, q)
+    n = int(i * 0.5) + 29
+    xs = np.stack([signals.sweep_noise(i, nch, n, stream=s) for s in range(nstreams)])
+    b = pkg.BatchConverter(cfg, nch, nstreams, n, engine="double", device=0)
+    nout = b.frames_out(n)
+    d_in = torch.from_numpy(xs).cuda()
+    d_nat = torch.zeros((nstreams, nch, nout), dtype=torch.float64, device="cuda")
+    b.process_native(d_in.data_ptr(), n, d_nat.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = d_nat.cpu().numpy()
+    plan = b.plan()
+    kinds = [st["kind"] for st in plan["stages"]]
+    names = [b.stage_kernel(k) for k in range(len(kinds))]
+    for k, kind in enumerate(kinds):
+        if kind == 1:                                   # RR_STAGE_DFT: no silent fall-back to the generic kernel
+            assert dft_kernel in names[k], names
+    for s in range(nstreams):
+        ref, _ = oraclelib.resample(ocfg, xs[s], engine="double", native=True)
+        assert ref.shape[0] == nout
+        err = np.abs(got[s].T - ref).max()
+        assert err <= FP64_TOL, "stream %d max |err| %g (%s)" % (s, err, names)
+    # the same through RR_pull's float rounding (interleaved float output written by the last stage's stores)
+    d_out = torch.zeros((nstreams, nout, nch), dtype=torch.float32, device="cuda")
+    b.process(d_in.data_ptr(), n, d_out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_out.cpu().numpy(), np.swapaxes(got, 1, 2).astype(np.float32))
+    b.close()
+
+
 @pytest.mark.parametrize("rates", [(48000, 44100, 2), (44100, 96000, 2), (384000, 48000, 8)], ids=lambda r: "%d-%d-%dch" % r)
 def test_many_identical_streams_agree(rates):
     """Stress for the persistent multi-group kernels (named barriers, warp-local FFT phases, LDGSTS pipelines):
