@@ -26,3 +26,10 @@ probe(44100, 48000, 2, 256, 10, engine="double")      # what RR_open selects for
 probe(48000, 44100, 1, 512, 10)                        # mono batch: lanes of different streams paired
 probe(44100, 48000, 2, 256, 10)                        # config 1 conversion as a batch
 probe(44100, 96000, 2, 256, 10)                        # config 2
+# the paths VERDICT r1 item 8 asked to be timed: interpolated polyphase stages (vpoly1-3, polyN_kernel) and DFT blocks
+# beyond shared memory (dft_big_kernel)
+probe(44100, 48001, 2, 64, 10)                         # vpoly2 (Best, irrational ratio)
+probe(44100, 48001, 2, 64, 10, quality=1)              # vpoly1 (Normal)
+probe(48000, 47999, 2, 64, 10, engine="double")        # vpoly3, fp64
+probe(44100, 48000, 2, 64, 10, bandwidth=99.5)         # N = 32768: dft_big_kernel, fp32
+probe(44100, 48000, 2, 64, 10, engine="double", bandwidth=99)   # N = 16384: dft_big_kernel, fp64
