@@ -895,6 +895,7 @@ template <class T> struct PolyParams {
   long long nout;                // outputs per lane in this launch
   int nlanes, tile;              // outputs per CTA tile
   int win_cap;                   // smem window capacity (samples)
+  int row_pitch;                 // vpolyN: elements between the coefficient rows a warp stages in shared memory (0: rows are read from global)
 };
 
 // 128-bit product helper: low and high 64 bits of a*b (a, b >= 0).
@@ -1216,6 +1217,33 @@ RR_PROG void poly0_dual_compute(const Poly0DualParams<T> &dp, const Poly0DualTil
   }
 }
 
+// One vpolyN output from a coefficient row in shared memory, taps in groups of one 16-byte chunk per coefficient order
+// (conflict-free vector loads for rows an odd number of chunks apart); same products, same order as the scalar form.
+template <class T, int ORDER> RR_PROG T polyN_eval_row(const T *row, const T *x, T t, int n)
+{
+  typedef Arith<T> A;
+  constexpr int kPer = 16 / (int)sizeof(T);
+  struct alignas(16) Q { T v[kPer]; };
+  T sum = (T)0;
+  for (int g = 0; g < n / kPer; ++g) {
+    T c[(ORDER + 1) * kPer];
+#pragma unroll
+    for (int i = 0; i <= ORDER; ++i) {
+      const Q qv = reinterpret_cast<const Q *>(row)[g * (ORDER + 1) + i];
+#pragma unroll
+      for (int k = 0; k < kPer; ++k) c[i * kPer + k] = qv.v[k];
+    }
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      T v = c[k * (ORDER + 1)];
+#pragma unroll
+      for (int o = 1; o <= ORDER; ++o) v = A::add(A::mul(v, t), c[k * (ORDER + 1) + o]);
+      sum = A::add(sum, A::mul(v, x[g * kPer + k]));
+    }
+  }
+  return sum;
+}
+
 // vpoly1..3: 32.32 fixed-point position, Horner-interpolated coefficients.
 template <class T, class InT, class OutT>
 RR_PROG void polyN_program(const PolyParams<T> &p, long long work, T *smem)
@@ -1240,13 +1268,15 @@ RR_PROG void polyN_program(const PolyParams<T> &p, long long work, T *smem)
   const int order = p.order;
 
   cta_for(win, [&](int j) { smem[j] = view_read<InT, T>(p.in, in_off, q0 + p.pre + j); });
-  cta_for(cnt, [&](int j) {
+  // one output: position and phase from the 32.32 accumulator, Horner-interpolated taps summed in tap order
+  auto position = [&](int j, int &q, int &phase, T &t) {
     const unsigned long long at = f0 + (unsigned long long)j * (unsigned long long)p.step;
-    const int q = (int)(at >> 32);
+    q = (int)(at >> 32);
     const uint32_t fraction = (uint32_t)at;
-    const int phase = (int)(fraction >> (32 - p.phase_bits));
-    const T t = A::mul((T)(uint32_t)(fraction << p.phase_bits), (T)(1.0 / 4294967296.0));
-    const T *c = p.coefs + (long long)phase * p.n * (order + 1), *x = smem + q;
+    phase = (int)(fraction >> (32 - p.phase_bits));
+    t = A::mul((T)(uint32_t)(fraction << p.phase_bits), (T)(1.0 / 4294967296.0));
+  };
+  auto evaluate = [&](const T *c, const T *x, T t) -> T {
     T sum = (T)0;
     if (order == 1)
       for (int k = 0; k < p.n; ++k)
@@ -1258,7 +1288,46 @@ RR_PROG void polyN_program(const PolyParams<T> &p, long long work, T *smem)
       for (int k = 0; k < p.n; ++k)
         sum = A::add(sum, A::mul(A::add(A::mul(A::add(A::mul(A::add(A::mul(c[4 * k], t), c[4 * k + 1]), t),
                                                        c[4 * k + 2]), t), c[4 * k + 3]), x[k]));
-    view_write<OutT, T>(p.out, out_off, p.out_preload + i0 + j, sum);
+    return sum;
+  };
+  const int row_elems = p.n * (order + 1);
+#if defined(__CUDA_ARCH__)
+  if (p.row_pitch > 0) {
+    // The phases of a warp's 32 outputs are scattered over the bank (up to 288 KB, L2-resident): a thread reading its
+    // own row touches 32 different lines per load instruction. Instead the warp copies its 32 rows with coalesced
+    // 16-byte loads into shared memory (row pitch an odd number of 16-byte units: conflict-free 16-byte reads), then
+    // every thread evaluates its output from its row.
+    constexpr int kPer = 16 / (int)sizeof(T);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int chunks = row_elems / kPer, pitch = p.row_pitch;
+    T *rows = smem + ((p.win_cap + kPer - 1) / kPer) * kPer + (size_t)warp * 32 * pitch;
+    for (int j0 = warp * 32; j0 < cnt; j0 += nwarps * 32) {
+      const int j = j0 + lane < cnt ? j0 + lane : cnt - 1;
+      int q, phase; T t;
+      position(j, q, phase, t);
+      const unsigned long long mine = (unsigned long long)(p.coefs + (long long)phase * row_elems);
+      for (int ch = lane; ch < 32 * chunks; ch += 32) {
+        const int r = ch / chunks, col = ch - r * chunks;
+        const float4 *src = reinterpret_cast<const float4 *>(__shfl_sync(0xffffffffu, mine, r));
+        *reinterpret_cast<float4 *>(rows + r * pitch + col * kPer) = __ldg(src + col);
+      }
+      __syncwarp();
+      if (j0 + lane < cnt) {
+        const T *row = rows + lane * pitch, *x = smem + q;
+        const T y = order == 1 ? polyN_eval_row<T, 1>(row, x, t, p.n) : order == 2 ? polyN_eval_row<T, 2>(row, x, t, p.n)
+                                                                                   : polyN_eval_row<T, 3>(row, x, t, p.n);
+        view_write<OutT, T>(p.out, out_off, p.out_preload + i0 + j, y);
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    return;
+  }
+#endif
+  cta_for(cnt, [&](int j) {
+    int q, phase; T t;
+    position(j, q, phase, t);
+    view_write<OutT, T>(p.out, out_off, p.out_preload + i0 + j, evaluate(p.coefs + (long long)phase * row_elems, smem + q, t));
   });
 }
 

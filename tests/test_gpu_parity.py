@@ -288,6 +288,31 @@ def test_many_identical_streams_agree(rates):
     b.close()
 
 
+@pytest.mark.parametrize("rates", [(44100, 48000, 2, 50), (192000, 44100, 8, 25), (384000, 48000, 8, 50), (32000, 24000, 2, 50)],
+                         ids=lambda r: "%d-%d-%dch-p%d" % r)
+def test_many_identical_streams_agree_fp64(rates):
+    """The same stress for the fp64 kernels (dft64_kernel's groups working in place on bit-reversed spectra behind named
+    barriers, the register-pipelined half-band, the TMA-staged two-slot polyphase stage): every one of hundreds of
+    identical streams must equal the first one bit for bit, twice in a row, and the first one the oracle within 1e-12."""
+    import torch
+    import foo_dsp_resampler_b200 as pkg
+    i, o, nch, ph = rates
+    cfg, ocfg = _cfgs(i, o, ph, 95, 0, 0)
+    nstreams, n = (400 if nch == 2 else 100), int(i * 0.5)
+    x = signals.sweep_noise(i, nch, n)
+    ref, _ = oraclelib.resample(ocfg, x, engine="double", native=True)
+    b = pkg.BatchConverter(cfg, nch, nstreams, n, engine="double", device=0)
+    nout = b.frames_out(n)
+    d_in = torch.from_numpy(x).cuda().unsqueeze(0).repeat(nstreams, 1, 1).contiguous()
+    for _ in range(2):
+        d_nat = torch.full((nstreams, nch, nout), 7.0, dtype=torch.float64, device="cuda")
+        b.process_native(d_in.data_ptr(), n, d_nat.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert bool((d_nat == d_nat[0:1]).all())
+        assert np.abs(d_nat[0].cpu().numpy().T - ref).max() <= FP64_TOL
+    b.close()
+
+
 def _fuzz_cases():
     import test_emulation
     return test_emulation.fuzz_cases(11, 20) + test_emulation.fuzz_cases(13, 30)
