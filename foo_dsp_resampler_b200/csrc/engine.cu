@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -2372,10 +2373,20 @@ template <class T> class Stream : public IStream {
 
   void release_retired() { for (void *p : retired_) be_free(p); retired_.clear(); }   // only when the stream is idle
 
+  // B200RATE_TRACE_STREAM=1: host-side time of the steps of push / pull, summed per handle and printed at close
+  bool trace_ = getenv("B200RATE_TRACE_STREAM") != nullptr;
+  double tr_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tr_calls_[2] = {0, 0};
+  static double tick() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
   ~Stream() override
   {
     DeviceScope scope(eng.device_id);
     if (s_) be_sync(s_);
+    if (trace_ && tr_calls_[0] && tr_calls_[1])
+      fprintf(stderr, "stream trace: %lld pushes: enqueue copy %.1f us, launch stages %.1f us, wait for the copy %.1f us | %lld pulls: "
+                      "enqueue copy %.1f us, wait %.1f us\n", tr_calls_[0], tr_[0] / tr_calls_[0], tr_[1] / tr_calls_[0], tr_[2] / tr_calls_[0],
+              tr_calls_[1], tr_[3] / tr_calls_[1], tr_[4] / tr_calls_[1]);
     release_retired();
     for (void *p : ring) be_free(p);
     be_free(stage_native);
@@ -2548,12 +2559,17 @@ template <class T> class Stream : public IStream {
     if ((rc = ensure_ring(0, W[0] + static_cast<long long>(frames)))) return rc;
     // deinterleave + convert (rate_base.h:565-569) happen in the first stage's loads: ring 0 keeps frames
     if (kEmulated || be_host_is_pinned(x)) {
+      const double t0 = trace_ ? tick() : 0;
       if ((rc = ring_h2d(0, W[0], static_cast<long long>(frames), x))) return rc;
       // the caller may refill its buffer as soon as we return: wait for the transfer (not for the kernels)
       if ((rc = be_event_record(user_in_done_, s_))) return rc;
       W[0] += static_cast<long long>(frames);
+      const double t1 = trace_ ? tick() : 0;
       if ((rc = process_stages())) return rc;
-      return be_event_sync(user_in_done_);
+      const double t2 = trace_ ? tick() : 0;
+      rc = be_event_sync(user_in_done_);
+      if (trace_) { tr_[0] += t1 - t0; tr_[1] += t2 - t1; tr_[2] += tick() - t2; ++tr_calls_[0]; }
+      return rc;
     }
     const int slot = static_cast<int>(push_seq_++ & 1);
     if (pin_in_busy_[slot]) { if ((rc = be_event_sync(pin_in_free_[slot]))) return rc; pin_in_busy_[slot] = false; }
@@ -2597,8 +2613,11 @@ template <class T> class Stream : public IStream {
         if ((rc = grow_pinned(&pin_out_, &pin_out_cap_, elems))) return rc;
         dst = pin_out_;
       }
+      const double t0 = trace_ ? tick() : 0;
       if ((rc = pop_frames(dst, n))) return rc;
+      const double t1 = trace_ ? tick() : 0;
       if ((rc = be_sync(s_))) return rc;
+      if (trace_) { tr_[3] += t1 - t0; tr_[4] += tick() - t1; ++tr_calls_[1]; }
       if (!retired_.empty()) release_retired();
       if (y && !direct) memcpy(y, pin_out_, sizeof(float) * elems);
       if (native) {
