@@ -719,7 +719,8 @@ static int launch_poly0_pair(const Poly0PairParams &pp, int threads, long long n
       const int dlo = static_cast<int>(pp.fast.base.step / pp.fast.base.L);
       for (int th = 0; th < pp.tslots * pp.P; ++th) {
 #define RR_P2(NT, D) if (pp.fast.base.n == NT && dlo == D) poly0_pair2_tile<NT, D>(pp, pt, buf.data(), poly0_pair2_setup<NT, D>(pp, t, slot_of.data(), th))
-        RR_P2(16, 0); RR_P2(16, 1); RR_P2(16, 2); RR_P2(24, 0); RR_P2(24, 1); RR_P2(24, 2); RR_P2(32, 0); RR_P2(32, 1); RR_P2(32, 2);
+        RR_P2(16, 0); RR_P2(16, 1); RR_P2(16, 2); RR_P2(24, 0); RR_P2(24, 1); RR_P2(24, 2); RR_P2(28, 0); RR_P2(28, 1); RR_P2(28, 2);
+        RR_P2(32, 0); RR_P2(32, 1); RR_P2(32, 2);
 #undef RR_P2
       }
       continue;
@@ -727,6 +728,7 @@ static int launch_poly0_pair(const Poly0PairParams &pp, int threads, long long n
     for (int th = 0; th < pp.tslots * pp.P * pp.PG; ++th) {
       if (pp.fast.base.n == 16) poly0_pair_tile<16>(pp, pt, buf.data(), poly0_pair_setup<16>(pp, t, slot_of.data(), th));
       else if (pp.fast.base.n == 24) poly0_pair_tile<24>(pp, pt, buf.data(), poly0_pair_setup<24>(pp, t, slot_of.data(), th));
+      else if (pp.fast.base.n == 28) poly0_pair_tile<28>(pp, pt, buf.data(), poly0_pair_setup<28>(pp, t, slot_of.data(), th));
       else poly0_pair_tile<32>(pp, pt, buf.data(), poly0_pair_setup<32>(pp, t, slot_of.data(), th));
     }
   }
@@ -736,12 +738,14 @@ static int launch_poly0_pair(const Poly0PairParams &pp, int threads, long long n
   if (pp.CL == 2) {
     const int dlo = static_cast<int>(pp.fast.base.step / pp.fast.base.L);
 #define RR_P2(NT, D) if (pp.fast.base.n == NT && dlo == D) return launch_persistent(poly0_pair2_kernel<NT, D>, pp, nwork, threads, smem, s)
-    RR_P2(16, 0); RR_P2(16, 1); RR_P2(16, 2); RR_P2(24, 0); RR_P2(24, 1); RR_P2(24, 2); RR_P2(32, 0); RR_P2(32, 1); RR_P2(32, 2);
+    RR_P2(16, 0); RR_P2(16, 1); RR_P2(16, 2); RR_P2(24, 0); RR_P2(24, 1); RR_P2(24, 2); RR_P2(28, 0); RR_P2(28, 1); RR_P2(28, 2);
+        RR_P2(32, 0); RR_P2(32, 1); RR_P2(32, 2);
 #undef RR_P2
     return RR_INTERNAL;
   }
   if (pp.fast.base.n == 16) return launch_persistent(poly0_pair_kernel<16>, pp, nwork, threads, smem, s);
   if (pp.fast.base.n == 24) return launch_persistent(poly0_pair_kernel<24>, pp, nwork, threads, smem, s);
+  if (pp.fast.base.n == 28) return launch_persistent(poly0_pair_kernel<28>, pp, nwork, threads, smem, s);   // Best quality, bandwidth >= 97 %
   return launch_persistent(poly0_pair_kernel<32>, pp, nwork, threads, smem, s);
 #endif
 }
@@ -841,13 +845,16 @@ template <class T> struct Launch {
 #endif
 #define RR_CALL16(I, O) RR_CALLN(I, O, 16)
 #define RR_CALL24(I, O) RR_CALLN(I, O, 24)
+#define RR_CALL28(I, O) RR_CALLN(I, O, 28)
 #define RR_CALL32(I, O) RR_CALLN(I, O, 32)
     if (p.base.n == 16) RR_DISPATCH_IO(RR_CALL16);
     if (p.base.n == 24) RR_DISPATCH_IO(RR_CALL24);
+    if (p.base.n == 28) RR_DISPATCH_IO(RR_CALL28);
     if (p.base.n == 32) RR_DISPATCH_IO(RR_CALL32);
     return RR_INTERNAL;
 #undef RR_CALL16
 #undef RR_CALL24
+#undef RR_CALL28
 #undef RR_CALL32
 #undef RR_CALLN
   }
@@ -1202,7 +1209,7 @@ template <class T> class Engine {
     p.in = in; p.out = out; p.out_preload = out_preload; p.out0 = w0; p.nout = wn; p.nlanes = nlanes;
     p.tile = kPolyTile;
     if constexpr (std::is_same<T, float>::value) {
-      if (use_pair_kernel_ && use_pair_poly_ && g.order == 0 && (g.n == 16 || g.n == 24 || g.n == 32) && !(nlanes & 1) &&
+      if (use_pair_kernel_ && use_pair_poly_ && g.order == 0 && (g.n == 16 || g.n == 24 || g.n == 28 || g.n == 32) && !(nlanes & 1) &&
           g.Lp >= 48 && g.Lp <= 512 && g.pstep < (1 << 16)) {
         // lane-pair kernel: one column per period (L <= 512 slots), P pairs of a stream and PG period groups per CTA
         Poly0PairParams pp;
@@ -1274,7 +1281,7 @@ template <class T> class Engine {
         }
       }
     }
-    if (g.order == 0 && (g.n == 16 || g.n == 24 || g.n == 32)) {
+    if (g.order == 0 && (g.n == 16 || g.n == 24 || g.n == 28 || g.n == 32)) {
       // phase-stationary kernel: needs enough phases to fill a CTA and a window that fits shared memory
       const int nch = in.nch;
       // lanes per CTA: as many channels of a stream as still leave >= 8 periods per tile in a 24 KB window

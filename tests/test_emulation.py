@@ -40,6 +40,9 @@ CASES = [
     (32000, 24000, "float", 50, 95, 0, 0, 2), (32000, 24000, "float", 50, 95, 1, 0, 2), (32000, 24000, "double", 50, 95, 0, 0, 1),
     (44100, 8000, "float", 50, 95, 0, 1, 2), (32000, 8000, "float", 50, 95, 0, 1, 1), (48000, 48000, "float", 50, 95, 0, 0, 2),
     (48000, 48000, "double", 50, 95, 0, 0, 3),
+    # Best quality above 96 % bandwidth: 28-tap polyphase banks (lane-pair, two-slot and generic kernels), N = 8192 blocks
+    (44100, 48000, "float", 50, 97, 0, 0, 2), (44100, 96000, "float", 50, 98, 0, 0, 2), (44100, 48000, "double", 50, 97, 0, 0, 2),
+    (44100, 48000, "float", 50, 97, 0, 0, 1),
     # N = 131072, the reference's table limit (rate_uni.c:134-189): bandwidth 99.9 %
     (44100, 48000, "float", 50, 99.9, 0, 0, 2), (96000, 48000, "double", 50, 99.9, 0, 0, 1),
 ]

@@ -72,6 +72,8 @@ BATCH_CASES = [
     (44100, 96000, 50, 95, 0, 1, 5, 2), (44100, 48000, 50, 95, 0, 0, 1, 6),
     # polyphase banks with many phases (L = 441, 250): CTA sizes near the kernels' launch bounds
     (50000, 44100, 50, 95, 0, 0, 2, 2), (44100, 50000, 50, 95, 0, 0, 2, 2),
+    # Best quality above 96 % bandwidth (inside the plugin's UI range): 28-tap polyphase banks, N = 8192 blocks
+    (44100, 48000, 50, 97, 0, 0, 2, 3), (44100, 96000, 50, 98, 0, 0, 2, 2), (44100, 48000, 50, 97, 0, 0, 1, 3),
     # F-domain / 4, time-domain / 4, h9 and h8 through the batch entry point
     (32000, 24000, 50, 95, 0, 0, 2, 2), (32000, 24000, 50, 95, 1, 0, 4, 1), (44100, 8000, 50, 95, 0, 1, 2, 3),
     (32000, 8000, 50, 95, 0, 1, 1, 2),
@@ -226,6 +228,7 @@ FP64_BATCH_CASES = [
     (192000, 44100, 25, 95, 0, 0, 8, 2, "dft64"), (384000, 48000, 50, 95, 0, 0, 8, 1, "dft64"), (44100, 11025, 50, 95, 0, 0, 2, 3, "dft64"),
     (32000, 24000, 50, 95, 0, 0, 2, 2, "dft64"), (32000, 24000, 50, 95, 1, 0, 3, 1, "dft64"), (48000, 32000, 50, 95, 0, 0, 2, 2, "dft64"),
     (96000, 48000, 75, 95, 0, 0, 1, 4, "dft64"), (50000, 40000, 50, 95, 0, 0, 2, 2, "dft64"), (8000, 48000, 50, 95, 0, 0, 1, 3, "dft"),      # zero-stuffed x3 (dft64) + x4 post stage (generic)
+    (44100, 48000, 50, 97, 0, 0, 2, 2, "dft64"),                # 28-tap polyphase bank, N = 8192
     (44100, 176400, 50, 95, 0, 0, 2, 2, "dft_kernel"),          # x4 F-domain up-sampling stays on the generic kernel
 ]
 

@@ -33,3 +33,7 @@ probe(44100, 48001, 2, 64, 10, quality=1)              # vpoly1 (Normal)
 probe(48000, 47999, 2, 64, 10, engine="double")        # vpoly3, fp64
 probe(44100, 48000, 2, 64, 10, bandwidth=99.5)         # N = 32768: dft_big_kernel, fp32
 probe(44100, 48000, 2, 64, 10, engine="double", bandwidth=99)   # N = 16384: dft_big_kernel, fp64
+# Best quality at 97 % bandwidth (inside the plugin's UI range): N = 8192 blocks, 28-tap polyphase banks
+probe(44100, 48000, 2, 256, 10, bandwidth=97)
+probe(44100, 48000, 2, 256, 10, engine="double", bandwidth=97)
+probe(44100, 48000, 2, 64, 10, bandwidth=99)                    # N = 16384 (largest block in shared memory), fp32
