@@ -21,6 +21,7 @@ extern __shared__ __align__(16) unsigned char rr_smem_raw[];
 
 // DFT stage of the fp64 engine (rate_kernels_f64.cuh): a CTA is `groups` independent groups of `gthreads` threads,
 // each a persistent worker with its own buffer behind the shared pass-twiddle rows.
+template <bool UPL>
 __global__ void __launch_bounds__(kD64MaxThreads, 1) dft64_kernel(const __grid_constant__ Dft64Params dp, long long nwork)
 {
   CD *twt = reinterpret_cast<CD *>(rr_smem_raw);
@@ -35,7 +36,7 @@ __global__ void __launch_bounds__(kD64MaxThreads, 1) dft64_kernel(const __grid_c
   if (w < nw && g.tid == 0) items[gi][0] = d64_make_item(dp, w);
   for (int n = 0; w < nw; w += stride, n ^= 1) {
     const int next = w + stride < nw ? w + stride : -1;
-    dft64_program(dp, g, twt, items[gi], n, next, buf);
+    dft64_program<UPL>(dp, g, twt, items[gi], n, next, buf);
   }
 }
 
@@ -94,7 +95,8 @@ int launch_dft64(const Dft64Params &dp, long long nwork, void *stream)
   for (long long w = 0; w < nwork; ++w) {
     D64Item items[2];
     items[0] = d64_make_item(dp, w);
-    dft64_program(dp, g, dp.tw, items, 0, -1, mem.data());
+    if (dp.mode == D64_UP2 && dp.up_bits > 1) dft64_program<true>(dp, g, dp.tw, items, 0, -1, mem.data());
+    else dft64_program<false>(dp, g, dp.tw, items, 0, -1, mem.data());
   }
   return RR_OK;
 #else
@@ -110,7 +112,8 @@ int launch_dft64(const Dft64Params &dp, long long nwork, void *stream)
     D64_TRY(cudaGetLastError());
     return RR_OK;
   };
-  return go(dft64_kernel);
+  if (dp.mode == D64_UP2 && dp.up_bits > 1) return go(dft64_kernel<true>);
+  return go(dft64_kernel<false>);
 #endif
 }
 

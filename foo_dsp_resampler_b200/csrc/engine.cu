@@ -1470,7 +1470,7 @@ template <class T> class Engine {
       const StageGeom &g = geom[i];
       Dft64Params &dp = dt.params;
       memset(&dp, 0, sizeof(dp));
-      if (g.in_mode == DFT_IN_FREQ_UP && g.L == 2 && g.step >= 1) dp.mode = D64_UP2;
+      if (g.in_mode == DFT_IN_FREQ_UP && (g.L == 2 || g.L == 4 || g.L == 8) && g.step >= 1) { dp.mode = D64_UP2; dp.up_bits = g.L == 2 ? 1 : g.L == 4 ? 2 : 3; }
       else if (g.Ni == g.Pf && g.step >= 1 && g.in_mode != DFT_IN_FREQ_UP) dp.mode = D64_SAME;
       else if (g.step < 0 && g.in_mode != DFT_IN_FREQ_UP && g.Pf == g.N) dp.mode = D64_DECIM;
       else return RR_OK;                                   // other shapes stay on the generic kernel
@@ -1499,10 +1499,11 @@ template <class T> class Engine {
       }
       dp.ntw = static_cast<int>(tw.size() / 2);
       dp.fslots = d64_buf_slots(dp.fb); dp.bslots = d64_buf_slots(dp.ib);
-      dp.hstride = dp.bslots + 4;                          // 4 mod 8: the two halves of a position sit in different bank groups
-      dp.group_slots = dp.mode == D64_UP2 ? 2 * dp.hstride : dp.mode == D64_SAME ? dp.fslots : dp.fslots + dp.bslots;
+      // 8 / L mod 8: the L transforms' slots of one position sit in different bank groups (stored by neighbouring threads)
+      dp.hstride = dp.bslots + (dp.mode == D64_UP2 ? 8 >> dp.up_bits : 4);
+      dp.group_slots = dp.mode == D64_UP2 ? (dp.hstride << dp.up_bits) : dp.mode == D64_SAME ? dp.fslots : dp.fslots + dp.bslots;
       // groups: 64 threads for blocks up to 1024 complex points, else 128; as many as shared memory and the launch bound allow
-      dp.gthreads = dp.fb <= 10 ? 64 : 128;
+      dp.gthreads = dp.fb + (dp.mode == D64_UP2 ? dp.up_bits - 1 : 0) <= 10 ? 64 : 128;
       if (const char *e = getenv("B200RATE_D64_GT")) dp.gthreads = atoi(e) == 64 ? 64 : atoi(e) == 256 ? 256 : 128;
       const size_t per_group = sizeof(CD) * static_cast<size_t>(dp.group_slots), fixed = sizeof(CD) * static_cast<size_t>(dp.ntw) + 2048;
       if (fixed + per_group > max_smem_) return RR_OK;
@@ -1686,10 +1687,11 @@ template <class T> class Engine {
       pp.fslots = 0;
       pp.bslots = std::max(pk_buf_slots(g.Pf >> 1), pk_buf_slots(g.Ni >> 1));
       pp.groups = pk_inplace_groups_;
-      // small launches (one stream): six groups per SM when that saves a whole round of items (each group is ~4 % slower)
+      // small launches (one stream): six groups per SM when the whole rounds of items that saves outweigh the slower
+      // rounds (six groups sharing an SM take 1.25x as long per round as five: 1.875 vs 1.80 ms in steady state)
       if (pp.groups == kPkInplaceGroups && nwork > 0 && !getenv("B200RATE_DFT_GROUPS")) {
         const long long r5 = (nwork + 5ll * num_sms_ - 1) / (5ll * num_sms_), r6 = (nwork + 6ll * num_sms_ - 1) / (6ll * num_sms_);
-        if (r6 < r5 && r6 * 21 <= r5 * 20) pp.groups = 6;
+        if (r6 * 5 < r5 * 4) pp.groups = 6;
       }
       if (pk_smem_layout(pp).total + 2048 <= max_smem_) {
         const PkSmemLayout lay = pk_smem_layout(pp);

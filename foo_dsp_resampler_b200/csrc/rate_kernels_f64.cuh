@@ -128,7 +128,7 @@ RR_HD int dslot(int p, int hb) { return p + (p >> 4) + (p >> hb); }
 RR_HD int d64_buf_slots(int bits) { return ((dslot((1 << bits) - 1, bits - 3) + 1 + 7) / 8) * 8; }
 
 enum D64Mode {
-  D64_UP2 = 0,     // F-domain up-sampling by 2, step 1 (44.1 <-> 48 family): inverse = 2 M-point halves
+  D64_UP2 = 0,     // F-domain up-sampling by 2 (44.1 <-> 48 family), 4 or 8: inverse = 2 / 4 / 8 independent M-point transforms
   D64_SAME = 1,    // Pf == Ni: plain / zero-stuffed input, step >= 1
   D64_DECIM = 2    // F-domain decimation by 2^m (step -m): separate inverse buffer
 };
@@ -151,6 +151,7 @@ struct Dft64Params {
   int groups, gthreads;
   int fslots, bslots, hstride;   // slots of the forward buffer, of the inverse buffer (D64_DECIM), of one half (D64_UP2)
   int group_slots;
+  int up_bits;                   // D64_UP2: log2 of the F-domain up-sampling factor (1, 2 or 3); the inverse is 2^up_bits transforms
   int lane_major;                // work order: consecutive items are consecutive blocks of one lane (else consecutive lanes of one block)
 };
 
@@ -242,14 +243,14 @@ RR_PROG void d64_stage_tile(const Dft64Params &dp, const Grp &g, const D64Item &
 }
 
 // The slow path: kept samples first + j * stride out of the inverse result in B (natural order), through the view.
-RR_PROG void d64_emit(const Dft64Params &dp, const Grp &g, const D64Item &it, const CD *B, int ntrans, int hs)
+RR_PROG void d64_emit(const Dft64Params &dp, const Grp &g, const D64Item &it, const CD *B, int lgnt, int hs)
 {
   const DftParams<double> &p = dp.base;
   const int hi = dp.ib - 3;
   grp_sync(g);
   for (int j = g.tid; j < it.count; j += g.size) {
     const int t = it.first + j * it.stride, n = t >> 1;
-    const int h = ntrans == 2 ? (n & 1) : 0, pos = ntrans == 2 ? (n >> 1) : n;
+    const int h = n & ((1 << lgnt) - 1), pos = n >> lgnt;
     const double v = reinterpret_cast<const double *>(B + h * hs + dslot(pos, hi))[t & 1];
     if (dp.out_f32) view_write<float, double>(p.out, it.d.out_off0, it.c0 + j, v);
     else view_write<double, double>(p.out, it.d.out_off0, it.c0 + j, v);
@@ -259,11 +260,12 @@ RR_PROG void d64_emit(const Dft64Params &dp, const Grp &g, const D64Item &it, co
 // One pass over `ntrans` transforms of 2^bits points each (buffers `tstride` slots apart): radix 2^LR butterflies on
 // sub-blocks of 2^lgS points. DIT = false: decimation in frequency (butterfly, then twiddles, results in bit-reversed
 // digit order); DIT = true: the transposed pass. LD(h, pos) / ST(h, pos, v) move element `pos` of transform h.
-// HFAST: consecutive threads take the same butterfly of the `ntrans` (1 or 2) transforms, so that the even / odd
+// HFAST: consecutive threads take the same butterfly of the `ntrans` = 2^lgnt transforms, so that the interleaved
 // complex samples the two halves of an up-sampling block produce are stored by neighbouring threads.
 template <int LR, bool INV, bool DIT, bool HFAST = false, class LD, class ST>
-RR_PROG void d64_pass(const Grp &g, int ntrans, int bits, int lgS, const CD *tw, LD ld, ST st)
+RR_PROG void d64_pass(const Grp &g, int lgnt, int bits, int lgS, const CD *tw, LD ld, ST st)
 {
+  const int ntrans = 1 << lgnt;
   constexpr int R = 1 << LR, U = 16 / R;                 // sixteen values in flight per thread whatever the radix
   const int lgs = lgS - LR, s = 1 << lgs, lgper = bits - LR, per = 1 << lgper, total = ntrans * per;
   for (int t0 = g.tid; t0 < total; t0 += U * g.size) {
@@ -274,7 +276,7 @@ RR_PROG void d64_pass(const Grp &g, int ntrans, int bits, int lgS, const CD *tw,
     for (int u = 0; u < U; ++u) {
       const int t = t0 + u * g.size;
       const bool live = t < total;
-      const int h = HFAST ? (t & (ntrans - 1)) : (t >> lgper), tt = HFAST ? (t >> (ntrans >> 1)) : (t & (per - 1));
+      const int h = HFAST ? (t & (ntrans - 1)) : (t >> lgper), tt = HFAST ? (t >> lgnt) : (t & (per - 1));
       const int pos0 = ((tt >> lgs) << lgS) | (tt & (s - 1));
 #pragma unroll
       for (int a = 0; a < R; ++a) e[u][a] = live ? ld(h, pos0 + (a << lgs)) : CD{0.0, 0.0};
@@ -283,7 +285,7 @@ RR_PROG void d64_pass(const Grp &g, int ntrans, int bits, int lgS, const CD *tw,
     for (int u = 0; u < U; ++u) {
       const int t = t0 + u * g.size;
       const bool live = t < total;
-      const int h = HFAST ? (t & (ntrans - 1)) : (t >> lgper), tt = HFAST ? (t >> (ntrans >> 1)) : (t & (per - 1));
+      const int h = HFAST ? (t & (ntrans - 1)) : (t >> lgper), tt = HFAST ? (t >> lgnt) : (t & (per - 1));
       const int j = tt & (s - 1), pos0 = ((tt >> lgs) << lgS) | j;
       if (!DIT) {
         d64_dif<LR, INV>(e[u]);
@@ -299,13 +301,13 @@ RR_PROG void d64_pass(const Grp &g, int ntrans, int bits, int lgS, const CD *tw,
 }
 
 template <bool INV, bool DIT, bool HFAST, class LD, class ST>
-RR_PROG void d64_pass_any(int lr, const Grp &g, int ntrans, int bits, int lgS, const CD *tw, LD ld, ST st)
+RR_PROG void d64_pass_any(int lr, const Grp &g, int lgnt, int bits, int lgS, const CD *tw, LD ld, ST st)
 {
   switch (lr) {
-    case 1: d64_pass<1, INV, DIT, HFAST>(g, ntrans, bits, lgS, tw, ld, st); break;
-    case 2: d64_pass<2, INV, DIT, HFAST>(g, ntrans, bits, lgS, tw, ld, st); break;
-    case 3: d64_pass<3, INV, DIT, HFAST>(g, ntrans, bits, lgS, tw, ld, st); break;
-    default: d64_pass<4, INV, DIT, HFAST>(g, ntrans, bits, lgS, tw, ld, st); break;
+    case 1: d64_pass<1, INV, DIT, HFAST>(g, lgnt, bits, lgS, tw, ld, st); break;
+    case 2: d64_pass<2, INV, DIT, HFAST>(g, lgnt, bits, lgS, tw, ld, st); break;
+    case 3: d64_pass<3, INV, DIT, HFAST>(g, lgnt, bits, lgS, tw, ld, st); break;
+    default: d64_pass<4, INV, DIT, HFAST>(g, lgnt, bits, lgS, tw, ld, st); break;
   }
 }
 
@@ -438,6 +440,67 @@ RR_PROG void d64_spectrum(const Dft64Params &dp, const Grp &g, CD *F, CD *B)
   grp_sync(g);
 }
 
+// Spectrum phase for F-domain up-sampling by L = 2^LR >= 4 (dft_filter.h:86-104 with its doubling copies): the Pf-point
+// spectrum repeats L/2 times below Nyquist, bin k + cM sees X[k] for even c and conj X[M-k] for odd c. A record (k, M-k)
+// of the forward result therefore determines the 2L bins k + cM and (M-k) + cM; bin k + cM pairs with (M-k) + (L-1-c)M
+// in the inverse pre-processing, and the L bins kappa + cM of one residue kappa meet in the first radix-L
+// decimation-in-frequency step of the inverse transform, which is done here: what is stored are the inputs of L
+// independent M-point transforms (transform h at B + h * hstride) whose outputs are the complex samples L n' + h.
+template <int LR>
+RR_PROG void d64_spectrum_up(const Dft64Params &dp, const Grp &g, CD *F, CD *B)
+{
+  constexpr int L = 1 << LR;
+  const int fb = dp.fb, M = 1 << fb, hf = fb - 3, Mi = L * M, hs = dp.hstride, half = M >> 1;
+  const CD *H = dp.H;
+  auto Fz = [&](int k) -> CD { return F[dslot(d64_rev(k & (M - 1), fb), hf)]; };
+  // radix-L step over c for residue kappa: e[c] = w[kappa + cM] -> transform h gets sum_c e[c] exp(2 pi i c h / L),
+  // times exp(2 pi i kappa h / Mi) = tw^h
+  auto finish = [&](CD (&e)[L], const CD &tw, bool twiddled, int slot) {
+    d64_dif<LR, true>(e);
+    if (twiddled) d64_twiddle<LR>(e, tw);
+#pragma unroll
+    for (int a = 0; a < L; ++a) B[d64_brev(a, LR) * hs + slot] = e[a];       // e[a] is output h = brev(a)
+  };
+  for (int k = g.tid; k <= half; k += g.size) {
+    if (k == 0) {
+      const CD z = F[0];
+      const double x0 = 2.0 * (z.x + z.y), xm = 2.0 * (z.x - z.y);           // 2 X[0], 2 X[M]: bins cM see them for even / odd c
+      CD e[L];
+      {
+        const double y0 = ldg(H).x * x0, yn = ldg(H + Mi).x * ((L & 1) ? xm : x0);
+        e[0] = CD{y0 + yn, y0 - yn};
+      }
+#pragma unroll
+      for (int c = 1; c < L / 2; ++c) {                                        // pairs (cM, (L-c)M), b = exp(i pi c / L)
+        const double xa = (c & 1) ? xm : x0, xb = ((L - c) & 1) ? xm : x0;
+        d64_merge(cd_scale(ldg(H + c * M), xa), cd_scale(ldg(H + (L - c) * M), xb), cd_rot16<true>(CD{1.0, 0.0}, 8 * c / L), e[c], e[L - c]);
+      }
+      e[L / 2] = cd_scale(cd_conj(cd_scale(ldg(H + (L / 2) * M), ((L / 2) & 1) ? xm : x0)), 2.0);   // its own partner: b = i
+      finish(e, CD{1.0, 0.0}, false, 0);
+      continue;
+    }
+    const CD b = ldg(dp.tb + k);                                               // exp(2 pi i k / Ni), Ni = 2 L M
+    CD b2 = cd_mul(b, b);                                                      // exp(2 pi i k / Mi)
+    CD a = b2;                                                                 // -> exp(2 pi i k / Pf) = b^(2L/2)... squared LR - 1 more times
+#pragma unroll
+    for (int r = 1; r < LR; ++r) a = cd_mul(a, a);
+    CD x1, x2;
+    d64_split(Fz(k), Fz(M - k), cd_conj(a), x1, x2);
+    const int ra = dslot(d64_rev(k, fb), hf), rb = dslot(d64_rev(M - k, fb), hf);
+    CD ea[L], eb[L];                                                           // w[k + cM], w[(M-k) + cM]
+#pragma unroll
+    for (int c = 0; c < L; ++c) {
+      const CD ya = cd_mul(ldg(H + k + c * M), (c & 1) ? cd_conj(x2) : x1);
+      const int cb = L - 1 - c;
+      const CD yb = cd_mul(ldg(H + (M - k) + cb * M), (cb & 1) ? cd_conj(x1) : x2);
+      d64_merge(ya, yb, cd_rot16<true>(b, 8 * c / L), ea[c], eb[cb]);          // b_{k + cM} = b exp(i pi c / L)
+    }
+    finish(ea, b2, true, ra);
+    if (k != half) finish(eb, cd_rot16<true>(cd_conj(b2), 16 / L), true, rb);  // exp(2 pi i (M-k) / Mi) = exp(2 pi i / L) conj(b2)
+  }
+  grp_sync(g);
+}
+
 // Ask L2 for the next item's tile while this item's inverse transform runs.
 RR_PROG void d64_tile_prefetch(const Dft64Params &dp, const Grp &g, const D64Item &it)
 {
@@ -456,6 +519,9 @@ RR_PROG void d64_tile_prefetch(const Dft64Params &dp, const Grp &g, const D64Ite
 
 // One work item (block b of one lane). items[slot] describes it; items[slot ^ 1] is filled for the next one.
 // `twt`: the pass twiddle rows (shared memory on the device), indexed by dp.tw_f / dp.tw_i.
+// UPL: the kernel instance for F-domain up-sampling by 4 / 8 (kept apart: the 2L values a thread holds in that spectrum
+// phase would otherwise perturb the register allocation of the x2 / 1:1 / decimating paths).
+template <bool UPL>
 RR_PROG void dft64_program(const Dft64Params &dp, const Grp &g, const CD *twt, D64Item *items, int slot, long long work_next, CD *buf)
 {
   const int MODE = dp.mode;
@@ -476,37 +542,40 @@ RR_PROG void dft64_program(const Dft64Params &dp, const Grp &g, const CD *twt, D
     const long long es = dp.base.in.elem_stride;
     // sample pair `pos` of the tile: samples 2 pos and 2 pos + 1 (dft_filter.h:86-116)
     if (kind == 1)
-      d64_pass_any<false, false, false>(lr0, g, 1, fb, lgS, tw0, [&](int, int pos) -> CD { return ldg(static_cast<const CD *>(src) + pos); }, stF);
+      d64_pass_any<false, false, false>(lr0, g, 0, fb, lgS, tw0, [&](int, int pos) -> CD { return ldg(static_cast<const CD *>(src) + pos); }, stF);
     else if (kind == 2 && dp.in_f32)
-      d64_pass_any<false, false, false>(lr0, g, 1, fb, lgS, tw0, [&](int, int pos) -> CD {
+      d64_pass_any<false, false, false>(lr0, g, 0, fb, lgS, tw0, [&](int, int pos) -> CD {
         const float *q = static_cast<const float *>(src) + 2ll * pos * es;
         return CD{(double)ldg(q), (double)ldg(q + es)};
       }, stF);
     else if (kind == 2)
-      d64_pass_any<false, false, false>(lr0, g, 1, fb, lgS, tw0, [&](int, int pos) -> CD {
+      d64_pass_any<false, false, false>(lr0, g, 0, fb, lgS, tw0, [&](int, int pos) -> CD {
         const double *q = static_cast<const double *>(src) + 2ll * pos * es;
         return CD{ldg(q), ldg(q + es)};
       }, stF);
     else {
       d64_stage_tile(dp, g, it, F);
-      d64_pass_any<false, false, false>(lr0, g, 1, fb, lgS, tw0, ldF, stF);
+      d64_pass_any<false, false, false>(lr0, g, 0, fb, lgS, tw0, ldF, stF);
     }
   }
   grp_sync(g);
   lgS -= dp.lr_f[0];
   for (int ps = 1; ps < dp.npf; ++ps) {
-    d64_pass<4, false, false>(g, 1, fb, lgS, dp.tw_f[ps] >= 0 ? twt + dp.tw_f[ps] : nullptr, ldF, stF);
+    d64_pass<4, false, false>(g, 0, fb, lgS, dp.tw_f[ps] >= 0 ? twt + dp.tw_f[ps] : nullptr, ldF, stF);
     grp_sync(g);
     lgS -= 4;
   }
 
-  if (MODE == D64_UP2) d64_spectrum<D64_UP2>(dp, g, F, B);
+  if constexpr (UPL) {
+    if (dp.up_bits == 2) d64_spectrum_up<2>(dp, g, F, B);
+    else d64_spectrum_up<3>(dp, g, F, B);
+  } else if (MODE == D64_UP2) d64_spectrum<D64_UP2>(dp, g, F, B);
   else if (MODE == D64_SAME) d64_spectrum<D64_SAME>(dp, g, F, B);
   else d64_spectrum<D64_DECIM>(dp, g, F, B);
   if (work_next >= 0) d64_tile_prefetch(dp, g, items[slot ^ 1]);   // published before the barriers of the forward transform
 
   // ---- inverse transform(s): DIT, the last pass stores the kept samples to global memory ----
-  const int ib = dp.ib, hi = ib - 3, nt = MODE == D64_UP2 ? 2 : 1, hs = dp.hstride;
+  const int ib = dp.ib, hi = ib - 3, nt = MODE == D64_UP2 ? dp.up_bits : 0, hs = dp.hstride;   // nt: log2 of the transforms
   auto ldB = [&](int h, int pos) -> CD { return B[h * hs + dslot(pos, hi)]; };
   auto stB = [&](int h, int pos, const CD &v) { B[h * hs + dslot(pos, hi)] = v; };
   lgS = 0;
@@ -516,7 +585,7 @@ RR_PROG void dft64_program(const Dft64Params &dp, const Grp &g, const CD *twt, D
     grp_sync(g);
   }
   {
-    const int lrl = dp.lr_i[dp.npi - 1], kind = it.out_kind, count = it.count, up = MODE == D64_UP2 ? 1 : 0;
+    const int lrl = dp.lr_i[dp.npi - 1], kind = it.out_kind, count = it.count, up = nt;
     const CD *twl = dp.tw_i[dp.npi - 1] >= 0 ? twt + dp.tw_i[dp.npi - 1] : nullptr;
     void *dst = it.dst;
     const long long es = dp.base.out.elem_stride;
@@ -524,20 +593,20 @@ RR_PROG void dft64_program(const Dft64Params &dp, const Grp &g, const CD *twt, D
     // complex output element n = real samples 2n and 2n + 1 of the inverse transform; the first `count` are kept
     if (kind == 1)
       d64_pass_any<true, true, true>(lrl, g, nt, ib, lgS, twl, ldB, [&](int h, int pos, const CD &v) {
-        const int n = up ? 2 * pos + h : pos;
+        const int n = (pos << up) + h;
         if (2 * n + 1 < count) static_cast<CD *>(dst)[n] = v;
         else if (2 * n < count) static_cast<double *>(dst)[2 * n] = v.x;
       });
     else if (kind == 2 && dp.out_f32)
       d64_pass_any<true, true, true>(lrl, g, nt, ib, lgS, twl, ldB, [&](int h, int pos, const CD &v) {
-        const int n = up ? 2 * pos + h : pos;
+        const int n = (pos << up) + h;
         float *q = static_cast<float *>(dst) + 2ll * n * es;
         if (2 * n < count) q[0] = (float)v.x;
         if (2 * n + 1 < count) q[es] = (float)v.y;
       });
     else if (kind == 2)
       d64_pass_any<true, true, true>(lrl, g, nt, ib, lgS, twl, ldB, [&](int h, int pos, const CD &v) {
-        const int n = up ? 2 * pos + h : pos;
+        const int n = (pos << up) + h;
         double *q = static_cast<double *>(dst) + 2ll * n * es;
         if (2 * n < count) q[0] = v.x;
         if (2 * n + 1 < count) q[es] = v.y;

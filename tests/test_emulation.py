@@ -43,6 +43,8 @@ CASES = [
     # Best quality above 96 % bandwidth: 28-tap polyphase banks (lane-pair, two-slot and generic kernels), N = 8192 blocks
     (44100, 48000, "float", 50, 97, 0, 0, 2), (44100, 96000, "float", 50, 98, 0, 0, 2), (44100, 48000, "double", 50, 97, 0, 0, 2),
     (44100, 48000, "float", 50, 97, 0, 0, 1),
+    # fp64 engine, F-domain up-sampling by 4 and 8 (dft64_kernel's radix-L split in the spectrum phase)
+    (44100, 176400, "double", 50, 95, 0, 0, 2), (44100, 192000, "double", 25, 95, 0, 0, 1), (8000, 384000, "double", 50, 95, 0, 0, 1),
     # N = 131072, the reference's table limit (rate_uni.c:134-189): bandwidth 99.9 %
     (44100, 48000, "float", 50, 99.9, 0, 0, 2), (96000, 48000, "double", 50, 99.9, 0, 0, 1),
 ]

@@ -229,7 +229,9 @@ FP64_BATCH_CASES = [
     (32000, 24000, 50, 95, 0, 0, 2, 2, "dft64"), (32000, 24000, 50, 95, 1, 0, 3, 1, "dft64"), (48000, 32000, 50, 95, 0, 0, 2, 2, "dft64"),
     (96000, 48000, 75, 95, 0, 0, 1, 4, "dft64"), (50000, 40000, 50, 95, 0, 0, 2, 2, "dft64"), (8000, 48000, 50, 95, 0, 0, 1, 3, "dft"),      # zero-stuffed x3 (dft64) + x4 post stage (generic)
     (44100, 48000, 50, 97, 0, 0, 2, 2, "dft64"),                # 28-tap polyphase bank, N = 8192
-    (44100, 176400, 50, 95, 0, 0, 2, 2, "dft_kernel"),          # x4 F-domain up-sampling stays on the generic kernel
+    (44100, 176400, 50, 95, 0, 0, 2, 2, "dft64"), (48000, 192000, 25, 95, 0, 1, 1, 3, "dft64"),   # x4 F-domain up-sampling
+    (44100, 192000, 50, 95, 0, 0, 2, 2, "dft64"),               # x2, polyphase, x4 post stage
+    (8000, 384000, 50, 95, 0, 0, 1, 2, "dft64"),                # x8 post stage
 ]
 
 

@@ -22,3 +22,6 @@ if len(sys.argv) > 1:
     probe(384000, 48000, 8, 8, 20)
     probe(44100, 96000, 2, 256, 10)
     probe(48000, 44100, 2, 256, 10)
+if len(sys.argv) > 1:
+    probe(44100, 176400, 2, 128, 10)                   # x4 F-domain up-sampling (one DFT stage)
+    probe(44100, 192000, 2, 128, 10)                   # x2, polyphase, x4 post stage
