@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(512) poly0_fast_kernel(const __grid_constant__
 #define RR_POLY0_PAIR_KERNEL_BODY(SETUP, TILE)                                                                        \
   const Poly0FastParams<float> &p = pp.fast;                                                                          \
   Pk *smem = reinterpret_cast<Pk *>(rr_smem_raw);                                                                     \
-  const int set = p.win * pp.P;                                                                                       \
+  const int set = p.win * pp.P + pp.dup;              /* one or two copies of the windows, then the slot table */       \
   uint16_t *slot_of = reinterpret_cast<uint16_t *>(smem + set);                                                       \
   __shared__ Poly0PairTile tiles[2];                                                                                  \
   __shared__ int cnt[17];                                                                                             \
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(512) poly0_fast_kernel(const __grid_constant__
   if (pp.spread) poly0_pair_deal(pp, tiles[0].t, slot_of, cnt, ovf, tid, nt); /* one column: holds for every tile */  \
   poly0_pair_load(pp, tiles[0].t, tiles[0].tma, tiles[0].head, smem, &bar, tid, nt);                                  \
   __syncthreads();                                                                                                    \
-  if (pp.spread) { poly0_pair_deal_overflow(pp, slot_of, cnt, ovf, tid); __syncthreads(); }                           \
+  if (pp.spread) { poly0_pair_deal_overflow(pp, tiles[0].t, slot_of, cnt, ovf, tid); __syncthreads(); }               \
   const auto st = SETUP;                                                                                              \
   unsigned phase = 0;                                                                                                 \
   for (int it = 0; w < nwork; w += gridDim.x, ++it) {                                                                 \
@@ -697,7 +697,7 @@ static int launch_halfband_pair(const HalfbandPairParams &hp, long long nwork, s
 
 static size_t poly0_pair_smem(const Poly0PairParams &pp)
 {
-  return sizeof(Pk) * static_cast<size_t>(pp.fast.win) * pp.P + 2 * static_cast<size_t>(pp.tslots) + 16;
+  return sizeof(Pk) * (static_cast<size_t>(pp.fast.win) * pp.P + static_cast<size_t>(pp.dup ? pp.dup : 0)) + 2 * static_cast<size_t>(pp.tslots) + 16;
 }
 static int launch_poly0_pair(const Poly0PairParams &pp, int threads, long long nwork, stream_t s)
 {
@@ -705,7 +705,7 @@ static int launch_poly0_pair(const Poly0PairParams &pp, int threads, long long n
 #ifdef B200RATE_EMU
   (void)s; (void)threads;
   if (getenv("B200RATE_TRACE")) fprintf(stderr, "poly0pair L %d n %d step %lld P %d PG %d CL %d tslots %d spread %d MM %d win %d nwork %lld\n", pp.fast.base.L, pp.fast.base.n, pp.fast.base.step, pp.P, pp.PG, pp.CL, pp.tslots, pp.spread, pp.fast.MM, pp.fast.win, nwork);
-  std::vector<Pk> buf(static_cast<size_t>(pp.fast.win) * pp.P + 1);
+  std::vector<Pk> buf(static_cast<size_t>(pp.fast.win) * pp.P + static_cast<size_t>(pp.dup) + 1);
   std::vector<uint16_t> slot_of(static_cast<size_t>(pp.tslots) + 1);
   for (long long w = 0; w < nwork; ++w) {
     const Poly0PairTile pt = poly0_pair_make_tile(pp, w);
@@ -713,7 +713,7 @@ static int launch_poly0_pair(const Poly0PairParams &pp, int threads, long long n
     int cnt[17] = {0};
     uint16_t ovf[kPolyDealOverflow];
     std::fill(slot_of.begin(), slot_of.end(), static_cast<uint16_t>(0xffff));
-    if (pp.spread) { poly0_pair_deal(pp, t, slot_of.data(), cnt, ovf, 0, 1); poly0_pair_deal_overflow(pp, slot_of.data(), cnt, ovf, 0); }
+    if (pp.spread) { poly0_pair_deal(pp, t, slot_of.data(), cnt, ovf, 0, 1); poly0_pair_deal_overflow(pp, t, slot_of.data(), cnt, ovf, 0); }
     poly0_pair_load(pp, t, pt.tma, pt.head, buf.data(), nullptr, 0, 1);
     if (pp.CL == 2) {
       const int dlo = static_cast<int>(pp.fast.base.step / pp.fast.base.L);
@@ -1244,10 +1244,13 @@ template <class T> class Engine {
         };
         int MM = 32;
         while (MM > 2 && window_of(MM) * pp.P * sizeof(Pk) > budget) MM -= 2;
+        pp.dup = 0;
         if (window_of(MM) * pp.P * sizeof(Pk) <= budget && nlanes % (2 * pp.P) == 0 && threads <= max_threads) {
           const long long periods = (wn + L - 1) / L;
           pp.fast.F = L; pp.fast.ncols = 1; pp.fast.MM = MM; pp.fast.CH = 2 * pp.P;
           pp.fast.win = static_cast<int>(window_of(MM));
+          // second copy of the windows 8 banks further (the window size is 8 mod 16 elements): full bank columns overflow into it
+          if (pp.spread && use_pair_dup_) pp.dup = pp.fast.win * pp.P + ((pp.P & 1) ? 0 : 8);
           pp.fast.mtiles = (periods + MM - 1) / MM;
           pp.fast.double_buffer = 0;
           const long long nwork = static_cast<long long>(nlanes / (2 * pp.P)) * pp.fast.mtiles;
@@ -1657,6 +1660,7 @@ template <class T> class Engine {
   // debugging switches: generic kernels only / per stage kind
   bool use_pair_kernel_ = getenv("B200RATE_NO_PAIR_KERNEL") == nullptr;
   bool use_pair_dft_ = getenv("B200RATE_NO_PAIR_DFT") == nullptr, use_pair_poly_ = getenv("B200RATE_NO_PAIR_POLY") == nullptr;
+  bool use_pair_dup_ = getenv("B200RATE_NO_PAIR_DUP") == nullptr;
   bool use_pair_half_ = getenv("B200RATE_NO_PAIR_HALF") == nullptr, use_pair_poly2_ = getenv("B200RATE_NO_PAIR_POLY2") == nullptr;
   int last_dft_kernel_ = 0;
 

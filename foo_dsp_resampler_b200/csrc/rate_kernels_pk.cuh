@@ -918,6 +918,8 @@ struct Poly0PairParams {
   int tslots;                    // threads along the slot dimension (multiple of 16, >= slots per column)
   int spread;                    // deal the slots over the banks (needs one column per period)
   int CL;                        // slots per thread: 1, or 2 adjacent slots sharing their input window (poly0_pair2_*)
+  int dup;                       // 0, or the element offset of a second copy of the windows that sits 8 eight-byte banks
+                                 // further: a slot whose bank column is full takes the column 8 banks away and reads that copy
 };
 
 // thread slot ts -> slot of the column (or 0xffff): slot_of[j * 16 + b] = the j-th slot (cluster) whose first
@@ -948,12 +950,20 @@ RR_PROG void poly0_pair_deal(const Poly0PairParams &pp, const Poly0Tile &t, uint
     }
   }
 }
-RR_PROG void poly0_pair_deal_overflow(const Poly0PairParams &pp, uint16_t *slot_of, const int *cnt, const uint16_t *ovf, int tid)
+RR_PROG void poly0_pair_deal_overflow(const Poly0PairParams &pp, const Poly0Tile &t, uint16_t *slot_of, const int *cnt, const uint16_t *ovf, int tid)
 {
   if (tid != 0) return;
-  const int n = cnt[16] < kPolyDealOverflow ? cnt[16] : kPolyDealOverflow;
+  const PolyParams<float> &p = pp.fast.base;
+  const int n = cnt[16] < kPolyDealOverflow ? cnt[16] : kPolyDealOverflow, rows = pp.tslots >> 4;
   int hole = 0;
   for (int k = 0; k < n; ++k) {
+    if (pp.dup) {                                         // a free row of the column 8 banks away: conflict-free through the second copy
+      const unsigned at_rel = (unsigned)t.r_first + (unsigned)ovf[k] * (unsigned)p.step;
+      const int b2 = (int)(((at_rel / (unsigned)p.L) & 15) ^ 8);
+      int j = 0;
+      while (j < rows && slot_of[j * 16 + b2] != 0xffff) ++j;
+      if (j < rows) { slot_of[j * 16 + b2] = (uint16_t)(ovf[k] | 0x8000); continue; }
+    }
     while (hole < pp.tslots && slot_of[hole] != 0xffff) ++hole;
     if (hole < pp.tslots) slot_of[hole] = ovf[k];
   }
@@ -972,18 +982,20 @@ RR_PROG void poly0_pair_load(const Poly0PairParams &pp, const Poly0Tile &t, int 
   if (tma) {
     if (tid != 0) return;
     const unsigned bytes = (unsigned)(((t.win + head + 1) & ~1) * (int)sizeof(Pk));
-    tma_bar_expect(bar, bytes * (unsigned)pp.P);
+    tma_bar_expect(bar, bytes * (unsigned)pp.P * (pp.dup ? 2u : 1u));
     for (int pr = 0; pr < pp.P; ++pr) {
       const float *s0 = view_ptr<const float>(p.in, lane_offset(p.in, t.lane0 + 2 * pr), c0) - 2 * head;
       tma_load_1d(buf + pr * fp.win, s0, bytes, bar);
+      if (pp.dup) tma_load_1d(buf + pp.dup + pr * fp.win, s0, bytes, bar);
     }
     return;
   }
   const bool direct = view_range_direct(p.in, c0, c0 + t.win);
   const int es = p.in.elem_stride;
+  for (int cp = 0; cp < (pp.dup ? 2 : 1); ++cp)
   for (int pr = 0; pr < pp.P; ++pr) {
     const long long off0 = lane_offset(p.in, t.lane0 + 2 * pr), off1 = lane_offset(p.in, t.lane0 + 2 * pr + 1);
-    Pk *dst = buf + pr * fp.win;
+    Pk *dst = buf + cp * pp.dup + pr * fp.win;
     const float *s0 = view_ptr<const float>(p.in, off0, c0), *s1 = view_ptr<const float>(p.in, off1, c0);
     if (direct && s1 == s0 + 1 && !(es & 1) && !((size_t)s0 & 7)) {
       for (int j = tid; j < t.win; j += nthreads) pk_async_copy8(dst + j, s0 + (long long)j * es);
@@ -1008,6 +1020,7 @@ RR_PROG void poly0_pair_load(const Poly0PairParams &pp, const Poly0Tile &t, int 
 // period, so neither depends on the tile), pair, period group and the coefficient row of the phase.
 template <int NT> struct Poly0PairThread {
   int fs, q, pr, g;              // fs < 0: no work (hole of the deal / padding)
+  int xoff;                      // 0, or pp.dup: which copy of the windows this thread reads
   float c[NT];
 };
 
@@ -1021,7 +1034,9 @@ RR_PROG Poly0PairThread<NT> poly0_pair_setup(const Poly0PairParams &pp, const Po
   const int rest = w - st.g * per_group;
   st.pr = rest / pp.tslots;
   const int ts = rest - st.pr * pp.tslots;
-  const int fs = st.g < pp.PG ? (pp.spread ? (int)slot_of[ts] : ts) : 0xffff;
+  const int raw = st.g < pp.PG ? (pp.spread ? (int)slot_of[ts] : ts) : 0xffff;
+  const int fs = raw == 0xffff ? raw : (raw & 0x7fff);
+  st.xoff = (raw != 0xffff && (raw & 0x8000)) ? pp.dup : 0;
   st.fs = fs < t.nslots ? fs : -1;
   const unsigned at_rel = (unsigned)t.r_first + (unsigned)(st.fs < 0 ? 0 : st.fs) * (unsigned)p.step;
   st.q = (int)(at_rel / (unsigned)p.L);
@@ -1088,7 +1103,7 @@ RR_PROG void poly0_pair_tile(const Poly0PairParams &pp, const Poly0PairTile &pt,
   const bool direct = pt.direct != 0;
   const bool packed_out = direct && d1 == d0 + 1 && !((size_t)d0 & 7) && !(dstep & 1);
   const int xstep = PG * (int)p.step;
-  const Pk *x = buf + st.pr * fp.win + pt.head + st.q + st.g * (int)p.step;
+  const Pk *x = buf + st.xoff + st.pr * fp.win + pt.head + st.q + st.g * (int)p.step;
   int m = st.g;
   auto emit = [&](int mm, Pk s) {
     if (packed_out) *reinterpret_cast<Pk *>(d0) = s;
@@ -1128,7 +1143,7 @@ RR_PROG void poly0_pair_tile(const Poly0PairParams &pp, const Poly0PairTile &pt,
 // fewer shared-memory reads per output (the kernel's bound). The second row is kept shifted by d in registers;
 // only its first and last window positions depend on d (one predicate). Same products, same order per output.
 template <int NT, int DLO> struct Poly0Pair2Thread {
-  int fs, q, pr;                 // fs < 0: no work
+  int fs, q, pr, xoff;           // fs < 0: no work; xoff: which copy of the windows (0 / pp.dup)
   bool d_lo, two;                // d == DLO; the second slot exists
   float c0[NT], c1[NT + 1];      // c1[j] multiplies window sample DLO + j when d == DLO, DLO + 1 + j - 1... see setup
 };
@@ -1140,7 +1155,9 @@ RR_PROG Poly0Pair2Thread<NT, DLO> poly0_pair2_setup(const Poly0PairParams &pp, c
   Poly0Pair2Thread<NT, DLO> st;
   st.pr = w / pp.tslots;
   const int ts = w - st.pr * pp.tslots;
-  const int fs = st.pr < pp.P ? (pp.spread ? (int)slot_of[ts] : 2 * ts) : 0xffff;
+  const int raw = st.pr < pp.P ? (pp.spread ? (int)slot_of[ts] : 2 * ts) : 0xffff;
+  const int fs = raw == 0xffff ? raw : (raw & 0x7fff);
+  st.xoff = (raw != 0xffff && (raw & 0x8000)) ? pp.dup : 0;
   st.fs = fs < t.nslots ? fs : -1;
   const unsigned at0 = (unsigned)t.r_first + (unsigned)(st.fs < 0 ? 0 : st.fs) * (unsigned)p.step;
   st.q = (int)(at0 / (unsigned)p.L);
@@ -1176,7 +1193,7 @@ RR_PROG void poly0_pair2_tile(const Poly0PairParams &pp, const Poly0PairTile &pt
   const bool direct = pt.direct != 0;
   const bool packed_out = direct && d1 == d0 + 1 && !((size_t)d0 & 7) && !(dstep & 1) && !(es & 1);
   const int xstep = (int)p.step;
-  const Pk *x = buf + st.pr * fp.win + pt.head + st.q;
+  const Pk *x = buf + st.xoff + st.pr * fp.win + pt.head + st.q;
   const bool dlo = st.d_lo, two = st.two;
   auto emit = [&](int mm, int which, Pk s) {             // output of slot fs + which in period mm
     float *e0 = d0 + which * es, *e1 = d1 + which * es;

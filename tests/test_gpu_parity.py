@@ -232,6 +232,7 @@ FP64_BATCH_CASES = [
     (44100, 176400, 50, 95, 0, 0, 2, 2, "dft64"), (48000, 192000, 25, 95, 0, 1, 1, 3, "dft64"),   # x4 F-domain up-sampling
     (44100, 192000, 50, 95, 0, 0, 2, 2, "dft64"),               # x2, polyphase, x4 post stage
     (8000, 384000, 50, 95, 0, 0, 1, 2, "dft64"),                # x8 post stage
+    (192000, 48000, 50, 95, 0, 0, 4, 2, "dft64"), (96000, 22050, 50, 95, 0, 1, 3, 2, "dft64"),   # half-band with 4 / 3 channels
 ]
 
 
