@@ -95,6 +95,16 @@ SYMBOLS = {
     "RRX_batch_last_launches": (C.c_int, [C.c_void_p]),
     "RRX_batch_flops": (C.c_double, [C.c_void_p, C.c_size_t]),
     "RRX_batch_close": (None, [C.POINTER(C.c_void_p)]),
+    "RRX_track_edge_lengths": (C.c_int, [C.c_uint, C.c_uint] + [C.POINTER(C.c_uint)] * 4),
+    "RRX_lpc_extrapolate2": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_size_t, C.c_size_t]),
+    "RRX_lpc_extrapolate_bkwd": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_size_t]),
+    "RRX_lpc_extrapolate_fwd": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_size_t]),
+    "RRX_lpc_extrapolate_batch": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_size_t,
+                                            C.c_size_t, C.c_void_p]),
+    "RRX_lpc_extend_tracks": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_size_t,
+                                        C.c_void_p]),
+    "RRX_lpc_analysis_dump": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_void_p,
+                                        C.c_void_p]),
     "RRX_last_error": (C.c_char_p, []),
     "RRX_version": (C.c_char_p, []),
 }

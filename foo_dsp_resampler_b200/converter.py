@@ -218,3 +218,65 @@ class BatchConverter:
             self.close()
         except Exception:
             pass
+
+
+LPC_ORDER = 32  # lpc/lpc.h:24
+
+
+def track_edge_lengths(in_rate, out_rate, lib=None):
+    """(add, drop, prime_len, inbuf_frames) as dsp_rate::reinit computes them (foo_dsp_rate.cpp:96-101)."""
+    lib = lib or _capi.product()
+    v = [C.c_uint(0) for _ in range(4)]
+    rc = lib.RRX_track_edge_lengths(int(in_rate), int(out_rate), *[C.byref(x) for x in v])
+    if rc != RR_OK:
+        raise RateError(lib, rc, "RRX_track_edge_lengths")
+    return tuple(int(x.value) for x in v)
+
+
+def lpc_extrapolate2(buf, first, data_len, extra_bkwd, extra_fwd, lpc_order=LPC_ORDER, lib=None):
+    """lpc_extrapolate2 (lpc/lpc.h:26) on a HOST array: ``buf`` is float32 [frames][nch], C-contiguous; the base segment
+    is frames [first, first + data_len); frames [first - extra_bkwd, first) and [first + data_len, ... + extra_fwd) are
+    written in place."""
+    lib = lib or _capi.product()
+    assert buf.dtype == np.float32 and buf.flags.c_contiguous and buf.ndim == 2
+    assert first >= extra_bkwd and first + data_len + extra_fwd <= buf.shape[0]
+    nch = buf.shape[1]
+    rc = lib.RRX_lpc_extrapolate2(buf.ctypes.data + first * nch * 4, int(data_len), nch, int(lpc_order),
+                                  int(extra_bkwd), int(extra_fwd))
+    if rc != RR_OK:
+        raise RateError(lib, rc, "RRX_lpc_extrapolate2")
+
+
+class TrackBatchConverter:
+    """Whole tracks, device resident, converted the way the plugin converts a track (foo_dsp_rate.cpp:130-313): `add`
+    frames predicted before the beginning and after the end (RRX_lpc_extend_tracks), everything pushed through the
+    rate engine (RRX_batch_process), `drop` output frames cut from both ends. Tracks of at most 2 * LPC_ORDER frames
+    are converted without extrapolation, like the plugin (foo_dsp_rate.cpp:222-237).
+
+    d_padded: float32 [nstreams][add + track_frames + add][nch] with the tracks in the middle (``padded_frames`` /
+    ``track_offset`` say where); d_work: float32 [nstreams][frames_out_padded][nch] scratch the engine writes; the
+    track's result is frames [drop, drop + frames_out) of every stream of d_work (``result_slice``)."""
+
+    def __init__(self, cfg, nchannels, nstreams, track_frames, engine="float", device=-1, lib=None):
+        self.lib = lib or _capi.product()
+        self.nch, self.nstreams, self.track_frames = int(nchannels), int(nstreams), int(track_frames)
+        self.add, self.drop, self.prime, _ = track_edge_lengths(cfg.in_rate, cfg.out_rate, self.lib)
+        if self.track_frames <= 2 * LPC_ORDER:
+            self.add = self.drop = 0
+        self.padded_frames = self.track_frames + 2 * self.add
+        self.track_offset = self.add
+        self.batch = BatchConverter(cfg, nchannels, nstreams, self.padded_frames, engine=engine, device=device, lib=self.lib)
+        self.frames_out_padded = self.batch.frames_out(self.padded_frames)
+        self.frames_out = self.frames_out_padded - 2 * self.drop
+        self.result_slice = slice(self.drop, self.drop + self.frames_out)
+
+    def process(self, d_padded, d_work, stream=0):
+        if self.add:
+            rc = self.lib.RRX_lpc_extend_tracks(d_padded, self.nstreams, self.track_frames, self.prime, self.nch, LPC_ORDER,
+                                                self.add, stream)
+            if rc != RR_OK:
+                raise RateError(self.lib, rc, "RRX_lpc_extend_tracks")
+        self.batch.process(d_padded, self.padded_frames, d_work, stream)
+
+    def close(self):
+        self.batch.close()

@@ -193,6 +193,41 @@ void RRX_multi_close(RRX_multi **m);
 void *RRX_host_alloc(size_t bytes);
 void RRX_host_free(void *p);
 
+/* ------------------------------------------------------------------------------------------------ */
+/* Part 3: track-edge extrapolation (the step next to the path in the caller)  */
+/* ------------------------------------------------------------------------------------------------ */
+/* The plugin does not feed a track's first and last frames to the rate engine as hard edges: it predicts
+ * N_samples_to_add_ frames before the beginning and after the end by linear prediction from the first / last
+ * PRIME_LEN_ frames, pushes them with the track, and drops N_samples_to_drop_ output frames at each end
+ * (foo_dsp_rate.cpp:96-101,165-167,241-313). These entry points run that prediction on the device, bit-identical to
+ * lpc/lpc.cpp, so that a device-resident batch conversion reproduces the plugin's track edges. */
+#define RRX_LPC_ORDER 32                                         /* lpc/lpc.h:24 */
+/* [host-only] foo_dsp_rate.cpp:96-101 + util.h:38-49: frames to add per edge at the input rate, frames to drop per
+ * edge at the output rate (the same duration), prime length, and the plugin's input block. NULL outputs are skipped. */
+int RRX_track_edge_lengths(unsigned in_rate, unsigned out_rate, unsigned *add, unsigned *drop, unsigned *prime_len,
+                           unsigned *inbuf_frames);
+/* lpc/lpc.h:26 lpc_extrapolate2, same arguments and memory layout: `data` is HOST memory pointing at frame 0 of
+ * data_len interleaved base frames; frames [-extra_bkwd, 0) and [data_len, data_len + extra_fwd) are written.
+ * lpc_order 1..32 (the reference's callers use LPC_ORDER = 32), else RR_INVPARAM. Blocking. */
+int RRX_lpc_extrapolate2(float *data, size_t data_len, int nchannels, int lpc_order, size_t extra_bkwd, size_t extra_fwd);
+/* lpc/lpc.h:28-38, the two inline wrappers. */
+int RRX_lpc_extrapolate_bkwd(float *data, size_t data_len, size_t prime_len, int nchannels, int lpc_order, size_t extra_bkwd);
+int RRX_lpc_extrapolate_fwd(float *data, size_t data_len, size_t prime_len, int nchannels, int lpc_order, size_t extra_fwd);
+/* Device-resident batch of the same operation: d_data points at frame 0 of stream 0's base segment, stream s starts
+ * stream_stride_frames * s frames later; every (stream, channel) lane is extrapolated independently. Asynchronous on
+ * `stream` (a cudaStream_t). */
+int RRX_lpc_extrapolate_batch(float *d_data, size_t nstreams, size_t stream_stride_frames, size_t data_len, int nchannels,
+                              int lpc_order, size_t extra_bkwd, size_t extra_fwd, void *stream);
+/* Both edges of whole tracks in one pair of launches: d_padded is float32 [nstreams][extra + track_frames + extra]
+ * [nchannels] with the tracks in the middle; the leading `extra` frames are predicted backward from the first
+ * min(prime_len, track_frames) frames, the trailing ones forward from the last (foo_dsp_rate.cpp:243-245). The padded
+ * buffer is what RRX_batch_process takes as d_in with frames_in = track_frames + 2 * extra. */
+int RRX_lpc_extend_tracks(float *d_padded, size_t nstreams, size_t track_frames, size_t prime_len, int nchannels,
+                          int lpc_order, size_t extra, void *stream);
+/* Test tap: per (stream, channel) lane 66 doubles -- lags 0..32, the 32 damped predictor coefficients, usable order. */
+int RRX_lpc_analysis_dump(const float *d_data, size_t nstreams, size_t stream_stride_frames, size_t data_len, int nchannels,
+                          int lpc_order, double *d_out, void *stream);
+
 /* Last CUDA error string seen by this library on the calling thread ("" if none). */
 const char *RRX_last_error(void);
 /* [host-only] Library version string. */
