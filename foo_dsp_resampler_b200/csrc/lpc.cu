@@ -27,6 +27,8 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <cstdlib>
+#include <mutex>
 #include <string>
 
 #include "b200_ratelib.h"
@@ -64,7 +66,9 @@ __device__ __forceinline__ float *lane_ptr(const LpcParams &p, long long lane)
   return p.data + s * p.stream_stride + c;
 }
 
-// lpc.cpp:111-166 on one thread; r[0..order], a[0..31] in shared memory. Returns the usable order.
+// lpc.cpp:111-166 on one thread; r[0..order], a[0..31] in shared memory, element i at [i * S] (S = 32: one column
+// per thread of a warp, conflict-free). Returns the usable order.
+template <int S>
 __device__ int levinson_damped(const double *r, int order, double *a)
 {
   double err = __dmul_rn(r[0], 1. + 1e-10);
@@ -72,33 +76,33 @@ __device__ int levinson_damped(const double *r, int order, double *a)
   int used = order;
   for (int i = 0; i < order; ++i) {
     if (err < floor_) {
-      for (int j = i; j < order; ++j) a[j] = 0;
+      for (int j = i; j < order; ++j) a[j * S] = 0;
       used = i;
       break;
     }
-    double k = -r[i + 1];
-    for (int j = 0; j < i; ++j) k = __dsub_rn(k, __dmul_rn(a[j], r[i - j]));
+    double k = -r[(i + 1) * S];
+    for (int j = 0; j < i; ++j) k = __dsub_rn(k, __dmul_rn(a[j * S], r[(i - j) * S]));
     k = __ddiv_rn(k, err);
-    a[i] = k;
+    a[i * S] = k;
     int j = 0;
     for (; j < i / 2; ++j) {
-      double lo = a[j], hi = a[i - 1 - j];
-      a[j] = __dadd_rn(lo, __dmul_rn(k, hi));
-      a[i - 1 - j] = __dadd_rn(hi, __dmul_rn(k, lo));
+      double lo = a[j * S], hi = a[(i - 1 - j) * S];
+      a[j * S] = __dadd_rn(lo, __dmul_rn(k, hi));
+      a[(i - 1 - j) * S] = __dadd_rn(hi, __dmul_rn(k, lo));
     }
-    if (i & 1) a[j] = __dadd_rn(a[j], __dmul_rn(a[j], k));
+    if (i & 1) a[j * S] = __dadd_rn(a[j * S], __dmul_rn(a[j * S], k));
     err = __dmul_rn(err, __dsub_rn(1.0, __dmul_rn(k, k)));
   }
   double damp = 0.999;
   for (int j = 0; j < used; ++j) {
-    a[j] = __dmul_rn(a[j], damp);
+    a[j * S] = __dmul_rn(a[j * S], damp);
     damp = __dmul_rn(damp, 0.999);
   }
   if (used == 0) {
     used = 1;
     a[0] = -1;
   }
-  for (int j = order; j < kOrd; ++j) a[j] = 0;
+  for (int j = order; j < kOrd; ++j) a[j * S] = 0;
   return used;
 }
 
@@ -163,7 +167,7 @@ __global__ void __launch_bounds__(32) lpc_analyse_kernel(const LpcParams p)
   if (l == 0) r_s[0] = acc0;
   __syncwarp();
   int used = 0;
-  if (l == 0) used = levinson_damped(r_s, p.order, a_s);
+  if (l == 0) used = levinson_damped<1>(r_s, p.order, a_s);
   __syncwarp();
   // history slot j (0 = oldest of the 32 samples behind an output) meets lpc[31 - j]
   const long long slot = static_cast<long long>(jb) * p.nlanes + lane;
@@ -177,11 +181,101 @@ __global__ void __launch_bounds__(32) lpc_analyse_kernel(const LpcParams p)
   }
 }
 
+// The same analysis for LARGE batches: one THREAD per (lane, job), 32 of them per warp. A thread keeps the last 32
+// windowed samples of its lane in registers (a delay line) and all 33 lag sums, so a term costs one shared-memory read
+// and 33 DFMAs instead of 33 reads -- the narrow kernel above is bound by the shared-memory pipe (4 wavefronts per
+// term), this one by the FP64 pipe. Each lag is still one sequential sum over ascending i. All jobs of a launch have
+// the same length (both entry points guarantee it). Raw samples of the next tile arrive by LDGSTS during the sums.
+constexpr int kWTile = 32;        // terms per tile
+constexpr int kWStep = 8;         // terms per unrolled trip; the delay line moves down by kWStep after each
+
+__global__ void __launch_bounds__(32) lpc_analyse_wide_kernel(const LpcParams p)
+{
+  __shared__ float stage[2][32][kWTile];            // raw samples [buffer][job of the warp][term]
+  __shared__ double cols[(2 * kOrd + 2) * 33];      // tile as doubles [term][job] (pitch 33), later r / a columns
+  const int l = threadIdx.x;
+  const long long slots = p.nlanes * p.njobs;
+  const long long g = static_cast<long long>(blockIdx.x) * 32 + l;
+  const bool live = g < slots;
+  const long long gl = live ? g : slots - 1;
+  const int jb = static_cast<int>(gl / p.nlanes);
+  const long long lane = gl - jb * p.nlanes;
+  const long long len = p.job[0].len;
+  const float *src = lane_ptr(p, lane) + p.job[jb].base * p.nch;
+  const float half = __fdiv_rn(static_cast<float>(static_cast<unsigned long long>(len + 1)), 2.0f);
+
+  // thread l fetches term l of every job of the warp: the 32 source pointers travel by shuffle
+  auto fetch = [&](int buf, long long t0) {
+    const long long i = t0 + l;
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+      const float *sk = reinterpret_cast<const float *>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(src), k));
+      if (i < len) {
+        const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(&stage[buf][k][l]));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(sk + i * p.nch));
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  double acc[kOrd + 1], dl[kOrd + kWStep];          // dl[j]: windowed sample kOrd - j behind the trip's first term
+#pragma unroll
+  for (int j = 0; j <= kOrd; ++j) acc[j] = 0;
+#pragma unroll
+  for (int j = 0; j < kOrd + kWStep; ++j) dl[j] = 0;
+  fetch(0, 0);
+  int buf = 0;
+  for (long long t0 = 0; t0 < len; t0 += kWTile, buf ^= 1) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    {   // window (lpc.cpp:84-91) and widen term l of every job
+      const long long i = t0 + l;
+      const float k = __fdiv_rn(__fsub_rn(static_cast<float>(static_cast<int>(i) + 1), half), half);
+      const float w = __fsub_rn(1.0f, __fmul_rn(k, k));
+#pragma unroll 8
+      for (int j = 0; j < 32; ++j) cols[l * 33 + j] = i < len ? static_cast<double>(__fmul_rn(stage[buf][j][l], w)) : 0.0;
+    }
+    __syncwarp();
+    if (t0 + kWTile < len) fetch(buf ^ 1, t0 + kWTile);
+    for (int t = 0; t < kWTile; t += kWStep) {
+#pragma unroll
+      for (int u = 0; u < kWStep; ++u) {
+        const double x = cols[(t + u) * 33 + l];
+        dl[kOrd + u] = x;
+        acc[0] = __fma_rn(x, x, acc[0]);
+#pragma unroll
+        for (int j = 1; j <= kOrd; ++j) acc[j] = __fma_rn(x, dl[kOrd + u - j], acc[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < kOrd; ++j) dl[j] = dl[j + kWStep];
+    }
+    __syncwarp();
+  }
+  // r and a columns of this thread: element i at cols[i * 32 + l]
+  double *r_c = cols + l, *a_c = cols + (kOrd + 1) * 32 + l;
+#pragma unroll
+  for (int j = 0; j <= kOrd; ++j) r_c[j * 32] = acc[j];
+  const int used = levinson_damped<32>(r_c, p.order, a_c);
+  if (!live) return;
+#pragma unroll 8
+  for (int j = 0; j < kOrd; ++j) p.coefs[g * kOrd + j] = static_cast<float>(a_c[(kOrd - 1 - j) * 32]);
+  if (p.debug) {
+    double *d = p.debug + g * (kOrd + 1 + kOrd + 1);
+    for (int j = 0; j <= kOrd; ++j) d[j] = r_c[j * 32];
+    for (int j = 0; j < kOrd; ++j) d[kOrd + 1 + j] = a_c[j * 32];
+    d[kOrd + 1 + kOrd] = used;
+  }
+}
+
 __device__ __forceinline__ float clamp10(float s)
 {
   return s > 10.f ? 10.f : (s < -10.f ? -10.f : s);
 }
 
+// U consecutive outputs per loop trip with compile-time register indices, then the accumulators move down by U
+// (U register moves per U samples). The fully unrolled form (U = 32, no moves) is a 39 KB loop body that runs out of
+// the instruction cache -- measured: 1.05 no-instruction stalls per issued instruction (profiles/README.md).
+template <int U>
 __global__ void __launch_bounds__(32) lpc_extend_kernel(const LpcParams p, const int nslots, const int4 slots)
 {
   // slots.{x,y,z,w}: (job * 2 + direction) of the chain groups present in this launch; direction 1 = backward
@@ -199,31 +293,34 @@ __global__ void __launch_bounds__(32) lpc_extend_kernel(const LpcParams p, const
   const long long step = back ? -static_cast<long long>(p.nch) : p.nch;
   float *origin = back ? base - p.nch : base + job.len * p.nch;
 
-  float c[kOrd], A[kOrd];
+  float c[kOrd], A[kOrd + U];                                   // A[k]: partial sum of output n0 + k
   const float *cf = p.coefs + (static_cast<long long>(jb) * p.nlanes + lane) * kOrd;
 #pragma unroll
   for (int j = 0; j < kOrd; ++j) c[j] = __ldg(cf + j);         // c[j] multiplies the sample 32 - j behind an output
 #pragma unroll
-  for (int j = 0; j < kOrd; ++j) A[j] = 0.f;
-  // the 32 base samples behind output 0, oldest first: sample m = s - 32 feeds outputs 0 .. s
+  for (int j = 0; j < kOrd + U; ++j) A[j] = 0.f;
+  // The loop starts 32 samples before the first new one: there a step takes its sample from the base segment instead
+  // of from its accumulator, which is how the 32 partial sums of outputs 0..31 get their base-segment terms (oldest
+  // first, from zero) with the code of the main loop.
+  float *out = origin - kOrd * step;
+  for (long long n0 = -kOrd; n0 < extra; n0 += U, out += U * step) {
 #pragma unroll
-  for (int s = 0; s < kOrd; ++s) {
-    const long long m = s - kOrd;
-    const bool inside = -m <= job.len;                          // a shorter base: nothing there (its coefficient is 0)
-    const float y = inside ? origin[m * step] : 0.f;
+    for (int s = 0; s < U; ++s) {
+      float y;
+      if (n0 < 0) {
+        y = -(n0 + s) <= job.len ? out[s * step] : 0.f;         // a shorter base: nothing there (its coefficient is 0)
+      } else {
+        y = clamp10(A[s]);
+        if (n0 + s < extra) out[s * step] = y;
+      }
+      // output n0 + s + d sits in A[s + d] and takes this sample with c[32 - d]; d = 32 opens a new sum
 #pragma unroll
-    for (int n = 0; n <= s; ++n) A[n] = __fsub_rn(A[n], __fmul_rn(y, c[kOrd - (n - s + kOrd)]));
-  }
-  for (long long n0 = 0; n0 < extra; n0 += kOrd) {
-#pragma unroll
-    for (int s = 0; s < kOrd; ++s) {
-      const float y = clamp10(A[s]);
-      if (n0 + s < extra) origin[(n0 + s) * step] = y;
-      A[s] = 0.f;
-      // output n0 + s + d sits in A[(s + d) & 31] and takes this sample with c[32 - d]
-#pragma unroll
-      for (int d = kOrd; d >= 1; --d) A[(s + d) & (kOrd - 1)] = __fsub_rn(A[(s + d) & (kOrd - 1)], __fmul_rn(y, c[kOrd - d]));
+      for (int d = 1; d <= kOrd; ++d) A[s + d] = __fsub_rn(A[s + d], __fmul_rn(y, c[kOrd - d]));
     }
+#pragma unroll
+    for (int k = 0; k < kOrd; ++k) A[k] = A[k + U];
+#pragma unroll
+    for (int k = kOrd; k < kOrd + U; ++k) A[k] = 0.f;
   }
 }
 
@@ -231,6 +328,52 @@ int cuda_fail(cudaError_t e, const char *what)
 {
   set_last_error(std::string(what) + ": " + cudaGetErrorString(e));
   return e == cudaErrorMemoryAllocation ? RR_ENOMEM : RR_INTERNAL;
+}
+
+// Stream-ordered scratch for the coefficient rows comes from a pool of the library's own, one per device, that keeps
+// its memory between calls (the default pool hands it back to the driver at every synchronisation, which put a
+// driver allocation of ~0.5 ms in front of every call).
+cudaError_t scratch_alloc(void **ptr, size_t bytes, cudaStream_t stream)
+{
+  static std::mutex mu;
+  static cudaMemPool_t pools[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaMallocAsync(ptr, bytes, stream);
+  cudaMemPool_t pool;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (!pools[dev]) {
+      cudaMemPoolProps props = {};
+      props.allocType = cudaMemAllocationTypePinned;
+      props.handleTypes = cudaMemHandleTypeNone;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = dev;
+      e = cudaMemPoolCreate(&pools[dev], &props);
+      if (e != cudaSuccess) { pools[dev] = nullptr; return e; }
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    pool = pools[dev];
+  }
+  return cudaMallocFromPoolAsync(ptr, bytes, pool, stream);
+}
+
+// Thread-per-job analysis once there are enough jobs, else warp-per-job. Measured on a B200 (profiles/README.md): the
+// warp-per-job kernel costs ~18 ps per (job, term) once the SMs are full, the thread-per-job kernel ~104 ns per term
+// whatever the job count up to one warp per SM sub-partition (18 944 jobs) -- they cross near 5 800 jobs.
+void launch_analysis(const LpcParams &p, cudaStream_t stream)
+{
+  const long long slots = p.nlanes * p.njobs;
+  static const char *force = getenv("B200RATE_LPC_ANALYSIS");     // "wide" / "narrow": probes only
+  bool wide = slots >= 6144 && (p.njobs == 1 || p.job[0].len == p.job[1].len);
+  if (force && force[0] == 'w' && (p.njobs == 1 || p.job[0].len == p.job[1].len)) wide = true;
+  if (force && force[0] == 'n') wide = false;
+  if (wide)
+    lpc_analyse_wide_kernel<<<static_cast<unsigned>((slots + 31) / 32), 32, 0, stream>>>(p);
+  else
+    lpc_analyse_kernel<<<dim3(static_cast<unsigned>(p.nlanes), p.njobs), 32, 0, stream>>>(p);
 }
 
 // Both kernels for up to two jobs on `stream`; the coefficient scratch is stream-ordered.
@@ -261,12 +404,19 @@ int run_jobs(float *d_data, size_t nstreams, long long stream_stride, int nch, i
   }
   if (nslots == 0) return RR_OK;
   if (p.nlanes > 0x7fffffffll) { set_last_error("lpc: too many lanes for one launch"); return RR_INVPARAM; }
-  cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&p.coefs), sizeof(float) * kOrd * p.nlanes * njobs, stream);
+  cudaError_t e = scratch_alloc(reinterpret_cast<void **>(&p.coefs), sizeof(float) * kOrd * p.nlanes * njobs, stream);
   if (e != cudaSuccess) return cuda_fail(e, "lpc: cudaMallocAsync");
-  lpc_analyse_kernel<<<dim3(static_cast<unsigned>(p.nlanes), njobs), 32, 0, stream>>>(p);
+  launch_analysis(p, stream);
   const long long chains = p.nlanes * nslots;
-  lpc_extend_kernel<<<static_cast<unsigned>((chains + 31) / 32), 32, 0, stream>>>(p, nslots,
-                                                                                 make_int4(codes[0], codes[1], codes[2], codes[3]));
+  const int4 sl = make_int4(codes[0], codes[1], codes[2], codes[3]);
+  const unsigned grid = static_cast<unsigned>((chains + 31) / 32);
+  static const int variant = getenv("B200RATE_LPC_UNROLL") ? atoi(getenv("B200RATE_LPC_UNROLL")) : 8;
+  switch (variant) {
+    case 4: lpc_extend_kernel<4><<<grid, 32, 0, stream>>>(p, nslots, sl); break;
+    case 16: lpc_extend_kernel<16><<<grid, 32, 0, stream>>>(p, nslots, sl); break;
+    case 32: lpc_extend_kernel<32><<<grid, 32, 0, stream>>>(p, nslots, sl); break;
+    default: lpc_extend_kernel<8><<<grid, 32, 0, stream>>>(p, nslots, sl); break;
+  }
   e = cudaGetLastError();
   cudaError_t e2 = cudaFreeAsync(p.coefs, stream);
   if (e != cudaSuccess) return cuda_fail(e, "lpc: kernel launch");
@@ -344,9 +494,9 @@ int RRX_lpc_analysis_dump(const float *d_data, size_t nstreams, size_t stream_st
   p.job[0] = LpcJob{0, static_cast<long long>(data_len), 0, 0};
   p.debug = d_out;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&p.coefs), sizeof(float) * kOrd * p.nlanes, st);
+  cudaError_t e = scratch_alloc(reinterpret_cast<void **>(&p.coefs), sizeof(float) * kOrd * p.nlanes, st);
   if (e != cudaSuccess) return cuda_fail(e, "lpc: cudaMallocAsync");
-  lpc_analyse_kernel<<<dim3(static_cast<unsigned>(p.nlanes), 1), 32, 0, st>>>(p);
+  launch_analysis(p, st);
   e = cudaGetLastError();
   cudaFreeAsync(p.coefs, st);
   return e == cudaSuccess ? RR_OK : cuda_fail(e, "lpc: kernel launch");

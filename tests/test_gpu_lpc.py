@@ -67,6 +67,29 @@ def test_inline_wrappers_of_lpc_h():
     assert lib.RRX_lpc_extrapolate2(p0, n, nch, 32, 0, 0) == _capi.RR_OK        # nothing to do
 
 
+def test_lags_and_predictor_bit_for_bit_thread_per_job_kernel():
+    """Enough lanes for lpc_analyse_wide_kernel (one thread per lane, delay line in registers)."""
+    import torch
+    lib = _capi.product()
+    nstreams, nch = 6400, 3
+    for n, order in ((333, 32), (64, 32), (1000, 7)):
+        x = np.stack([lpclib.signal(s % 7, n, nch, seed=40 + s % 13) for s in range(64)])
+        x = np.ascontiguousarray(np.tile(x, (nstreams // 64, 1, 1)))
+        x[64:] *= np.float32(0.75)
+        d = torch.from_numpy(x).cuda()
+        out = torch.zeros((nstreams * nch, 66), dtype=torch.float64, device="cuda")
+        assert lib.RRX_lpc_analysis_dump(d.data_ptr(), nstreams, n, n, nch, order, out.data_ptr(), None) == _capi.RR_OK
+        torch.cuda.synchronize()
+        o = out.cpu().numpy()
+        for s in list(range(0, 70)) + [nstreams - 1]:
+            for c in range(nch):
+                r, a, used = lpclib.oracle_analyse(x[s], c, order)
+                row = o[s * nch + c]
+                assert np.array_equal(_bits(row[:order + 1]), _bits(r)), (n, s, c)
+                assert np.array_equal(_bits(row[33:33 + order]), _bits(a)), (n, s, c)
+                assert not row[33 + order:65].any() and int(row[65]) == used
+
+
 def test_lags_and_predictor_bit_for_bit():
     import torch
     lib = _capi.product()
@@ -86,14 +109,18 @@ def test_lags_and_predictor_bit_for_bit():
 
 
 @pytest.mark.parametrize("nstreams,nch,n,bk,fw", [(5, 2, 2400, 2400, 2400), (67, 1, 1024, 100, 333), (3, 6, 3000, 0, 500),
-                                                   (40, 2, 2205, 2205, 0)])
+                                                   (40, 2, 2205, 2205, 0),
+                                                   # >= 6144 (lane, job) slots: the thread-per-job analysis kernel
+                                                   (9600, 2, 200, 33, 70), (19001, 1, 97, 40, 0)])
 def test_device_batch_of_streams(nstreams, nch, n, bk, fw):
     import torch
     lib = _capi.product()
     stride = bk + n + fw + 7                                   # streams need not be packed
     host = np.zeros((nstreams, stride, nch), np.float32)
     for s in range(nstreams):
-        host[s, bk:bk + n] = lpclib.signal(s % 7, n, nch, seed=11 + s)
+        host[s, bk:bk + n] = lpclib.signal(s % 7, n, nch, seed=11 + s % 50)
+        if s >= 350:
+            host[s] *= np.float32(1.0 - 0.4 * s / nstreams)
     want = host.copy()
     for s in range(nstreams):
         lpclib.oracle_extrapolate2(want[s], bk, n, bk, fw)
