@@ -42,6 +42,20 @@ WORKLOADS = {
 }
 
 
+# what binds each dominant kernel, from its ncu --set full capture (profiles/r2_ncu_full_*.txt, profiles/README.md)
+LIMITERS = {
+    "dftp_kernel": "shared-memory pipe: l1tex 88 % busy (343 M wavefronts per 256-stream launch, 8 % of them bank conflicts) "
+                   "moving FFT passes through shared memory; 20 warps per SM (96 registers x 640 threads, 185 KB shared memory), "
+                   "issue 41 %, DRAM 19 % (profiles/r2_ncu_full_cfg4x256.txt) -- not HBM, although `bound` is reported against "
+                   "the HBM roof as the contract asks; `alu` is the arithmetic fraction",
+    "poly0_pair2_kernel": "shared-memory pipe: l1tex 84 % busy (24 x 8 B of window per output pair), DRAM 39 %",
+    "poly0_pair_kernel": "shared-memory pipe (window reads), DRAM ~35 %",
+    "halfband_pair_kernel": "shared-memory pipe: l1tex 86 % busy (8-byte window fills + 16-byte window reads), DRAM 41 %",
+    "dft64_kernel": "latency of DFMA / LDS chains at 12 warps per SM (160 registers): issue 50 %, shared-memory pipe 61 %, DRAM 19 %",
+    "poly0_dual_kernel": "shared-memory latency on 8-byte window reads; DRAM ~35 %",
+    "halfband_kernel": "shared-memory pipe and latency (fp64, eight outputs per thread); DRAM ~45 %",
+}
+
 _JSON_FD = None     # saved stdout when the process-level stdout has been redirected (multi-rank runs)
 
 
@@ -301,6 +315,53 @@ def run_reference_arm(args, rank, world):
 # ------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------
+def track_edges(torch, pkg, in_rate, out_rate, nch, nstreams, reps=5):
+    """The step next to the path in the caller: LPC extrapolation of both edges of `nstreams`
+    tracks (RRX_lpc_extend_tracks, csrc/lpc.cu), CUDA events on the launching stream; the reference's lpc/lpc.cpp
+    (oracle/_ref/libref_lpc.so, one host thread) is timed on a sample of 8 tracks and compared bit for bit --
+    this is the cpu_baseline leg of that step, the only place this function touches the checker."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import lpclib
+    lib = pkg.product()
+    add, drop, prime, _ = pkg.track_edge_lengths(in_rate, out_rate)
+    frames = 2 * prime                               # the edges only touch the ends of a track
+    padded = frames + 2 * add
+    rng = np.random.default_rng(5)
+    one = lpclib.signal(0, frames, nch, seed=3)
+    host = np.zeros((nstreams, padded, nch), np.float32)
+    host[:, add:add + frames] = one[None] * rng.uniform(0.5, 1.0, (nstreams, 1, 1)).astype(np.float32)
+    d = torch.from_numpy(host).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms = []
+    for r in range(reps + 3):
+        e0.record()
+        rc = lib.RRX_lpc_extend_tracks(d.data_ptr(), nstreams, frames, prime, nch, pkg.LPC_ORDER, add, st)
+        e1.record()
+        if rc != 0:
+            raise RuntimeError("RRX_lpc_extend_tracks: %s" % lib.RRX_last_error())
+        torch.cuda.synchronize()
+        if r >= 3:
+            ms.append(e0.elapsed_time(e1))
+    sample = min(nstreams, 8)
+    got = d[:sample].cpu().numpy()
+    want = host[:sample].copy()
+    kind = "reference" if lpclib.ref_available() else "port"
+    fn = lpclib.ref_extrapolate2 if kind == "reference" else lpclib.oracle_extrapolate2
+    t0 = time.perf_counter()
+    for s in range(sample):
+        fn(want[s], add, prime, add, 0)
+        fn(want[s], add + frames - prime, prime, 0, add)
+    cpu_ms = (time.perf_counter() - t0) / sample * 1e3
+    t = sorted(ms)[len(ms) // 2]
+    return {"what": "LPC extrapolation of both track edges (lpc/lpc.cpp), %d tracks x %d ch, prime %d, add %d frames per edge"
+                    % (nstreams, nch, prime, add),
+            "ms": t, "gpu_launches": 2, "predicted_Msamples_per_s": 2 * add * nstreams * nch / t / 1e3,
+            "cpu_baseline": {"ms_per_track": cpu_ms, "cores": 1, "kind": kind, "sample": "%d tracks" % sample},
+            "bit_exact_vs_cpu_sample": bool(np.array_equal(got.view(np.uint32), want.view(np.uint32)))}
+
+
 def make_input(torch, nstreams, frames, nch, in_rate, seconds, seed):
     """Synthetic sweep + noise (SURVEY.md 8d shape), generated on the device in bounded slabs (both along streams
     and along time, so a 1.25-hour 8-channel window needs no multi-GB temporaries)."""
@@ -485,9 +546,7 @@ class Measurement:
             roof = {"bound": "hbm", "kernel": kname, "stage": dom, "achieved": alg / dur / 1e6, "peak": peak_hbm, "unit": "GB/s",
                     "frac": alg / dur / 1e6 / peak_hbm, "traffic": traffic, "peak_source": how, "ms_per_launch": dur,
                     "algorithmic_bytes_per_launch": alg, "share_of_step": dur / self.ms_step,
-                    "limiter": "instruction issue / latency: 16 warps per SM (128 registers x 512 threads, 221 KB of shared memory), "
-                               "dependent un-fused FP chains and shared-memory round trips between FFT phases; neither HBM, the "
-                               "shared-memory pipe nor the FP pipe is saturated (profiles/README.md)",
+                    "limiter": LIMITERS.get(kfamily, "see the kernel's ncu summary in profiles/README.md"),
                     "alu": {"achieved_tflops": kflops / dur / 1e9, "peak_tflops": alu_peak,
                             "frac": (kflops / dur / 1e9 / alu_peak) if alu_peak else None, "peak_source": alu_how},
                     "stage_kernels": [self.b.stage_kernel(i) for i in range(n)], "stage_ms": self.stage_ms}
@@ -731,6 +790,13 @@ def main():
             except Exception as exc:  # noqa: BLE001
                 configs.append({"workload": w2, "error": str(exc)})
 
+    edges = None
+    if world == 1 and not args.no_configs and not args.streams:
+        try:
+            edges = track_edges(torch, pkg, WORKLOADS[wl][0], WORKLOADS[wl][1], WORKLOADS[wl][2], WORKLOADS[wl][6])
+        except Exception as exc:  # noqa: BLE001
+            edges = {"error": str(exc)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -757,6 +823,8 @@ def main():
             line["gather"] = gather
         if configs:
             line["configs"] = configs
+        if edges:
+            line["track_edges"] = edges
         emit_json(line)
     if dist:
         dist.barrier()
