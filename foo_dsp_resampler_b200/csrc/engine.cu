@@ -347,8 +347,8 @@ __global__ void __launch_bounds__(512) poly0_fast_kernel(const __grid_constant__
 // of a pair-interleaved FIFO, else with LDGSTS copies by all threads.
 #define RR_POLY0_PAIR_KERNEL_BODY(SETUP, TILE)                                                                        \
   const Poly0FastParams<float> &p = pp.fast;                                                                          \
-  Pk *smem = reinterpret_cast<Pk *>(rr_smem_raw);                                                                     \
-  const int set = p.win * pp.P + pp.dup;              /* one or two copies of the windows, then the slot table */       \
+  Pk *smem = reinterpret_cast<Pk *>(rr_smem_raw) + 2;  /* 16 bytes of slack in front: a shifted window starts at -1 */  \
+  const int set = p.win * pp.P;                        /* the windows, then the slot table */                          \
   uint16_t *slot_of = reinterpret_cast<uint16_t *>(smem + set);                                                       \
   __shared__ Poly0PairTile tiles[2];                                                                                  \
   __shared__ int cnt[17];                                                                                             \
@@ -697,15 +697,16 @@ static int launch_halfband_pair(const HalfbandPairParams &hp, long long nwork, s
 
 static size_t poly0_pair_smem(const Poly0PairParams &pp)
 {
-  return sizeof(Pk) * (static_cast<size_t>(pp.fast.win) * pp.P + static_cast<size_t>(pp.dup ? pp.dup : 0)) + 2 * static_cast<size_t>(pp.tslots) + 16;
+  return sizeof(Pk) * (static_cast<size_t>(pp.fast.win) * pp.P + 2) + 2 * static_cast<size_t>(pp.tslots) + 16;
 }
 static int launch_poly0_pair(const Poly0PairParams &pp, int threads, long long nwork, stream_t s)
 {
   if (nwork <= 0) return RR_OK;
 #ifdef B200RATE_EMU
   (void)s; (void)threads;
-  if (getenv("B200RATE_TRACE")) fprintf(stderr, "poly0pair L %d n %d step %lld P %d PG %d CL %d tslots %d spread %d MM %d win %d nwork %lld\n", pp.fast.base.L, pp.fast.base.n, pp.fast.base.step, pp.P, pp.PG, pp.CL, pp.tslots, pp.spread, pp.fast.MM, pp.fast.win, nwork);
-  std::vector<Pk> buf(static_cast<size_t>(pp.fast.win) * pp.P + static_cast<size_t>(pp.dup) + 1);
+  if (getenv("B200RATE_TRACE")) fprintf(stderr, "poly0pair L %d n %d step %lld P %d PG %d CL %d tslots %d spread %d shift %d MM %d win %d nwork %lld\n", pp.fast.base.L, pp.fast.base.n, pp.fast.base.step, pp.P, pp.PG, pp.CL, pp.tslots, pp.spread, pp.shift, pp.fast.MM, pp.fast.win, nwork);
+  std::vector<Pk> bufv(static_cast<size_t>(pp.fast.win) * pp.P + 8);
+  struct { Pk *p; Pk *data() const { return p; } } buf = {bufv.data() + 2};   // slack either side, like the kernel's buffer
   std::vector<uint16_t> slot_of(static_cast<size_t>(pp.tslots) + 1);
   for (long long w = 0; w < nwork; ++w) {
     const Poly0PairTile pt = poly0_pair_make_tile(pp, w);
@@ -1212,7 +1213,7 @@ template <class T> class Engine {
       if (use_pair_kernel_ && use_pair_poly_ && g.order == 0 && (g.n == 16 || g.n == 24 || g.n == 28 || g.n == 32) && !(nlanes & 1) &&
           g.Lp >= 48 && g.Lp <= 512 && g.pstep < (1 << 16)) {
         // lane-pair kernel: one column per period (L <= 512 slots), P pairs of a stream and PG period groups per CTA
-        Poly0PairParams pp;
+        Poly0PairParams pp{};
         pp.fast.base = p;
         const int L = g.Lp, step = static_cast<int>(g.pstep);
         const int r_first = static_cast<int>((((g.at0 + static_cast<i128>(w0) * g.pstep) % L) + L) % L);
@@ -1225,9 +1226,29 @@ template <class T> class Engine {
         int rows = (ncl + 15) / 16;
         auto spill_of = [&](int r) { int sp = 0; for (int b2 = 0; b2 < 16; ++b2) sp += std::max(0, bucket[b2] - r); return sp; };
         const int max_threads = pp.CL == 2 ? 256 : 512;      // launch bounds of poly0_pair2_kernel / poly0_pair_kernel
-        if (spill_of(rows) > ncl / 10 && 16 * (rows + 1) <= max_threads) ++rows;   // a few idle lanes cost less than two-way conflicts
+        // two-slot kernel: move clusters of overfull banks one bank down by starting their window a sample early
+        // (Poly0PairParams::shift): m[b] clusters leave bank b for bank b - 1 until no bank holds more than `rows`
+        pp.shift = 0;
+        if (pp.CL == 2 && use_pair_shift_) {
+          const int rows0 = (ncl + 15) / 16;
+          int mv[16] = {0};
+          bool ok = false;
+          for (int pass = 0; pass < 64 && !ok; ++pass) {
+            ok = true;
+            for (int b2 = 0; b2 < 16; ++b2) {
+              const int load = bucket[b2] - mv[b2] + mv[(b2 + 1) & 15];
+              if (load > rows0) { mv[b2] += load - rows0; ok = false; }
+            }
+          }
+          for (int b2 = 0; b2 < 16; ++b2) ok = ok && mv[b2] >= 0 && mv[b2] <= bucket[b2];
+          if (ok) {
+            pp.shift = 1; rows = rows0;
+            for (int b2 = 0; b2 < 16; ++b2) pp.keep[b2] = static_cast<unsigned char>(bucket[b2] - mv[b2]);
+          }
+        }
+        if (!pp.shift && spill_of(rows) > ncl / 10 && 16 * (rows + 1) <= max_threads) ++rows;   // a few idle lanes cost less than two-way conflicts
         pp.spread = 1; pp.tslots = 16 * rows;               // overfull banks spill into the holes (poly0_pair_deal_overflow)
-        if (maxb > 2 * rows || spill_of(rows) > kPolyDealOverflow) pp.spread = 0;   // few distinct banks (steep up-sampling): keep order
+        if (!pp.shift && (maxb > 2 * rows || spill_of(rows) > kPolyDealOverflow)) pp.spread = 0;   // few distinct banks (steep up-sampling): keep order
         pp.P = 1;
         while (!(in.nch & 1) && !(out.nch & 1) && in.nch == out.nch && 2 * pp.P < in.nch && in.nch % (4 * pp.P) == 0 &&
                pp.tslots * 2 * pp.P <= 256)
@@ -1244,13 +1265,10 @@ template <class T> class Engine {
         };
         int MM = 32;
         while (MM > 2 && window_of(MM) * pp.P * sizeof(Pk) > budget) MM -= 2;
-        pp.dup = 0;
         if (window_of(MM) * pp.P * sizeof(Pk) <= budget && nlanes % (2 * pp.P) == 0 && threads <= max_threads) {
           const long long periods = (wn + L - 1) / L;
           pp.fast.F = L; pp.fast.ncols = 1; pp.fast.MM = MM; pp.fast.CH = 2 * pp.P;
           pp.fast.win = static_cast<int>(window_of(MM));
-          // second copy of the windows 8 banks further (the window size is 8 mod 16 elements): full bank columns overflow into it
-          if (pp.spread && use_pair_dup_) pp.dup = pp.fast.win * pp.P + ((pp.P & 1) ? 0 : 8);
           pp.fast.mtiles = (periods + MM - 1) / MM;
           pp.fast.double_buffer = 0;
           const long long nwork = static_cast<long long>(nlanes / (2 * pp.P)) * pp.fast.mtiles;
@@ -1660,7 +1678,7 @@ template <class T> class Engine {
   // debugging switches: generic kernels only / per stage kind
   bool use_pair_kernel_ = getenv("B200RATE_NO_PAIR_KERNEL") == nullptr;
   bool use_pair_dft_ = getenv("B200RATE_NO_PAIR_DFT") == nullptr, use_pair_poly_ = getenv("B200RATE_NO_PAIR_POLY") == nullptr;
-  bool use_pair_dup_ = getenv("B200RATE_NO_PAIR_DUP") == nullptr;
+  bool use_pair_shift_ = getenv("B200RATE_NO_PAIR_SHIFT") == nullptr;   // probes: the old deal with overflow into holes
   bool use_pair_half_ = getenv("B200RATE_NO_PAIR_HALF") == nullptr, use_pair_poly2_ = getenv("B200RATE_NO_PAIR_POLY2") == nullptr;
   int last_dft_kernel_ = 0;
 

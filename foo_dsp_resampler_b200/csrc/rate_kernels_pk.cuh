@@ -918,8 +918,13 @@ struct Poly0PairParams {
   int tslots;                    // threads along the slot dimension (multiple of 16, >= slots per column)
   int spread;                    // deal the slots over the banks (needs one column per period)
   int CL;                        // slots per thread: 1, or 2 adjacent slots sharing their input window (poly0_pair2_*)
-  int dup;                       // 0, or the element offset of a second copy of the windows that sits 8 eight-byte banks
-                                 // further: a slot whose bank column is full takes the column 8 banks away and reads that copy
+  // Shifted windows (poly0_pair2_*): the first input samples of a period's slot clusters do not fall evenly into the 16
+  // eight-byte bank pairs (cfg4: 2 ... 7 clusters per bank for 5 rows of threads). A cluster of an overfull bank b is
+  // moved to bank b - 1 by starting its window ONE SAMPLE EARLIER (that extra sample carries no tap), which makes every
+  // half-warp read 16 different banks in every step. keep[b]: clusters that stay in bank b (rows 0 .. keep[b] - 1); the
+  // others go to bank b - 1, rows keep[b - 1] ... Solved on the host from the same bank counts the device deal sees.
+  int shift;
+  unsigned char keep[16];
 };
 
 // thread slot ts -> slot of the column (or 0xffff): slot_of[j * 16 + b] = the j-th slot (cluster) whose first
@@ -927,6 +932,7 @@ struct Poly0PairParams {
 // rows) goes to an overflow list and is put into the remaining holes by poly0_pair_deal_overflow after a barrier
 // (a few two-way conflicts instead of idle threads). cnt: 16 bank counters + 1 overflow counter, zero on entry.
 constexpr int kPolyDealOverflow = 128;
+constexpr int kPolyShifted = 0x8000;                       // flag in slot_of: this cluster's window starts one sample early
 RR_PROG void poly0_pair_deal(const Poly0PairParams &pp, const Poly0Tile &t, uint16_t *slot_of, int *cnt, uint16_t *ovf, int tid,
                              int nthreads)
 {
@@ -939,6 +945,12 @@ RR_PROG void poly0_pair_deal(const Poly0PairParams &pp, const Poly0Tile &t, uint
 #else
     const int j = cnt[b]++;
 #endif
+    if (pp.shift) {                                        // every cluster has a conflict-free place (host-solved)
+      const int b2 = (b + 15) & 15;
+      if (j < pp.keep[b]) slot_of[j * 16 + b] = (uint16_t)fs;
+      else slot_of[(pp.keep[b2] + j - pp.keep[b]) * 16 + b2] = (uint16_t)(fs | kPolyShifted);
+      continue;
+    }
     if (j * 16 + b < pp.tslots) slot_of[j * 16 + b] = (uint16_t)fs;
     else {
 #if defined(__CUDA_ARCH__)
@@ -952,18 +964,11 @@ RR_PROG void poly0_pair_deal(const Poly0PairParams &pp, const Poly0Tile &t, uint
 }
 RR_PROG void poly0_pair_deal_overflow(const Poly0PairParams &pp, const Poly0Tile &t, uint16_t *slot_of, const int *cnt, const uint16_t *ovf, int tid)
 {
-  if (tid != 0) return;
-  const PolyParams<float> &p = pp.fast.base;
-  const int n = cnt[16] < kPolyDealOverflow ? cnt[16] : kPolyDealOverflow, rows = pp.tslots >> 4;
+  if (tid != 0 || pp.shift) return;
+  (void)t;
+  const int n = cnt[16] < kPolyDealOverflow ? cnt[16] : kPolyDealOverflow;
   int hole = 0;
   for (int k = 0; k < n; ++k) {
-    if (pp.dup) {                                         // a free row of the column 8 banks away: conflict-free through the second copy
-      const unsigned at_rel = (unsigned)t.r_first + (unsigned)ovf[k] * (unsigned)p.step;
-      const int b2 = (int)(((at_rel / (unsigned)p.L) & 15) ^ 8);
-      int j = 0;
-      while (j < rows && slot_of[j * 16 + b2] != 0xffff) ++j;
-      if (j < rows) { slot_of[j * 16 + b2] = (uint16_t)(ovf[k] | 0x8000); continue; }
-    }
     while (hole < pp.tslots && slot_of[hole] != 0xffff) ++hole;
     if (hole < pp.tslots) slot_of[hole] = ovf[k];
   }
@@ -982,20 +987,18 @@ RR_PROG void poly0_pair_load(const Poly0PairParams &pp, const Poly0Tile &t, int 
   if (tma) {
     if (tid != 0) return;
     const unsigned bytes = (unsigned)(((t.win + head + 1) & ~1) * (int)sizeof(Pk));
-    tma_bar_expect(bar, bytes * (unsigned)pp.P * (pp.dup ? 2u : 1u));
+    tma_bar_expect(bar, bytes * (unsigned)pp.P);
     for (int pr = 0; pr < pp.P; ++pr) {
       const float *s0 = view_ptr<const float>(p.in, lane_offset(p.in, t.lane0 + 2 * pr), c0) - 2 * head;
       tma_load_1d(buf + pr * fp.win, s0, bytes, bar);
-      if (pp.dup) tma_load_1d(buf + pp.dup + pr * fp.win, s0, bytes, bar);
     }
     return;
   }
   const bool direct = view_range_direct(p.in, c0, c0 + t.win);
   const int es = p.in.elem_stride;
-  for (int cp = 0; cp < (pp.dup ? 2 : 1); ++cp)
   for (int pr = 0; pr < pp.P; ++pr) {
     const long long off0 = lane_offset(p.in, t.lane0 + 2 * pr), off1 = lane_offset(p.in, t.lane0 + 2 * pr + 1);
-    Pk *dst = buf + cp * pp.dup + pr * fp.win;
+    Pk *dst = buf + pr * fp.win;
     const float *s0 = view_ptr<const float>(p.in, off0, c0), *s1 = view_ptr<const float>(p.in, off1, c0);
     if (direct && s1 == s0 + 1 && !(es & 1) && !((size_t)s0 & 7)) {
       for (int j = tid; j < t.win; j += nthreads) pk_async_copy8(dst + j, s0 + (long long)j * es);
@@ -1020,7 +1023,6 @@ RR_PROG void poly0_pair_load(const Poly0PairParams &pp, const Poly0Tile &t, int 
 // period, so neither depends on the tile), pair, period group and the coefficient row of the phase.
 template <int NT> struct Poly0PairThread {
   int fs, q, pr, g;              // fs < 0: no work (hole of the deal / padding)
-  int xoff;                      // 0, or pp.dup: which copy of the windows this thread reads
   float c[NT];
 };
 
@@ -1035,8 +1037,7 @@ RR_PROG Poly0PairThread<NT> poly0_pair_setup(const Poly0PairParams &pp, const Po
   st.pr = rest / pp.tslots;
   const int ts = rest - st.pr * pp.tslots;
   const int raw = st.g < pp.PG ? (pp.spread ? (int)slot_of[ts] : ts) : 0xffff;
-  const int fs = raw == 0xffff ? raw : (raw & 0x7fff);
-  st.xoff = (raw != 0xffff && (raw & 0x8000)) ? pp.dup : 0;
+  const int fs = raw;
   st.fs = fs < t.nslots ? fs : -1;
   const unsigned at_rel = (unsigned)t.r_first + (unsigned)(st.fs < 0 ? 0 : st.fs) * (unsigned)p.step;
   st.q = (int)(at_rel / (unsigned)p.L);
@@ -1103,7 +1104,7 @@ RR_PROG void poly0_pair_tile(const Poly0PairParams &pp, const Poly0PairTile &pt,
   const bool direct = pt.direct != 0;
   const bool packed_out = direct && d1 == d0 + 1 && !((size_t)d0 & 7) && !(dstep & 1);
   const int xstep = PG * (int)p.step;
-  const Pk *x = buf + st.xoff + st.pr * fp.win + pt.head + st.q + st.g * (int)p.step;
+  const Pk *x = buf + st.pr * fp.win + pt.head + st.q + st.g * (int)p.step;
   int m = st.g;
   auto emit = [&](int mm, Pk s) {
     if (packed_out) *reinterpret_cast<Pk *>(d0) = s;
@@ -1142,10 +1143,15 @@ RR_PROG void poly0_pair_tile(const Poly0PairParams &pp, const Poly0PairTile &pt,
 // d = DLO or DLO + 1 with DLO = floor(step / L), so one pass over NT + DLO + 1 window samples feeds both: 1.8x
 // fewer shared-memory reads per output (the kernel's bound). The second row is kept shifted by d in registers;
 // only its first and last window positions depend on d (one predicate). Same products, same order per output.
+// A thread whose cluster was moved one bank down by the deal (pp.shift) starts its pass one sample early: window
+// position j then carries tap j - 1 of the first output, so the pass covers NT + DLO + 2 positions for everybody and
+// each thread skips the one or two positions at either end that carry no tap of its outputs (predicates, no zero taps:
+// a sample outside an output's window never touches it, whatever it holds).
 template <int NT, int DLO> struct Poly0Pair2Thread {
-  int fs, q, pr, xoff;           // fs < 0: no work; xoff: which copy of the windows (0 / pp.dup)
-  bool d_lo, two;                // d == DLO; the second slot exists
-  float c0[NT], c1[NT + 1];      // c1[j] multiplies window sample DLO + j when d == DLO, DLO + 1 + j - 1... see setup
+  int fs, q, pr;                 // fs < 0: no work; q: first window sample of the pass (already moved by sh)
+  int sh, f1;                    // the first output's taps start at position sh (0 / 1), the second's at DLO + f1 (0 / 1 / 2)
+  bool two;                      // the second slot exists
+  float c0[NT + 1], c1[NT + 2];  // by window position: c0[j] at position j, c1[j] at position DLO + j
 };
 
 template <int NT, int DLO>
@@ -1156,23 +1162,26 @@ RR_PROG Poly0Pair2Thread<NT, DLO> poly0_pair2_setup(const Poly0PairParams &pp, c
   st.pr = w / pp.tslots;
   const int ts = w - st.pr * pp.tslots;
   const int raw = st.pr < pp.P ? (pp.spread ? (int)slot_of[ts] : 2 * ts) : 0xffff;
-  const int fs = raw == 0xffff ? raw : (raw & 0x7fff);
-  st.xoff = (raw != 0xffff && (raw & 0x8000)) ? pp.dup : 0;
+  const int fs = raw == 0xffff ? raw : (raw & (kPolyShifted - 1));
+  st.sh = (raw != 0xffff && (raw & kPolyShifted)) ? 1 : 0;
   st.fs = fs < t.nslots ? fs : -1;
   const unsigned at0 = (unsigned)t.r_first + (unsigned)(st.fs < 0 ? 0 : st.fs) * (unsigned)p.step;
-  st.q = (int)(at0 / (unsigned)p.L);
-  const int r0 = (int)(at0 - (unsigned)st.q * (unsigned)p.L);
+  const int q0 = (int)(at0 / (unsigned)p.L);
+  const int r0 = (int)(at0 - (unsigned)q0 * (unsigned)p.L);
   const unsigned at1 = at0 + (unsigned)p.step;
   const int q1 = (int)(at1 / (unsigned)p.L), r1 = (int)(at1 - (unsigned)q1 * (unsigned)p.L);
+  st.q = q0 - st.sh;
   st.two = st.fs >= 0 && st.fs + 1 < t.nslots;
-  st.d_lo = q1 - st.q == DLO;
+  st.f1 = q1 - q0 - DLO + st.sh;                          // d = DLO or DLO + 1
   const float *row0 = p.coefs + (long long)r0 * NT, *row1 = p.coefs + (long long)(st.two ? r1 : r0) * NT;
 #pragma unroll
-  for (int k = 0; k < NT; ++k) st.c0[k] = ldg(row0 + k);
-  // window position DLO + j (j = 0 .. NT) carries tap j of the second output when d == DLO, tap j - 1 when d == DLO + 1
-#pragma unroll
   for (int j = 0; j <= NT; ++j) {
-    const int k = st.d_lo ? j : j - 1;
+    const int k = j - st.sh;
+    st.c0[j] = (k >= 0 && k < NT) ? ldg(row0 + k) : 0.f;
+  }
+#pragma unroll
+  for (int j = 0; j <= NT + 1; ++j) {
+    const int k = j - st.f1;
     st.c1[j] = (k >= 0 && k < NT) ? ldg(row1 + k) : 0.f;
   }
   return st;
@@ -1193,10 +1202,11 @@ RR_PROG void poly0_pair2_tile(const Poly0PairParams &pp, const Poly0PairTile &pt
   const bool direct = pt.direct != 0;
   const bool packed_out = direct && d1 == d0 + 1 && !((size_t)d0 & 7) && !(dstep & 1) && !(es & 1);
   const int xstep = (int)p.step;
-  const Pk *x = buf + st.xoff + st.pr * fp.win + pt.head + st.q;
-  const bool dlo = st.d_lo, two = st.two;
-  auto emit = [&](int mm, int which, Pk s) {             // output of slot fs + which in period mm
-    float *e0 = d0 + which * es, *e1 = d1 + which * es;
+  const Pk *x = buf + st.pr * fp.win + pt.head + st.q;       // st.q may be -1: the buffer has two elements of slack in front
+  const bool two = st.two, sh = st.sh != 0;
+  const int f1 = st.f1;
+  auto emit = [&](int mm, int which, int ahead, Pk s) {  // output of slot fs + which in period mm (= `ahead` periods past d0)
+    float *e0 = d0 + which * es + ahead * dstep, *e1 = d1 + which * es + ahead * dstep;
     if (packed_out) *reinterpret_cast<Pk *>(e0) = s;
     else if (direct) { *e0 = s.a; *e1 = s.b; }
     else {
@@ -1208,21 +1218,44 @@ RR_PROG void poly0_pair2_tile(const Poly0PairParams &pp, const Poly0PairTile &pt
       }
     }
   };
-  for (int m = 0; m < t.mcount; ++m, x += xstep, d0 += dstep, d1 += dstep) {
-    Pk s0 = pk_bcast(0.0f), s1 = pk_bcast(0.0f);
+  // which window positions carry a tap of the first / second output (see Poly0Pair2Thread)
+  auto on0 = [&](int j) { return j == 0 ? !sh : (j == NT ? sh : true); };
+  auto on1 = [&](int jj) { return jj == 0 ? f1 == 0 : (jj == 1 ? f1 <= 1 : (jj == NT ? f1 >= 1 : (jj == NT + 1 ? f1 == 2 : true))); };
+  int m = 0;
+  // two periods at a time: four independent sums per thread (the pass is bound by the latency of its LDS -> FMUL2 ->
+  // FFMA2 chains once the bank conflicts are gone), same products in the same order per output
+  for (; m + 1 < t.mcount; m += 2, x += 2 * xstep, d0 += 2 * dstep, d1 += 2 * dstep) {
+    const Pk *xb = x + xstep;
+    Pk s0 = pk_bcast(0.0f), s1 = pk_bcast(0.0f), u0 = pk_bcast(0.0f), u1 = pk_bcast(0.0f);
 #pragma unroll
-    for (int j = 0; j < NT + DLO + 1; ++j) {
-      const Pk xv = pk_load8(x + j);
-      if (j < NT) s0 = A::addp(s0, A::mul(pk_bcast(st.c0[j]), xv));
-      if (j >= DLO) {
-        const int jj = j - DLO;                           // 0 .. NT
-        if (jj == 0) { if (dlo) s1 = A::addp(s1, A::mul(pk_bcast(st.c1[0]), xv)); }
-        else if (jj == NT) { if (!dlo) s1 = A::addp(s1, A::mul(pk_bcast(st.c1[NT]), xv)); }
-        else s1 = A::addp(s1, A::mul(pk_bcast(st.c1[jj]), xv));
+    for (int j = 0; j < NT + DLO + 2; ++j) {
+      const Pk xv = pk_load8(x + j), xw = pk_load8(xb + j);
+      if (j <= NT && on0(j)) {
+        const Pk c = pk_bcast(st.c0[j]);
+        s0 = A::addp(s0, A::mul(c, xv));
+        u0 = A::addp(u0, A::mul(c, xw));
+      }
+      if (j >= DLO && on1(j - DLO)) {
+        const Pk c = pk_bcast(st.c1[j - DLO]);
+        s1 = A::addp(s1, A::mul(c, xv));
+        u1 = A::addp(u1, A::mul(c, xw));
       }
     }
-    emit(m, 0, s0);
-    if (two) emit(m, 1, s1);
+    emit(m, 0, 0, s0);
+    if (two) emit(m, 1, 0, s1);
+    emit(m + 1, 0, 1, u0);
+    if (two) emit(m + 1, 1, 1, u1);
+  }
+  if (m < t.mcount) {
+    Pk s0 = pk_bcast(0.0f), s1 = pk_bcast(0.0f);
+#pragma unroll
+    for (int j = 0; j < NT + DLO + 2; ++j) {
+      const Pk xv = pk_load8(x + j);
+      if (j <= NT && on0(j)) s0 = A::addp(s0, A::mul(pk_bcast(st.c0[j]), xv));
+      if (j >= DLO && on1(j - DLO)) s1 = A::addp(s1, A::mul(pk_bcast(st.c1[j - DLO]), xv));
+    }
+    emit(m, 0, 0, s0);
+    if (two) emit(m, 1, 0, s1);
   }
 }
 
