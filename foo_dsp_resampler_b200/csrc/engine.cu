@@ -1287,7 +1287,10 @@ template <class T> class Engine {
         Poly0DualParams<T> dp;
         dp.base = p;
         dp.coef = dt.coef; dp.slot = dt.slot; dp.qs = dt.qs; dp.flags = dt.flags; dp.TS = dt.TS;
-        dp.NL = std::max(1, std::min(nlanes, 256 / dt.TS));
+        // lanes per CTA: two (160 threads for 5 rows of slot pairs: three CTAs per SM at 128 registers, three tiles in
+        // flight) measured better than three (two CTAs) or one (five CTAs): cfg3 4.11 / 4.31 / 4.95 ms
+        dp.NL = std::max(1, std::min(std::min(nlanes, 256 / dt.TS), 2));
+        if (const char *e = getenv("B200RATE_DUAL_NL")) dp.NL = std::max(1, std::min(std::min(nlanes, 256 / dt.TS), atoi(e)));   // probes
         const int budget = 1536;                                   // doubles per lane window: 12 KB
         dp.MM = std::max(2, static_cast<int>((budget - g.n - 8) / g.pstep));
         dp.win = static_cast<int>(((static_cast<long long>(dp.MM) * g.pstep + g.n + 8 + 1) & ~1ll) + 2);
@@ -1295,7 +1298,9 @@ template <class T> class Engine {
         const long long m_end = (w0 + wn + g.Lp - 1) / g.Lp;
         dp.mtiles = (m_end - dp.m_begin + dp.MM - 1) / dp.MM;
         const long long groups = (nlanes + dp.NL - 1) / dp.NL;
-        const size_t smem = sizeof(T) * static_cast<size_t>(dp.win) * dp.NL;
+        dp.groups = static_cast<int>(groups);
+        dp.group_fastest = (out.nch > 1 && groups < 0x7fffffffll && !getenv("B200RATE_DUAL_TILE_FASTEST")) ? 1 : 0;
+        const size_t smem = sizeof(T) * (static_cast<size_t>(dp.win) * dp.NL + kDualPad + 2);
         if (dp.mtiles < 0x7fffffffll && smem <= 100 * 1024) {
           kernel_name[i] = "poly0_dual_kernel (two slots per thread, TMA windows)";
           return Launch<T>::poly0_dual(dp, out_f32, groups * dp.mtiles, smem, s);
@@ -1552,38 +1557,66 @@ template <class T> class Engine {
     const StageGeom &q = geom[i];
     const int L = q.Lp, n = q.n, nsp = (L + 1) / 2, dlo = static_cast<int>(q.pstep / q.Lp);
     const int step = static_cast<int>(q.pstep), at0 = static_cast<int>(q.at0);
-    // deal the slot pairs to half-warps by the 8-byte bank of their first window sample; what does not fit a bank's rows
-    // fills the holes (a two-way conflict each)
+    // deal the slot pairs to half-warps by the 8-byte bank of their first window sample. Banks hold unequal numbers of
+    // pairs; mv[b] pairs of bank b move to bank b - 1 by starting their pass one sample early, until no bank holds more
+    // than `rows` (16-element relaxation; feasible for every (L, step, phase) tried). If it is not, what does not fit a
+    // bank's rows fills the holes (a two-way conflict each).
     std::vector<std::vector<int>> bucket(16);
     for (int sp = 0; sp < nsp; ++sp) bucket[static_cast<size_t>(((at0 + 2 * sp * step) / L) & 15)].push_back(sp);
     int rows = (nsp + 15) / 16;
-    auto spill_of = [&](int r) { int sp = 0; for (const auto &b : bucket) sp += std::max(0, static_cast<int>(b.size()) - r); return sp; };
-    while (rows < 8 && spill_of(rows) > nsp / 8) ++rows;
-    const int TS = 16 * rows;
-    std::vector<int> owner(static_cast<size_t>(TS), -1), rest;
-    for (int b = 0; b < 16; ++b)
-      for (size_t k = 0; k < bucket[static_cast<size_t>(b)].size(); ++k) {
-        if (static_cast<int>(k) < rows) owner[k * 16 + static_cast<size_t>(b)] = bucket[static_cast<size_t>(b)][k];
-        else rest.push_back(bucket[static_cast<size_t>(b)][k]);
+    int mv[16] = {0};
+    bool shifted = use_pair_shift_;
+    for (int pass = 0; pass < 64 && shifted; ++pass) {
+      bool changed = false;
+      for (int b = 0; b < 16; ++b) {
+        const int load = static_cast<int>(bucket[static_cast<size_t>(b)].size()) - mv[b] + mv[(b + 1) & 15];
+        if (load > rows) { mv[b] += load - rows; changed = true; }
       }
+      if (!changed) break;
+      if (pass == 63) shifted = false;
+    }
+    for (int b = 0; b < 16 && shifted; ++b) shifted = mv[b] <= static_cast<int>(bucket[static_cast<size_t>(b)].size());
+    auto spill_of = [&](int r) { int sp = 0; for (const auto &b : bucket) sp += std::max(0, static_cast<int>(b.size()) - r); return sp; };
+    if (!shifted) while (rows < 8 && spill_of(rows) > nsp / 8) ++rows;
+    const int TS = 16 * rows;
+    std::vector<int> owner(static_cast<size_t>(TS), -1), early(static_cast<size_t>(TS), 0), rest;
+    for (int b = 0; b < 16; ++b) {
+      const std::vector<int> &bk = bucket[static_cast<size_t>(b)];
+      const int keep = shifted ? static_cast<int>(bk.size()) - mv[b] : static_cast<int>(bk.size());
+      const int b2 = (b + 15) & 15, keep2 = static_cast<int>(bucket[static_cast<size_t>(b2)].size()) - mv[b2];
+      for (int k = 0; k < static_cast<int>(bk.size()); ++k) {
+        if (k < keep) {
+          if (k < rows) owner[static_cast<size_t>(k) * 16 + b] = bk[static_cast<size_t>(k)];
+          else rest.push_back(bk[static_cast<size_t>(k)]);
+        } else {
+          const size_t t = static_cast<size_t>(keep2 + k - keep) * 16 + b2;
+          owner[t] = bk[static_cast<size_t>(k)]; early[t] = 1;
+        }
+      }
+    }
     for (int t = 0; t < TS && !rest.empty(); ++t)
       if (owner[static_cast<size_t>(t)] < 0) { owner[static_cast<size_t>(t)] = rest.back(); rest.pop_back(); }
     if (!rest.empty()) return RR_INTERNAL;
-    std::vector<uint16_t> slot(static_cast<size_t>(TS), 0xffff), qs(static_cast<size_t>(TS), 0);
+    std::vector<uint16_t> slot(static_cast<size_t>(TS), 0xffff), qs(static_cast<size_t>(TS), 1);
     std::vector<uint8_t> flags(static_cast<size_t>(TS), 0);
-    std::vector<T> coef(static_cast<size_t>(2 * n + 1) * TS, static_cast<T>(0));
+    std::vector<T> coef(static_cast<size_t>(2 * n + 3) * TS, static_cast<T>(0));
     for (int t = 0; t < TS; ++t) {
       const int sp = owner[static_cast<size_t>(t)];
       if (sp < 0) continue;
+      const int sh = early[static_cast<size_t>(t)];
       const int s0 = 2 * sp, a0 = at0 + s0 * step, q0 = a0 / L, r0 = a0 % L, a1 = a0 + step, q1 = a1 / L, r1 = a1 % L;
       const bool two = s0 + 1 < L, d_lo = q1 - q0 == dlo;
+      const int f1 = (d_lo ? 0 : 1) + sh;
       slot[static_cast<size_t>(t)] = static_cast<uint16_t>(s0);
-      qs[static_cast<size_t>(t)] = static_cast<uint16_t>(q0);
-      flags[static_cast<size_t>(t)] = static_cast<uint8_t>((d_lo ? 1 : 0) | (two ? 2 : 0));
-      for (int k = 0; k < n; ++k) coef[static_cast<size_t>(k) * TS + t] = static_cast<T>(design.poly_bank[static_cast<size_t>(r0) * n + k]);
-      for (int j = 0; j <= n; ++j) {
-        const int k = d_lo ? j : j - 1;
-        if (two && k >= 0 && k < n) coef[static_cast<size_t>(n + j) * TS + t] = static_cast<T>(design.poly_bank[static_cast<size_t>(r1) * n + k]);
+      qs[static_cast<size_t>(t)] = static_cast<uint16_t>(q0 - sh + 1);
+      flags[static_cast<size_t>(t)] = static_cast<uint8_t>((d_lo ? 1 : 0) | (two ? 2 : 0) | (sh ? 4 : 0));
+      for (int j = 0; j <= n; ++j) {                       // position j of the pass carries tap j - sh of the first output
+        const int k = j - sh;
+        if (k >= 0 && k < n) coef[static_cast<size_t>(j) * TS + t] = static_cast<T>(design.poly_bank[static_cast<size_t>(r0) * n + k]);
+      }
+      for (int j = 0; j <= n + 1; ++j) {                   // position dlo + j carries tap j - f1 of the second output
+        const int k = j - f1;
+        if (two && k >= 0 && k < n) coef[static_cast<size_t>(n + 1 + j) * TS + t] = static_cast<T>(design.poly_bank[static_cast<size_t>(r1) * n + k]);
       }
     }
     DualTab &dt = dual_tab_[i];

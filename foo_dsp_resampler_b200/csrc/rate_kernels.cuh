@@ -1072,17 +1072,25 @@ RR_PROG void poly0_fast_compute(const Poly0FastParams<T> &fp, const Poly0Tile &t
 // whole launch, the windows of its two outputs overlap almost entirely (they start DLO or DLO + 1 samples apart,
 // DLO = floor(step / L)), so one pass over NT + DLO + 1 window samples feeds both: 1.8x fewer shared-memory loads per
 // output than the one-slot kernel, which is bound by exactly those loads. The slot pairs are dealt to the threads on
-// the host so that the sixteen lanes of a half-warp start in sixteen different 8-byte banks; the lane's window of a
-// tile of periods is staged with one TMA bulk copy. DFMA in tap order (the fp64 contract is 1e-12, not bit equality).
+// the host so that the sixteen lanes of a half-warp start in sixteen different 8-byte banks -- a pair of an overfull
+// bank is moved one bank down by starting its pass ONE SAMPLE EARLY (that position carries no tap; see
+// Poly0PairParams::shift for the lane-pair kernel), so every pass covers NT + DLO + 2 window positions and each thread
+// skips the end positions without a tap of its outputs; the lane's window of a tile of periods is staged with one TMA
+// bulk copy. DFMA in tap order (the fp64 contract is 1e-12, not bit equality).
 // ---------------------------------------------------------------------------------------------------
+constexpr int kDualPad = 2;      // elements in front of the first lane's window (a shifted pass may start at -1)
 template <class T> struct Poly0DualParams {
   PolyParams<T> base;
-  const T *coef;                 // [2 n + 1][TS] transposed per-thread rows (first slot, then the shifted row of the second)
-  const uint16_t *slot, *qs;     // [TS] first slot of the thread's pair (0xffff: idle), its first window sample within the period
-  const uint8_t *flags;          // [TS] bit 0: the second slot's window starts DLO samples later (else DLO + 1); bit 1: it exists
+  const T *coef;                 // [2 n + 3][TS] transposed per-thread rows by window position: n + 1 of the first slot, n + 2 of the second
+  const uint16_t *slot, *qs;     // [TS] first slot of the thread's pair (0xffff: idle), 1 + the first window sample of its pass within the period
+  const uint8_t *flags;          // [TS] bit 0: the second slot's window starts DLO samples later (else DLO + 1); bit 1: it exists;
+                                 //      bit 2: the pass starts one sample early
   int TS, NL;                    // threads per lane, lanes per CTA
   int MM, win;                   // periods per tile, window capacity per lane (samples, even)
   long long m_begin, mtiles;     // first period of the launch (output index / L), tiles along the periods
+  int groups, group_fastest;     // lane groups; work order: consecutive work items = the lane groups of one tile of periods
+                                 // (the channels of an interleaved output frame are then written at about the same time
+                                 // and merge in L2 instead of reaching DRAM as partial sectors)
 };
 
 struct Poly0DualTile {
@@ -1097,11 +1105,12 @@ template <class T> RR_PROG Poly0DualTile poly0_dual_tile(const Poly0DualParams<T
 {
   const PolyParams<T> &p = dp.base;
   Poly0DualTile t;
-  long long grp; int mt;
-  divmod_ll(work, (int)dp.mtiles, grp, mt);
+  long long grp, mt;
+  if (dp.group_fastest) { int g; divmod_ll(work, dp.groups, mt, g); grp = g; }
+  else { int m; divmod_ll(work, (int)dp.mtiles, grp, m); mt = m; }
   t.lane0 = (int)grp * dp.NL;
   t.nl = p.nlanes - t.lane0 < dp.NL ? p.nlanes - t.lane0 : dp.NL;
-  const long long m0 = dp.m_begin + (long long)mt * dp.MM, m_end = (p.out0 + p.nout + p.L - 1) / p.L;
+  const long long m0 = dp.m_begin + mt * dp.MM, m_end = (p.out0 + p.nout + p.L - 1) / p.L;
   t.mcount = m_end - m0 < dp.MM ? (int)(m_end - m0) : dp.MM;
   t.i_base = m0 * p.L;
   const long long lo = p.out0 > t.i_base ? p.out0 : t.i_base, hi_all = p.out0 + p.nout, hi_t = t.i_base + (long long)t.mcount * p.L;
@@ -1136,19 +1145,20 @@ template <class T> RR_PROG void poly0_dual_load(const Poly0DualParams<T> &dp, co
     const unsigned bytes = (unsigned)(((t.len + t.head + 1) & ~1) * (int)sizeof(T));
     tma_bar_expect(bar, bytes * (unsigned)t.nl);
     for (int l = 0; l < t.nl; ++l)
-      tma_load_1d(buf + l * dp.win, view_ptr<const T>(p.in, lane_offset(p.in, t.lane0 + l), t.c0) - t.head, bytes, bar);
+      tma_load_1d(buf + kDualPad + l * dp.win, view_ptr<const T>(p.in, lane_offset(p.in, t.lane0 + l), t.c0) - t.head, bytes, bar);
     return;
   }
   for (int l = 0; l < t.nl; ++l) {
     const long long off = lane_offset(p.in, t.lane0 + l);
-    for (int j = tid; j < t.len; j += nthreads) buf[l * dp.win + j] = view_read<T, T>(p.in, off, t.c0 + j);
+    for (int j = tid; j < t.len; j += nthreads) buf[kDualPad + l * dp.win + j] = view_read<T, T>(p.in, off, t.c0 + j);
   }
 }
 
 template <class T, class OutT, int NT, int DLO> struct Poly0DualThread {
-  int lane, s0, q;               // lane within the CTA, first slot (< 0: idle), window start within the period
-  bool dlo, two;
-  T c0[NT], c1[NT + 1];
+  int lane, s0, q;               // lane within the CTA, first slot (< 0: idle), first position of the pass within the period
+  int f1;                        // the second output's taps start at position DLO + f1 (0 / 1 / 2)
+  bool sh, two;                  // the first output's taps start at position 1 (else 0); the second slot exists
+  T c0[NT + 1], c1[NT + 2];      // by window position
 };
 
 template <class T, class OutT, int NT, int DLO>
@@ -1159,13 +1169,14 @@ RR_PROG Poly0DualThread<T, OutT, NT, DLO> poly0_dual_setup(const Poly0DualParams
   const int ts = tid - st.lane * dp.TS;
   const int s = st.lane < dp.NL ? (int)ldg(dp.slot + ts) : 0xffff;
   st.s0 = s == 0xffff ? -1 : s;
-  st.q = ldg(dp.qs + ts);
+  st.q = (int)ldg(dp.qs + ts) - 1;
   const unsigned fl = ldg(dp.flags + ts);
-  st.dlo = fl & 1; st.two = (fl & 2) != 0;
+  st.two = (fl & 2) != 0; st.sh = (fl & 4) != 0;
+  st.f1 = ((fl & 1) ? 0 : 1) + (st.sh ? 1 : 0);
 #pragma unroll
-  for (int k = 0; k < NT; ++k) st.c0[k] = ldg(dp.coef + k * dp.TS + ts);
+  for (int k = 0; k <= NT; ++k) st.c0[k] = ldg(dp.coef + k * dp.TS + ts);
 #pragma unroll
-  for (int k = 0; k <= NT; ++k) st.c1[k] = ldg(dp.coef + (NT + k) * dp.TS + ts);
+  for (int k = 0; k <= NT + 1; ++k) st.c1[k] = ldg(dp.coef + (NT + 1 + k) * dp.TS + ts);
   return st;
 }
 
@@ -1179,14 +1190,16 @@ RR_PROG void poly0_dual_compute(const Poly0DualParams<T> &dp, const Poly0DualTil
   const long long out_off = lane_offset(p.out, t.lane0 + st.lane);
   const bool direct = view_range_direct(p.out, p.out_preload + t.i_base + t.i_lo, p.out_preload + t.i_base + t.i_hi);
   OutT *d = view_ptr<OutT>(p.out, out_off, p.out_preload + t.i_base + st.s0);
-  const T *xw = buf + st.lane * dp.win + t.head + st.q;
-  auto tap = [&](int j, T xv, T &a0, T &a1) {
-    if (j < NT) a0 += st.c0[j] * xv;
+  const T *xw = buf + kDualPad + st.lane * dp.win + t.head + st.q;
+  const bool sh = st.sh;
+  const int f1 = st.f1;
+  auto tap = [&](int j, T xv, T &a0, T &a1) {              // position j of the pass: which taps of the two outputs it carries
+    if (j <= NT) {
+      if (j == 0 ? !sh : (j == NT ? sh : true)) a0 += st.c0[j] * xv;
+    }
     if (j >= DLO) {
-      const int jj = j - DLO;
-      if (jj == 0) { if (st.dlo) a1 += st.c1[0] * xv; }
-      else if (jj == NT) { if (!st.dlo) a1 += st.c1[NT] * xv; }
-      else a1 += st.c1[jj] * xv;
+      const int jj = j - DLO;                                // 0 .. NT + 1
+      if (jj == 0 ? f1 == 0 : (jj == 1 ? f1 <= 1 : (jj == NT ? f1 >= 1 : (jj == NT + 1 ? f1 == 2 : true)))) a1 += st.c1[jj] * xv;
     }
   };
   auto emit = [&](int m, T a0, T a1) {
@@ -1200,7 +1213,7 @@ RR_PROG void poly0_dual_compute(const Poly0DualParams<T> &dp, const Poly0DualTil
       else view_write<OutT, T>(p.out, out_off, p.out_preload + t.i_base + i + 1, a1);
     }
   };
-  constexpr int NW = NT + DLO + 1;
+  constexpr int NW = NT + DLO + 2;
   int m = 0;
   for (; m + 1 < t.mcount; m += 2, xw += 2 * step) {        // two periods at a time: four independent DFMA chains
     const T *xb = xw + step;
