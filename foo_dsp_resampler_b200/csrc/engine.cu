@@ -1252,7 +1252,12 @@ template <class T> class Engine {
         pp.P = 1;
         while (!(in.nch & 1) && !(out.nch & 1) && in.nch == out.nch && 2 * pp.P < in.nch && in.nch % (4 * pp.P) == 0 &&
                pp.tslots * 2 * pp.P <= 256)
-          pp.P *= 2;                                          // several pairs per CTA only as channels of one stream
+          pp.P *= 2;                                          // several pairs per CTA as channels of one stream ...
+        // ... or the stereo pairs of two consecutive streams: 74 slot pairs of a period fill 5 full warps instead of
+        // 2.3 of 3 (the two-slot kernel is bound by issue and latency, not by a pipe)
+        if (pp.CL == 2 && pp.P == 1 && in.nch == 2 && out.nch == 2 && nlanes % 4 == 0 && pp.tslots * 2 <= 256 &&
+            pp.tslots % 32 != 0 && !getenv("B200RATE_PAIR2_P1"))
+          pp.P = 2;
         // one period group; as many CTAs per SM as 64 registers per thread allow (1024 threads), each with one
         // window buffer of an even number of periods (the other CTAs cover its load)
         pp.PG = 1;

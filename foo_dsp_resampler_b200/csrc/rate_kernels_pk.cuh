@@ -1055,6 +1055,8 @@ struct Poly0PairTile {
   Poly0Tile t;
   float *d_base;                 // first output sample of the tile (slot 0, period 0) of lane t.lane0
   long long lane1;               // elements from a pair's first lane to its second (the two need not share a stream)
+  long long pair_stride;         // elements from one pair of the CTA to the next in the output (channels of one stream, or
+                                 // stereo pairs of consecutive streams)
   long long i_end;               // outputs at or beyond this index do not exist
   int direct;                    // every output of the tile exists and is stored contiguously
   int tma, head;                 // the windows are staged by bulk copies; window sample j then sits at buffer index head + j
@@ -1070,6 +1072,7 @@ RR_PROG Poly0PairTile poly0_pair_make_tile(const Poly0PairParams &pp, long long 
   pt.direct = i_tile_end <= pt.i_end && view_range_direct(p.out, p.out_preload + pt.t.i_first, p.out_preload + i_tile_end);
   pt.d_base = view_ptr<float>(p.out, lane_offset(p.out, pt.t.lane0), p.out_preload + pt.t.i_first);
   pt.lane1 = lane_offset(p.out, pt.t.lane0 + 1) - lane_offset(p.out, pt.t.lane0);
+  pt.pair_stride = pp.P > 1 ? lane_offset(p.out, pt.t.lane0 + 2) - lane_offset(p.out, pt.t.lane0) : 0;
   // bulk-copy staging: every window of the tile a contiguous range of adjacent stereo frames, one sample of slack
   // either side inside the view (the copies are rounded out to 16-byte boundaries)
   const long long c0 = pt.t.q_first + p.pre;
@@ -1096,9 +1099,9 @@ RR_PROG void poly0_pair_tile(const Poly0PairParams &pp, const Poly0PairTile &pt,
   const Poly0Tile &t = pt.t;
   const Poly0FastParams<float> &fp = pp.fast;
   const PolyParams<float> &p = fp.base;
-  const int L = p.L, PG = pp.PG, es = p.out.elem_stride, cs = p.out.ch_stride;
-  // the P pairs of a CTA are channels of one stream: lane offsets differ by multiples of the channel stride
-  const int rel = (st.fs + st.g * L) * es + 2 * st.pr * cs;   // P > 1 only for pairs of one stream
+  const int L = p.L, PG = pp.PG, es = p.out.elem_stride;
+  // the P pairs of a CTA are equally spaced in the output: channels of one stream, or stereo pairs of consecutive streams
+  const long long rel = (long long)(st.fs + st.g * L) * es + st.pr * pt.pair_stride;
   float *d0 = pt.d_base + rel, *d1 = d0 + pt.lane1;
   const int dstep = PG * L * es;                          // between this thread's consecutive outputs
   const bool direct = pt.direct != 0;
@@ -1195,8 +1198,8 @@ RR_PROG void poly0_pair2_tile(const Poly0PairParams &pp, const Poly0PairTile &pt
   const Poly0Tile &t = pt.t;
   const Poly0FastParams<float> &fp = pp.fast;
   const PolyParams<float> &p = fp.base;
-  const int L = p.L, es = p.out.elem_stride, cs = p.out.ch_stride;
-  const int rel = st.fs * es + 2 * st.pr * cs;               // P > 1 only for pairs of one stream
+  const int L = p.L, es = p.out.elem_stride;
+  const long long rel = (long long)st.fs * es + st.pr * pt.pair_stride;   // the P pairs of a CTA are equally spaced in the output
   float *d0 = pt.d_base + rel, *d1 = d0 + pt.lane1;
   const int dstep = L * es;
   const bool direct = pt.direct != 0;
