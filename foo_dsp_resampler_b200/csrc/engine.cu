@@ -1255,14 +1255,18 @@ template <class T> class Engine {
           pp.P *= 2;                                          // several pairs per CTA as channels of one stream ...
         // ... or the stereo pairs of two consecutive streams: 74 slot pairs of a period fill 5 full warps instead of
         // 2.3 of 3 (the two-slot kernel is bound by issue and latency, not by a pipe)
-        if (pp.CL == 2 && pp.P == 1 && in.nch == 2 && out.nch == 2 && nlanes % 4 == 0 && pp.tslots * 2 <= 256 &&
+        if (pp.P == 1 && in.nch == 2 && out.nch == 2 && nlanes % 4 == 0 && pp.tslots * 2 <= 256 &&
             pp.tslots % 32 != 0 && !getenv("B200RATE_PAIR2_P1"))
           pp.P = 2;
         // one period group; as many CTAs per SM as 64 registers per thread allow (1024 threads), each with one
         // window buffer of an even number of periods (the other CTAs cover its load)
         pp.PG = 1;
         const int threads = pp.tslots * pp.P;
-        const int ctas = std::max(1, std::min(16, 1024 / threads));
+        // window budget per CTA from the CTAs an SM will hold: 1024 threads' worth, but at 80 registers a 160-thread CTA
+        // fits four times (measured with 6 / 5 / 4 / 3 assumed: cfg4 0.825 / 0.804 / 0.792 / 0.860 ms per 256 streams)
+        int ctas = std::max(1, std::min(16, 1024 / threads));
+        if (threads >= 160) ctas = std::min(ctas, 4);
+        if (const char *e = getenv("B200RATE_PAIR_CTAS")) ctas = std::max(1, atoi(e));          // probes
         const size_t budget = std::min<size_t>(64 * 1024, (max_smem_ - 2048) / ctas - 1024);
         auto window_of = [&](int mm) {
           const long long wd = ((L - 1) + static_cast<long long>(L - 1) * step) / L + static_cast<long long>(mm - 1) * step + g.n + 1 + 4;
