@@ -1313,6 +1313,12 @@ RR_PROG HalfbandPairTile halfband_pair_tile(const HalfbandPairParams &hp, long l
 // Stage the window of a tile, split by sample parity: even u -> P0[g][u/2]; odd u -> P1[g][(u+1)/2 + shift], so
 // that the centre tap of output j (u = 2j + reach) sits at P1[j + 4]; odd samples below the first centre tap
 // (index < 4) are never read and not stored. Asynchronous (LDGSTS): returns after committing the copies.
+// Shared-memory index of window element i (8-byte units from the start of the buffer). A thread reads its window as
+// 16-byte chunks and neighbouring threads start 32 bytes apart, so lanes t and t + 4 of a quarter-warp would meet in
+// the same banks (two wavefronts per LDS.128: 42 % of the kernel's wavefronts were such conflicts while l1tex was 86 %
+// busy). Swapping the two 16-byte chunk pairs of every second 128-byte line moves lane t + 4 one chunk over.
+RR_HD int hb_swz(int i) { return i ^ ((i >> 3) & 2); }
+
 template <int NC>
 RR_PROG void halfband_pair_load(const HalfbandPairParams &hp, const HalfbandPairTile &t, Pk *smem, int tid, int nthreads)
 {
@@ -1320,7 +1326,7 @@ RR_PROG void halfband_pair_load(const HalfbandPairParams &hp, const HalfbandPair
   const int G = hp.G, gbits = G == 4 ? 2 : G == 2 ? 1 : 0;      // G is 1, 2 or 4
   // the odd array starts 8 values (16 banks) further so that the even and the odd sample of a frame pair never
   // share a bank
-  Pk *P0 = smem, *P1 = smem + (long long)G * p.half + 8;
+  const int o1 = G * p.half + 8;                         // first element of the odd array
   const int shift = 4 - NC, win = t.win;
   const int ics = p.in.ch_stride, ies = p.in.elem_stride;
   // lane l of the tile relative to its first lane: channels of one stream when G > 1, any two lanes when G == 1
@@ -1334,19 +1340,19 @@ RR_PROG void halfband_pair_load(const HalfbandPairParams &hp, const HalfbandPair
     for (int w = tid; w < (npairs_u << gbits); w += nthreads) {
       const int g = w & (G - 1), f = w >> gbits;
       const float *sp = src0 + (2 * f) * ies + 2 * g;
-      pk_async_copy8(P0 + g * p.half + f, sp);
+      pk_async_copy8(smem + hb_swz(g * p.half + f), sp);
       const int io = f + 1 + shift;
-      if (2 * f + 1 < win && io >= 4) pk_async_copy8(P1 + g * p.half + io, sp + ies);
+      if (2 * f + 1 < win && io >= 4) pk_async_copy8(smem + hb_swz(o1 + g * p.half + io), sp + ies);
     }
   } else if (direct) {
     // planar lanes (or any regular strides): lane by lane, frame pairs fastest
     for (int l = 0; l < 2 * G; ++l) {
       const float *sl = src0 + lane_rel(l);
-      float *d0 = &P0[(l >> 1) * p.half].a + (l & 1), *d1 = &P1[(l >> 1) * p.half].a + (l & 1);
+      const int b0 = (l >> 1) * p.half, b1 = o1 + b0;
       for (int f = tid; f < npairs_u; f += nthreads) {
-        async_copy_elem<float>(d0 + 2 * f, sl + (long long)(2 * f) * ies, true);
+        async_copy_elem<float>(&smem[hb_swz(b0 + f)].a + (l & 1), sl + (long long)(2 * f) * ies, true);
         const int io = f + 1 + shift;
-        if (2 * f + 1 < win && io >= 4) async_copy_elem<float>(d1 + 2 * io, sl + (long long)(2 * f + 1) * ies, true);
+        if (2 * f + 1 < win && io >= 4) async_copy_elem<float>(&smem[hb_swz(b1 + io)].a + (l & 1), sl + (long long)(2 * f + 1) * ies, true);
       }
     }
   } else {
@@ -1356,8 +1362,8 @@ RR_PROG void halfband_pair_load(const HalfbandPairParams &hp, const HalfbandPair
       const float *src = view_addr<float>(p.in, t.in_off0 + lane_rel(l), t.x0 + u, &valid);
       if (u & 1) {
         const int io = ((u + 1) >> 1) + shift;
-        if (io >= 4) async_copy_elem<float>(&P1[g * p.half + io].a + (l & 1), src, valid);
-      } else async_copy_elem<float>(&P0[g * p.half + (u >> 1)].a + (l & 1), src, valid);
+        if (io >= 4) async_copy_elem<float>(&smem[hb_swz(o1 + g * p.half + io)].a + (l & 1), src, valid);
+      } else async_copy_elem<float>(&smem[hb_swz(g * p.half + (u >> 1))].a + (l & 1), src, valid);
     }
   }
   async_copy_commit();
@@ -1371,21 +1377,22 @@ RR_PROG void halfband_pair_compute(const HalfbandPairParams &hp, const float (&c
   const HalfbandParams<float> &p = hp.base;
   constexpr int c = NC;
   const int G = hp.G, cnt = t.cnt;
-  const Pk *P0 = smem, *P1 = smem + (long long)G * p.half + 8;
+  const int o1 = G * p.half + 8;                         // first element of the odd array
   const int qbits = p.qbits;                             // log2(tile / 4)
   const int ocs = p.out.ch_stride, oes = p.out.elem_stride;
   const long long lane1 = G > 1 ? ocs : t.out_lane1;
   for (int w = tid; w < (G << qbits); w += nthreads) {
     const int g = w >> qbits, j = 4 * (w & ((1 << qbits) - 1));
     if (j >= cnt) continue;
-    const Pk *e = P0 + g * p.half + j, *o = P1 + g * p.half + j + 4;
-    // outputs j..j+3 use P0[j .. j+2c+2] and the centres P1[j+4 .. j+7]; rows are 16-byte aligned
+    const int e = g * p.half + j, o = o1 + g * p.half + j + 4;
+    // outputs j..j+3 use even-array elements j .. j+2c+2 and the centres, odd-array elements j+4 .. j+7; rows are 16-byte
+    // aligned, element index -> shared-memory position through hb_swz (whole 16-byte chunks move)
     constexpr int kVecs = (2 * c + 3 + 1) / 2;
     Pk x[2 * kVecs], ctr[4];
 #pragma unroll
-    for (int i = 0; i < kVecs; ++i) { const CPk v = reinterpret_cast<const CPk *>(e)[i]; x[2 * i] = v.x; x[2 * i + 1] = v.y; }
+    for (int i = 0; i < kVecs; ++i) { const CPk v = *reinterpret_cast<const CPk *>(smem + hb_swz(e + 2 * i)); x[2 * i] = v.x; x[2 * i + 1] = v.y; }
 #pragma unroll
-    for (int i = 0; i < 2; ++i) { const CPk v = reinterpret_cast<const CPk *>(o)[i]; ctr[2 * i] = v.x; ctr[2 * i + 1] = v.y; }
+    for (int i = 0; i < 2; ++i) { const CPk v = *reinterpret_cast<const CPk *>(smem + hb_swz(o + 2 * i)); ctr[2 * i] = v.x; ctr[2 * i + 1] = v.y; }
     Pk y[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
