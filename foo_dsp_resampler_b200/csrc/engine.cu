@@ -1179,7 +1179,7 @@ template <class T> class Engine {
                                 !(out.nch & 1);
           hp.G = group_ok ? nchan / 2 : 1;
           hp.base.CH = 2 * hp.G;
-          hp.base.tile = kHalfTile / (2 * hp.G);             // outputs per pair per CTA, power of two
+          hp.base.tile = half_pair_tile_ / (2 * hp.G);       // outputs per pair per CTA, power of two
           hp.base.qbits = 0;
           while ((4 << hp.base.qbits) < hp.base.tile) ++hp.base.qbits;
           // rows of 8-byte values: 16-byte aligned (even) and 4 mod 16, so the pairs of a frame land 8 banks apart
@@ -1720,6 +1720,9 @@ template <class T> class Engine {
   // debugging switches: generic kernels only / per stage kind
   bool use_pair_kernel_ = getenv("B200RATE_NO_PAIR_KERNEL") == nullptr;
   bool use_pair_dft_ = getenv("B200RATE_NO_PAIR_DFT") == nullptr, use_pair_poly_ = getenv("B200RATE_NO_PAIR_POLY") == nullptr;
+  // outputs per CTA tile of halfband_pair_kernel: two work units per thread and tile halve the barriers per output
+  // (cfg5 stages 0 / 1: 1.095 + 0.660 / 0.832 + 0.496 / 0.805 + 0.441 / 0.913 + 0.518 ms for 1024 / 2048 / 4096 / 8192)
+  int half_pair_tile_ = getenv("B200RATE_HALF_TILE") ? std::max(512, std::min(8192, atoi(getenv("B200RATE_HALF_TILE")))) : 2 * kHalfTile;
   bool use_pair_shift_ = getenv("B200RATE_NO_PAIR_SHIFT") == nullptr;   // probes: the old deal with overflow into holes
   bool use_pair_half_ = getenv("B200RATE_NO_PAIR_HALF") == nullptr, use_pair_poly2_ = getenv("B200RATE_NO_PAIR_POLY2") == nullptr;
   int last_dft_kernel_ = 0;
