@@ -1195,7 +1195,7 @@ template <class T> class Engine {
       const bool group_ok = in.ch_stride == 1 && out.nch == nchan && nlanes % nchan == 0 &&
                             (nchan == 2 || nchan == 4 || nchan == 8);
       p.CH = group_ok ? nchan : 1;
-      p.tile = kHalfTile / p.CH;                          // power of two (the window must fit kHbRaw registers per thread)
+      p.tile = (sizeof(T) == 8 && !getenv("B200RATE_HALF_TILE_G2048") ? 2 * kHalfTile : kHalfTile) / p.CH;   // power of two (the window must fit kHbRaw registers per thread)
       p.qbits = 0;
       while ((4 << p.qbits) < p.tile) ++p.qbits;
       p.half = ((p.tile + 2 * p.ncoef + 8 + 31) / 32) * 32 + 4;
@@ -1722,7 +1722,8 @@ template <class T> class Engine {
   bool use_pair_dft_ = getenv("B200RATE_NO_PAIR_DFT") == nullptr, use_pair_poly_ = getenv("B200RATE_NO_PAIR_POLY") == nullptr;
   // outputs per CTA tile of halfband_pair_kernel: two work units per thread and tile halve the barriers per output
   // (cfg5 stages 0 / 1: 1.095 + 0.660 / 0.832 + 0.496 / 0.805 + 0.441 / 0.913 + 0.518 ms for 1024 / 2048 / 4096 / 8192).
-  // The generic kernel stays at kHalfTile: its window travels through kHbRaw registers per thread.
+  // The generic kernel's fp64 instance likewise (1.210 -> 1.089 ms on cfg3 stage 0); its window travels through kHbRaw
+  // registers per thread, which bounds the tile.
   int half_pair_tile_ = getenv("B200RATE_HALF_TILE") ? std::max(512, std::min(8192, atoi(getenv("B200RATE_HALF_TILE")))) : 2 * kHalfTile;
   bool use_pair_shift_ = getenv("B200RATE_NO_PAIR_SHIFT") == nullptr;   // probes: the old deal with overflow into holes
   bool use_pair_half_ = getenv("B200RATE_NO_PAIR_HALF") == nullptr, use_pair_poly2_ = getenv("B200RATE_NO_PAIR_POLY2") == nullptr;

@@ -1398,7 +1398,7 @@ RR_PROG HbTile<InT, OutT> hb_make_tile(const HalfbandParams<T> &p, long long wor
 // The window of a tile travels global -> registers -> shared memory in two steps, so that a persistent CTA can have
 // the loads of its next tile in flight while it computes the current one. Thread `tid` of `nthreads` takes elements
 // w = tid + k * nthreads, k < kHbRaw (vector path: 16-byte groups of four channels, k < kHbRaw / 4).
-constexpr int kHbRaw = 20;
+constexpr int kHbRaw = 40;
 template <class InT> struct HbRegs { InT v[kHbRaw]; };
 template <class T, class InT, class OutT> RR_HD bool hb_vec_path(const HalfbandParams<T> &p, const HbTile<InT, OutT> &tl)
 {
