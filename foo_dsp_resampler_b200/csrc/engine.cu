@@ -1300,8 +1300,10 @@ template <class T> class Engine {
         // flight) measured better than three (two CTAs) or one (five CTAs): cfg3 4.11 / 4.31 / 4.95 ms
         dp.NL = std::max(1, std::min(std::min(nlanes, 256 / dt.TS), 2));
         if (const char *e = getenv("B200RATE_DUAL_NL")) dp.NL = std::max(1, std::min(std::min(nlanes, 256 / dt.TS), atoi(e)));   // probes
-        const int budget = 1536;                                   // doubles per lane window: 12 KB
-        dp.MM = std::max(2, static_cast<int>((budget - g.n - 8) / g.pstep));
+        // periods per tile: about ten (measured on cfg3, step 320: 4 / 7 / 9 / 12 periods 1.342 / 1.131 / 1.106 / 1.127 ms;
+        // 44.1 -> 48 kHz, step 147: 10 / 15 / 20 periods 1.962 / 2.036 / 2.149 ms), within 4096 doubles per lane window
+        const int budget = getenv("B200RATE_DUAL_BUDGET") ? std::max(1024, std::min(6144, atoi(getenv("B200RATE_DUAL_BUDGET")))) : 4096;
+        dp.MM = std::max(2, std::min(getenv("B200RATE_DUAL_BUDGET") ? 64 : 10, static_cast<int>((budget - g.n - 8) / g.pstep)));
         dp.win = static_cast<int>(((static_cast<long long>(dp.MM) * g.pstep + g.n + 8 + 1) & ~1ll) + 2);
         dp.m_begin = w0 / g.Lp;
         const long long m_end = (w0 + wn + g.Lp - 1) / g.Lp;
