@@ -208,7 +208,9 @@ int RRX_track_edge_lengths(unsigned in_rate, unsigned out_rate, unsigned *add, u
                            unsigned *inbuf_frames);
 /* lpc/lpc.h:26 lpc_extrapolate2, same arguments and memory layout: `data` is HOST memory pointing at frame 0 of
  * data_len interleaved base frames; frames [-extra_bkwd, 0) and [data_len, data_len + extra_fwd) are written.
- * lpc_order 1..32 (the reference's callers use LPC_ORDER = 32), else RR_INVPARAM. Blocking. */
+ * lpc_order 1..32 (the reference's callers use LPC_ORDER = 32), else RR_INVPARAM. Blocking. Runs on the calling thread's
+ * current CUDA device (the device-resident entry points below: on the device that owns d_data); no device: RR_INTERNAL
+ * with the CUDA error in RRX_last_error -- there is no host fallback. */
 int RRX_lpc_extrapolate2(float *data, size_t data_len, int nchannels, int lpc_order, size_t extra_bkwd, size_t extra_fwd);
 /* lpc/lpc.h:28-38, the two inline wrappers. */
 int RRX_lpc_extrapolate_bkwd(float *data, size_t data_len, size_t prime_len, int nchannels, int lpc_order, size_t extra_bkwd);
